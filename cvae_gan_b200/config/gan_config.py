@@ -1,0 +1,23 @@
+"""Mirror of the names/values the hot path reads from /root/reference/src/config/gan_config.py:1-21.
+Module-level constants, mutated in place by callers and read at CALL time, like the reference."""
+epochs: int = 500
+batch_size: int = 128      # GLOBAL batch; a data-parallel rank processes batch_size // world_size rows
+
+z_size: int = 128
+
+g_lr: float = 2e-4
+g_loop_num: int = 3
+
+d_lr: float = 2e-4
+d_loop_num: int = 5
+
+c_lr: float = 1e-4
+c_loop_num: int = 5
+
+cvae_gan_config = {
+    'lambda_recon': 1.0,
+    'lambda_kl': 0.1,
+    'lambda_adv': 1.0,
+    'lambda_class': 0.5,
+    'confidence_threshold': 0.5,
+}

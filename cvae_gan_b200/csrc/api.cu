@@ -1,0 +1,291 @@
+// cvaegan_b200 - extern "C" entry points (see include/cvaegan_b200.h for the contract).
+#include "engine.cuh"
+
+namespace cvg {
+const char* last_error();
+int comm_unique_id(void* out128);
+int comm_init(Engine& e, const void* id128, int rank, int world);
+void comm_destroy(Engine& e);
+}  // namespace cvg
+
+using namespace cvg;
+
+struct CvgHandle {
+  Engine e;
+};
+
+#define H_OR_FAIL(h)                      \
+  if (!(h)) {                             \
+    cvg::set_error("null handle");        \
+    return 1;                             \
+  }
+
+extern "C" {
+
+const char* cvg_last_error(void) { return cvg::last_error(); }
+int cvg_abi_version(void) { return CVG_ABI_VERSION; }
+
+int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
+  if (!cfg || !out) CVG_FAIL("cvg_create: null argument");
+  *out = nullptr;
+  int dev = 0;
+  CVG_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CVG_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    CVG_FAIL(std::string("cvaegan_b200 runs on sm_100 (B200) only; device is sm_") + std::to_string(prop.major) +
+             std::to_string(prop.minor) + " - there is no fallback path");
+  if (cfg->feature_num < 1 || cfg->label_num < 1 || cfg->z_size < 4 || cfg->max_batch < 1)
+    CVG_FAIL("cvg_create: bad dimensions");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) CVG_FAIL("cvg_create: bad rank/world_size");
+  CvgHandle* h = new CvgHandle();
+  Engine& e = h->e;
+  e.cfg = *cfg;
+  e.F = cfg->feature_num;
+  e.K = cfg->label_num;
+  e.Z = cfg->z_size;
+  e.world = cfg->world_size;
+  e.rank = cfg->rank;
+  e.num_sms = prop.multiProcessorCount;
+  if (build_layouts(e) != 0) {
+    delete h;
+    return 1;
+  }
+  cudaError_t err = cudaFuncSetAttribute(gemm_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(gemm_mn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(gemm_mn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (err != cudaSuccess) {
+    cvg::set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+    delete h;
+    return 1;
+  }
+  *out = h;
+  return 0;
+}
+
+void cvg_destroy(CvgHandle* h) {
+  if (!h) return;
+  comm_destroy(h->e);
+  delete h;
+}
+
+int cvg_net_sizes(const CvgHandle* h, int net, int64_t* n_param_floats, int64_t* n_state_floats) {
+  H_OR_FAIL(h);
+  if (net < 0 || net >= CVG_NUM_NETS) CVG_FAIL("bad net id");
+  if (n_param_floats) *n_param_floats = h->e.lay[net].n_param;
+  if (n_state_floats) *n_state_floats = h->e.lay[net].n_state;
+  return 0;
+}
+
+int cvg_tensor_table(const CvgHandle* h, int net, CvgTensorDesc* out, int32_t capacity, int32_t* count) {
+  H_OR_FAIL(h);
+  if (net < 0 || net >= CVG_NUM_NETS) CVG_FAIL("bad net id");
+  const auto& t = h->e.lay[net].table;
+  if (count) *count = (int32_t)t.size();
+  if (out) {
+    if (capacity < (int32_t)t.size()) CVG_FAIL("tensor table capacity too small");
+    for (size_t i = 0; i < t.size(); ++i) out[i] = t[i];
+  }
+  return 0;
+}
+
+int64_t cvg_workspace_bytes(const CvgHandle* h) { return h ? workspace_bytes(h->e) : -1; }
+
+int cvg_bind_net(CvgHandle* h, int net, float* params, float* grads, float* adam_m, float* adam_v, float* state) {
+  H_OR_FAIL(h);
+  if (net < 0 || net >= CVG_NUM_NETS) CVG_FAIL("bad net id");
+  if (!params || !grads || !adam_m || !adam_v) CVG_FAIL("cvg_bind_net: null buffer");
+  if (h->e.lay[net].n_state > 0 && !state) CVG_FAIL("cvg_bind_net: this network needs a state buffer");
+  if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)adam_m | (uintptr_t)adam_v | (uintptr_t)state) & 15) != 0)
+    CVG_FAIL("cvg_bind_net: buffers must be 16-byte aligned");
+  NetBuffers& b = h->e.buf[net];
+  b.params = params; b.grads = grads; b.m = adam_m; b.v = adam_v; b.state = state;
+  return 0;
+}
+
+int cvg_bind_workspace(CvgHandle* h, void* workspace, int64_t bytes, void* stream) {
+  H_OR_FAIL(h);
+  if (!workspace) CVG_FAIL("null workspace");
+  CVG_TRY(carve_workspace(h->e, workspace, bytes));
+  // rows beyond the batch are never read un-masked, but start from a defined state
+  CVG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)bytes, (cudaStream_t)stream));
+  return 0;
+}
+
+int cvg_set_adam_step(CvgHandle* h, int net, int64_t t) {
+  H_OR_FAIL(h);
+  if (net < 0 || net >= CVG_NUM_NETS) CVG_FAIL("bad net id");
+  h->e.adam_t[net] = t;
+  return 0;
+}
+int64_t cvg_get_adam_step(const CvgHandle* h, int net) {
+  if (!h || net < 0 || net >= CVG_NUM_NETS) return -1;
+  return h->e.adam_t[net];
+}
+
+int cvg_comm_unique_id(void* out128) {
+  if (!out128) CVG_FAIL("null argument");
+  return comm_unique_id(out128);
+}
+int cvg_comm_init(CvgHandle* h, const void* id128, int rank, int world_size) {
+  H_OR_FAIL(h);
+  if (world_size != h->e.cfg.world_size || rank != h->e.cfg.rank) CVG_FAIL("rank/world_size differ from cvg_create");
+  return comm_init(h->e, id128, rank, world_size);
+}
+
+int cvg_step_d(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
+               uint64_t counter, int flags, float* loss_out, void* stream) {
+  H_OR_FAIL(h);
+  if (!x_real) CVG_FAIL("null x_real");
+  if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
+  return step_d(h->e, x_real, label, B, noise, seed, counter, flags, loss_out, (cudaStream_t)stream);
+}
+int cvg_step_c(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
+               uint64_t counter, int flags, float* loss_out, void* stream) {
+  H_OR_FAIL(h);
+  if (!x_real) CVG_FAIL("null x_real");
+  if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
+  return step_c(h->e, x_real, label, B, noise, seed, counter, flags, loss_out, (cudaStream_t)stream);
+}
+int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
+               uint64_t counter, float lambda_class_now, int flags, float* loss_out, void* stream) {
+  H_OR_FAIL(h);
+  if (!x_real) CVG_FAIL("null x_real");
+  if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
+  return step_g(h->e, x_real, label, B, noise, seed, counter, lambda_class_now, flags, loss_out, (cudaStream_t)stream);
+}
+
+int cvg_adam(CvgHandle* h, int net_mask, void* stream) {
+  H_OR_FAIL(h);
+  return run_adam(h->e, net_mask, (cudaStream_t)stream);
+}
+
+int cvg_sample_rows(CvgHandle* h, const float* class_rows, int64_t n, int64_t B_global, int64_t draw_offset,
+                    int B_local, uint64_t seed, uint64_t counter, float* x_out, int64_t* idx_out, void* stream) {
+  H_OR_FAIL(h);
+  if (!class_rows || !x_out || n < 1 || B_local < 1 || draw_offset < 0 || draw_offset + B_local > B_global)
+    CVG_FAIL("cvg_sample_rows: bad argument");
+  sample_rows_kernel<<<(B_local + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      class_rows, n, B_global, draw_offset, B_local, h->e.F, seed, counter, x_out, (long long*)idx_out);
+  CVG_CUDA(cudaGetLastError());
+  h->e.launches++;
+  return 0;
+}
+
+int cvg_generate(CvgHandle* h, int label, int64_t n, const float* z, uint64_t seed, uint64_t row_offset, int train_mode,
+                 float* x_out, void* stream) {
+  H_OR_FAIL(h);
+  if (n < 0 || (n > 0 && !x_out)) CVG_FAIL("cvg_generate: bad argument");
+  return generate(h->e, label, n, z, seed, row_offset, train_mode, x_out, (cudaStream_t)stream);
+}
+
+int cvg_generate_filter(CvgHandle* h, int label, int64_t n, float thr, const float* z, uint64_t seed,
+                        uint64_t row_offset, float* x_out, int64_t* idx_out, int64_t capacity,
+                        unsigned long long* count_out, float* logits_out, uint8_t* keep_out, void* stream) {
+  H_OR_FAIL(h);
+  if (n < 0 || !count_out || (capacity > 0 && !x_out)) CVG_FAIL("cvg_generate_filter: bad argument");
+  return generate_filter(h->e, label, n, thr, z, seed, row_offset, x_out, idx_out, capacity, count_out, logits_out,
+                         keep_out, (cudaStream_t)stream);
+}
+
+int cvg_filter_logits(const float* logits, int64_t n, int K, int label, float thr, uint8_t* keep_out, void* stream) {
+  if (!logits || !keep_out || n < 0) CVG_FAIL("cvg_filter_logits: bad argument");
+  if (K < 1 || K > FILTER_MAXK) CVG_FAIL("cvg_filter_logits: K must be in [1, 32]");
+  if (n == 0) return 0;
+  filter_logits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, n, K, label, thr, keep_out);
+  CVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cvg_filter_compact(const float* x, const float* logits, int64_t n, int F, int K, int label, float thr,
+                       uint64_t row_offset, float* x_out, int64_t* idx_out, int64_t capacity,
+                       unsigned long long* count_out, void* stream) {
+  if (!x || !logits || !count_out || n < 0) CVG_FAIL("cvg_filter_compact: bad argument");
+  if (K < 1 || K > FILTER_MAXK) CVG_FAIL("cvg_filter_compact: K must be in [1, 32]");
+  if (n == 0) return 0;
+  filter_compact_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, logits, n, 0, F, K, label, thr, row_offset, x_out, (long long*)idx_out, capacity, count_out, nullptr, nullptr);
+  CVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cvg_classifier_forward(CvgHandle* h, const float* x, int64_t n, float* logits_out, void* stream) {
+  H_OR_FAIL(h);
+  if (!x || !logits_out || n < 0) CVG_FAIL("cvg_classifier_forward: bad argument");
+  return classifier_forward(h->e, x, n, logits_out, (cudaStream_t)stream);
+}
+int cvg_encoder_forward(CvgHandle* h, const float* x, int label, int64_t n, float* mu_out, float* logvar_out,
+                        void* stream) {
+  H_OR_FAIL(h);
+  if (!x || !mu_out || !logvar_out || n < 0) CVG_FAIL("cvg_encoder_forward: bad argument");
+  return encoder_forward(h->e, x, label, n, mu_out, logvar_out, (cudaStream_t)stream);
+}
+
+int cvg_patience_scan(const uint8_t* keep, int64_t n, int64_t num, int chunk, int patience, int64_t* rows_consumed,
+                      int64_t* rows_accepted) {
+  if (!keep || !rows_consumed || !rows_accepted || chunk < 1) CVG_FAIL("cvg_patience_scan: bad argument");
+  int64_t pos = 0, got = 0;
+  while (got < num && patience > 0) {
+    const int64_t c = (num - got) < chunk ? (num - got) : chunk;
+    if (pos + c > n) CVG_FAIL("cvg_patience_scan: row stream too short");
+    int64_t k = 0;
+    for (int64_t i = 0; i < c; ++i) k += keep[pos + i] ? 1 : 0;
+    pos += c;
+    got += k;
+    if (k == 0) --patience;
+  }
+  *rows_consumed = pos;
+  *rows_accepted = got;
+  return 0;
+}
+
+int cvg_debug_read(CvgHandle* h, const char* name, int pass, int rows, float* dst, int* features_out, void* stream) {
+  H_OR_FAIL(h);
+  if (!name) CVG_FAIL("null name");
+  Engine& e = h->e;
+  const Workspace& w = e.ws;
+  if (!e.ws_base) CVG_FAIL("workspace not bound");
+  const std::string n(name);
+  const float* p = nullptr;
+  int C = 0;
+  auto idx = [&](const char* prefix) -> int {
+    const size_t L = strlen(prefix);
+    if (n.size() == L + 1 && n.compare(0, L, prefix) == 0 && n[L] >= '0' && n[L] <= '2') return n[L] - '0';
+    return -1;
+  };
+  int i;
+  if (n == "xT") { p = w.xT; C = e.F; }
+  else if (n == "z") { p = w.z; C = e.Z; }
+  else if ((i = idx("g_h")) >= 0) { p = w.g_h[i]; C = e.gh[i]; }
+  else if ((i = idx("g_dy")) >= 0) { p = w.g_dy[i]; C = e.gh[i]; }
+  else if (n == "g_out") { p = w.g_out; C = e.F; }
+  else if (n == "g_dout") { p = w.g_dout; C = e.F; }
+  else if ((i = idx("e_h")) >= 0) { p = w.e_h[i]; C = e.eh[i]; }
+  else if ((i = idx("e_dy")) >= 0) { p = w.e_dy[i]; C = e.eh[i]; }
+  else if (n == "e_ml") { p = w.e_ml; C = 2 * e.Z; }
+  else if (n == "e_dml") { p = w.e_dml; C = 2 * e.Z; }
+  else if ((i = idx("d_a")) >= 0) { p = w.d_a[i]; C = e.dh[i]; }
+  else if ((i = idx("d_g")) >= 0) { p = w.d_g[i]; C = e.dh[i]; }
+  else if (n == "d_s") { p = w.d_s; C = 1; }
+  else if (n == "c_a1") { p = w.c_a1; C = e.ch[0]; }
+  else if (n == "c_h2") { p = w.c_h2; C = e.ch[1]; }
+  else if (n == "c_a2") { p = w.c_a2; C = e.ch[1]; }
+  else if (n == "c_a3") { p = w.c_a3; C = e.ch[2]; }
+  else if (n == "c_logit") { p = w.c_logit; C = e.K; }
+  else if (n == "c_dlogit") { p = w.c_dlogit; C = e.K; }
+  else if ((i = idx("c_g")) >= 0) { p = w.c_g[i]; C = e.ch[i]; }
+  else if (n == "dx") { p = w.dx; C = e.F; }
+  else CVG_FAIL("cvg_debug_read: unknown buffer name");
+  if (features_out) *features_out = C;
+  if (!dst) return 0;
+  if (rows < 1 || rows > w.ld || pass < 0 || pass > 1) CVG_FAIL("cvg_debug_read: bad rows/pass");
+  to_row_major_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p + (size_t)pass * C * w.ld, rows, C, w.ld, dst);
+  CVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int64_t cvg_launch_count(const CvgHandle* h) { return h ? h->e.launches : -1; }
+
+}  // extern "C"

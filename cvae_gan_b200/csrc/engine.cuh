@@ -1,0 +1,124 @@
+// cvaegan_b200 - engine state: network layouts, borrowed buffers, workspace carving.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "misc_kernels.cuh"
+
+typedef struct ncclComm* ncclComm_t;
+
+namespace cvg {
+
+constexpr int STAT_C = 1024;   // max features of a BatchNorm layer (stats slots are [2][STAT_C])
+
+// feature-major workspace (all float matrices are [features][ld], two pass slots where noted)
+struct Workspace {
+  int ld = 0;          // rows rounded up to 64
+  int rows_cap = 0;
+  // inputs / noise
+  float* xT = nullptr;      // [F][ld]
+  float* z = nullptr;       // [2][Z][ld]      slot 0: z (D/C steps) or eps (G step); slot 1: z_prior (G step)
+  uint8_t* d_m1 = nullptr;  // [2][H1][ld]
+  uint8_t* d_m2 = nullptr;  // [2][H2][ld]
+  uint8_t* c_m1 = nullptr;
+  uint8_t* c_m2 = nullptr;
+  // generator
+  float *g_h[3] = {nullptr, nullptr, nullptr};   // [2][Hi][ld] pre-BN
+  float* g_out = nullptr;                        // [2][F][ld]
+  float *g_dy[3] = {nullptr, nullptr, nullptr};
+  float* g_dout = nullptr;                       // [2][F][ld]
+  // encoder
+  float *e_h[3] = {nullptr, nullptr, nullptr};   // [Hi][ld]
+  float* e_ml = nullptr;                         // [2Z][ld]  mu | logvar
+  float *e_dy[3] = {nullptr, nullptr, nullptr};
+  float* e_dml = nullptr;
+  // critic
+  float *d_a[3] = {nullptr, nullptr, nullptr};   // [2][Hi][ld] post activation/dropout
+  float* d_s = nullptr;                          // [2][1][ld]
+  float *d_g[3] = {nullptr, nullptr, nullptr};   // [2][Hi][ld] grads w.r.t. pre-activations
+  // classifier
+  float* c_a1 = nullptr;    // [2][H1][ld]
+  float* c_h2 = nullptr;    // [2][H2][ld]
+  float* c_a2 = nullptr;
+  float* c_rs = nullptr;    // [2][2][ld]
+  float* c_a3 = nullptr;    // [2][H3][ld]
+  float* c_logit = nullptr; // [2][K][ld]
+  float* c_dlogit = nullptr;
+  float *c_g[3] = {nullptr, nullptr, nullptr};
+  float* dx = nullptr;      // [F][ld]
+  // spectral norm scratch
+  float* sn_sigma = nullptr;      // [2][4]
+  float* sn_inv_sigma = nullptr;  // [4][2]
+  float* sn_u = nullptr;          // [2][sn_snap]
+  float* sn_v = nullptr;
+  long long sn_snap = 0;
+  float* sn_G = nullptr;          // [2][n_param(D)] per-pass raw critic gradients
+  // accumulators (doubles), zeroed every step
+  double* acc = nullptr;
+  size_t acc_bytes = 0;
+  double* loss = nullptr;         // [L_COUNT]
+  double* g_fst = nullptr;        // [3 layers][2 pass][2][STAT_C]
+  double* g_bst = nullptr;
+  double* e_fst = nullptr;        // [3][1][2][STAT_C]
+  double* e_bst = nullptr;
+  // generation scratch
+  unsigned long long* gen_count = nullptr;
+};
+
+struct Engine {
+  CvgConfig cfg{};
+  int F = 0, K = 0, Z = 0;
+  int eh[3]{}, gh[3]{}, dh[3]{}, ch[3]{};
+  NetLayout lay[4];
+  NetBuffers buf[4];
+  int64_t adam_t[4] = {0, 0, 0, 0};
+  Workspace ws;
+  void* ws_base = nullptr;
+  int64_t ws_bytes = 0;
+  int64_t launches = 0;
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
+  int num_sms = 148;
+
+  float* P(int net, int64_t off) const { return buf[net].params + off; }
+  float* G(int net, int64_t off) const { return buf[net].grads + off; }
+  float* S(int net, int64_t off) const { return buf[net].state + off; }
+};
+
+struct CvgHandleImpl {
+  Engine e;
+};
+
+// layout.cu
+int build_layouts(Engine& e);
+int64_t workspace_bytes(const Engine& e);
+int carve_workspace(Engine& e, void* base, int64_t bytes);
+
+// train.cu
+int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed, uint64_t counter,
+           int flags, float* loss_out, cudaStream_t st);
+int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed, uint64_t counter,
+           int flags, float* loss_out, cudaStream_t st);
+int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed, uint64_t counter,
+           float lambda_class, int flags, float* loss_out, cudaStream_t st);
+int run_adam(Engine& e, int net_mask, cudaStream_t st);
+int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st);
+int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st);
+
+// generate.cu
+int generate(Engine& e, int label, int64_t n, const float* z, uint64_t seed, uint64_t row_offset, int train_mode,
+             float* x_out, cudaStream_t st);
+int generate_filter(Engine& e, int label, int64_t n, float thr, const float* z, uint64_t seed, uint64_t row_offset,
+                    float* x_out, int64_t* idx_out, int64_t capacity, unsigned long long* count_out, float* logits_out,
+                    uint8_t* keep_out, cudaStream_t st);
+int classifier_forward(Engine& e, const float* x, int64_t n, float* logits_out, cudaStream_t st);
+int encoder_forward(Engine& e, const float* x, int label, int64_t n, float* mu_out, float* lv_out, cudaStream_t st);
+
+// shared launch helpers (train.cu)
+int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st);
+int launch_dw(Engine& e, const DwArgs& g, cudaStream_t st);
+int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int label, int M, float Bg, bool local_bn,
+                  cudaStream_t st);
+int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool train, int M, cudaStream_t st);
+int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn, cudaStream_t st);
+
+}  // namespace cvg

@@ -1,0 +1,614 @@
+// cvaegan_b200 - tiled FP32 GEMM kernels with fused prologues / epilogues.
+//
+// Data layout in HBM: every activation / gradient matrix is FEATURE-MAJOR, [features][ld] with the
+// batch row index contiguous (ld = rows rounded up to 64).  With that layout all three GEMMs of a
+// layer read both operands with 16-byte coalesced loads and no transposition:
+//   forward   Y[n][m]  = sum_r A[r][m] * W[n][r]          (gemm_mn_kernel<true>)
+//   backward  dA[j][m] = sum_r dY[r][m] * W[r][j]         (gemm_mn_kernel<false>)
+//   weight    dW[n][k] = sum_m dY[n][m] * A[k][m]         (gemm_dw_kernel)
+// Operand transforms (BatchNorm+LeakyReLU of the producing layer, reparameterisation, BatchNorm
+// backward) are applied while the tile is staged into shared memory, so normalised activations are
+// never written to memory; epilogues fuse bias / one-hot column / 1/sigma / activation / dropout /
+// batch-moment accumulation / KL / activation derivatives.
+#pragma once
+#include "common.cuh"
+
+namespace cvg {
+
+constexpr int TBM = 64;   // tile rows (batch)
+constexpr int TBN = 64;   // tile cols (features)
+constexpr int TBK = 16;   // reduction chunk
+constexpr int GEMM_THREADS = 256;
+
+enum { OP_PLAIN = 0, OP_BN_ACT = 1, OP_REPARAM = 2, OP_BN_BWD = 3, OP_CONST = 4 };
+enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
+enum { EP_LINEAR = 0, EP_DBN = 1, EP_DACT = 2, EP_STORE = 3, EP_REPARAM_BWD = 4 };
+
+// Reference to one BatchNorm layer's statistics.
+struct BnRef {
+  const double* fstats = nullptr;  // [pass][2][C]  sum h, sum h^2 over the (global) batch   (train)
+  long long sf = 0;
+  const double* bstats = nullptr;  // [pass][2][C]  sum dy, sum dy*xhat                       (backward)
+  long long sb = 0;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float* rmean = nullptr;          // running stats: source in eval mode, update target in train mode
+  float* rvar = nullptr;
+  int C = 0;
+  int eval = 0;
+  int update_running = 0;          // CTA (0,0,0) applies the momentum update for all passes, in order
+};
+
+struct Operand {
+  int kind = OP_PLAIN;
+  int rows = 0;                    // feature rows available (reduction length)
+  const float* p = nullptr;        // [rows][ld] (+ pass * sp)
+  long long sp = 0;
+  const float* h = nullptr;        // OP_BN_BWD: pre-BN activations of the same layer
+  long long sh = 0;
+  const float* mu = nullptr;       // OP_REPARAM (pass == reparam_pass): mu + eps * exp(0.5 * logvar)
+  const float* lv = nullptr;
+  const float* eps = nullptr;
+  int reparam_pass = -1;
+  float cst = 0.f;                 // OP_CONST
+  BnRef bn;
+};
+
+// number of float constants an operand keeps in shared memory
+__host__ __device__ inline int operand_const_floats(const Operand& o) {
+  if (o.kind == OP_BN_ACT) return 3 * o.bn.C;
+  if (o.kind == OP_BN_BWD) return 5 * o.bn.C;
+  return 0;
+}
+
+struct GemmArgs {
+  int M = 0, ld = 0, npass = 1;
+  float Bg = 1.f;                  // global batch rows (M * world)
+  int R = 0;                       // reduction length
+  int N = 0;                       // output features
+  Operand a;
+  const float* W = nullptr;        // <true>: W[n*ldw + wcol0 + r]   <false>: W[r*ldw + wcol0 + n]
+  int ldw = 0, wcol0 = 0;
+  float bn_eps = 1e-5f, momentum = 0.1f, slope = 0.2f;
+  // ---- epilogue ----
+  int ekind = EP_LINEAR;
+  const float* bias = nullptr;     // [N]
+  const float* wlabel = nullptr;   // one-hot column: bias'[n] = bias[n] + scale * wlabel[n*ldwl]
+  int ldwl = 0;
+  const float* scale = nullptr;    // per-pass device scalar (1/sigma) or null
+  int act = ACT_NONE;
+  const uint8_t* mask = nullptr;   // [N][ld] keep mask (+ pass * smask)
+  long long smask = 0;
+  float keep_inv = 1.f;
+  float* Y = nullptr;              // [N][ld] (+ pass * sY)
+  long long sY = 0;
+  int accumulate = 0;
+  double* ostats = nullptr;        // [pass][2][N]
+  long long sostats = 0;
+  double* osum = nullptr;          // [pass] sum of all outputs
+  double* kl_acc = nullptr;        // KL accumulation over the (mu | logvar) head outputs
+  int kl_split = 0;
+  const float* prev = nullptr;     // EP_DBN: h_prev ; EP_DACT: a_prev   [N][ld] (+ pass * sprev)
+  long long sprev = 0;
+  BnRef prev_bn;                   // EP_DBN
+  const float* mu = nullptr;       // EP_REPARAM_BWD
+  const float* lv = nullptr;
+  const float* eps = nullptr;
+  float kl_coef = 0.f;
+  int only_pass = -1;              // if >= 0 the grid has one pass slot mapped to this pass index
+};
+
+struct DwArgs {
+  int M = 0, ld = 0, npass = 1;
+  float Bg = 1.f;
+  int N = 0, K = 0;                // dW is [N][K] inside a [N][ldw] matrix at column wcol0
+  Operand p;                       // dY operand, rows = N
+  Operand q;                       // activation operand, rows = K
+  float* dW = nullptr;
+  long long sdW = 0;               // per-pass stride (spectral-norm layers keep per-pass gradients)
+  int ldw = 0, wcol0 = 0;
+  float* db = nullptr;             // [N] or null
+  int label_col = -1;              // one-hot column receives the bias gradient as well
+  float* dgamma = nullptr;         // BatchNorm affine grads come straight from p.bn.bstats
+  float* dbeta = nullptr;
+  int add_affine = 0;
+  int rows_per_cta = 256;
+  float bn_eps = 1e-5f, slope = 0.2f;
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-CTA BatchNorm constants
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bn_mean_rstd(const BnRef& bn, int pass, int c, float Bg, float eps, float& mean,
+                                             float& rstd, float& var_biased) {
+  if (bn.eval) {
+    mean = bn.rmean[c];
+    var_biased = bn.rvar[c];
+  } else {
+    const double* s = bn.fstats + (long long)pass * bn.sf;
+    double m = s[c] / (double)Bg;
+    double v = s[bn.C + c] / (double)Bg - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var_biased = (float)v;
+  }
+  rstd = 1.0f / sqrtf(var_biased + eps);
+}
+
+// fills cs[] for an operand; all threads of the CTA participate; caller syncs afterwards
+__device__ __forceinline__ void operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs) {
+  if (o.kind == OP_BN_ACT) {
+    const int C = o.bn.C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mean, rstd, var;
+      bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd, var);
+      // y = (h - mean) * (gamma * rstd) + beta : the subtraction is exact-ish even when |mean| >> std
+      cs[c] = o.bn.gamma[c] * rstd;
+      cs[C + c] = o.bn.beta[c];
+      cs[2 * C + c] = mean;
+    }
+  } else if (o.kind == OP_BN_BWD) {
+    const int C = o.bn.C;
+    const double* bs = o.bn.bstats + (long long)pass * o.bn.sb;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mean, rstd, var;
+      bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd, var);
+      cs[c] = o.bn.gamma[c] * rstd;                 // c1
+      cs[C + c] = (float)(bs[c] / (double)Bg);      // c2 = dbeta / B
+      cs[2 * C + c] = (float)(bs[C + c] / (double)Bg);  // c3 = dgamma / B
+      cs[3 * C + c] = mean;
+      cs[4 * C + c] = rstd;
+    }
+  }
+}
+
+// BatchNorm running-stat momentum update, done once (CTA 0) by the kernel that consumes the layer.
+__device__ __forceinline__ void bn_update_running(const BnRef& bn, int npass, float Bg, float momentum) {
+  for (int c = threadIdx.x; c < bn.C; c += blockDim.x) {
+    float rm = bn.rmean[c], rv = bn.rvar[c];
+    for (int p = 0; p < npass; ++p) {
+      const double* s = bn.fstats + (long long)p * bn.sf;
+      double m = s[c] / (double)Bg;
+      double v = s[bn.C + c] / (double)Bg - m * m;
+      if (v < 0.0) v = 0.0;
+      double unb = v * ((double)Bg / ((double)Bg - 1.0));
+      rm = (1.0f - momentum) * rm + momentum * (float)m;
+      rv = (1.0f - momentum) * rv + momentum * (float)unb;
+    }
+    bn.rmean[c] = rm;
+    bn.rvar[c] = rv;
+  }
+}
+
+__device__ __forceinline__ float act_lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+// Loads 4 consecutive batch rows (m..m+3) of feature row r of an operand, transformed; rows >= M and
+// feature rows >= o.rows read as 0.
+__device__ __forceinline__ float4 load_operand(const Operand& o, const float* cs, int pass, int r, int m, int M,
+                                               int ld, float slope) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r >= o.rows || m >= M) return v;
+  const size_t off = (size_t)r * ld + m;
+  switch (o.kind) {
+    case OP_PLAIN:
+      v = ld4(o.p + (long long)pass * o.sp + off);
+      break;
+    case OP_BN_ACT: {
+      v = ld4(o.p + (long long)pass * o.sp + off);
+      const float sc = cs[r], sh = cs[o.bn.C + r], mean = cs[2 * o.bn.C + r];
+      v.x = act_lrelu(fmaf(v.x - mean, sc, sh), slope);
+      v.y = act_lrelu(fmaf(v.y - mean, sc, sh), slope);
+      v.z = act_lrelu(fmaf(v.z - mean, sc, sh), slope);
+      v.w = act_lrelu(fmaf(v.w - mean, sc, sh), slope);
+    } break;
+    case OP_REPARAM:
+      if (pass == o.reparam_pass) {
+        float4 mu = ld4(o.mu + off), lv = ld4(o.lv + off), e = ld4(o.eps + off);
+        v.x = mu.x + e.x * expf(0.5f * lv.x);
+        v.y = mu.y + e.y * expf(0.5f * lv.y);
+        v.z = mu.z + e.z * expf(0.5f * lv.z);
+        v.w = mu.w + e.w * expf(0.5f * lv.w);
+      } else {
+        v = ld4(o.p + (long long)pass * o.sp + off);
+      }
+      break;
+    case OP_BN_BWD: {
+      const int C = o.bn.C;
+      float4 dy = ld4(o.p + (long long)pass * o.sp + off);
+      float4 h = ld4(o.h + (long long)pass * o.sh + off);
+      const float c1 = cs[r], c2 = cs[C + r], c3 = cs[2 * C + r], mean = cs[3 * C + r], rstd = cs[4 * C + r];
+      v.x = c1 * (dy.x - c2 - (h.x - mean) * rstd * c3);
+      v.y = c1 * (dy.y - c2 - (h.y - mean) * rstd * c3);
+      v.z = c1 * (dy.z - c2 - (h.z - mean) * rstd * c3);
+      v.w = c1 * (dy.w - c2 - (h.w - mean) * rstd * c3);
+    } break;
+    case OP_CONST:
+      v = make_float4(o.cst, o.cst, o.cst, o.cst);
+      break;
+  }
+  if (m + 3 >= M) {
+    if (m + 1 >= M) v.y = 0.f;
+    if (m + 2 >= M) v.z = 0.f;
+    if (m + 3 >= M) v.w = 0.f;
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C[m][n] = sum_r A[r][m] * B[r][n]   (64 x 64 tile, 256 threads, 4 x 4 per thread)
+// ------------------------------------------------------------------------------------------------
+template <bool WT>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g) {
+  extern __shared__ __align__(16) float dyn_smem[];
+  __shared__ __align__(16) float As[2][TBK][TBM];
+  __shared__ __align__(16) float Bs[2][TBK][TBN];
+
+  const int tid = threadIdx.x;
+  const int pass = g.only_pass >= 0 ? g.only_pass : (int)blockIdx.z;
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+  float* cs_a = dyn_smem;                                  // operand constants
+  float* cs_e = dyn_smem + operand_const_floats(g.a);      // epilogue constants (EP_DBN: 4 * C)
+
+  // ---- preamble: per-feature constants ---------------------------------------------------------
+  operand_consts(g.a, pass, g.Bg, g.bn_eps, cs_a);
+  if (g.ekind == EP_DBN) {
+    const int C = g.prev_bn.C;
+    for (int c = tid; c < C; c += GEMM_THREADS) {
+      float mean, rstd, var;
+      bn_mean_rstd(g.prev_bn, pass, c, g.Bg, g.bn_eps, mean, rstd, var);
+      cs_e[c] = g.prev_bn.gamma[c] * rstd;
+      cs_e[C + c] = g.prev_bn.beta[c];
+      cs_e[2 * C + c] = mean;
+      cs_e[3 * C + c] = rstd;
+    }
+  }
+  if (g.a.kind == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && blockIdx.x == 0 && blockIdx.y == 0 &&
+      blockIdx.z == 0) {
+    bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum);
+  }
+  __syncthreads();
+
+  // ---- staging maps ------------------------------------------------------------------------------
+  const int a_r = tid >> 4, a_m = (tid & 15) * 4;
+  const bool wvec = ((g.ldw | g.wcol0) & 3) == 0;
+  const int bt_n = tid & 63, bt_kg = tid >> 6;        // WT:  W[n][r..r+3] -> Bs[r..r+3][n]
+  const int bn_r = tid >> 4, bn_n = (tid & 15) * 4;   // !WT: W[r][n..n+3] -> Bs[r][n..n+3]
+
+  auto load_b = [&](int r0) -> float4 {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (WT) {
+      const int n = n0 + bt_n, r = r0 + bt_kg * 4;
+      if (n < g.N) {
+        const float* src = g.W + (size_t)n * g.ldw + g.wcol0 + r;
+        if (wvec && r + 3 < g.R) {
+          w = ld4(src);
+        } else {
+          if (r < g.R) w.x = src[0];
+          if (r + 1 < g.R) w.y = src[1];
+          if (r + 2 < g.R) w.z = src[2];
+          if (r + 3 < g.R) w.w = src[3];
+        }
+      }
+    } else {
+      const int r = r0 + bn_r, n = n0 + bn_n;
+      if (r < g.R) {
+        const float* src = g.W + (size_t)r * g.ldw + g.wcol0 + n;
+        if (wvec && n + 3 < g.N) {
+          w = ld4(src);
+        } else {
+          if (n < g.N) w.x = src[0];
+          if (n + 1 < g.N) w.y = src[1];
+          if (n + 2 < g.N) w.z = src[2];
+          if (n + 3 < g.N) w.w = src[3];
+        }
+      }
+    }
+    return w;
+  };
+  auto store_b = [&](int buf, float4 w) {
+    if (WT) {
+      Bs[buf][bt_kg * 4 + 0][bt_n] = w.x;
+      Bs[buf][bt_kg * 4 + 1][bt_n] = w.y;
+      Bs[buf][bt_kg * 4 + 2][bt_n] = w.z;
+      Bs[buf][bt_kg * 4 + 3][bt_n] = w.w;
+    } else {
+      st4(&Bs[buf][bn_r][bn_n], w);
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+  const int nchunks = (g.R + TBK - 1) / TBK;
+
+  float4 ra = load_operand(g.a, cs_a, pass, a_r, m0 + a_m, g.M, g.ld, g.slope);
+  float4 rb = load_b(0);
+  st4(&As[0][a_r][a_m], ra);
+  store_b(0, rb);
+  __syncthreads();
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) {
+      ra = load_operand(g.a, cs_a, pass, (c + 1) * TBK + a_r, m0 + a_m, g.M, g.ld, g.slope);
+      rb = load_b((c + 1) * TBK);
+    }
+#pragma unroll
+    for (int kk = 0; kk < TBK; ++kk) {
+      const float4 a = ld4(&As[cur][kk][tm]);
+      const float4 b = ld4(&Bs[cur][kk][tn]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+      acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+      acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+    }
+    if (c + 1 < nchunks) {
+      st4(&As[cur ^ 1][a_r][a_m], ra);
+      store_b(cur ^ 1, rb);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ------------------------------------------------------------------------------------
+  const int m = m0 + tm;
+  const float scale = g.scale ? g.scale[pass] : 1.0f;
+  const bool rowv[4] = {m < g.M, m + 1 < g.M, m + 2 < g.M, m + 3 < g.M};
+  double tot = 0.0, klsum = 0.0;
+
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tn + j;
+    const bool nvalid = n < g.N;   // warp-uniform per half-warp (tn shared by 16 lanes)
+    float y[4] = {acc[0][j], acc[1][j], acc[2][j], acc[3][j]};
+    // batch moments are accumulated in double from the first addition: for a single-class batch the
+    // pre-activations have |mean| >> std, and E[x^2] - mean^2 cancels ~mean^2/var digits
+    double s1 = 0.0, s2 = 0.0;
+    if (nvalid) {
+      const size_t off = (size_t)n * g.ld + m;
+      if (g.ekind == EP_LINEAR) {
+        float b = g.bias ? g.bias[n] : 0.f;
+        if (g.wlabel) b += scale * g.wlabel[(size_t)n * g.ldwl];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = fmaf(y[i], scale, b);
+        if (g.kl_acc) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rowv[i]) klsum += (n < g.kl_split) ? 0.5 * (double)y[i] * (double)y[i]
+                                                   : -0.5 * (1.0 + (double)y[i] - (double)expf(y[i]));
+        }
+        if (g.ostats) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rowv[i]) { s1 += (double)y[i]; s2 += (double)y[i] * (double)y[i]; }
+        }
+        if (g.act == ACT_LRELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = act_lrelu(y[i], g.slope);
+        } else if (g.act == ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
+        } else if (g.act == ACT_SIGMOID) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = 1.0f / (1.0f + expf(-y[i]));
+        }
+        if (g.mask) {
+          const uchar4 mk = *reinterpret_cast<const uchar4*>(g.mask + (long long)pass * g.smask + off);
+          y[0] = mk.x ? y[0] * g.keep_inv : 0.f;
+          y[1] = mk.y ? y[1] * g.keep_inv : 0.f;
+          y[2] = mk.z ? y[2] * g.keep_inv : 0.f;
+          y[3] = mk.w ? y[3] * g.keep_inv : 0.f;
+        }
+        if (g.osum) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rowv[i]) tot += (double)y[i];
+        }
+        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (g.ekind == EP_DBN) {
+        const int C = g.prev_bn.C;
+        const float4 h = ld4(g.prev + (long long)pass * g.sprev + off);
+        const float hh[4] = {h.x, h.y, h.z, h.w};
+        const float sc = cs_e[n], sh = cs_e[C + n], mean = cs_e[2 * C + n], rstd = cs_e[3 * C + n];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pre = fmaf(hh[i] - mean, sc, sh);
+          const float dy = rowv[i] ? (pre > 0.f ? y[i] : y[i] * g.slope) : 0.f;
+          y[i] = dy;
+          s1 += (double)dy;
+          s2 += (double)(dy * ((hh[i] - mean) * rstd));
+        }
+        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (g.ekind == EP_DACT) {
+        const float4 ap = ld4(g.prev + (long long)pass * g.sprev + off);
+        const float aa[4] = {ap.x, ap.y, ap.z, ap.w};
+        float keep[4] = {1.f, 1.f, 1.f, 1.f};
+        if (g.mask) {
+          const uchar4 mk = *reinterpret_cast<const uchar4*>(g.mask + (long long)pass * g.smask + off);
+          keep[0] = mk.x ? g.keep_inv : 0.f;
+          keep[1] = mk.y ? g.keep_inv : 0.f;
+          keep[2] = mk.z ? g.keep_inv : 0.f;
+          keep[3] = mk.w ? g.keep_inv : 0.f;
+        }
+        const float neg = (g.act == ACT_LRELU) ? g.slope : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float d = y[i] * scale * keep[i];
+          y[i] = aa[i] > 0.f ? d : d * neg;
+        }
+        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (g.ekind == EP_STORE) {
+        float* dst = g.Y + (long long)pass * g.sY + off;
+        float4 o = make_float4(y[0] * scale, y[1] * scale, y[2] * scale, y[3] * scale);
+        if (g.accumulate) {
+          const float4 old = ld4(dst);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        st4(dst, o);
+      } else if (g.ekind == EP_REPARAM_BWD) {
+        // y = dL/dz_enc for latent feature n.  dmu = dz + kl_coef*mu ; dlogvar = dz*eps*0.5*exp(0.5 lv)
+        // + kl_coef*0.5*(exp(lv)-1)   
+        const float4 mu = ld4(g.mu + off), lv = ld4(g.lv + off), e = ld4(g.eps + off);
+        const float mm[4] = {mu.x, mu.y, mu.z, mu.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w}, ee[4] = {e.x, e.y, e.z, e.w};
+        float dmu[4], dlv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dmu[i] = rowv[i] ? y[i] + g.kl_coef * mm[i] : 0.f;
+          dlv[i] = rowv[i] ? y[i] * ee[i] * 0.5f * expf(0.5f * ll[i]) + g.kl_coef * 0.5f * (expf(ll[i]) - 1.0f) : 0.f;
+        }
+        st4(g.Y + off, make_float4(dmu[0], dmu[1], dmu[2], dmu[3]));
+        st4(g.Y + (size_t)(g.N + n) * g.ld + m, make_float4(dlv[0], dlv[1], dlv[2], dlv[3]));
+      }
+    }
+    if (g.ostats) {   // uniform branch; the 16 lanes of a half-warp share column n
+      s1 = half_warp_sum_d(s1);
+      s2 = half_warp_sum_d(s2);
+      if ((tid & 15) == 0 && nvalid) {
+        double* st = g.ostats + (long long)pass * g.sostats;
+        atomicAdd(st + n, s1);
+        atomicAdd(st + g.N + n, s2);
+      }
+    }
+  }
+  if (g.osum) {
+    tot = warp_sum_d(tot);
+    if ((tid & 31) == 0) atomicAdd(g.osum + pass, tot);
+  }
+  if (g.kl_acc) {
+    klsum = warp_sum_d(klsum);
+    if ((tid & 31) == 0) atomicAdd(g.kl_acc, klsum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dW[n][k] += sum_m P[n][m] * Q[k][m]   (64 x 64 tile of dW per CTA, batch split over blockIdx.z)
+// ------------------------------------------------------------------------------------------------
+constexpr int DW_MC = 32;          // batch rows per staged chunk
+constexpr int DW_LDS = DW_MC + 4;  // padded row (conflict-free 128-bit reads across rows)
+
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_dw_kernel(const DwArgs g, int nsplit) {
+  extern __shared__ __align__(16) float dyn_smem[];
+  float* Ps = dyn_smem;                            // [2][64][DW_LDS]
+  float* Qs = Ps + 2 * 64 * DW_LDS;                // [2][64][DW_LDS]
+  float* cs_p = Qs + 2 * 64 * DW_LDS;
+  float* cs_q = cs_p + operand_const_floats(g.p);
+
+  const int tid = threadIdx.x;
+  const int pass = blockIdx.z / nsplit, split = blockIdx.z % nsplit;
+  const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int mbeg = split * g.rows_per_cta;
+  const int mend = min(g.M, mbeg + g.rows_per_cta);
+
+  operand_consts(g.p, pass, g.Bg, g.bn_eps, cs_p);
+  operand_consts(g.q, pass, g.Bg, g.bn_eps, cs_q);
+  // BatchNorm affine gradients are exactly the backward batch sums (appendix A.2): dbeta = sum dy,
+  // dgamma = sum dy*xhat.  One CTA per pass adds them to the gradient buffer.
+  if (g.add_affine && g.dgamma && blockIdx.x == 0 && blockIdx.y == 0 && split == 0) {
+    const double* bs = g.p.bn.bstats + (long long)pass * g.p.bn.sb;
+    for (int c = tid; c < g.p.bn.C; c += GEMM_THREADS) {
+      atomicAdd(g.dbeta + c, (float)bs[c]);
+      atomicAdd(g.dgamma + c, (float)bs[g.p.bn.C + c]);
+    }
+  }
+  __syncthreads();
+  if (mbeg >= mend) return;
+
+  const int l_row = tid >> 3, l_m = (tid & 7) * 4;   // two rows per thread: l_row, l_row + 32
+  const int tk = tid & 15, tn = tid >> 4;            // thread computes rows tn+16i (n) x tk+16j (k)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_bias = (g.db != nullptr || g.label_col >= 0) && blockIdx.x == 0 && tk == 0;
+
+  float4 rp[2], rq[2];
+  auto gload = [&](int mb) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int row = l_row + 32 * t;
+      int mm = mb + l_m;
+      // rows beyond this CTA's slice must not contribute: clamp through M = mend
+      rp[t] = load_operand(g.p, cs_p, pass, n0 + row, mm, mend, g.ld, g.slope);
+      rq[t] = load_operand(g.q, cs_q, pass, k0 + row, mm, mend, g.ld, g.slope);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int row = l_row + 32 * t;
+      st4(Ps + ((size_t)buf * 64 + row) * DW_LDS + l_m, rp[t]);
+      st4(Qs + ((size_t)buf * 64 + row) * DW_LDS + l_m, rq[t]);
+    }
+  };
+
+  const int nchunks = (mend - mbeg + DW_MC - 1) / DW_MC;
+  gload(mbeg);
+  sstore(0);
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) gload(mbeg + (c + 1) * DW_MC);
+    const float* P = Ps + (size_t)cur * 64 * DW_LDS;
+    const float* Q = Qs + (size_t)cur * 64 * DW_LDS;
+#pragma unroll
+    for (int mm = 0; mm < DW_MC; mm += 4) {
+      float4 p[4], q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = ld4(P + (tn + 16 * i) * DW_LDS + mm);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = ld4(Q + (tk + 16 * j) * DW_LDS + mm);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(p[i].x, q[j].x, acc[i][j]);
+          acc[i][j] = fmaf(p[i].y, q[j].y, acc[i][j]);
+          acc[i][j] = fmaf(p[i].z, q[j].z, acc[i][j]);
+          acc[i][j] = fmaf(p[i].w, q[j].w, acc[i][j]);
+        }
+      if (do_bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bsum[i] += (p[i].x + p[i].y) + (p[i].z + p[i].w);
+      }
+    }
+    if (c + 1 < nchunks) sstore(cur ^ 1);
+    __syncthreads();
+  }
+
+  float* dW = g.dW + (long long)pass * g.sdW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + tn + 16 * i;
+    if (n >= g.N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk + 16 * j;
+      if (k < g.K) atomicAdd(dW + (size_t)n * g.ldw + g.wcol0 + k, acc[i][j]);
+    }
+    if (do_bias) {
+      if (g.db) atomicAdd(g.db + n, bsum[i]);
+      if (g.label_col >= 0) atomicAdd(dW + (size_t)n * g.ldw + g.label_col, bsum[i]);
+    }
+  }
+}
+
+inline size_t gemm_mn_smem(const GemmArgs& g) {
+  size_t f = operand_const_floats(g.a);
+  if (g.ekind == EP_DBN) f += 4 * (size_t)g.prev_bn.C;
+  return f * sizeof(float);
+}
+inline size_t gemm_dw_smem(const DwArgs& g) {
+  size_t f = 4 * 64 * DW_LDS + operand_const_floats(g.p) + operand_const_floats(g.q);
+  return f * sizeof(float);
+}
+
+}  // namespace cvg

@@ -1,0 +1,575 @@
+// cvaegan_b200 - row-wise and element-wise kernels (LayerNorm, cross-entropy, spectral norm, Adam,
+// Philox noise, sampling, filter).  Activations are feature-major [features][ld] (see gemm.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace cvg {
+
+// ------------------------------------------------------------------------------------------------
+// accumulator slots (doubles, zeroed at the start of every step)
+// ------------------------------------------------------------------------------------------------
+enum {
+  L_DREAL = 0,  // sum of D(x_real) scores          (cvae_gan.py:118-119)
+  L_DFAKE = 1,  // sum of D(x_fake) scores          (cvae_gan.py:122-123, 188-189)
+  L_CE0 = 2,    // sum of -log softmax[label], pass 0
+  L_CE1 = 3,    // pass 1
+  L_RECON = 4,  // sum (x_rec - x)^2                (cvae_gan.py:184)
+  L_KL = 5,     // sum -0.5(1 + lv - mu^2 - e^lv)   (cvae_gan.py:185)
+  L_COUNT = 8
+};
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward (classifier layer 2, cvae_gan_models.py:268-270): one thread per batch row.
+//   n = (h - mean) * rstd * g + b ; a = dropout(relu(n))
+// ------------------------------------------------------------------------------------------------
+struct LnArgs {
+  int M, ld, C, npass;
+  const float* h; long long sh;        // [C][ld] pre-LN
+  const float* g; const float* b;
+  float eps;
+  const uint8_t* mask; long long smask; float keep_inv;   // null in eval mode
+  float* a; long long sa;              // [C][ld] output
+  float* rs; long long srs;            // [2][ld] mean, rstd per row
+};
+
+__global__ void ln_fwd_kernel(const LnArgs g) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pass = blockIdx.y;
+  if (m >= g.M) return;
+  const float* h = g.h + (long long)pass * g.sh + m;
+  float s = 0.f;
+  for (int c = 0; c < g.C; ++c) s += h[(size_t)c * g.ld];
+  const float mean = s / (float)g.C;
+  float v = 0.f;
+  for (int c = 0; c < g.C; ++c) {
+    const float d = h[(size_t)c * g.ld] - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = 1.0f / sqrtf(v / (float)g.C + g.eps);
+  float* a = g.a + (long long)pass * g.sa + m;
+  const uint8_t* mk = g.mask ? g.mask + (long long)pass * g.smask + m : nullptr;
+  for (int c = 0; c < g.C; ++c) {
+    float n = (h[(size_t)c * g.ld] - mean) * rstd * g.g[c] + g.b[c];
+    n = fmaxf(n, 0.f);
+    if (mk) n = mk[(size_t)c * g.ld] ? n * g.keep_inv : 0.f;
+    a[(size_t)c * g.ld] = n;
+  }
+  if (g.rs) {
+    float* rs = g.rs + (long long)pass * g.srs;
+    rs[m] = mean;
+    rs[g.ld + m] = rstd;
+  }
+}
+
+// LayerNorm backward (appendix A.3): in place on dn -> dh.  dn already contains the ReLU/dropout
+// derivative.  Optionally accumulates the affine gradients (classifier step only).
+struct LnBwdArgs {
+  int M, ld, C, npass;
+  float* dn; long long sdn;            // in: dL/dn, out: dL/dh
+  const float* h; long long sh;
+  const float* rs; long long srs;
+  const float* g;
+  float* dg; float* db;                // null -> skipped
+};
+
+__global__ void ln_bwd_kernel(const LnBwdArgs g) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pass = blockIdx.y;
+  const bool valid = m < g.M;
+  const int mm = valid ? m : 0;
+  const float* h = g.h + (long long)pass * g.sh + mm;
+  float* dn = g.dn + (long long)pass * g.sdn + mm;
+  const float* rs = g.rs + (long long)pass * g.srs;
+  const float mean = rs[mm], rstd = rs[g.ld + mm];
+  float s1 = 0.f, s2 = 0.f;
+  if (valid) {
+    for (int c = 0; c < g.C; ++c) {
+      const float xh = (h[(size_t)c * g.ld] - mean) * rstd;
+      const float dx = dn[(size_t)c * g.ld] * g.g[c];
+      s1 += dx;
+      s2 = fmaf(dx, xh, s2);
+    }
+  }
+  s1 /= (float)g.C;
+  s2 /= (float)g.C;
+  for (int c = 0; c < g.C; ++c) {
+    float d = 0.f, xh = 0.f;
+    if (valid) {
+      xh = (h[(size_t)c * g.ld] - mean) * rstd;
+      d = dn[(size_t)c * g.ld];
+      dn[(size_t)c * g.ld] = rstd * (d * g.g[c] - s1 - xh * s2);
+    }
+    if (g.dg) {   // uniform
+      const float a = warp_sum(d * xh), b = warp_sum(d);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(g.dg + c, a);
+        atomicAdd(g.db + c, b);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax cross-entropy with one shared target label (cvae_gan.py:147,151,194): one thread per row.
+//   loss += -(l[y] - max - log sum exp(l - max)) ; dlogit = (softmax - onehot) * coef
+// ------------------------------------------------------------------------------------------------
+struct CeArgs {
+  int M, ld, K, npass, label;
+  const float* logits; long long sl;   // [K][ld]
+  float* dlogits; long long sd;        // [K][ld]
+  float coef;                          // 1/Bg (classifier step) or lambda_class/Bg (generator step)
+  double* loss;                        // [npass] accumulators
+};
+
+__global__ void ce_kernel(const CeArgs g) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pass = blockIdx.y;
+  double nll = 0.0;
+  if (m < g.M) {
+    const float* l = g.logits + (long long)pass * g.sl + m;
+    float mx = -INFINITY;
+    for (int k = 0; k < g.K; ++k) mx = fmaxf(mx, l[(size_t)k * g.ld]);
+    float s = 0.f;
+    for (int k = 0; k < g.K; ++k) s += expf(l[(size_t)k * g.ld] - mx);
+    const float lse = logf(s);
+    nll = -(double)(l[(size_t)g.label * g.ld] - mx - lse);
+    float* d = g.dlogits + (long long)pass * g.sd + m;
+    for (int k = 0; k < g.K; ++k) {
+      const float p = expf(l[(size_t)k * g.ld] - mx - lse);
+      d[(size_t)k * g.ld] = (p - (k == g.label ? 1.f : 0.f)) * g.coef;
+    }
+  }
+  nll = warp_sum_d(nll);
+  if ((threadIdx.x & 31) == 0 && nll != 0.0) atomicAdd(g.loss + pass, nll);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generator output seed gradient (cvae_gan.py:184 + sigmoid backward), element-wise over [F][ld]:
+//   pass 0 (x_recon): dout = lambda_recon * 2 (o - x) / (Bg F)     and  recon += (o - x)^2
+//   pass 1 (x_fake) : dout = dx (accumulated input gradient of critic + classifier)
+//   dpre = dout * o * (1 - o)
+// ------------------------------------------------------------------------------------------------
+struct SeedArgs {
+  int M, ld, F;
+  const float* out; long long sout;    // [2][F][ld] sigmoid outputs
+  const float* x;                      // [F][ld] real batch
+  const float* dx;                     // [F][ld]
+  float* dpre; long long sdpre;        // [2][F][ld]
+  float coef_recon;
+  double* recon_acc;
+};
+
+__global__ void g_seed_kernel(const SeedArgs g) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pass = blockIdx.y;
+  const int f = idx / g.ld, m = idx % g.ld;
+  double sq = 0.0;
+  if (f < g.F) {
+    const size_t off = (size_t)f * g.ld + m;
+    float d = 0.f;
+    if (m < g.M) {
+      const float o = g.out[(long long)pass * g.sout + off];
+      float dout;
+      if (pass == 0) {
+        const float diff = o - g.x[off];
+        sq = (double)diff * (double)diff;
+        dout = g.coef_recon * 2.0f * diff;
+      } else {
+        dout = g.dx[off];
+      }
+      d = dout * (1.0f - o) * o;
+    }
+    g.dpre[(long long)pass * g.sdpre + off] = d;
+  }
+  if (pass == 0) {
+    sq = warp_sum_d(sq);
+    if ((threadIdx.x & 31) == 0 && sq != 0.0) atomicAdd(g.recon_acc, sq);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// spectral norm (torch _SpectralNorm.forward, appendix A.4): one CTA per critic layer.  For each of
+// `npass` consecutive train-mode forwards: u <- normalize(W v), v <- normalize(W^T u), sigma = u.(W v).
+// Snapshots of (u, v, sigma) per pass are kept for the backward term.
+// ------------------------------------------------------------------------------------------------
+constexpr int SN_MAXDIM = 1024;
+struct SnLayer {
+  const float* W; int rows, cols;
+  float* u; float* v;
+  int snap_off;      // offset (floats) of this layer in the snapshot buffers
+};
+struct SnArgs {
+  SnLayer L[4];
+  int npass, do_power;
+  float eps;
+  float* sigma;      // [npass][4]
+  float* inv_sigma;  // [4][npass]   (per layer contiguous over passes: GemmArgs.scale[pass])
+  float* u_snap; float* v_snap; long long ssnap;   // [npass][ssnap]
+};
+
+__global__ void __launch_bounds__(256) sn_power_kernel(const SnArgs g) {
+  __shared__ float su[SN_MAXDIM], sv[SN_MAXDIM], st[SN_MAXDIM];
+  __shared__ double red[32];
+  const SnLayer L = g.L[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  for (int i = tid; i < L.rows; i += blockDim.x) su[i] = L.u[i];
+  for (int i = tid; i < L.cols; i += blockDim.x) sv[i] = L.v[i];
+  __syncthreads();
+  for (int p = 0; p < g.npass; ++p) {
+    if (g.do_power) {
+      // t = W v
+      for (int n = w; n < L.rows; n += nw) {
+        float s = 0.f;
+        for (int k = lane; k < L.cols; k += 32) s = fmaf(L.W[(size_t)n * L.cols + k], sv[k], s);
+        s = warp_sum(s);
+        if (lane == 0) st[n] = s;
+      }
+      __syncthreads();
+      double q = 0.0;
+      for (int i = tid; i < L.rows; i += blockDim.x) q += (double)st[i] * st[i];
+      q = block_sum_d(q, red);
+      float nrm = fmaxf((float)sqrt(q), g.eps);
+      for (int i = tid; i < L.rows; i += blockDim.x) su[i] = st[i] / nrm;
+      __syncthreads();
+      // s = W^T u
+      for (int k = tid; k < L.cols; k += blockDim.x) {
+        float s = 0.f;
+        for (int n = 0; n < L.rows; ++n) s = fmaf(L.W[(size_t)n * L.cols + k], su[n], s);
+        st[k] = s;
+      }
+      __syncthreads();
+      q = 0.0;
+      for (int i = tid; i < L.cols; i += blockDim.x) q += (double)st[i] * st[i];
+      q = block_sum_d(q, red);
+      nrm = fmaxf((float)sqrt(q), g.eps);
+      for (int i = tid; i < L.cols; i += blockDim.x) sv[i] = st[i] / nrm;
+      __syncthreads();
+    }
+    // sigma = u . (W v)
+    double sg = 0.0;
+    for (int n = w; n < L.rows; n += nw) {
+      float s = 0.f;
+      for (int k = lane; k < L.cols; k += 32) s = fmaf(L.W[(size_t)n * L.cols + k], sv[k], s);
+      s = warp_sum(s);
+      if (lane == 0) sg += (double)s * su[n];
+    }
+    sg = block_sum_d(sg, red);
+    if (tid == 0) {
+      g.sigma[p * 4 + blockIdx.x] = (float)sg;
+      g.inv_sigma[blockIdx.x * 2 + p] = 1.0f / (float)sg;
+    }
+    float* us = g.u_snap + (long long)p * g.ssnap + L.snap_off;
+    float* vs = g.v_snap + (long long)p * g.ssnap + L.snap_off;
+    for (int i = tid; i < L.rows; i += blockDim.x) us[i] = su[i];
+    for (int i = tid; i < L.cols; i += blockDim.x) vs[i] = sv[i];
+    __syncthreads();
+  }
+  if (g.do_power) {
+    for (int i = tid; i < L.rows; i += blockDim.x) L.u[i] = su[i];
+    for (int i = tid; i < L.cols; i += blockDim.x) L.v[i] = sv[i];
+  }
+}
+
+// Gradient through W/sigma (appendix A.4): with G_p = dL/dWhat of pass p,
+//   dL/dW += sum_p [ G_p / sigma_p - (<G_p, W> / sigma_p^2) u_p v_p^T ]
+struct SnGradArgs {
+  SnLayer L[4];
+  int npass;
+  const float* Gp; long long sG;    // per-pass raw gradients, same layout/offsets as the param buffer
+  long long w_off[4];               // offset of each layer's weight in the param buffer
+  const float* inv_sigma;           // [4][2]
+  const float* u_snap; const float* v_snap; long long ssnap;
+  float* grad;                      // param-layout gradient buffer (accumulated into)
+  float* last_bias_grad;            // d(score bias): rows * sum_p seed_p, added analytically (exactly 0 in step D,
+  float last_bias_value;            // where autograd's -1/B and +1/B sums cancel bit for bit)
+};
+
+__global__ void __launch_bounds__(256) sn_grad_kernel(const SnGradArgs g) {
+  __shared__ double red[32];
+  const int l = blockIdx.x;
+  const SnLayer L = g.L[l];
+  const int n_el = L.rows * L.cols;
+  double dots[2] = {0.0, 0.0};
+  for (int p = 0; p < g.npass; ++p) {
+    const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
+    double d = 0.0;
+    for (int i = threadIdx.x; i < n_el; i += blockDim.x) d += (double)G[i] * (double)L.W[i];
+    dots[p] = block_sum_d(d, red);
+  }
+  for (int i = threadIdx.x; i < n_el; i += blockDim.x) {
+    const int n = i / L.cols, k = i % L.cols;
+    float acc = 0.f;
+    for (int p = 0; p < g.npass; ++p) {
+      const float is = g.inv_sigma[l * 2 + p];
+      const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
+      const float u = g.u_snap[(long long)p * g.ssnap + L.snap_off + n];
+      const float v = g.v_snap[(long long)p * g.ssnap + L.snap_off + k];
+      acc += G[i] * is - (float)(dots[p] * (double)is * (double)is) * u * v;
+    }
+    g.grad[g.w_off[l] + i] += acc;
+  }
+  if (l == 3 && threadIdx.x == 0 && g.last_bias_grad) *g.last_bias_grad += g.last_bias_value;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, appendix A.8) over up to two flat parameter segments; also turns the loss
+// accumulators into the user's loss_out.  The gradient is cleared after use.
+// ------------------------------------------------------------------------------------------------
+struct AdamSeg {
+  float* p; float* g; float* m; float* v;
+  long long n;
+  float lr, bc1, bc2_sqrt;
+};
+struct AdamArgs {
+  AdamSeg seg[2];
+  int nseg;
+  float b1, b2, eps;
+  int clear_grad;
+};
+
+__global__ void adam_kernel(const AdamArgs a) {
+  const AdamSeg s = a.seg[blockIdx.y];
+  const float step_size = s.lr / s.bc1;
+  const float w = 1.0f - a.b1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = s.g[i];
+    float m = s.m[i], v = s.v[i];
+    // exp_avg.lerp_(grad, 1 - beta1)  (torch lerp: weight < 0.5 ? a + w (b - a) : b - (b - a)(1 - w))
+    m = (w < 0.5f) ? m + w * (g - m) : g - (g - m) * (1.0f - w);
+    v = v * a.b2 + (1.0f - a.b2) * g * g;
+    const float denom = sqrtf(v) / s.bc2_sqrt + a.eps;
+    s.p[i] = s.p[i] - step_size * (m / denom);
+    s.m[i] = m;
+    s.v[i] = v;
+    if (a.clear_grad) s.g[i] = 0.f;
+  }
+}
+
+// losses: accumulators (double, local sums) -> float partials in the gradient tail (so the data
+// parallel all-reduce sums them with the gradients) -> loss_out after the reduction.
+__global__ void pack_loss_kernel(const double* acc, float* tail) {
+  if (threadIdx.x < L_COUNT) tail[threadIdx.x] = (float)acc[threadIdx.x];
+}
+// kind 0: step_d, 1: step_c, 2: step_g
+__global__ void unpack_loss_kernel(const float* tail, float* out, int kind, float Bg, float F, int clear, float* tail_w) {
+  if (threadIdx.x == 0) {
+    if (kind == 0) {
+      const float r = tail[L_DREAL] / Bg, f = tail[L_DFAKE] / Bg;
+      out[0] = -r + f; out[1] = r; out[2] = f; out[3] = 0.f;
+    } else if (kind == 1) {
+      const float r = tail[L_CE0] / Bg, f = tail[L_CE1] / Bg;
+      out[0] = r + f; out[1] = r; out[2] = f; out[3] = 0.f;
+    } else {
+      out[0] = tail[L_RECON] / (Bg * F);
+      out[1] = tail[L_KL] / Bg;
+      out[2] = -tail[L_DFAKE] / Bg;
+      out[3] = tail[L_CE0] / Bg;
+    }
+  }
+  __syncthreads();
+  if (clear && threadIdx.x < CVG_GRAD_TAIL) tail_w[threadIdx.x] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// noise: either transposes an injected row-major tensor into the feature-major workspace or draws it
+// from Philox keyed by (seed, counter, stream, pass, global row, feature group).
+// ------------------------------------------------------------------------------------------------
+struct FillJob {
+  void* out;             // float* (normal) or uint8_t* (mask), feature-major [npass][nfeat][ld]
+  const void* injected;  // row-major [npass][M][nfeat] or null
+  int kind;              // 0 normal float, 1 keep-mask uint8
+  int nfeat, npass, stream;
+};
+struct FillArgs {
+  FillJob job[6];
+  int njobs;
+  int M, ld;
+  uint64_t seed, counter, row_base;
+  float keep_prob;
+};
+
+__global__ void fill_noise_kernel(const FillArgs a) {
+  const FillJob j = a.job[blockIdx.y];
+  const int ngroups = (j.nfeat + 3) >> 2;
+  const long long total = (long long)j.npass * ngroups * a.M;
+  const uint32_t keep_thr = (uint32_t)((double)a.keep_prob * 4294967296.0);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(t % a.M);
+    const int fg = (int)((t / a.M) % ngroups);
+    const int pass = (int)(t / ((long long)a.M * ngroups));
+    float vals[4];
+    uint8_t bits[4];
+    if (j.injected) {
+      for (int i = 0; i < 4; ++i) {
+        const int f = fg * 4 + i;
+        if (f < j.nfeat) {
+          const size_t src = ((size_t)pass * a.M + m) * j.nfeat + f;
+          if (j.kind == 0) vals[i] = ((const float*)j.injected)[src];
+          else bits[i] = ((const uint8_t*)j.injected)[src] ? 1 : 0;
+        }
+      }
+    } else {
+      const U4 r = philox_at(a.seed, a.counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
+      if (j.kind == 0) {
+        box_muller(r.x, r.y, vals[0], vals[1]);
+        box_muller(r.z, r.w, vals[2], vals[3]);
+      } else {
+        bits[0] = r.x < keep_thr; bits[1] = r.y < keep_thr; bits[2] = r.z < keep_thr; bits[3] = r.w < keep_thr;
+      }
+    }
+    for (int i = 0; i < 4; ++i) {
+      const int f = fg * 4 + i;
+      if (f < j.nfeat) {
+        const size_t dst = ((size_t)pass * j.nfeat + f) * a.ld + m;
+        if (j.kind == 0) ((float*)j.out)[dst] = vals[i];
+        else ((uint8_t*)j.out)[dst] = bits[i];
+      }
+    }
+  }
+}
+
+// row-major [M][F] (optionally gathered through idx) -> feature-major [F][ld]
+__global__ void to_feature_major_kernel(const float* src, const long long* idx, int M, int F, int ld, float* dst) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const long long r = idx ? idx[m] : m;
+  for (int f = 0; f < F; ++f) dst[(size_t)f * ld + m] = src[(size_t)r * F + f];
+}
+// feature-major [F][ld] -> row-major [M][F]
+__global__ void to_row_major_kernel(const float* src, int M, int F, int ld, float* dst) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  for (int f = 0; f < F; ++f) dst[(size_t)m * F + f] = src[(size_t)f * ld + m];
+}
+
+// ------------------------------------------------------------------------------------------------
+// _get_target_samples on the device (cvae_gan.py:247-260)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+// keyed bijection of [0, 2^(2*half)) (balanced Feistel, 6 rounds)
+__device__ __forceinline__ uint64_t feistel(uint64_t x, int half, const uint32_t* keys) {
+  const uint32_t maskh = (half >= 32) ? 0xFFFFFFFFu : ((1u << half) - 1u);
+  uint32_t L = (uint32_t)(x >> half) & maskh, R = (uint32_t)x & maskh;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const uint32_t f = mix32(R ^ keys[r]) & maskh;
+    const uint32_t nl = R;
+    R = L ^ f;
+    L = nl;
+  }
+  return ((uint64_t)L << half) | R;
+}
+
+__global__ void sample_rows_kernel(const float* rows, long long n, long long B, long long draw_offset, int B_local,
+                                   int F, uint64_t seed, uint64_t counter, float* x_out, long long* idx_out) {
+  const int il = blockIdx.x * blockDim.x + threadIdx.x;
+  if (il >= B_local) return;
+  const long long i = draw_offset + il;      // index of this draw in the global batch
+  long long r;
+  if (n == B) {
+    r = i;                                   // all rows, no draw (cvae_gan.py:254-256)
+  } else if (n < B) {                        // with replacement (cvae_gan.py:250-253)
+    const U4 u = philox_at(seed, counter, RS_SAMPLE, 0, (uint64_t)i, 0);
+    const uint64_t w = ((uint64_t)u.x << 32) | u.y;
+    r = (long long)(w % (uint64_t)n);
+  } else {                                   // B distinct rows: first B images of a keyed permutation of [0, n)
+    int bits = 1;
+    while ((1ll << bits) < n) ++bits;
+    const int half = (bits + 1) >> 1;
+    uint32_t keys[6];
+    const U4 k0 = philox_at(seed, counter, RS_SAMPLE, 1, 0, 0), k1 = philox_at(seed, counter, RS_SAMPLE, 1, 1, 0);
+    keys[0] = k0.x; keys[1] = k0.y; keys[2] = k0.z; keys[3] = k0.w; keys[4] = k1.x; keys[5] = k1.y;
+    uint64_t x = (uint64_t)i;
+    do { x = feistel(x, half, keys); } while (x >= (uint64_t)n);   // cycle walking keeps it a bijection on [0, n)
+    r = (long long)x;
+  }
+  if (idx_out) idx_out[il] = r;
+  for (int f = 0; f < F; ++f) x_out[(size_t)il * F + f] = rows[(size_t)r * F + f];
+}
+
+// ------------------------------------------------------------------------------------------------
+// filter decision (cvae_gan.py:366-370).  Softmax arithmetic follows torch's CUDA warp softmax for
+// K <= 32 (softmax_warp_forward: exp(x - max) accumulated by a xor-butterfly over next_pow2(K)
+// lanes, then a true division) so the decision equals torch.softmax -> torch.max on the same logits.
+// ------------------------------------------------------------------------------------------------
+constexpr int FILTER_MAXK = 32;
+
+template <typename LoadLogit>
+__device__ __forceinline__ bool filter_decide(LoadLogit ld, int K, int label, float thr) {
+  float e[FILTER_MAXK];
+  int P = 1;
+  while (P < K) P <<= 1;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) { e[k] = ld(k); mx = fmaxf(mx, e[k]); }
+  bool nan = false;
+#pragma unroll 1
+  for (int k = 0; k < P; ++k) {
+    if (k < K) { nan |= (e[k] != e[k]); e[k] = expf(e[k] - mx); } else e[k] = 0.f;
+  }
+  // butterfly sum: offsets P/2, P/4, ..., 1 (value on lane 0)
+  float s[FILTER_MAXK];
+  for (int k = 0; k < P; ++k) s[k] = e[k];
+  for (int o = P >> 1; o > 0; o >>= 1)
+    for (int k = 0; k < o; ++k) s[k] = s[k] + s[k + o];
+  const float sum = s[0];
+  float best = -INFINITY;
+  int arg = 0;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const float p = e[k] / sum;
+    if (p > best) { best = p; arg = k; }
+  }
+  return !nan && (best > thr) && (arg == label);
+}
+
+__global__ void filter_logits_kernel(const float* logits, long long n, int K, int label, float thr, uint8_t* keep) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* l = logits + i * K;
+  keep[i] = filter_decide([&](int k) { return l[k]; }, K, label, thr) ? 1 : 0;
+}
+
+// Decision + order-preserving-within-block compaction.  FM = logits/x feature-major [.][ld] (fused
+// generation path) or row-major (standalone filter over materialised tensors).
+template <bool FM>
+__global__ void __launch_bounds__(256) filter_compact_kernel(const float* x, const float* logits, long long n, int ld,
+                                                             int F, int K, int label, float thr, uint64_t row_offset,
+                                                             float* x_out, long long* idx_out, long long capacity,
+                                                             unsigned long long* count, float* logits_out,
+                                                             uint8_t* keep_out) {
+  __shared__ int warp_cnt[8];
+  __shared__ unsigned long long base;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (i < n) {
+    if (FM) keep = filter_decide([&](int k) { return logits[(size_t)k * ld + i]; }, K, label, thr);
+    else keep = filter_decide([&](int k) { return logits[i * K + k]; }, K, label, thr);
+    if (keep_out) keep_out[i] = keep ? 1 : 0;
+    if (logits_out) {
+      for (int k = 0; k < K; ++k) logits_out[i * K + k] = FM ? logits[(size_t)k * ld + i] : logits[i * K + k];
+    }
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[w] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int k = 0; k < 8; ++k) { const int c = warp_cnt[k]; warp_cnt[k] = tot; tot += c; }
+    base = tot ? atomicAdd(count, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (keep) {
+    const long long pos = (long long)base + warp_cnt[w] + __popc(bal & ((1u << lane) - 1u));
+    if (pos < capacity) {
+      for (int f = 0; f < F; ++f) x_out[pos * F + f] = FM ? x[(size_t)f * ld + i] : x[i * F + f];
+      if (idx_out) idx_out[pos] = (long long)(row_offset + (uint64_t)i);
+    }
+  }
+}
+
+}  // namespace cvg

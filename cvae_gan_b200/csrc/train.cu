@@ -1,0 +1,906 @@
+// cvaegan_b200 - the three optimiser steps of a label visit (cvae_gan.py:104-216), as sequences of
+// fused kernels on one stream.  Data parallel: batch rows are sharded; BatchNorm batch moments and
+// the flat gradient buffers are all-reduced with NCCL between / after the kernels.
+#include <dlfcn.h>
+#include <math.h>
+
+#include "engine.cuh"
+
+namespace cvg {
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time from the libnccl.so.2 that torch already loaded (no link dependency).
+// ------------------------------------------------------------------------------------------------
+struct Id128 {
+  char b[128];   // ncclUniqueId is a 128-byte opaque struct passed by value
+};
+struct NcclApi {
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.ok) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) CVG_FAIL(std::string("cannot load libnccl: ") + dlerror());
+  *(void**)&g_nccl.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+  *(void**)&g_nccl.CommInitRank = dlsym(h, "ncclCommInitRank");
+  *(void**)&g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
+  *(void**)&g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+  *(void**)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) CVG_FAIL("libnccl lacks required symbols");
+  g_nccl.ok = true;
+  return 0;
+}
+
+int comm_unique_id(void* out128) {
+  CVG_TRY(load_nccl());
+  int r = g_nccl.GetUniqueId(out128);
+  if (r != 0) CVG_FAIL(std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  return 0;
+}
+
+int comm_init(Engine& e, const void* id128, int rank, int world) {
+  CVG_TRY(load_nccl());
+  Id128 id;
+  memcpy(id.b, id128, 128);
+  int r = g_nccl.CommInitRank(&e.comm, world, id, rank);
+  if (r != 0) CVG_FAIL(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  e.world = world;
+  e.rank = rank;
+  return 0;
+}
+
+void comm_destroy(Engine& e) {
+  if (e.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e.comm);
+  e.comm = nullptr;
+}
+
+int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st) {
+  if (e.world <= 1) return 0;
+  if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
+  int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e.comm, st);
+  if (r != 0) CVG_FAIL("ncclAllReduce(f32) failed");
+  return 0;
+}
+int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st) {
+  if (e.world <= 1) return 0;
+  if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
+  int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, e.comm, st);
+  if (r != 0) CVG_FAIL("ncclAllReduce(f64) failed");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+#ifndef CVG_LAUNCH_CHECK
+#define CVG_LAUNCH_CHECK()                 \
+  do {                                     \
+    CVG_CUDA(cudaGetLastError());          \
+    e.launches++;                          \
+  } while (0)
+#endif
+
+int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
+  dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, g.only_pass >= 0 ? 1 : g.npass);
+  const size_t smem = gemm_mn_smem(g);
+  if (wt) gemm_mn_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(g);
+  else gemm_mn_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(g);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
+  DwArgs g = g0;
+  const int kt = (g.K + 63) / 64, nt = (g.N + 63) / 64;
+  const int target = 2 * e.num_sms;
+  int nsplit = (target + kt * nt * g.npass - 1) / (kt * nt * g.npass);
+  const int max_split = (g.M + DW_MC - 1) / DW_MC;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  int rows = (g.M + nsplit - 1) / nsplit;
+  rows = ((rows + DW_MC - 1) / DW_MC) * DW_MC;
+  nsplit = (g.M + rows - 1) / rows;
+  g.rows_per_cta = rows;
+  dim3 grid(kt, nt, g.npass * nsplit);
+  gemm_dw_kernel<<<grid, GEMM_THREADS, gemm_dw_smem(g), st>>>(g, nsplit);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+static const LinearP& lin(const Engine& e, int net, int l) { return e.lay[net].lin[l]; }
+
+static double* fst_of(const Engine& e, int net, int l) {
+  return net == CVG_NET_GENERATOR ? e.ws.g_fst + (size_t)l * 2 * 2 * STAT_C : e.ws.e_fst + (size_t)l * 2 * STAT_C;
+}
+static double* bst_of(const Engine& e, int net, int l) {
+  return net == CVG_NET_GENERATOR ? e.ws.g_bst + (size_t)l * 2 * 2 * STAT_C : e.ws.e_bst + (size_t)l * 2 * STAT_C;
+}
+
+static BnRef bn_ref(const Engine& e, int net, int l, bool eval, bool update) {
+  const LinearP& p = lin(e, net, l);
+  BnRef b;
+  b.fstats = fst_of(e, net, l);
+  b.sf = 2 * STAT_C;
+  b.bstats = bst_of(e, net, l);
+  b.sb = 2 * STAT_C;
+  b.gamma = e.P(net, p.gamma);
+  b.beta = e.P(net, p.beta);
+  b.rmean = e.S(net, p.rmean);
+  b.rvar = e.S(net, p.rvar);
+  b.C = p.out;
+  b.eval = eval ? 1 : 0;
+  b.update_running = (update && !eval) ? 1 : 0;
+  return b;
+}
+
+static GemmArgs base_args(const Engine& e, int M, float Bg_bn, int npass) {
+  GemmArgs g;
+  g.M = M;
+  g.ld = e.ws.ld;
+  g.npass = npass;
+  g.Bg = Bg_bn;
+  g.bn_eps = e.cfg.bn_eps;
+  g.momentum = e.cfg.bn_momentum;
+  g.slope = e.cfg.lrelu_slope;
+  return g;
+}
+
+static DwArgs base_dw(const Engine& e, int M, float Bg_bn, int npass) {
+  DwArgs g;
+  g.M = M;
+  g.ld = e.ws.ld;
+  g.npass = npass;
+  g.Bg = Bg_bn;
+  g.bn_eps = e.cfg.bn_eps;
+  g.slope = e.cfg.lrelu_slope;
+  return g;
+}
+
+static int sync_stats(Engine& e, double* p, int npass, bool local_bn, cudaStream_t st) {
+  if (e.world <= 1 || local_bn) return 0;
+  return comm_all_reduce_f64(e, p, (int64_t)npass * 2 * STAT_C, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// noise + inputs
+// ------------------------------------------------------------------------------------------------
+static int launch_fill(Engine& e, FillArgs& a, cudaStream_t st) {
+  if (a.njobs == 0) return 0;
+  long long mx = 0;
+  for (int i = 0; i < a.njobs; ++i) {
+    long long t = (long long)a.job[i].npass * ((a.job[i].nfeat + 3) / 4) * a.M;
+    if (t > mx) mx = t;
+  }
+  int blocks = (int)((mx + 255) / 256);
+  if (blocks > 4 * e.num_sms) blocks = 4 * e.num_sms;
+  if (blocks < 1) blocks = 1;
+  fill_noise_kernel<<<dim3(blocks, a.njobs), 256, 0, st>>>(a);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+static void add_job(FillArgs& a, void* out, const void* inj, int kind, int nfeat, int npass, int stream) {
+  FillJob& j = a.job[a.njobs++];
+  j.out = out;
+  j.injected = inj;
+  j.kind = kind;
+  j.nfeat = nfeat;
+  j.npass = npass;
+  j.stream = stream;
+}
+
+static int stage_x(Engine& e, const float* x_real, int M, cudaStream_t st) {
+  to_feature_major_kernel<<<(M + 127) / 128, 128, 0, st>>>(x_real, nullptr, M, e.F, e.ws.ld, e.ws.xT);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward passes
+// ------------------------------------------------------------------------------------------------
+int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int label, int M, float Bg, bool local_bn,
+                  cudaStream_t st) {
+  const int net = CVG_NET_GENERATOR;
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  for (int l = 0; l < 4; ++l) {
+    const LinearP& p = lin(e, net, l);
+    GemmArgs g = base_args(e, M, Bg, npass);
+    g.R = (l == 0) ? e.Z : p.in;
+    g.N = p.out;
+    if (l == 0) {
+      g.a.kind = reparam_pass0 ? OP_REPARAM : OP_PLAIN;
+      g.a.rows = e.Z;
+      g.a.p = w.z;
+      g.a.sp = (long long)e.Z * ld;
+      g.a.mu = w.e_ml;
+      g.a.lv = w.e_ml + (size_t)e.Z * ld;
+      g.a.eps = w.z;
+      g.a.reparam_pass = reparam_pass0 ? 0 : -1;
+      g.wlabel = e.P(net, p.w) + e.Z + label;   // one-hot concat == adding column Z+label (appendix A.1)
+      g.ldwl = p.in;
+    } else {
+      g.a.kind = OP_BN_ACT;
+      g.a.rows = p.in;
+      g.a.p = w.g_h[l - 1];
+      g.a.sp = (long long)p.in * ld;
+      g.a.bn = bn_ref(e, net, l - 1, !train, true);
+    }
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    g.bias = e.P(net, p.b);
+    if (l < 3) {
+      g.Y = w.g_h[l];
+      g.sY = (long long)p.out * ld;
+      if (train) {
+        g.ostats = fst_of(e, net, l);
+        g.sostats = 2 * STAT_C;
+      }
+    } else {
+      g.act = ACT_SIGMOID;
+      g.Y = w.g_out;
+      g.sY = (long long)e.F * ld;
+    }
+    CVG_TRY(launch_mn(e, true, g, st));
+    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 2, local_bn, st));
+  }
+  return 0;
+}
+
+int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn, cudaStream_t st) {
+  const int net = CVG_NET_ENCODER;
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  for (int l = 0; l < 4; ++l) {
+    const LinearP& p = lin(e, net, l);
+    GemmArgs g = base_args(e, M, Bg, 1);
+    g.R = (l == 0) ? e.F : p.in;
+    g.N = p.out;
+    if (l == 0) {
+      g.a.kind = OP_PLAIN;
+      g.a.rows = e.F;
+      g.a.p = w.xT;
+      g.wlabel = e.P(net, p.w) + e.F + label;
+      g.ldwl = p.in;
+    } else {
+      g.a.kind = OP_BN_ACT;
+      g.a.rows = p.in;
+      g.a.p = w.e_h[l - 1];
+      g.a.bn = bn_ref(e, net, l - 1, !train, true);
+    }
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    g.bias = e.P(net, p.b);
+    if (l < 3) {
+      g.Y = w.e_h[l];
+      if (train) {
+        g.ostats = fst_of(e, net, l);
+        g.sostats = 2 * STAT_C;
+      }
+    } else {
+      g.Y = w.e_ml;
+      if (train) {
+        g.kl_acc = w.loss + L_KL;
+        g.kl_split = e.Z;
+      }
+    }
+    CVG_TRY(launch_mn(e, true, g, st));
+    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 1, local_bn, st));
+  }
+  return 0;
+}
+
+static int launch_sn(Engine& e, int npass, bool do_power, cudaStream_t st) {
+  const int net = CVG_NET_DISCRIMINATOR;
+  SnArgs a;
+  int off = 0;
+  for (int l = 0; l < 4; ++l) {
+    const LinearP& p = lin(e, net, l);
+    a.L[l].W = e.P(net, p.w);
+    a.L[l].rows = p.out;
+    a.L[l].cols = p.in;
+    a.L[l].u = e.S(net, p.u);
+    a.L[l].v = e.S(net, p.v);
+    a.L[l].snap_off = off;
+    off += ((p.out > p.in ? p.out : p.in) + 3) & ~3;
+  }
+  a.npass = npass;
+  a.do_power = do_power ? 1 : 0;
+  a.eps = e.cfg.sn_eps;
+  a.sigma = e.ws.sn_sigma;
+  a.inv_sigma = e.ws.sn_inv_sigma;
+  a.u_snap = e.ws.sn_u;
+  a.v_snap = e.ws.sn_v;
+  a.ssnap = e.ws.sn_snap;
+  sn_power_kernel<<<4, 256, 0, st>>>(a);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// critic forward (train mode).  xin: feature-major [F][ld] (+ pass * sxin).
+static int fwd_critic(Engine& e, const float* xin, long long sxin, int npass, int label, int M, double* osum,
+                      cudaStream_t st) {
+  const int net = CVG_NET_DISCRIMINATOR;
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const float keep_inv = 1.0f / (1.0f - e.cfg.dropout_p);
+  for (int l = 0; l < 4; ++l) {
+    const LinearP& p = lin(e, net, l);
+    GemmArgs g = base_args(e, M, (float)M, npass);
+    g.R = (l == 0) ? e.F : p.in;
+    g.N = p.out;
+    g.a.kind = OP_PLAIN;
+    g.a.rows = g.R;
+    if (l == 0) {
+      g.a.p = xin;
+      g.a.sp = sxin;
+      g.wlabel = e.P(net, p.w) + e.F + label;
+      g.ldwl = p.in;
+    } else {
+      g.a.p = w.d_a[l - 1];
+      g.a.sp = (long long)p.in * ld;
+    }
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    g.bias = e.P(net, p.b);
+    g.scale = w.sn_inv_sigma + l * 2;
+    if (l < 3) {
+      g.act = ACT_LRELU;
+      g.Y = w.d_a[l];
+      g.sY = (long long)p.out * ld;
+      if (l == 0) { g.mask = w.d_m1; g.smask = (long long)p.out * ld; g.keep_inv = keep_inv; }
+      if (l == 1) { g.mask = w.d_m2; g.smask = (long long)p.out * ld; g.keep_inv = keep_inv; }
+    } else {
+      g.Y = w.d_s;
+      g.sY = (long long)ld;
+      g.osum = osum;
+    }
+    CVG_TRY(launch_mn(e, true, g, st));
+  }
+  return 0;
+}
+
+int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool train, int M, cudaStream_t st) {
+  const int net = CVG_NET_CLASSIFIER;
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const float keep_inv = 1.0f / (1.0f - e.cfg.dropout_p);
+  for (int l = 0; l < 4; ++l) {
+    const LinearP& p = lin(e, net, l);
+    GemmArgs g = base_args(e, M, (float)M, npass);
+    g.R = p.in;
+    g.N = p.out;
+    g.a.kind = OP_PLAIN;
+    g.a.rows = p.in;
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    g.bias = e.P(net, p.b);
+    g.sY = (long long)p.out * ld;
+    if (l == 0) {
+      g.a.p = xin; g.a.sp = sxin;
+      g.act = ACT_RELU;
+      g.Y = w.c_a1;
+      if (train) { g.mask = w.c_m1; g.smask = (long long)p.out * ld; g.keep_inv = keep_inv; }
+    } else if (l == 1) {
+      g.a.p = w.c_a1; g.a.sp = (long long)p.in * ld;
+      g.Y = w.c_h2;
+    } else if (l == 2) {
+      g.a.p = w.c_a2; g.a.sp = (long long)p.in * ld;
+      g.act = ACT_RELU;
+      g.Y = w.c_a3;
+    } else {
+      g.a.p = w.c_a3; g.a.sp = (long long)p.in * ld;
+      g.Y = w.c_logit;
+    }
+    CVG_TRY(launch_mn(e, true, g, st));
+    if (l == 1) {
+      LnArgs a;
+      a.M = M; a.ld = w.ld; a.C = p.out; a.npass = npass;
+      a.h = w.c_h2; a.sh = (long long)p.out * ld;
+      a.g = e.P(net, p.gamma); a.b = e.P(net, p.beta);
+      a.eps = e.cfg.ln_eps;
+      a.mask = train ? w.c_m2 : nullptr; a.smask = (long long)p.out * ld; a.keep_inv = keep_inv;
+      a.a = w.c_a2; a.sa = (long long)p.out * ld;
+      a.rs = w.c_rs; a.srs = 2 * (long long)ld;
+      ln_fwd_kernel<<<dim3((M + 63) / 64, npass), 64, 0, st>>>(a);
+      CVG_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward passes
+// ------------------------------------------------------------------------------------------------
+// critic backward.  seed[pass] = dL/dscore (constant over rows).  want_dw: accumulate per-pass raw
+// gradients into ws.sn_G (+ bias grads into the grad buffer).  want_dx: write dL/dx into ws.dx.
+static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, int label, int M, const float* seed,
+                      bool want_dw, bool want_dx, cudaStream_t st) {
+  const int net = CVG_NET_DISCRIMINATOR;
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const float keep_inv = 1.0f / (1.0f - e.cfg.dropout_p);
+  const long long sG = e.lay[net].n_param;
+  for (int l = 3; l >= 0; --l) {
+    const LinearP& p = lin(e, net, l);
+    // dY operand of this layer
+    Operand dy;
+    if (l == 3) {
+      dy.kind = OP_CONST; dy.rows = 1; dy.cst = seed[0];
+    } else {
+      dy.kind = OP_PLAIN; dy.rows = p.out; dy.p = w.d_g[l]; dy.sp = (long long)p.out * ld;
+    }
+    if (want_dw) {
+      // OP_CONST carries one value: run the two passes of layer 4 as separate launches
+      const int reps = (l == 3 && npass > 1) ? npass : 1;
+      for (int r = 0; r < reps; ++r) {
+        DwArgs d = base_dw(e, M, (float)M, reps > 1 ? 1 : npass);
+        d.N = p.out;
+        d.K = (l == 0) ? e.F : p.in;
+        d.p = dy;
+        if (l == 3) d.p.cst = seed[reps > 1 ? r : 0];
+        d.q.kind = OP_PLAIN;
+        d.q.rows = d.K;
+        if (l == 0) { d.q.p = xin + (reps > 1 ? r * sxin : 0); d.q.sp = sxin; }
+        else { d.q.p = w.d_a[l - 1] + (reps > 1 ? (long long)r * p.in * ld : 0); d.q.sp = (long long)p.in * ld; }
+        d.dW = w.sn_G + p.w + (reps > 1 ? r * sG : 0);
+        d.sdW = sG;
+        d.ldw = p.in;
+        d.db = (l == 3) ? nullptr : e.G(net, p.b);   // score-bias gradient is added analytically (sn_grad_kernel)
+        d.label_col = (l == 0) ? e.F + label : -1;
+        CVG_TRY(launch_dw(e, d, st));
+      }
+    }
+    if (l == 0 && !want_dx) break;
+    GemmArgs g = base_args(e, M, (float)M, npass);
+    g.R = p.out;
+    g.N = (l == 0) ? e.F : p.in;
+    g.a = dy;
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    g.scale = w.sn_inv_sigma + l * 2;
+    if (l == 0) {
+      g.ekind = EP_STORE;
+      g.Y = w.dx;
+      g.accumulate = 0;
+      CVG_TRY(launch_mn(e, false, g, st));
+    } else {
+      g.ekind = EP_DACT;
+      g.act = ACT_LRELU;
+      g.prev = w.d_a[l - 1];
+      g.sprev = (long long)p.in * ld;
+      if (l - 1 == 0) { g.mask = w.d_m1; g.smask = (long long)p.in * ld; g.keep_inv = keep_inv; }
+      if (l - 1 == 1) { g.mask = w.d_m2; g.smask = (long long)p.in * ld; g.keep_inv = keep_inv; }
+      g.Y = w.d_g[l - 1];
+      g.sY = (long long)p.in * ld;
+      if (l == 3 && npass > 1) {
+        for (int r = 0; r < npass; ++r) {   // per-pass constant seed
+          GemmArgs gr = g;
+          gr.a.cst = seed[r];
+          gr.only_pass = r;
+          CVG_TRY(launch_mn(e, false, gr, st));
+        }
+      } else {
+        CVG_TRY(launch_mn(e, false, g, st));
+      }
+    }
+  }
+  return 0;
+}
+
+// classifier backward from ws.c_dlogit.
+static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass, int M, bool want_dw, bool want_dx,
+                          bool dx_accumulate, cudaStream_t st) {
+  const int net = CVG_NET_CLASSIFIER;
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const float keep_inv = 1.0f / (1.0f - e.cfg.dropout_p);
+  for (int l = 3; l >= 0; --l) {
+    const LinearP& p = lin(e, net, l);
+    Operand dy;
+    dy.kind = OP_PLAIN;
+    dy.rows = p.out;
+    if (l == 3) { dy.p = w.c_dlogit; dy.sp = (long long)e.K * ld; }
+    else { dy.p = w.c_g[l]; dy.sp = (long long)p.out * ld; }
+    if (want_dw) {
+      DwArgs d = base_dw(e, M, (float)M, npass);
+      d.N = p.out;
+      d.K = p.in;
+      d.p = dy;
+      d.q.kind = OP_PLAIN;
+      d.q.rows = p.in;
+      if (l == 0) { d.q.p = xin; d.q.sp = sxin; }
+      else if (l == 1) { d.q.p = w.c_a1; d.q.sp = (long long)p.in * ld; }
+      else if (l == 2) { d.q.p = w.c_a2; d.q.sp = (long long)p.in * ld; }
+      else { d.q.p = w.c_a3; d.q.sp = (long long)p.in * ld; }
+      d.dW = e.G(net, p.w);
+      d.sdW = 0;
+      d.ldw = p.in;
+      d.db = e.G(net, p.b);
+      CVG_TRY(launch_dw(e, d, st));
+    }
+    if (l == 0 && !want_dx) break;
+    GemmArgs g = base_args(e, M, (float)M, npass);
+    g.R = p.out;
+    g.N = p.in;
+    g.a = dy;
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    if (l == 0) {
+      g.ekind = EP_STORE;
+      g.Y = w.dx;
+      g.accumulate = dx_accumulate ? 1 : 0;
+    } else {
+      g.ekind = EP_DACT;
+      g.act = ACT_RELU;
+      g.sprev = (long long)p.in * ld;
+      g.sY = (long long)p.in * ld;
+      g.Y = w.c_g[l - 1];
+      if (l == 3) g.prev = w.c_a3;
+      if (l == 2) { g.prev = w.c_a2; g.mask = w.c_m2; g.smask = (long long)p.in * ld; g.keep_inv = keep_inv; }
+      if (l == 1) { g.prev = w.c_a1; g.mask = w.c_m1; g.smask = (long long)p.in * ld; g.keep_inv = keep_inv; }
+    }
+    CVG_TRY(launch_mn(e, false, g, st));
+    if (l == 2) {   // c_g[1] holds dL/dn -> LayerNorm backward in place -> dL/dh2
+      const LinearP& p1 = lin(e, net, 1);
+      LnBwdArgs a;
+      a.M = M; a.ld = w.ld; a.C = p1.out; a.npass = npass;
+      a.dn = w.c_g[1]; a.sdn = (long long)p1.out * ld;
+      a.h = w.c_h2; a.sh = (long long)p1.out * ld;
+      a.rs = w.c_rs; a.srs = 2 * (long long)ld;
+      a.g = e.P(net, p1.gamma);
+      a.dg = want_dw ? e.G(net, p1.gamma) : nullptr;
+      a.db = want_dw ? e.G(net, p1.beta) : nullptr;
+      ln_bwd_kernel<<<dim3((M + 63) / 64, npass), 64, 0, st>>>(a);
+      CVG_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
+// BatchNorm MLP backward shared by generator (npass 2) and encoder (npass 1).
+//   top_dy      : dL/d(pre-activation of the last Linear) [Ntop][ld] per pass
+//   h[], dy[]   : the net's pre-BN activations and gradient scratch
+struct BnNetBwd {
+  int net, npass;
+  float* const* h;
+  float* const* dy;
+  const float* top_dy;
+  long long s_top;
+  Operand first_in;        // input operand of layer 0 (x, z or reparameterised z)
+  int first_K;             // its width
+  int label_col;
+  bool want_first_dx;      // generator: dL/dz_enc of pass 0 -> encoder head gradient
+};
+
+static int bwd_bn_net(Engine& e, const BnNetBwd& b, int M, float Bg_bn, float kl_coef, bool local_bn, cudaStream_t st) {
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const int net = b.net;
+  for (int l = 3; l >= 0; --l) {
+    const LinearP& p = lin(e, net, l);
+    Operand dy;
+    if (l == 3) {
+      dy.kind = OP_PLAIN; dy.rows = p.out; dy.p = b.top_dy; dy.sp = b.s_top;
+    } else {
+      dy.kind = OP_BN_BWD; dy.rows = p.out;
+      dy.p = b.dy[l]; dy.sp = (long long)p.out * ld;
+      dy.h = b.h[l]; dy.sh = (long long)p.out * ld;
+      dy.bn = bn_ref(e, net, l, false, false);
+    }
+    // ---- dX first: it produces the batch sums the next layer's kernels need -----------------------
+    if (l > 0) {
+      const LinearP& pp = lin(e, net, l - 1);
+      GemmArgs g = base_args(e, M, Bg_bn, b.npass);
+      g.R = p.out;
+      g.N = p.in;
+      g.a = dy;
+      g.W = e.P(net, p.w);
+      g.ldw = p.in;
+      g.ekind = EP_DBN;
+      g.prev = b.h[l - 1];
+      g.sprev = (long long)pp.out * ld;
+      g.prev_bn = bn_ref(e, net, l - 1, false, false);
+      g.Y = b.dy[l - 1];
+      g.sY = (long long)pp.out * ld;
+      g.ostats = bst_of(e, net, l - 1);
+      g.sostats = 2 * STAT_C;
+      CVG_TRY(launch_mn(e, false, g, st));
+      CVG_TRY(sync_stats(e, bst_of(e, net, l - 1), b.npass, local_bn, st));
+    } else if (b.want_first_dx) {
+      GemmArgs g = base_args(e, M, Bg_bn, b.npass);
+      g.only_pass = 0;
+      g.R = p.out;
+      g.N = e.Z;
+      g.a = dy;
+      g.W = e.P(net, p.w);
+      g.ldw = p.in;
+      g.ekind = EP_REPARAM_BWD;
+      g.mu = w.e_ml;
+      g.lv = w.e_ml + (size_t)e.Z * ld;
+      g.eps = w.z;
+      g.kl_coef = kl_coef;
+      g.Y = w.e_dml;
+      CVG_TRY(launch_mn(e, false, g, st));
+    }
+    // ---- dW, db, and the BatchNorm affine gradients of this layer ------------------------------------
+    DwArgs d = base_dw(e, M, Bg_bn, b.npass);
+    d.N = p.out;
+    d.p = dy;
+    if (l == 0) {
+      d.K = b.first_K;
+      d.q = b.first_in;
+      d.label_col = b.label_col;
+    } else {
+      d.K = p.in;
+      d.q.kind = OP_BN_ACT;
+      d.q.rows = p.in;
+      d.q.p = b.h[l - 1];
+      d.q.sp = (long long)p.in * ld;
+      d.q.bn = bn_ref(e, net, l - 1, false, false);
+    }
+    d.dW = e.G(net, p.w);
+    d.sdW = 0;
+    d.ldw = p.in;
+    d.db = e.G(net, p.b);
+    if (l < 3) {
+      d.dgamma = e.G(net, p.gamma);
+      d.dbeta = e.G(net, p.beta);
+      // with global BatchNorm the sums are already global: only rank 0 contributes them before the
+      // gradient all-reduce (sum).  With local BatchNorm every rank adds its own.
+      d.add_affine = (e.world <= 1 || local_bn || e.rank == 0) ? 1 : 0;
+    }
+    CVG_TRY(launch_dw(e, d, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam + losses
+// ------------------------------------------------------------------------------------------------
+static float net_lr(const Engine& e, int net) {
+  if (net == CVG_NET_DISCRIMINATOR) return e.cfg.d_lr;
+  if (net == CVG_NET_CLASSIFIER) return e.cfg.c_lr;
+  return e.cfg.g_lr;
+}
+
+int run_adam(Engine& e, int net_mask, cudaStream_t st) {
+  AdamArgs a;
+  a.nseg = 0;
+  a.b1 = e.cfg.adam_beta1;
+  a.b2 = e.cfg.adam_beta2;
+  a.eps = e.cfg.adam_eps;
+  a.clear_grad = 1;
+  long long nmax = 0;
+  for (int net = 0; net < 4; ++net) {
+    if (!(net_mask & (1 << net))) continue;
+    if (a.nseg == 2) CVG_FAIL("cvg_adam: at most two networks per call");
+    const int64_t t = ++e.adam_t[net];
+    AdamSeg& s = a.seg[a.nseg++];
+    s.p = e.buf[net].params; s.g = e.buf[net].grads; s.m = e.buf[net].m; s.v = e.buf[net].v;
+    s.n = e.lay[net].n_param;
+    const double bc1 = 1.0 - pow((double)e.cfg.adam_beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)e.cfg.adam_beta2, (double)t);
+    s.lr = (float)((double)net_lr(e, net) / bc1);   // torch: step_size = lr / bias_correction1 (in double)
+    s.bc1 = 1.0f;
+    s.bc2_sqrt = (float)sqrt(bc2);
+    if (s.n > nmax) nmax = s.n;
+  }
+  if (a.nseg == 0) return 0;
+  int blocks = (int)((nmax + 255) / 256);
+  if (blocks > 2 * e.num_sms) blocks = 2 * e.num_sms;
+  adam_kernel<<<dim3(blocks, a.nseg), 256, 0, st>>>(a);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// pack local loss sums into the first net's gradient tail, all-reduce gradients (+tail), Adam, unpack
+static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, float* loss_out, cudaStream_t st) {
+  int first = -1;
+  for (int net = 0; net < 4; ++net)
+    if (net_mask & (1 << net)) { first = net; break; }
+  float* tail = e.buf[first].grads + e.lay[first].n_param;
+  pack_loss_kernel<<<1, 32, 0, st>>>(e.ws.loss, tail);
+  CVG_LAUNCH_CHECK();
+  for (int net = 0; net < 4; ++net)
+    if (net_mask & (1 << net))
+      CVG_TRY(comm_all_reduce_f32(e, e.buf[net].grads, e.lay[net].n_param + (net == first ? CVG_GRAD_TAIL : 0), st));
+  if (loss_out) {
+    unpack_loss_kernel<<<1, 32, 0, st>>>(tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, 1, tail);
+    CVG_LAUNCH_CHECK();
+  }
+  if (!(flags & CVG_STEP_NO_UPDATE)) CVG_TRY(run_adam(e, net_mask, st));
+  return 0;
+}
+
+static int check_step(Engine& e, int B) {
+  if (!e.ws_base) CVG_FAIL("workspace not bound");
+  for (int n = 0; n < 4; ++n)
+    if (!e.buf[n].params || !e.buf[n].grads || (!e.buf[n].state && e.lay[n].n_state > 0)) CVG_FAIL("network buffers not bound");
+  if (B < 1 || B > e.ws.rows_cap) CVG_FAIL("batch size exceeds max_batch");
+  if ((int64_t)B * e.world < 2) CVG_FAIL("BatchNorm in train mode needs more than 1 row");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step D (cvae_gan.py:104-128)
+// ------------------------------------------------------------------------------------------------
+int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, uint64_t seed, uint64_t counter,
+           int flags, float* loss_out, cudaStream_t st) {
+  CVG_TRY(check_step(e, B));
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const bool local_bn = flags & CVG_STEP_LOCAL_BN;
+  const float Bg = (float)B * (float)e.world;
+  const float Bg_bn = local_bn ? (float)B : Bg;
+  const int D = CVG_NET_DISCRIMINATOR;
+  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  CVG_CUDA(cudaMemsetAsync(w.sn_G, 0, sizeof(float) * 2 * e.lay[D].n_param, st));
+  FillArgs f;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = seed; f.counter = counter; f.row_base = (uint64_t)e.rank * B;
+  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
+  add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 2, RS_DMASK1);
+  add_job(f, w.d_m2, nz ? nz->d_mask2 : nullptr, 1, e.dh[1], 2, RS_DMASK2);
+  CVG_TRY(launch_fill(e, f, st));
+  CVG_TRY(stage_x(e, x_real, B, st));
+  // G(z) under no_grad, still in train mode: batch stats, running stats updated (cvae_gan.py:113-115)
+  CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  CVG_TRY(launch_sn(e, 2, true, st));   // D(real) then D(fake): two consecutive power iterations
+  const long long sx = w.g_out - w.xT;  // pass 0 reads xT, pass 1 reads g_out (pass slot 0)
+  CVG_TRY(fwd_critic(e, w.xT, sx, 2, label, B, w.loss + L_DREAL, st));
+  const float seedv[2] = {-1.0f / Bg, 1.0f / Bg};   // d_loss = -mean D(real) + mean D(fake)
+  CVG_TRY(bwd_critic(e, w.xT, sx, 2, label, B, seedv, true, false, st));
+  {
+    SnGradArgs a;
+    int off = 0;
+    for (int l = 0; l < 4; ++l) {
+      const LinearP& p = lin(e, D, l);
+      a.L[l].W = e.P(D, p.w); a.L[l].rows = p.out; a.L[l].cols = p.in;
+      a.L[l].u = nullptr; a.L[l].v = nullptr; a.L[l].snap_off = off;
+      off += ((p.out > p.in ? p.out : p.in) + 3) & ~3;
+      a.w_off[l] = p.w;
+    }
+    a.npass = 2;
+    a.Gp = w.sn_G; a.sG = e.lay[D].n_param;
+    a.inv_sigma = w.sn_inv_sigma;
+    a.u_snap = w.sn_u; a.v_snap = w.sn_v; a.ssnap = w.sn_snap;
+    a.grad = e.buf[D].grads;
+    a.last_bias_grad = e.G(D, lin(e, D, 3).b);
+    a.last_bias_value = (float)B * (seedv[0] + seedv[1]);
+    sn_grad_kernel<<<4, 256, 0, st>>>(a);
+    CVG_LAUNCH_CHECK();
+  }
+  return finish_step(e, 1 << D, 0, B, flags, loss_out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// step C (cvae_gan.py:131-157)
+// ------------------------------------------------------------------------------------------------
+int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, uint64_t seed, uint64_t counter,
+           int flags, float* loss_out, cudaStream_t st) {
+  CVG_TRY(check_step(e, B));
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const bool local_bn = flags & CVG_STEP_LOCAL_BN;
+  const float Bg = (float)B * (float)e.world;
+  const float Bg_bn = local_bn ? (float)B : Bg;
+  const int C = CVG_NET_CLASSIFIER;
+  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  FillArgs f;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = seed; f.counter = counter; f.row_base = (uint64_t)e.rank * B;
+  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
+  add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 2, RS_CMASK1);
+  add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 2, RS_CMASK2);
+  CVG_TRY(launch_fill(e, f, st));
+  CVG_TRY(stage_x(e, x_real, B, st));
+  CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  const long long sx = w.g_out - w.xT;
+  CVG_TRY(fwd_classifier(e, w.xT, sx, 2, true, B, st));
+  CeArgs c;
+  c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 2; c.label = label;
+  c.logits = w.c_logit; c.sl = (long long)e.K * ld;
+  c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
+  c.coef = 1.0f / Bg;
+  c.loss = w.loss + L_CE0;
+  ce_kernel<<<dim3((B + 127) / 128, 2), 128, 0, st>>>(c);
+  CVG_LAUNCH_CHECK();
+  CVG_TRY(bwd_classifier(e, w.xT, sx, 2, B, true, false, false, st));
+  return finish_step(e, 1 << C, 1, B, flags, loss_out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// step E+G (cvae_gan.py:160-216)
+// ------------------------------------------------------------------------------------------------
+int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, uint64_t seed, uint64_t counter,
+           float lambda_class, int flags, float* loss_out, cudaStream_t st) {
+  CVG_TRY(check_step(e, B));
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const bool local_bn = flags & CVG_STEP_LOCAL_BN;
+  const float Bg = (float)B * (float)e.world;
+  const float Bg_bn = local_bn ? (float)B : Bg;
+  const int E = CVG_NET_ENCODER, G = CVG_NET_GENERATOR;
+  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  FillArgs f;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = seed; f.counter = counter; f.row_base = (uint64_t)e.rank * B;
+  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  add_job(f, w.z, nz ? nz->eps : nullptr, 0, e.Z, 1, RS_EPS);                     // slot 0: eps
+  add_job(f, w.z + (size_t)e.Z * ld, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);      // slot 1: z_prior
+  add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 1, RS_DMASK1);
+  add_job(f, w.d_m2, nz ? nz->d_mask2 : nullptr, 1, e.dh[1], 1, RS_DMASK2);
+  add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
+  add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
+  CVG_TRY(launch_fill(e, f, st));
+  CVG_TRY(stage_x(e, x_real, B, st));
+
+  // forward: E -> (mu, logvar); G on z_enc (pass 0) and z_prior (pass 1); D and C on x_fake
+  CVG_TRY(fwd_encoder(e, true, label, B, Bg_bn, local_bn, st));
+  CVG_TRY(fwd_generator(e, 2, true, true, label, B, Bg_bn, local_bn, st));
+  const float* x_fake = w.g_out + (size_t)e.F * ld;
+  CVG_TRY(launch_sn(e, 1, true, st));
+  CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, st));
+  CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, st));
+  CeArgs c;
+  c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
+  c.logits = w.c_logit; c.sl = (long long)e.K * ld;
+  c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
+  c.coef = lambda_class / Bg;
+  c.loss = w.loss + L_CE0;
+  ce_kernel<<<dim3((B + 127) / 128, 1), 128, 0, st>>>(c);
+  CVG_LAUNCH_CHECK();
+
+  // backward to x_fake: adv = -mean D(x_fake) (cvae_gan.py:189), then the classification term
+  const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
+  CVG_TRY(bwd_critic(e, x_fake, 0, 1, label, B, seedv, false, true, st));
+  if (lambda_class != 0.f) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, st));
+
+  // generator output gradients: recon MSE on pass 0, dx on pass 1, through the sigmoid
+  SeedArgs s;
+  s.M = B; s.ld = w.ld; s.F = e.F;
+  s.out = w.g_out; s.sout = (long long)e.F * ld;
+  s.x = w.xT; s.dx = w.dx;
+  s.dpre = w.g_dout; s.sdpre = (long long)e.F * ld;
+  s.coef_recon = e.cfg.lambda_recon / (Bg * (float)e.F);
+  s.recon_acc = w.loss + L_RECON;
+  g_seed_kernel<<<dim3((unsigned)((e.F * ld + 255) / 256), 2), 256, 0, st>>>(s);
+  CVG_LAUNCH_CHECK();
+
+  const LinearP& g0 = lin(e, G, 0);
+  BnNetBwd gb;
+  gb.net = G; gb.npass = 2;
+  gb.h = w.g_h; gb.dy = w.g_dy;
+  gb.top_dy = w.g_dout; gb.s_top = (long long)e.F * ld;
+  gb.first_in.kind = OP_REPARAM; gb.first_in.rows = e.Z;
+  gb.first_in.p = w.z; gb.first_in.sp = (long long)e.Z * ld;
+  gb.first_in.mu = w.e_ml; gb.first_in.lv = w.e_ml + (size_t)e.Z * ld; gb.first_in.eps = w.z;
+  gb.first_in.reparam_pass = 0;
+  gb.first_K = e.Z;
+  gb.label_col = e.Z + label;
+  gb.want_first_dx = true;
+  (void)g0;
+  CVG_TRY(bwd_bn_net(e, gb, B, Bg_bn, e.cfg.lambda_kl / Bg, local_bn, st));
+
+  BnNetBwd eb;
+  eb.net = E; eb.npass = 1;
+  eb.h = w.e_h; eb.dy = w.e_dy;
+  eb.top_dy = w.e_dml; eb.s_top = 0;
+  eb.first_in.kind = OP_PLAIN; eb.first_in.rows = e.F; eb.first_in.p = w.xT;
+  eb.first_K = e.F;
+  eb.label_col = e.F + label;
+  eb.want_first_dx = false;
+  CVG_TRY(bwd_bn_net(e, eb, B, Bg_bn, 0.f, local_bn, st));
+
+  return finish_step(e, (1 << E) | (1 << G), 2, B, flags, loss_out, st);
+}
+
+}  // namespace cvg

@@ -1,0 +1,279 @@
+"""`CVAEGAN` - drop-in for /root/reference/src/cvae_gan.py:9-397 whose training and generation run
+in hand-written sm_100a CUDA kernels behind the C ABI (include/cvaegan_b200.h).
+
+Same surface as the reference class: construct with no arguments after the dataset/config globals
+are set, `fit(dataset)`, `generate_samples`, `generate_qualified_samples`, `samples`, `loss_history`,
+`encoder / generator / discriminator / classifier`, `lambda_*`, `plot_loss_history`,
+`reconstruct_samples`.  Config names are read from `config.gan_config` at CALL time like the
+reference (cvae_gan.py:100,104,108).
+
+Randomness: the reference draws from torch's generators; this implementation draws everything inside
+the kernels from Philox4x32-10 keyed by `torch.initial_seed()` (set by `set_random_state`) and a
+step counter, with rows keyed by their GLOBAL index, so a run is reproducible and independent of the
+number of GPUs.  Parity against the reference is checked with injected noise (tests/).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+
+from . import config as _config
+from . import datasets as _datasets
+from . import models
+from ._lib import NET_CLASSIFIER, NET_DISCRIMINATOR, NET_ENCODER, NET_GENERATOR
+from .engine import Engine, patience_scan
+
+
+def lambda_class_at(e: int, lambda_class: float) -> float:
+    """cvae_gan.py:198-204: 0 for e < 200, linear ramp over [200, 500), then the full weight."""
+    if e < 200:
+        return 0.0
+    if e < 500:
+        return lambda_class * ((e - 200) / 300)
+    return lambda_class
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class CVAEGAN:
+    def __init__(self, config=None, datasets=None, max_rows: int = None):
+        """`config` / `datasets`: modules with the reference's names (defaults: this package's mirrors;
+        pass the reference's own `src.config`, `src.datasets` to run inside its scripts)."""
+        self.config = config or _config
+        self.datasets = datasets or _datasets
+        gc = self.config.gan_config
+        self.feature_num = self.datasets.feature_num
+        self.label_num = self.datasets.label_num
+        self.rank, self.world_size = _dist_info()
+
+        # same construction (and CPU-generator draw) order as cvae_gan.py:19-39
+        self.encoder = models.CVAEGANEncoderModel(self.feature_num, self.label_num, gc.z_size)
+        self.generator = models.CVAEGANGeneratorModel(gc.z_size, self.label_num, self.feature_num)
+        self.discriminator = models.CVAEGANDiscriminatorModel(self.feature_num, self.label_num)
+        self.classifier = models.CVAEGANClassifierModel(self.feature_num, self.label_num)
+
+        self.samples = dict()
+        cc = gc.cvae_gan_config
+        self.lambda_recon = cc['lambda_recon']
+        self.lambda_kl = cc['lambda_kl']
+        self.lambda_adv = cc['lambda_adv']
+        self.lambda_class = cc['lambda_class']
+        self.loss_history = {'recon_loss': [], 'kl_loss': [], 'adv_loss': [], 'class_loss': []}
+
+        rows = max_rows or max(int(gc.batch_size) // self.world_size, 1 << 14)
+        self.engine = Engine(self.feature_num, self.label_num, gc.z_size, rows,
+                             lambda_recon=self.lambda_recon, lambda_kl=self.lambda_kl, lambda_adv=self.lambda_adv,
+                             g_lr=gc.g_lr, d_lr=gc.d_lr, c_lr=gc.c_lr, world_size=self.world_size, rank=self.rank)
+        for net, mod in ((NET_ENCODER, self.encoder), (NET_GENERATOR, self.generator),
+                         (NET_DISCRIMINATOR, self.discriminator), (NET_CLASSIFIER, self.classifier)):
+            mod.attach(self.engine, net)
+        self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        self._counter = 0          # one Philox counter value per optimiser step / sampling call
+        self._gen_rows = 0         # rows of the generation noise stream consumed so far
+        self._bn_calls = {NET_ENCODER: 0, NET_GENERATOR: 0}
+
+    # ------------------------------------------------------------------------------------------------
+    def _next(self) -> int:
+        self._counter += 1
+        return self._counter
+
+    def _sync_bn_counters(self):
+        for net, mod in ((NET_ENCODER, self.encoder), (NET_GENERATOR, self.generator)):
+            k = self._bn_calls[net]
+            if k:
+                for m in mod.modules():
+                    if isinstance(m, torch.nn.BatchNorm1d):
+                        m.num_batches_tracked += k
+                self._bn_calls[net] = 0
+
+    def fit(self, dataset):
+        """cvae_gan.py:59-236."""
+        gc = self.config.gan_config
+        eng = self.engine
+        for m in (self.encoder, self.generator, self.discriminator, self.classifier):
+            m.train()
+        self._divide_samples(dataset)
+        # fresh optimisers every fit(), like cvae_gan.py:75-97
+        for net in range(4):
+            eng.adam_m[net].zero_()
+            eng.adam_v[net].zero_()
+            eng.grads[net].zero_()
+            eng.set_adam_step(net, 0)
+        lam = gc.cvae_gan_config['lambda_class']
+        g_loss = torch.zeros(4, dtype=torch.float32, device=eng.device)
+        scratch = torch.zeros(4, dtype=torch.float32, device=eng.device)
+        for e in range(gc.epochs):
+            for target_label in self.samples.keys():
+                for _ in range(gc.d_loop_num):
+                    x = self._get_target_samples(target_label, gc.batch_size)
+                    eng.step_d(x, target_label, seed=self._seed, counter=self._next(), loss_out=scratch)
+                    self._bn_calls[NET_GENERATOR] += 1
+                for _ in range(gc.c_loop_num):
+                    x = self._get_target_samples(target_label, gc.batch_size)
+                    eng.step_c(x, target_label, seed=self._seed, counter=self._next(), loss_out=scratch)
+                    self._bn_calls[NET_GENERATOR] += 1
+                for _ in range(gc.g_loop_num):
+                    x = self._get_target_samples(target_label, gc.batch_size)
+                    eng.step_g(x, target_label, lambda_class_at(e, lam), seed=self._seed, counter=self._next(),
+                               loss_out=g_loss)
+                    self._bn_calls[NET_GENERATOR] += 2
+                    self._bn_calls[NET_ENCODER] += 1
+            # one read-back per epoch: the last label's last generator step (cvae_gan.py:219-222)
+            recon, kl, adv, cls = g_loss.tolist()
+            self.loss_history['recon_loss'].append(recon)
+            self.loss_history['kl_loss'].append(kl)
+            self.loss_history['adv_loss'].append(adv)
+            self.loss_history['class_loss'].append(cls)
+            if e % 50 == 0:
+                print(f"CVAE-GAN训练轮次: {e}/{gc.epochs}, 重构损失: {recon:.4f}, KL损失: {kl:.4f}, "
+                      f"对抗损失: {adv:.4f}, 分类损失: {cls:.4f}")
+        self._sync_bn_counters()
+        for m in (self.encoder, self.generator, self.discriminator, self.classifier):
+            m.eval()
+
+    def _divide_samples(self, dataset) -> None:
+        """cvae_gan.py:238-245, without the O(N^2) per-row torch.cat: one stable partition on the device.
+        Key order = first occurrence in the data, rows keep their order, exactly like the reference."""
+        if hasattr(dataset, "tensors"):
+            x, y = dataset.tensors()
+        elif hasattr(self.datasets, "tr_samples") and len(self.datasets.tr_labels) == len(dataset):
+            x, y = self.datasets.tr_samples, self.datasets.tr_labels
+        else:
+            xs, ys = zip(*[dataset[i] for i in range(len(dataset))])
+            x, y = torch.stack(list(xs)), torch.stack(list(ys))
+        x = x.to(self.engine.device, torch.float32)
+        y = y.to(self.engine.device).long()
+        labels, first = [], {}
+        uniq = torch.unique(y)
+        for lab in uniq.tolist():
+            first[lab] = int((y == lab).nonzero()[0])
+        labels = sorted(first, key=first.get)
+        for lab in labels:
+            rows = x[y == lab].contiguous()
+            if lab not in self.samples:
+                self.samples[lab] = rows
+            else:
+                self.samples[lab] = torch.cat([self.samples[lab], rows])
+
+    def _get_target_samples(self, label: int, num: int) -> torch.Tensor:
+        """cvae_gan.py:247-260 on the device (three branches by class size); returns this rank's shard."""
+        return self.engine.sample_rows(self.samples[label], int(num), seed=self._seed, counter=self._next())
+
+    # ------------------------------------------------------------------------------------------------
+    def plot_loss_history(self):
+        """cvae_gan.py:263-337 (needs matplotlib, which is not part of the hot path)."""
+        import matplotlib.pyplot as plt
+        out_dir = getattr(getattr(self.config, "path_config", None), "gan_outs", None)
+        if out_dir is None:
+            import pathlib
+            out_dir = pathlib.Path(".")
+        titles = (('recon_loss', 'Reconstruction Loss', 'blue'), ('kl_loss', 'KL divergence loss', 'green'),
+                  ('adv_loss', 'Adversarial Loss', 'red'), ('class_loss', 'Classification Loss', 'purple'))
+        plt.figure(figsize=(12, 8))
+        for i, (key, title, color) in enumerate(titles):
+            plt.subplot(2, 2, i + 1)
+            plt.plot(self.loss_history[key], color=color)
+            plt.xlabel('Epoch')
+            plt.ylabel('Loss')
+            plt.title(title)
+        plt.tight_layout()
+        plt.savefig(out_dir / 'cvae_gan_loss_history.jpg')
+        plt.close()
+        plt.figure(figsize=(12, 6))
+        for key, title, color in titles:
+            vals = self.loss_history[key]
+            plt.plot([abs(v) for v in vals] if key == 'adv_loss' else vals, label=title, color=color)
+        plt.xlabel('Epoch')
+        plt.ylabel('Loss')
+        plt.legend()
+        plt.grid(True, alpha=0.3)
+        plt.savefig(out_dir / 'cvae_gan_combined_loss.jpg')
+        plt.close()
+
+    # ------------------------------------------------------------------------------------------------
+    def generate_samples(self, target_label: int, num: int):
+        """cvae_gan.py:339-345: G(randn[num, Z], onehot) in whatever mode G is in, returned on the CPU."""
+        out = self.engine.generate(int(target_label), int(num), seed=self._seed, row_offset=self._gen_rows,
+                                   train_mode=self.generator.training)
+        self._gen_rows += int(num)
+        if self.generator.training:
+            self._bn_calls[NET_GENERATOR] += 1
+            self._sync_bn_counters()
+        return out.cpu()
+
+    def generate_qualified_samples(self, target_label: int, num: int, confidence_threshold: float = None):
+        """cvae_gan.py:347-378.  The reference draws chunks of <= 10 rows and stops after 20 empty chunks;
+        rows are independent in eval mode, so here the noise stream is generated, classified and filtered
+        in large fused batches and the chunk/patience bookkeeping is replayed on the keep mask
+        (cvg_patience_scan): the result is the same prefix of accepted rows of the stream."""
+        if confidence_threshold is None:
+            confidence_threshold = self.config.gan_config.cvae_gan_config['confidence_threshold']
+        eng = self.engine
+        num = int(num)
+        if self.generator.training:
+            raise RuntimeError("generate_qualified_samples before fit(): the generator is in train mode "
+                               "(batch statistics over chunks of 10 rows); call fit() or generator.eval() first")
+        keeps, xs, idxs = [], [], []
+        produced, accepted = 0, 0
+        base = self._gen_rows
+        consumed, got = 0, 0
+        while True:
+            rate = (accepted + 1) / (produced + 2)
+            want = int(min(max(1024, 1.5 * (num - accepted) / rate + 256), 1 << 22))
+            want = max(want, 200 + 10)   # patience 20 x chunk 10 of pure rejects must fit
+            x, idx, cnt, _, keep = eng.generate_filter(int(target_label), want, float(confidence_threshold),
+                                                       seed=self._seed, row_offset=base + produced, want_keep=True)
+            c = int(cnt.item())
+            keeps.append(keep.cpu())
+            xs.append(x[:c])
+            idxs.append(idx[:c])
+            produced += want
+            accepted += c
+            try:
+                consumed, got = patience_scan(torch.cat(keeps), num)
+                break
+            except Exception as ex:          # stream too short for the loop to terminate: extend it
+                if "too short" not in str(ex):
+                    raise
+        self.classifier.train()              # the reference leaves C in train mode (cvae_gan.py:363)
+        self._gen_rows = base + consumed
+        if got == 0:
+            return torch.tensor([])
+        x = torch.cat(xs)
+        idx = torch.cat(idxs)
+        sel = idx < (base + consumed)
+        x, idx = x[sel], idx[sel]
+        order = torch.argsort(idx)
+        return x[order][:got].cpu()
+
+    def reconstruct_samples(self, samples: torch.Tensor, labels: torch.Tensor):
+        """cvae_gan.py:380-397.  The reference ALWAYS raises here: it hands 1-D labels to the generator,
+        whose forward requires a 2-D one-hot condition (cvae_gan_models.py:142-143).  Kept as is; use
+        `reconstruct()` for a working E -> G round trip."""
+        raise ValueError(f"条件应为2D张量，实际: {labels.shape}")
+
+    def reconstruct(self, samples: torch.Tensor, label: int):
+        """Working variant: x -> E (eval) -> z = mu + eps*std -> G (eval), all rows share one label."""
+        eng = self.engine
+        mu, lv = eng.encoder_forward(samples, int(label))
+        z = (mu + torch.randn_like(mu) * torch.exp(0.5 * lv)).contiguous()
+        return eng.generate(int(label), z.size(0), z=z, train_mode=False).cpu()
+
+    # ------------------------------------------------------------------------------------------------
+    def state_dict(self):
+        self._sync_bn_counters()
+        return OrderedDict((n, getattr(self, n).state_dict()) for n in
+                           ("encoder", "generator", "discriminator", "classifier"))
+
+    def load_state_dict(self, sd):
+        for net, n in enumerate(("encoder", "generator", "discriminator", "classifier")):
+            self.engine.load_state(net, sd[n])
+            for k, v in sd[n].items():
+                if k.endswith("num_batches_tracked"):
+                    dict(getattr(self, n).named_buffers())[k].fill_(int(v))

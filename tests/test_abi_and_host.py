@@ -1,0 +1,132 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol the header declares; host
+logic (patience scan, lambda schedule, model mirrors) matches the oracle / the reference fixtures.
+No compute calls are made (there is no GPU in this container)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvae_gan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from cvae_gan_b200 import _lib
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from cvae_gan_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "cvaegan_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(cvg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cvg_abi_version() == 1
+
+
+def test_create_fails_loudly_without_sm100(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cvae_gan_b200 import CvgError, Engine, _lib
+    cfg = _lib.CvgConfig(10, 5, 128, 64, 1, 0, 1, .1, 1, 2e-4, 2e-4, 1e-4, .5, .999, 1e-8, .1, 1e-5, 1e-5, 1e-12, .2, .3)
+    h = C.c_void_p()
+    assert lib.cvg_create(C.byref(cfg), C.byref(h)) != 0
+    assert lib.cvg_last_error()
+    with pytest.raises(CvgError):
+        Engine(10, 5)          # no silent CPU path
+
+
+def test_patience_scan_matches_oracle(lib):
+    from cvae_gan_b200.engine import patience_scan
+    g = torch.Generator().manual_seed(0)
+    for p_acc, num in ((0.5, 57), (0.02, 40), (0.0, 10), (1.0, 33), (0.3, 1), (0.1, 1000)):
+        keep = torch.rand(50000, generator=g) < p_acc
+        assert patience_scan(keep, num) == O.patience_scan(keep, num)
+    with pytest.raises(Exception, match="too short"):
+        patience_scan(torch.zeros(15, dtype=torch.bool), 5)
+
+
+def test_lambda_class_schedule_matches_oracle():
+    from cvae_gan_b200 import lambda_class_at
+    for e in (0, 1, 199, 200, 201, 350, 499, 500, 10000):
+        assert lambda_class_at(e, 0.5) == O.lambda_class_schedule(e, 0.5)
+
+
+def test_model_mirrors_reproduce_reference_init(golden_dir):
+    """Same seed -> same starting parameters as the reference constructor (fixture: reference state_dicts
+    right after `set_random_state(); CVAEGAN()`, see oracle/make_golden.py)."""
+    import random
+    from cvae_gan_b200 import models
+    npz = np.load(os.path.join(golden_dir, "ref_fit_a.npz"))
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)
+    nets = {
+        "encoder": models.CVAEGANEncoderModel(10, 5, 128),
+        "generator": models.CVAEGANGeneratorModel(128, 5, 10),
+        "discriminator": models.CVAEGANDiscriminatorModel(10, 5),
+        "classifier": models.CVAEGANClassifierModel(10, 5),
+    }
+    for name, mod in nets.items():
+        sd = mod.state_dict()
+        ref_keys = [k.split("/", 2)[2] for k in npz.files if k.startswith(f"init/{name}/")]
+        assert list(sd.keys()) == ref_keys
+        for k, v in sd.items():
+            ref = torch.from_numpy(npz[f"init/{name}/{k}"])
+            assert torch.equal(v, ref), (name, k)
+        assert [k for k, _, _ in O.tensor_table(name, 10, 5, 128)] == ref_keys
+
+
+def test_model_mirrors_keep_reference_error_behaviour():
+    from cvae_gan_b200 import models
+    torch.manual_seed(1)
+    E = models.CVAEGANEncoderModel(10, 5)
+    G = models.CVAEGANGeneratorModel(128, 5, 10)
+    D = models.CVAEGANDiscriminatorModel(10, 5)
+    Cm = models.CVAEGANClassifierModel(10, 5)
+    with pytest.raises(ValueError):
+        E(torch.zeros(4, 11), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(ValueError):
+        E(torch.zeros(4, 10), torch.zeros(4, 2))
+    with pytest.raises(ValueError):
+        G(torch.zeros(4, 128), torch.zeros(4, dtype=torch.long))       # 1-D condition (cvae_gan_models.py:142)
+    with pytest.raises(ValueError):
+        G(torch.zeros(4, 127), torch.zeros(4, 5))
+    with pytest.raises(ValueError):
+        D(torch.zeros(4, 10), torch.zeros(3, dtype=torch.long))
+    E.eval(); G.eval(); D.eval(); Cm.eval()
+    mu, lv = E(torch.rand(4, 10), torch.tensor([0, 1, 2, 3]))
+    assert mu.shape == (4, 128) and lv.shape == (4, 128)
+    assert G(torch.randn(4, 128), torch.eye(5)[:4]).shape == (4, 10)
+    assert D(torch.rand(4, 10), torch.tensor([1, 1, 1, 1])).shape == (4, 1)
+    assert Cm(torch.rand(4, 10)).shape == (4, 5)
+
+
+def test_oracle_models_equal_mirror_forward():
+    """The torch mirrors (state containers) and the oracle compute the same function."""
+    from cvae_gan_b200 import models
+    torch.manual_seed(3)
+    mods = {"encoder": models.CVAEGANEncoderModel(10, 5), "generator": models.CVAEGANGeneratorModel(128, 5, 10),
+            "discriminator": models.CVAEGANDiscriminatorModel(10, 5), "classifier": models.CVAEGANClassifierModel(10, 5)}
+    orc = O.OracleCVAEGAN(10, 5).load_state({k: m.state_dict() for k, m in mods.items()})
+    for m in mods.values():
+        m.eval()
+    x = torch.rand(16, 10)
+    z = torch.randn(16, 128)
+    with torch.no_grad():
+        assert torch.allclose(mods["generator"](z, torch.eye(5)[torch.full((16,), 2)]),
+                              O.generator_forward(orc.sd["generator"], z, 2, False), atol=1e-6)
+        assert torch.allclose(mods["classifier"](x), O.classifier_forward(orc.sd["classifier"], x, False), atol=1e-6)
+        assert torch.allclose(mods["discriminator"](x, torch.full((16,), 1)),
+                              O.discriminator_forward(orc.sd["discriminator"], x, 1, False), atol=1e-6)
+        mu, lv = mods["encoder"](x, torch.full((16,), 4))
+        omu, olv = O.encoder_forward(orc.sd["encoder"], x, 4, False)
+        assert torch.allclose(mu, omu, atol=1e-6) and torch.allclose(lv, olv, atol=1e-6)

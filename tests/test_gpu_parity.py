@@ -1,0 +1,266 @@
+"""GPU parity tests: CUDA engine (through the C ABI) vs the oracle on identical inputs, noise and masks.
+Run on a B200 with `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cvae_gan_oracle as O
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _single_thread_cpu():
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    yield
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-step gradients (no update): every parameter gradient of every network, three shapes
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F_,K,B", [(10, 5, 64), (10, 4, 200), (30, 5, 128), (10, 5, 333)])
+@pytest.mark.parametrize("kind", ["d", "c", "g"])
+def test_step_losses_and_gradients(kind, F_, K, B):
+    orc, eng, g = P.make_pair(F_, K, B, seed=5 + B)
+    x, y = P.make_data(F_, K, [B] * K, seed=1)
+    xb = x[y == (K - 1)][:B].contiguous()
+    eng.zero_grads()
+    ref, got, grads = P.run_step(kind, orc, eng, xb, K - 1, g, lambda_class=0.25, update=False)
+    assert P.losses_close(ref, got), (ref, got)
+    report = []
+    nets = {"d": ["discriminator"], "c": ["classifier"], "g": ["encoder", "generator"]}[kind]
+    P.compare_grads(eng, orc, nets, grads, report)
+    # pre-BN biases: the reference gradient itself is pure round-off (see parity.PRE_BN_BIASES)
+    report = [r for r in report if not any(r[0].endswith(k) for ks in P.PRE_BN_BIASES.values() for k in ks)]
+    P.assert_report(report, f"step_{kind} gradients")
+    # side effects of the forward passes: BN running stats, SN u/v
+    rep2 = []
+    P.compare_state(eng, orc, rep2, loose_prebn_atol=1e-3)
+    P.assert_report(rep2, f"step_{kind} state")
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# trajectory: two label visits (5 D + 5 C + 3 G steps each) with Adam updates, lambda_class != 0
+# ---------------------------------------------------------------------------------------------------
+def test_two_label_visits_trajectory():
+    F_, K, B = 10, 5, 256
+    orc, eng, g = P.make_pair(F_, K, B, seed=21)
+    x, y = P.make_data(F_, K, [400, 256, 100, 300, 300], seed=2)
+    orc.divide_samples(x, y)
+    step = 0
+    for label in (0, 3):
+        for kind, reps in (("d", 5), ("c", 5), ("g", 3)):
+            for _ in range(reps):
+                idx = torch.randperm(len(orc.samples[label]), generator=g)[:B]
+                xb = orc.samples[label][idx].contiguous()
+                ref, got, _ = P.run_step(kind, orc, eng, xb, label, g, lambda_class=0.25, update=True)
+                assert P.losses_close(ref, got), (step, kind, ref, got)
+                step += 1
+    report = []
+    # 6 generator steps of lr 2e-4 on round-off gradients: allow |delta| up to 6 * lr on those biases
+    P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5)
+    P.assert_report(report, "parameters after two label visits")
+    assert eng.get_adam_step(2) == 10 and eng.get_adam_step(3) == 10 and eng.get_adam_step(0) == 6
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# generation and the fused generate -> classify -> filter -> compact path
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 10, 777, 5000])
+def test_generate_eval_matches_oracle(n):
+    orc, eng, g = P.make_pair(10, 5, 64, seed=31)
+    z = torch.randn(n, 128, generator=g)
+    with torch.no_grad():
+        ref = O.generator_forward(orc.sd["generator"], z, 3, False)
+    got = eng.generate(3, n, z=z.cuda())
+    ok, worst, mx = P.close(got, ref)
+    assert ok, (worst, mx)
+    eng.close()
+
+
+def test_generate_train_mode_updates_running_stats():
+    orc, eng, g = P.make_pair(10, 5, 128, seed=32)
+    z = torch.randn(100, 128, generator=g)
+    with torch.no_grad():
+        ref = O.generator_forward(orc.sd["generator"], z, 1, True)
+    got = eng.generate(1, 100, z=z.cuda(), train_mode=True)
+    ok, worst, mx = P.close(got, ref)
+    assert ok, (worst, mx)
+    rep = []
+    P.compare_state(eng, orc, rep, nets=("generator",))
+    P.assert_report(rep, "generator running stats after train-mode generate")
+    eng.close()
+
+
+@pytest.mark.parametrize("thr,label", [(0.0, 0), (0.2, 2), (0.5, 4)])
+def test_generate_filter_matches_oracle(thr, label):
+    orc, eng, g = P.make_pair(10, 5, 4096, seed=33)
+    n = 10000   # > max_batch: exercises chunking
+    z = torch.randn(n, 128, generator=g)
+    xo, lo, keep_o = orc.generate_filter_stream(label, z, thr)
+    xg, idx, cnt, lg, kg = eng.generate_filter(label, n, thr, z=z.cuda(), want_logits=True, want_keep=True)
+    ok, worst, mx = P.close(lg, lo)
+    assert ok, ("logits", worst, mx)
+    # bit-exact decision on IDENTICAL logits (north_star): oracle filter applied to the kernel's logits
+    assert torch.equal(kg.bool().cpu(), O.filter_logits(lg.cpu(), label, thr))
+    # and against the oracle's own logits except where the max probability is within round-off of thr
+    probs = torch.softmax(lo, 1).max(1).values
+    decided = (probs - thr).abs() > 1e-5
+    arg_ok = torch.softmax(lo, 1).topk(2, 1).values
+    decided &= (arg_ok[:, 0] - arg_ok[:, 1]) > 1e-5
+    assert torch.equal(kg.bool().cpu()[decided], keep_o[decided])
+    c = int(cnt.item())
+    assert c == int(kg.sum())
+    order = torch.argsort(idx[:c])
+    kept_rows = torch.nonzero(kg.cpu()).flatten()
+    assert torch.equal(idx[:c][order].cpu(), kept_rows)
+    full = eng.generate(label, n, z=z.cuda())
+    assert torch.equal(xg[:c][order].cpu(), full.cpu()[kept_rows])      # compaction moves rows verbatim
+    eng.close()
+
+
+def test_generate_filter_capacity_and_offsets():
+    orc, eng, g = P.make_pair(10, 5, 1024, seed=34)
+    xg, idx, cnt, _, kg = eng.generate_filter(1, 3000, 0.0, seed=7, row_offset=1000, capacity=5, want_keep=True)
+    c = int(cnt.item())
+    assert c == int(kg.sum())                 # counted beyond capacity, written only up to it
+    assert (idx[:min(c, 5)] >= 1000).all()
+    # Philox rows are keyed by global row: generating [1000, 4000) in one call or two gives the same rows
+    a = eng.generate(1, 3000, seed=7, row_offset=1000)
+    b1 = eng.generate(1, 1234, seed=7, row_offset=1000)
+    b2 = eng.generate(1, 3000 - 1234, seed=7, row_offset=1000 + 1234)
+    assert torch.equal(a, torch.cat([b1, b2]))
+    eng.close()
+
+
+def test_philox_noise_is_standard_normal():
+    """In-kernel prior noise: push z through an identity-like check - the generator with injected z drawn
+    from torch and with in-kernel Philox must give outputs with the same distribution."""
+    orc, eng, g = P.make_pair(10, 5, 8192, seed=35)
+    n = 200000
+    a = eng.generate(2, n, seed=123)
+    b = eng.generate(2, n, z=torch.randn(n, 128, generator=g).cuda())
+    assert torch.allclose(a.mean(0), b.mean(0), atol=4e-3)
+    assert torch.allclose(a.std(0), b.std(0), rtol=3e-2, atol=1e-3)
+    assert not torch.equal(a[:1000], eng.generate(2, 1000, seed=124))
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# filter decision: golden fixture produced by the reference's own expression + torch CUDA softmax
+# ---------------------------------------------------------------------------------------------------
+def test_filter_logits_golden_and_torch_cuda(golden_dir):
+    from cvae_gan_b200.engine import Engine
+    eng = Engine(10, 5, 128, max_batch=64)
+    npz = np.load(os.path.join(golden_dir, "ref_filter.npz"))
+    logits = torch.from_numpy(npz["logits"])
+    n = logits.shape[0]
+    for lab in range(5):
+        for thr in (0.0, 0.2, 0.5, 0.9):
+            want = torch.from_numpy(np.unpackbits(npz[f"keep_l{lab}_thr{thr}"])[:n].astype(bool))
+            got = eng.filter_logits(logits.cuda(), lab, thr).cpu()
+            assert torch.equal(got, want), (lab, thr, int((got != want).sum()))
+    g = torch.Generator().manual_seed(5)
+    for K in (2, 4, 5, 8, 11, 32):
+        lg = (torch.randn(100000, K, generator=g) * 2).cuda()
+        lg[:100] = 0.0
+        lg[100:200, 0] = float("nan")
+        for thr in (0.3, 0.5):
+            pr = torch.softmax(lg, dim=1)
+            mp, am = torch.max(pr, dim=1)
+            want = (mp > thr) & (am == 1)
+            got = eng.filter_logits(lg, 1, thr)
+            assert torch.equal(got, want), (K, thr, int((got != want).sum()))
+    eng.close()
+
+
+def test_filter_compact_standalone():
+    from cvae_gan_b200.engine import Engine
+    eng = Engine(10, 5, 128, max_batch=64)
+    g = torch.Generator().manual_seed(9)
+    n = 100003
+    x = torch.rand(n, 10, generator=g).cuda()
+    lg = (torch.randn(n, 5, generator=g) * 2).cuda()
+    keep = eng.filter_logits(lg, 3, 0.5)
+    xo, idx, cnt = eng.filter_compact(x, lg, 3, 0.5, row_offset=17)
+    c = int(cnt.item())
+    assert c == int(keep.sum())
+    order = torch.argsort(idx[:c])
+    rows = torch.nonzero(keep).flatten()
+    assert torch.equal(idx[:c][order] - 17, rows)
+    assert torch.equal(xo[:c][order], x[rows])
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Adam, sampling, inference wrappers
+# ---------------------------------------------------------------------------------------------------
+def test_adam_matches_torch_optim():
+    from cvae_gan_b200.engine import Engine
+    eng = Engine(10, 5, 128, max_batch=64)
+    g = torch.Generator().manual_seed(2)
+    net = 3
+    n = eng.params[net].numel()
+    p0 = torch.randn(n, generator=g) * 0.05
+    eng.params[net].copy_(p0)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-4, betas=(0.5, 0.999))
+    for _ in range(7):
+        gr = torch.randn(n, generator=g) * 0.01
+        eng.grads[net][:n].copy_(gr)
+        eng.adam(1 << net)
+        ref_p.grad = gr.clone()
+        opt.step()
+    assert torch.allclose(eng.params[net].cpu(), ref_p.detach(), rtol=1e-5, atol=1e-8)
+    assert float(eng.grads[net][:n].abs().max()) == 0.0       # gradient cleared after use
+    assert eng.get_adam_step(net) == 7
+    eng.close()
+
+
+def test_sample_rows_three_branches():
+    from cvae_gan_b200.engine import Engine
+    eng = Engine(10, 5, 128, max_batch=64)
+    g = torch.Generator().manual_seed(4)
+    for n, B in ((30, 64), (64, 64), (1000, 64), (100000, 4096), (4097, 4096)):
+        rows = torch.rand(n, 10, generator=g).cuda()
+        x, idx = eng.sample_rows(rows, B, seed=9, counter=3, want_idx=True)
+        assert x.shape == (B, 10)
+        assert int(idx.min()) >= 0 and int(idx.max()) < n
+        assert torch.equal(x, rows[idx])
+        if n == B:
+            assert torch.equal(idx.cpu(), torch.arange(B))        # all rows, in order (cvae_gan.py:254-256)
+        if n > B:
+            assert idx.unique().numel() == B                      # without replacement
+        x2, idx2 = eng.sample_rows(rows, B, seed=9, counter=4, want_idx=True)
+        if n != B:
+            assert not torch.equal(idx, idx2)                     # a new draw every call
+    # uniformity of the keyed permutation: every row of a class is drawn about equally often
+    n, B = 1000, 100
+    rows = torch.rand(n, 10, generator=g).cuda()
+    hits = torch.zeros(n)
+    for c in range(400):
+        _, idx = eng.sample_rows(rows, B, seed=1, counter=c, want_idx=True)
+        hits[idx.cpu()] += 1
+    assert hits.min() > 10 and hits.max() < 80 and abs(float(hits.mean()) - 40) < 1e-6
+    eng.close()
+
+
+def test_classifier_and_encoder_forward():
+    orc, eng, g = P.make_pair(10, 5, 256, seed=41)
+    x = torch.rand(1000, 10, generator=g)
+    ok, worst, mx = P.close(eng.classifier_forward(x.cuda()), orc.classify_eval(x))
+    assert ok, (worst, mx)
+    with torch.no_grad():
+        mu, lv = O.encoder_forward(orc.sd["encoder"], x, 2, False)
+    gmu, glv = eng.encoder_forward(x.cuda(), 2)
+    assert P.close(gmu, mu)[0] and P.close(glv, lv)[0]
+    eng.close()
+
+
+def test_smoke_entry():
+    P.run_parity_smoke()
