@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py - CVAE-GAN training throughput (train samples/s) on synthetic Car-Hacking-shaped data.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation (oracle port)
+
+Workload (BASELINE.json configs[1]; SURVEY.md 8d "C2"): F=10 features (CAN ID, DLC, 8 data bytes), K=5
+classes, Z=128, fp32, batch 4096 rows PER GPU (weak scaling: global batch 4096*N).  One bench "step" is
+ONE LABEL VISIT of the reference's training loop (cvae_gan.py:102-216): 5 critic + 5 classifier +
+3 encoder/generator optimiser steps, each on a freshly sampled batch => 13 * batch train samples.
+metric = train samples/s = 13 * global_batch * steps / time   (BASELINE.md section 3).
+
+Timed region of `value`: class tables resident in HBM, row sampling (_get_target_samples) on the
+device, 13 optimiser steps per visit, nothing read back.  `e2e`: the same visits driven through the
+public step API with each step's batch copied from PINNED HOST memory (H2D) and each step's losses
+copied back (D2H) inside the timed region.  Inputs are larger than L2: the class tables total 200 MB
+and every step gathers random rows from them.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_, K_, Z_ = 10, 5, 128
+BATCH_PER_GPU = 4096
+ROWS_PER_CLASS = 1_000_000          # 5 * 1e6 * 40 B = 200 MB > 126 MB L2
+D_LOOP, C_LOOP, G_LOOP = 5, 5, 3    # gan_config.py:7,10,13
+OPT_STEPS = D_LOOP + C_LOOP + G_LOOP
+# minimal algorithmic work per train sample, F=10 K=5 (SURVEY.md 8d / BASELINE.md section 3)
+FLOP_PER_SAMPLE = 873_945
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_class_tables(device, rows_per_class, seed=0):
+    """Car-Hacking-shaped rows in [0,1]: per class a centre + spread (make_blobs -> minmax_scale, utils.py:56-66)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    tabs = []
+    for k in range(K_):
+        c = torch.rand(F_, generator=g)
+        gd = torch.Generator(device=device).manual_seed(seed * 100 + k)
+        t = (c.to(device) + 0.08 * torch.randn(rows_per_class, F_, generator=gd, device=device)).clamp_(0, 1)
+        tabs.append(t.contiguous())
+    return tabs
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path, timed on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def time_cpu_port(visits: int, warm: int, batch: int, threads: int, rows_per_class=20000):
+    """Label visits of the reference algorithm (oracle port, torch CPU ops, torch RNG like the reference)."""
+    import torch
+    from oracle import cvae_gan_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(0)
+    cfg = O.OracleConfig(batch_size=batch)
+    orc = O.OracleCVAEGAN(F_, K_, cfg).init_like_reference(g)
+    orc.make_optimizers()
+    xs = [(torch.rand(F_, generator=g) + 0.08 * torch.randn(rows_per_class, F_, generator=g)).clamp(0, 1) for _ in range(K_)]
+    for k in range(K_):
+        orc.samples[k] = xs[k]
+    noise = O.TorchNoise()
+
+    def visit(label):
+        for _ in range(D_LOOP):
+            orc.step_d(orc.get_target_samples(label, batch, noise), label, noise)
+        for _ in range(C_LOOP):
+            orc.step_c(orc.get_target_samples(label, batch, noise), label, noise)
+        for _ in range(G_LOOP):
+            orc.step_g(orc.get_target_samples(label, batch, noise), label, noise, 0.25)
+
+    for i in range(warm):
+        visit(i % K_)
+    t0 = time.perf_counter()
+    for i in range(visits):
+        visit(i % K_)
+    dt = time.perf_counter() - t0
+    return OPT_STEPS * batch * visits / dt, dt / visits
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    batch = BATCH_PER_GPU * args.gpus
+    # bounded sample: each "step" is one label visit at the arm's global batch
+    visits = max(1, min(args.steps, 6 if args.gpus > 1 else 12))
+    val, per = time_cpu_port(visits, min(args.warmup, 1), batch, cores)
+    line = {
+        "impl": "reference", "metric": "train_samples_per_s", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": visits, "warmup": min(args.warmup, 1), "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CVAE-GAN label visits (5D+5C+3G steps), F=10 K=5 Z=128, global batch {batch}",
+                   "global_batch": batch, "device": "host CPU", "torch_threads": cores},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{visits} label visits ({visits * OPT_STEPS} optimiser steps) at batch {batch}, "
+                                   "oracle port of src/cvae_gan.py on torch CPU ops"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cvae_gan_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = BATCH_PER_GPU
+    Bg = B * world
+    eng = Engine(F_, K_, Z_, max_batch=B, world_size=world, rank=rank)
+    # reference-distributed random-init weights (no checkpoints offline)
+    from cvae_gan_b200 import models
+    torch.manual_seed(0)
+    mods = [models.CVAEGANEncoderModel(F_, K_, Z_), models.CVAEGANGeneratorModel(Z_, K_, F_),
+            models.CVAEGANDiscriminatorModel(F_, K_), models.CVAEGANClassifierModel(F_, K_)]
+    for net, m in enumerate(mods):
+        eng.load_state(net, m.state_dict())
+    tabs = synth_class_tables(dev, ROWS_PER_CLASS, seed=0)
+    seed = 1234
+    ctr = [0]
+    loss = torch.zeros(OPT_STEPS, 4, device=dev)
+
+    def nxt():
+        ctr[0] += 1
+        return ctr[0]
+
+    def visit_resident(label):
+        rows = tabs[label]
+        i = 0
+        for _ in range(D_LOOP):
+            x = eng.sample_rows(rows, Bg, seed=seed, counter=nxt())
+            eng.step_d(x, label, seed=seed, counter=nxt(), loss_out=loss[i]); i += 1
+        for _ in range(C_LOOP):
+            x = eng.sample_rows(rows, Bg, seed=seed, counter=nxt())
+            eng.step_c(x, label, seed=seed, counter=nxt(), loss_out=loss[i]); i += 1
+        for _ in range(G_LOOP):
+            x = eng.sample_rows(rows, Bg, seed=seed, counter=nxt())
+            eng.step_g(x, label, 0.25, seed=seed, counter=nxt(), loss_out=loss[i]); i += 1
+
+    # e2e: batches come from pinned host memory, losses go back to pinned host memory
+    ring = 4 * OPT_STEPS
+    gcpu = torch.Generator().manual_seed(rank + 1)
+    host_batches = torch.empty(ring, B, F_).pin_memory()
+    for r in range(ring):
+        idx = torch.randint(0, ROWS_PER_CLASS, (B,), generator=gcpu)
+        host_batches[r].copy_(tabs[r % K_][idx.to(dev)].cpu())
+    host_loss = torch.zeros(OPT_STEPS, 4).pin_memory()
+    x_dev = torch.empty(B, F_, device=dev)
+    slot = [0]
+
+    def visit_e2e(label):
+        i = 0
+        for kind, reps in (("d", D_LOOP), ("c", C_LOOP), ("g", G_LOOP)):
+            for _ in range(reps):
+                x_dev.copy_(host_batches[slot[0] % ring], non_blocking=True)
+                slot[0] += 1
+                if kind == "d":
+                    eng.step_d(x_dev, label, seed=seed, counter=nxt(), loss_out=loss[i])
+                elif kind == "c":
+                    eng.step_c(x_dev, label, seed=seed, counter=nxt(), loss_out=loss[i])
+                else:
+                    eng.step_g(x_dev, label, 0.25, seed=seed, counter=nxt(), loss_out=loss[i])
+                i += 1
+        host_loss.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the losses of this visit
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i % K_)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i % K_)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    warm = args.warmup if args.quick else max(args.warmup, 3)
+    if args.quick:
+        ms = timed(visit_resident, args.steps, warm)
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "launches": eng.launch_count()}), flush=True)
+        eng.close()
+        return
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = eng.launch_count()
+    ms = timed(visit_resident, args.steps, warm)
+    launches = (eng.launch_count() - l0) * args.steps // (args.steps + warm)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(visit_e2e, args.steps, 1)
+    value = OPT_STEPS * Bg * args.steps / (ms * 1e-3)
+    e2e = OPT_STEPS * Bg * args.steps / (ms_e2e * 1e-3)
+    final_losses = loss.tolist()
+    ok = all(all(v == v and abs(v) < 1e6 for v in row) for row in final_losses)
+
+    # ---- roofline of the dominant kernel class, measured live with CUDA events around each launch ----
+    pk = peaks()
+    eng.profile(True)
+    for i in range(2):
+        visit_resident(i % K_)
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    top = max(prof, key=lambda k: prof[k][2])
+    n_l, fl, t_ms = prof[top]
+    achieved = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+    total_gemm_ms = sum(v[2] for v in prof.values())
+    roofline = {
+        "bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 dense (sustained)",
+        "note": "fp32 SIMT FFMA kernels (exact-fp32 parity path); peak quoted is the measured bf16 tensor peak as the "
+                "contract requires - the fp32 CUDA-core ceiling of a B200 is ~74 TFLOP/s nominal",
+        "launches_profiled": n_l, "avg_launch_us": 1e3 * t_ms / max(n_l, 1),
+        "gemm_share_of_step": total_gemm_ms / 2 / (ms / args.steps),
+        "per_class": {k: {"launches": v[0], "tflops": (v[1] / (v[2] * 1e-3) / 1e12) if v[2] > 0 else 0.0, "ms": v[2]}
+                      for k, v in prof.items()},
+        "whole_step_tflops": value * FLOP_PER_SAMPLE / 1e12,
+    }
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v8, _ = time_cpu_port(2, 1, BATCH_PER_GPU, cores)
+            cpu = {"value": v8, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"2 label visits (26 optimiser steps) at batch {BATCH_PER_GPU}, oracle port of src/cvae_gan.py, "
+                             f"torch CPU ops, {cores} threads"}
+        line = {
+            "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "CVAE-GAN training, Car-Hacking shape F=10 K=5 Z=128, fp32, batch 4096 per GPU "
+                                   "(BASELINE.json configs[1]); step = one label visit = 5 D + 5 C + 3 E/G optimiser steps",
+                       "global_batch": Bg, "batch_per_gpu": B, "opt_steps_per_step": OPT_STEPS,
+                       "parallelism": f"dp{world}", "l2": "inputs larger than L2: 200 MB class tables, random row gather per step",
+                       "losses_finite": ok},
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": OPT_STEPS * B * F_ * 4,
+                    "d2h_bytes_per_step": OPT_STEPS * 16, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling aid (ncu): resident loop only, no e2e/cpu legs; NOT a bench number")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

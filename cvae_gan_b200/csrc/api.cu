@@ -286,6 +286,37 @@ int cvg_debug_read(CvgHandle* h, const char* name, int pass, int rows, float* ds
   return 0;
 }
 
+int cvg_profile_enable(CvgHandle* h, int enable) {
+  H_OR_FAIL(h);
+  Engine& e = h->e;
+  for (auto& r : e.prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  e.prof_recs.clear();
+  e.prof = enable != 0;
+  return 0;
+}
+
+int cvg_profile_read(CvgHandle* h, int kernel_class, int64_t* launches, double* flops, double* ms) {
+  H_OR_FAIL(h);
+  if (!launches || !flops || !ms) CVG_FAIL("cvg_profile_read: null argument");
+  Engine& e = h->e;
+  *launches = 0;
+  *flops = 0.0;
+  *ms = 0.0;
+  for (auto& r : e.prof_recs) {
+    if (r.cls != kernel_class) continue;
+    CVG_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CVG_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    *launches += 1;
+    *flops += r.flops;
+    *ms += (double)t;
+  }
+  return 0;
+}
+
 int64_t cvg_launch_count(const CvgHandle* h) { return h ? h->e.launches : -1; }
 
 }  // extern "C"

@@ -64,7 +64,15 @@ struct Workspace {
   unsigned long long* gen_count = nullptr;
 };
 
+struct ProfRec {
+  cudaEvent_t a, b;
+  int cls;
+  double flops;
+};
+
 struct Engine {
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
   CvgConfig cfg{};
   int F = 0, K = 0, Z = 0;
   int eh[3]{}, gh[3]{}, dh[3]{}, ch[3]{};

@@ -126,8 +126,9 @@ __device__ __forceinline__ void bn_mean_rstd(const BnRef& bn, int pass, int c, f
     var_biased = bn.rvar[c];
   } else {
     const double* s = bn.fstats + (long long)pass * bn.sf;
-    double m = s[c] / (double)Bg;
-    double v = s[bn.C + c] / (double)Bg - m * m;
+    const double inv = 1.0 / (double)Bg;
+    double m = s[c] * inv;
+    double v = s[bn.C + c] * inv - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var_biased = (float)v;

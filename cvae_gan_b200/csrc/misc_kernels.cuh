@@ -32,29 +32,61 @@ struct LnArgs {
   float* rs; long long srs;            // [2][ld] mean, rstd per row
 };
 
-__global__ void ln_fwd_kernel(const LnArgs g) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+// CTA = 256 threads = 32 batch rows (lane) x 8 feature groups (warp); each thread keeps C/8 features of its
+// row in registers, row moments are combined through shared memory (two-pass variance like torch).
+constexpr int LN_ROWS = 32;
+constexpr int LN_MAXF = 32;   // features per thread (C <= 256)
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs g) {
+  __shared__ float red[8][LN_ROWS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m = blockIdx.x * LN_ROWS + lane;
   const int pass = blockIdx.y;
-  if (m >= g.M) return;
-  const float* h = g.h + (long long)pass * g.sh + m;
+  const bool valid = m < g.M;
+  const int fpt = (g.C + 7) / 8;            // features per thread
+  const int c0 = w * fpt;
+  const float* h = g.h + (long long)pass * g.sh + (valid ? m : 0);
+  float v[LN_MAXF];
   float s = 0.f;
-  for (int c = 0; c < g.C; ++c) s += h[(size_t)c * g.ld];
-  const float mean = s / (float)g.C;
-  float v = 0.f;
-  for (int c = 0; c < g.C; ++c) {
-    const float d = h[(size_t)c * g.ld] - mean;
-    v = fmaf(d, d, v);
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int c = c0 + i;
+    v[i] = (i < fpt && c < g.C && valid) ? h[(size_t)c * g.ld] : 0.f;
+    s += v[i];
   }
-  const float rstd = 1.0f / sqrtf(v / (float)g.C + g.eps);
+  red[w][lane] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k][lane];
+  const float mean = tot / (float)g.C;
+  __syncthreads();
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int c = c0 + i;
+    if (i < fpt && c < g.C) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  }
+  red[w][lane] = q;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k][lane];
+  const float rstd = 1.0f / sqrtf(tot / (float)g.C + g.eps);
+  if (!valid) return;
   float* a = g.a + (long long)pass * g.sa + m;
   const uint8_t* mk = g.mask ? g.mask + (long long)pass * g.smask + m : nullptr;
-  for (int c = 0; c < g.C; ++c) {
-    float n = (h[(size_t)c * g.ld] - mean) * rstd * g.g[c] + g.b[c];
-    n = fmaxf(n, 0.f);
-    if (mk) n = mk[(size_t)c * g.ld] ? n * g.keep_inv : 0.f;
-    a[(size_t)c * g.ld] = n;
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int c = c0 + i;
+    if (i < fpt && c < g.C) {
+      float n = (v[i] - mean) * rstd * g.g[c] + g.b[c];
+      n = fmaxf(n, 0.f);
+      if (mk) n = mk[(size_t)c * g.ld] ? n * g.keep_inv : 0.f;
+      a[(size_t)c * g.ld] = n;
+    }
   }
-  if (g.rs) {
+  if (g.rs && w == 0) {
     float* rs = g.rs + (long long)pass * g.srs;
     rs[m] = mean;
     rs[g.ld + m] = rstd;
@@ -72,36 +104,48 @@ struct LnBwdArgs {
   float* dg; float* db;                // null -> skipped
 };
 
-__global__ void ln_bwd_kernel(const LnBwdArgs g) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs g) {
+  __shared__ float red1[8][LN_ROWS], red2[8][LN_ROWS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int m = blockIdx.x * LN_ROWS + lane;
   const int pass = blockIdx.y;
   const bool valid = m < g.M;
   const int mm = valid ? m : 0;
+  const int fpt = (g.C + 7) / 8;
+  const int c0 = w * fpt;
   const float* h = g.h + (long long)pass * g.sh + mm;
   float* dn = g.dn + (long long)pass * g.sdn + mm;
   const float* rs = g.rs + (long long)pass * g.srs;
   const float mean = rs[mm], rstd = rs[g.ld + mm];
+  float xh[LN_MAXF], d[LN_MAXF];
   float s1 = 0.f, s2 = 0.f;
-  if (valid) {
-    for (int c = 0; c < g.C; ++c) {
-      const float xh = (h[(size_t)c * g.ld] - mean) * rstd;
-      const float dx = dn[(size_t)c * g.ld] * g.g[c];
-      s1 += dx;
-      s2 = fmaf(dx, xh, s2);
-    }
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int c = c0 + i;
+    const bool on = i < fpt && c < g.C && valid;
+    xh[i] = on ? (h[(size_t)c * g.ld] - mean) * rstd : 0.f;
+    d[i] = on ? dn[(size_t)c * g.ld] : 0.f;
+    const float dx = on ? d[i] * g.g[c] : 0.f;
+    s1 += dx;
+    s2 = fmaf(dx, xh[i], s2);
   }
+  red1[w][lane] = s1;
+  red2[w][lane] = s2;
+  __syncthreads();
+  s1 = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1 += red1[k][lane]; s2 += red2[k][lane]; }
   s1 /= (float)g.C;
   s2 /= (float)g.C;
-  for (int c = 0; c < g.C; ++c) {
-    float d = 0.f, xh = 0.f;
-    if (valid) {
-      xh = (h[(size_t)c * g.ld] - mean) * rstd;
-      d = dn[(size_t)c * g.ld];
-      dn[(size_t)c * g.ld] = rstd * (d * g.g[c] - s1 - xh * s2);
-    }
-    if (g.dg) {   // uniform
-      const float a = warp_sum(d * xh), b = warp_sum(d);
-      if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int c = c0 + i;
+    const bool on = i < fpt && c < g.C;       // warp-uniform
+    if (!on) continue;
+    if (valid) dn[(size_t)c * g.ld] = rstd * (d[i] * g.g[c] - s1 - xh[i] * s2);
+    if (g.dg) {
+      const float a = warp_sum(d[i] * xh[i]), b = warp_sum(d[i]);
+      if (lane == 0) {
         atomicAdd(g.dg + c, a);
         atomicAdd(g.db + c, b);
       }
@@ -207,18 +251,25 @@ struct SnArgs {
   float* u_snap; float* v_snap; long long ssnap;   // [npass][ssnap]
 };
 
-__global__ void __launch_bounds__(256) sn_power_kernel(const SnArgs g) {
+constexpr int SN_THREADS = 1024;
+
+__global__ void __launch_bounds__(SN_THREADS) sn_power_kernel(const SnArgs g) {
   __shared__ float su[SN_MAXDIM], sv[SN_MAXDIM], st[SN_MAXDIM];
+  __shared__ float part[SN_THREADS];
   __shared__ double red[32];
   const SnLayer L = g.L[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   for (int i = tid; i < L.rows; i += blockDim.x) su[i] = L.u[i];
   for (int i = tid; i < L.cols; i += blockDim.x) sv[i] = L.v[i];
   __syncthreads();
+  // column-parallel W^T u: thread (k = tid % cp, group = tid / cp) sums rows group, group + ng, ...
+  int cp = 1;
+  while (cp < L.cols) cp <<= 1;
+  if (cp > SN_THREADS) cp = SN_THREADS;
+  const int ng = SN_THREADS / cp, kq = tid % cp, gq = tid / cp;
   for (int p = 0; p < g.npass; ++p) {
     if (g.do_power) {
-      // t = W v
-      for (int n = w; n < L.rows; n += nw) {
+      for (int n = w; n < L.rows; n += nw) {          // t = W v
         float s = 0.f;
         for (int k = lane; k < L.cols; k += 32) s = fmaf(L.W[(size_t)n * L.cols + k], sv[k], s);
         s = warp_sum(s);
@@ -231,13 +282,20 @@ __global__ void __launch_bounds__(256) sn_power_kernel(const SnArgs g) {
       float nrm = fmaxf((float)sqrt(q), g.eps);
       for (int i = tid; i < L.rows; i += blockDim.x) su[i] = st[i] / nrm;
       __syncthreads();
-      // s = W^T u
-      for (int k = tid; k < L.cols; k += blockDim.x) {
+      for (int k0 = 0; k0 < L.cols; k0 += cp) {       // s = W^T u
+        const int k = k0 + kq;
         float s = 0.f;
-        for (int n = 0; n < L.rows; ++n) s = fmaf(L.W[(size_t)n * L.cols + k], su[n], s);
-        st[k] = s;
+        if (k < L.cols)
+          for (int n = gq; n < L.rows; n += ng) s = fmaf(L.W[(size_t)n * L.cols + k], su[n], s);
+        part[tid] = s;
+        __syncthreads();
+        if (gq == 0 && k < L.cols) {
+          float t = 0.f;
+          for (int j = 0; j < ng; ++j) t += part[j * cp + kq];
+          st[k] = t;
+        }
+        __syncthreads();
       }
-      __syncthreads();
       q = 0.0;
       for (int i = tid; i < L.cols; i += blockDim.x) q += (double)st[i] * st[i];
       q = block_sum_d(q, red);
@@ -245,8 +303,7 @@ __global__ void __launch_bounds__(256) sn_power_kernel(const SnArgs g) {
       for (int i = tid; i < L.cols; i += blockDim.x) sv[i] = st[i] / nrm;
       __syncthreads();
     }
-    // sigma = u . (W v)
-    double sg = 0.0;
+    double sg = 0.0;                                  // sigma = u . (W v)
     for (int n = w; n < L.rows; n += nw) {
       float s = 0.f;
       for (int k = lane; k < L.cols; k += 32) s = fmaf(L.W[(size_t)n * L.cols + k], sv[k], s);
@@ -284,19 +341,25 @@ struct SnGradArgs {
   float last_bias_value;            // where autograd's -1/B and +1/B sums cancel bit for bit)
 };
 
-__global__ void __launch_bounds__(256) sn_grad_kernel(const SnGradArgs g) {
+// <G_p, W> per (layer, pass): grid (chunks, 4, npass); dots[layer * 2 + pass] accumulates in double
+__global__ void __launch_bounds__(256) sn_dot_kernel(const SnGradArgs g, double* dots) {
   __shared__ double red[32];
-  const int l = blockIdx.x;
+  const int l = blockIdx.y, p = blockIdx.z;
   const SnLayer L = g.L[l];
   const int n_el = L.rows * L.cols;
-  double dots[2] = {0.0, 0.0};
-  for (int p = 0; p < g.npass; ++p) {
-    const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
-    double d = 0.0;
-    for (int i = threadIdx.x; i < n_el; i += blockDim.x) d += (double)G[i] * (double)L.W[i];
-    dots[p] = block_sum_d(d, red);
-  }
-  for (int i = threadIdx.x; i < n_el; i += blockDim.x) {
+  const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
+  double d = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x)
+    d += (double)G[i] * (double)L.W[i];
+  d = block_sum_d(d, red);
+  if (threadIdx.x == 0 && d != 0.0) atomicAdd(dots + l * 2 + p, d);
+}
+
+__global__ void __launch_bounds__(256) sn_grad_kernel(const SnGradArgs g, const double* dots) {
+  const int l = blockIdx.y;
+  const SnLayer L = g.L[l];
+  const int n_el = L.rows * L.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
     const int n = i / L.cols, k = i % L.cols;
     float acc = 0.f;
     for (int p = 0; p < g.npass; ++p) {
@@ -304,11 +367,11 @@ __global__ void __launch_bounds__(256) sn_grad_kernel(const SnGradArgs g) {
       const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
       const float u = g.u_snap[(long long)p * g.ssnap + L.snap_off + n];
       const float v = g.v_snap[(long long)p * g.ssnap + L.snap_off + k];
-      acc += G[i] * is - (float)(dots[p] * (double)is * (double)is) * u * v;
+      acc += G[i] * is - (float)(dots[l * 2 + p] * (double)is * (double)is) * u * v;
     }
     g.grad[g.w_off[l] + i] += acc;
   }
-  if (l == 3 && threadIdx.x == 0 && g.last_bias_grad) *g.last_bias_grad += g.last_bias_value;
+  if (l == 3 && blockIdx.x == 0 && threadIdx.x == 0 && g.last_bias_grad) *g.last_bias_grad += g.last_bias_value;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,11 +88,29 @@ int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st) {
   } while (0)
 #endif
 
+static void prof_begin(Engine& e, int cls, double flops, cudaStream_t st) {
+  if (!e.prof) return;
+  ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.cls = cls;
+  r.flops = flops;
+  cudaEventRecord(r.a, st);
+  e.prof_recs.push_back(r);
+}
+static void prof_end(Engine& e, cudaStream_t st) {
+  if (!e.prof) return;
+  cudaEventRecord(e.prof_recs.back().b, st);
+}
+
 int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
-  dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, g.only_pass >= 0 ? 1 : g.npass);
+  const int zp = g.only_pass >= 0 ? 1 : g.npass;
+  dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, zp);
   const size_t smem = gemm_mn_smem(g);
+  prof_begin(e, wt ? 0 : 1, 2.0 * g.M * (double)g.N * g.R * zp, st);
   if (wt) gemm_mn_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(g);
   else gemm_mn_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(g);
+  prof_end(e, st);
   CVG_LAUNCH_CHECK();
   return 0;
 }
@@ -110,7 +128,9 @@ int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
   nsplit = (g.M + rows - 1) / rows;
   g.rows_per_cta = rows;
   dim3 grid(kt, nt, g.npass * nsplit);
+  prof_begin(e, 2, 2.0 * g.M * (double)g.N * g.K * g.npass, st);
   gemm_dw_kernel<<<grid, GEMM_THREADS, gemm_dw_smem(g), st>>>(g, nsplit);
+  prof_end(e, st);
   CVG_LAUNCH_CHECK();
   return 0;
 }
@@ -320,7 +340,7 @@ static int launch_sn(Engine& e, int npass, bool do_power, cudaStream_t st) {
   a.u_snap = e.ws.sn_u;
   a.v_snap = e.ws.sn_v;
   a.ssnap = e.ws.sn_snap;
-  sn_power_kernel<<<4, 256, 0, st>>>(a);
+  sn_power_kernel<<<4, SN_THREADS, 0, st>>>(a);
   CVG_LAUNCH_CHECK();
   return 0;
 }
@@ -410,7 +430,7 @@ int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool 
       a.mask = train ? w.c_m2 : nullptr; a.smask = (long long)p.out * ld; a.keep_inv = keep_inv;
       a.a = w.c_a2; a.sa = (long long)p.out * ld;
       a.rs = w.c_rs; a.srs = 2 * (long long)ld;
-      ln_fwd_kernel<<<dim3((M + 63) / 64, npass), 64, 0, st>>>(a);
+      ln_fwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
       CVG_LAUNCH_CHECK();
     }
   }
@@ -559,7 +579,7 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       a.g = e.P(net, p1.gamma);
       a.dg = want_dw ? e.G(net, p1.gamma) : nullptr;
       a.db = want_dw ? e.G(net, p1.beta) : nullptr;
-      ln_bwd_kernel<<<dim3((M + 63) / 64, npass), 64, 0, st>>>(a);
+      ln_bwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
       CVG_LAUNCH_CHECK();
     }
   }
@@ -776,7 +796,10 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
     a.grad = e.buf[D].grads;
     a.last_bias_grad = e.G(D, lin(e, D, 3).b);
     a.last_bias_value = (float)B * (seedv[0] + seedv[1]);
-    sn_grad_kernel<<<4, 256, 0, st>>>(a);
+    double* dots = w.loss + 8;   // 8 zeroed accumulator slots after the loss sums
+    sn_dot_kernel<<<dim3(16, 4, 2), 256, 0, st>>>(a, dots);
+    CVG_LAUNCH_CHECK();
+    sn_grad_kernel<<<dim3(32, 4), 256, 0, st>>>(a, dots);
     CVG_LAUNCH_CHECK();
   }
   return finish_step(e, 1 << D, 0, B, flags, loss_out, st);

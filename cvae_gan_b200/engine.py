@@ -260,6 +260,18 @@ class Engine:
         check(self.lib.cvg_debug_read(self.h, name.encode(), pas, rows, _ptr(out), C.byref(c), _stream()))
         return out
 
+    def profile(self, enable: bool):
+        check(self.lib.cvg_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{class: (launches, algorithmic flops, device ms)} for fwd / dx / dw GEMM launches."""
+        out = {}
+        for cls, name in enumerate(("gemm_fwd", "gemm_dx", "gemm_dw")):
+            n, f, ms = C.c_int64(), C.c_double(), C.c_double()
+            check(self.lib.cvg_profile_read(self.h, cls, C.byref(n), C.byref(f), C.byref(ms)))
+            out[name] = (n.value, f.value, ms.value)
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.cvg_launch_count(self.h))
 

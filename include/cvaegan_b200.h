@@ -187,6 +187,13 @@ int cvg_patience_scan(const uint8_t* keep_host, int64_t n, int64_t num, int chun
  * "c_g0".."c_g2", "dx".  *features_out receives the feature count.  dst may be NULL to query it. */
 int cvg_debug_read(CvgHandle* h, const char* name, int pass, int rows, float* dst, int* features_out, void* stream);
 
+/* Measurement hook for bench.py: when enabled, every GEMM launch is bracketed by CUDA events on its
+ * stream.  cvg_profile_read synchronises and returns, per kernel class (0 = forward GEMM, 1 = input-
+ * gradient GEMM, 2 = weight-gradient GEMM), the launches, the ALGORITHMIC flops (2*M*N*K per launch)
+ * and the summed device time in ms since the last enable.  Not used while `value` is being timed. */
+int cvg_profile_enable(CvgHandle* h, int enable);
+int cvg_profile_read(CvgHandle* h, int kernel_class, int64_t* launches, double* flops, double* ms);
+
 /* Number of kernels this handle has launched since creation (bench.py reports it as gpu_launches). */
 int64_t cvg_launch_count(const CvgHandle* h);
 
