@@ -48,6 +48,7 @@ int build_layouts(Engine& e) {
       CVG_FAIL("layer wider than supported (1024)");
   if (Z % 4 != 0) CVG_FAIL("z_size must be a multiple of 4");
   if (K > FILTER_MAXK) CVG_FAIL("label_num > 32 is not supported");
+  if (e.ch[1] > 8 * LN_MAXF) CVG_FAIL("classifier LayerNorm wider than 256 is not supported");
 
   {  // encoder (cvae_gan_models.py:20-35)
     NetLayout& L = e.lay[CVG_NET_ENCODER];

@@ -58,7 +58,9 @@ def test_two_label_visits_trajectory():
                 idx = torch.randperm(len(orc.samples[label]), generator=g)[:B]
                 xb = orc.samples[label][idx].contiguous()
                 ref, got, _ = P.run_step(kind, orc, eng, xb, label, g, lambda_class=0.25, update=True)
-                assert P.losses_close(ref, got), (step, kind, ref, got)
+                # critic scores are O(0.3) here and their batch mean crosses zero: allow 1e-3 of that
+                # scale (Adam turns round-off-level gradient differences into +-lr parameter steps)
+                assert P.losses_close(ref, got, atol=3e-4), (step, kind, ref, got)
                 step += 1
     report = []
     # 6 generator steps of lr 2e-4 on round-off gradients: allow |delta| up to 6 * lr on those biases
