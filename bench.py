@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 F_, K_, Z_ = 10, 5, 128
-BATCH_PER_GPU = 4096
+BATCH_PER_GPU = int(os.environ.get("CVG_BENCH_BATCH", "4096"))   # 4096 = BASELINE.json configs[1]; env override is a probe only
 ROWS_PER_CLASS = 1_000_000          # 5 * 1e6 * 40 B = 200 MB > 126 MB L2
 D_LOOP, C_LOOP, G_LOOP = 5, 5, 3    # gan_config.py:7,10,13
 OPT_STEPS = D_LOOP + C_LOOP + G_LOOP

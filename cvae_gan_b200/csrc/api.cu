@@ -51,16 +51,6 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
     delete h;
     return 1;
   }
-  cudaError_t err = cudaFuncSetAttribute(gemm_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(gemm_mn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  if (err == cudaSuccess)
-    err = cudaFuncSetAttribute(gemm_mn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  if (err != cudaSuccess) {
-    cvg::set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
-    delete h;
-    return 1;
-  }
   *out = h;
   return 0;
 }

@@ -19,6 +19,7 @@ constexpr int TBM = 64;   // tile rows (batch)
 constexpr int TBN = 64;   // tile cols (features)
 constexpr int TBK = 16;   // reduction chunk
 constexpr int GEMM_THREADS = 256;
+constexpr int RED_LD = TBM + 4;   // padded row of the split-K partial tiles
 
 enum { OP_PLAIN = 0, OP_BN_ACT = 1, OP_REPARAM = 2, OP_BN_BWD = 3, OP_CONST = 4 };
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_SIGMOID = 3 };
@@ -137,8 +138,9 @@ __device__ __forceinline__ void bn_mean_rstd(const BnRef& bn, int pass, int c, f
 }
 
 // fills cs[] for an operand; all threads of the CTA participate; caller syncs afterwards
+template <int KIND>
 __device__ __forceinline__ void operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs) {
-  if (o.kind == OP_BN_ACT) {
+  if (KIND == OP_BN_ACT) {
     const int C = o.bn.C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float mean, rstd, var;
@@ -148,7 +150,7 @@ __device__ __forceinline__ void operand_consts(const Operand& o, int pass, float
       cs[C + c] = o.bn.beta[c];
       cs[2 * C + c] = mean;
     }
-  } else if (o.kind == OP_BN_BWD) {
+  } else if (KIND == OP_BN_BWD) {
     const int C = o.bn.C;
     const double* bs = o.bn.bstats + (long long)pass * o.bn.sb;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -185,43 +187,73 @@ __device__ __forceinline__ float act_lrelu(float x, float slope) { return x > 0.
 
 // Loads 4 consecutive batch rows (m..m+3) of feature row r of an operand, transformed; rows >= M and
 // feature rows >= o.rows read as 0.
-__device__ __forceinline__ float4 load_operand(const Operand& o, const float* cs, int pass, int r, int m, int M,
-                                               int ld, float slope) {
+// Operand staging is split in two so that global loads stay in flight across the FFMA block: load_raw only
+// ISSUES the loads (no dependent arithmetic), finish_operand applies the transform right before the value is
+// stored to shared memory one chunk later.  Rows >= M and feature rows >= o.rows read as 0.
+struct Raw {
+  float4 a, b, c;
+};
+
+template <int KIND>
+__device__ __forceinline__ void load_raw(const Operand& o, int pass, int r, int m, int M, int ld, Raw& w) {
+  if (r >= o.rows || m >= M) return;
+  const size_t off = (size_t)r * ld + m;
+  switch (KIND) {
+    case OP_PLAIN:
+    case OP_BN_ACT:
+      w.a = ld4(o.p + (long long)pass * o.sp + off);
+      break;
+    case OP_REPARAM:
+      if (pass == o.reparam_pass) {
+        w.a = ld4(o.mu + off);
+        w.b = ld4(o.lv + off);
+        w.c = ld4(o.eps + off);
+      } else {
+        w.a = ld4(o.p + (long long)pass * o.sp + off);
+      }
+      break;
+    case OP_BN_BWD:
+      w.a = ld4(o.p + (long long)pass * o.sp + off);
+      w.b = ld4(o.h + (long long)pass * o.sh + off);
+      break;
+    case OP_CONST:
+      break;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ float4 finish_operand(const Operand& o, const float* cs, int pass, int r, int m, int M,
+                                                 float slope, const Raw& w) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (r >= o.rows || m >= M) return v;
-  const size_t off = (size_t)r * ld + m;
-  switch (o.kind) {
+  switch (KIND) {
     case OP_PLAIN:
-      v = ld4(o.p + (long long)pass * o.sp + off);
+      v = w.a;
       break;
     case OP_BN_ACT: {
-      v = ld4(o.p + (long long)pass * o.sp + off);
       const float sc = cs[r], sh = cs[o.bn.C + r], mean = cs[2 * o.bn.C + r];
-      v.x = act_lrelu(fmaf(v.x - mean, sc, sh), slope);
-      v.y = act_lrelu(fmaf(v.y - mean, sc, sh), slope);
-      v.z = act_lrelu(fmaf(v.z - mean, sc, sh), slope);
-      v.w = act_lrelu(fmaf(v.w - mean, sc, sh), slope);
+      v.x = act_lrelu(fmaf(w.a.x - mean, sc, sh), slope);
+      v.y = act_lrelu(fmaf(w.a.y - mean, sc, sh), slope);
+      v.z = act_lrelu(fmaf(w.a.z - mean, sc, sh), slope);
+      v.w = act_lrelu(fmaf(w.a.w - mean, sc, sh), slope);
     } break;
     case OP_REPARAM:
       if (pass == o.reparam_pass) {
-        float4 mu = ld4(o.mu + off), lv = ld4(o.lv + off), e = ld4(o.eps + off);
-        v.x = mu.x + e.x * expf(0.5f * lv.x);
-        v.y = mu.y + e.y * expf(0.5f * lv.y);
-        v.z = mu.z + e.z * expf(0.5f * lv.z);
-        v.w = mu.w + e.w * expf(0.5f * lv.w);
+        v.x = w.a.x + w.c.x * expf(0.5f * w.b.x);
+        v.y = w.a.y + w.c.y * expf(0.5f * w.b.y);
+        v.z = w.a.z + w.c.z * expf(0.5f * w.b.z);
+        v.w = w.a.w + w.c.w * expf(0.5f * w.b.w);
       } else {
-        v = ld4(o.p + (long long)pass * o.sp + off);
+        v = w.a;
       }
       break;
     case OP_BN_BWD: {
       const int C = o.bn.C;
-      float4 dy = ld4(o.p + (long long)pass * o.sp + off);
-      float4 h = ld4(o.h + (long long)pass * o.sh + off);
       const float c1 = cs[r], c2 = cs[C + r], c3 = cs[2 * C + r], mean = cs[3 * C + r], rstd = cs[4 * C + r];
-      v.x = c1 * (dy.x - c2 - (h.x - mean) * rstd * c3);
-      v.y = c1 * (dy.y - c2 - (h.y - mean) * rstd * c3);
-      v.z = c1 * (dy.z - c2 - (h.z - mean) * rstd * c3);
-      v.w = c1 * (dy.w - c2 - (h.w - mean) * rstd * c3);
+      v.x = c1 * (w.a.x - c2 - (w.b.x - mean) * rstd * c3);
+      v.y = c1 * (w.a.y - c2 - (w.b.y - mean) * rstd * c3);
+      v.z = c1 * (w.a.z - c2 - (w.b.z - mean) * rstd * c3);
+      v.w = c1 * (w.a.w - c2 - (w.b.w - mean) * rstd * c3);
     } break;
     case OP_CONST:
       v = make_float4(o.cst, o.cst, o.cst, o.cst);
@@ -238,8 +270,8 @@ __device__ __forceinline__ float4 load_operand(const Operand& o, const float* cs
 // ------------------------------------------------------------------------------------------------
 // C[m][n] = sum_r A[r][m] * B[r][n]   (64 x 64 tile, 256 threads, 4 x 4 per thread)
 // ------------------------------------------------------------------------------------------------
-template <bool WT>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g) {
+template <bool WT, int AK, int EK>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mn_kernel(const GemmArgs g) {
   extern __shared__ __align__(16) float dyn_smem[];
   __shared__ __align__(16) float As[2][TBK][TBM];
   __shared__ __align__(16) float Bs[2][TBK][TBN];
@@ -251,8 +283,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
   float* cs_e = dyn_smem + operand_const_floats(g.a);      // epilogue constants (EP_DBN: 4 * C)
 
   // ---- preamble: per-feature constants ---------------------------------------------------------
-  operand_consts(g.a, pass, g.Bg, g.bn_eps, cs_a);
-  if (g.ekind == EP_DBN) {
+  operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a);
+  if (EK == EP_DBN) {
     const int C = g.prev_bn.C;
     for (int c = tid; c < C; c += GEMM_THREADS) {
       float mean, rstd, var;
@@ -263,7 +295,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
       cs_e[3 * C + c] = rstd;
     }
   }
-  if (g.a.kind == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && blockIdx.x == 0 && blockIdx.y == 0 &&
+  if (AK == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && blockIdx.x == 0 && blockIdx.y == 0 &&
       blockIdx.z == 0) {
     bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum);
   }
@@ -317,45 +349,77 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
     }
   };
 
-  float acc[4][4];
+  // Split-K inside the CTA: four 64-thread groups each take 4 of the 16 k-steps of a chunk with an 8 x 8
+  // register tile (64 independent FFMAs per 4 LDS.128), which hides the shared-memory round trip that a
+  // 4 x 4 tile with two warps per scheduler cannot.  Partials meet in shared memory before the epilogue.
+  float acc8[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc8[i][j] = 0.f;
+  const int grp = tid >> 6, t64 = tid & 63;
+  const int tm8 = (t64 & 7) * 4, tn8 = (t64 >> 3) * 4;
 
   const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
   const int nchunks = (g.R + TBK - 1) / TBK;
 
-  float4 ra = load_operand(g.a, cs_a, pass, a_r, m0 + a_m, g.M, g.ld, g.slope);
-  float4 rb = load_b(0);
-  st4(&As[0][a_r][a_m], ra);
-  store_b(0, rb);
+  // Register prefetch runs TWO chunks ahead of the FFMA block (an L2 round trip is longer than one
+  // chunk of math when only one or two CTAs are resident per SM).
+  auto compute = [&](int cur) {
+#pragma unroll
+    for (int q = 0; q < TBK / 4; ++q) {
+      const int kk = grp * (TBK / 4) + q;
+      const float4 a0 = ld4(&As[cur][kk][tm8]), a1 = ld4(&As[cur][kk][32 + tm8]);
+      const float4 b0 = ld4(&Bs[cur][kk][tn8]), b1 = ld4(&Bs[cur][kk][32 + tn8]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc8[i][j] = fmaf(av[i], bv[j], acc8[i][j]);
+    }
+  };
+  auto gload = [&](int c, Raw& xa, float4& xb) {
+    load_raw<AK>(g.a, pass, c * TBK + a_r, m0 + a_m, g.M, g.ld, xa);
+    xb = load_b(c * TBK);
+  };
+  auto sstore = [&](int buf, int c, const Raw& xa, const float4& xb) {
+    st4(&As[buf][a_r][a_m], finish_operand<AK>(g.a, cs_a, pass, c * TBK + a_r, m0 + a_m, g.M, g.slope, xa));
+    store_b(buf, xb);
+  };
+  Raw ra;
+  float4 rb;
+  gload(0, ra, rb);
+  sstore(0, 0, ra, rb);
   __syncthreads();
-
   for (int c = 0; c < nchunks; ++c) {
     const int cur = c & 1;
-    if (c + 1 < nchunks) {
-      ra = load_operand(g.a, cs_a, pass, (c + 1) * TBK + a_r, m0 + a_m, g.M, g.ld, g.slope);
-      rb = load_b((c + 1) * TBK);
-    }
-#pragma unroll
-    for (int kk = 0; kk < TBK; ++kk) {
-      const float4 a = ld4(&As[cur][kk][tm]);
-      const float4 b = ld4(&Bs[cur][kk][tn]);
-      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
-      acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
-      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
-      acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
-      acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
-      acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
-      acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
-      acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
-    }
-    if (c + 1 < nchunks) {
-      st4(&As[cur ^ 1][a_r][a_m], ra);
-      store_b(cur ^ 1, rb);
-    }
+    if (c + 1 < nchunks) gload(c + 1, ra, rb);     // loads stay in flight across the FFMA block
+    compute(cur);
+    if (c + 1 < nchunks) sstore(cur ^ 1, c + 1, ra, rb);
     __syncthreads();
+  }
+
+  // ---- reduce the four K-slices: part[g][n][m] (m contiguous, row padded to RED_LD) ----------------------
+  float* part = dyn_smem + ((operand_const_floats(g.a) + ((EK == EP_DBN) ? 4 * g.prev_bn.C : 0) + 3) & ~3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = (j < 4) ? tn8 + j : 32 + tn8 + (j - 4);
+    float* row = part + ((size_t)grp * TBN + n) * RED_LD;
+    st4(row + tm8, make_float4(acc8[0][j], acc8[1][j], acc8[2][j], acc8[3][j]));
+    st4(row + 32 + tm8, make_float4(acc8[4][j], acc8[5][j], acc8[6][j], acc8[7][j]));
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 v = ld4(part + (size_t)(tn + j) * RED_LD + tm);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float4 w = ld4(part + ((size_t)q * TBN + tn + j) * RED_LD + tm);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    acc[0][j] = v.x; acc[1][j] = v.y; acc[2][j] = v.z; acc[3][j] = v.w;
   }
 
   // ---- epilogue ------------------------------------------------------------------------------------
@@ -374,7 +438,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
     double s1 = 0.0, s2 = 0.0;
     if (nvalid) {
       const size_t off = (size_t)n * g.ld + m;
-      if (g.ekind == EP_LINEAR) {
+      if (EK == EP_LINEAR) {
         float b = g.bias ? g.bias[n] : 0.f;
         if (g.wlabel) b += scale * g.wlabel[(size_t)n * g.ldwl];
 #pragma unroll
@@ -413,7 +477,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
             if (rowv[i]) tot += (double)y[i];
         }
         st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
-      } else if (g.ekind == EP_DBN) {
+      } else if (EK == EP_DBN) {
         const int C = g.prev_bn.C;
         const float4 h = ld4(g.prev + (long long)pass * g.sprev + off);
         const float hh[4] = {h.x, h.y, h.z, h.w};
@@ -427,7 +491,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
           s2 += (double)(dy * ((hh[i] - mean) * rstd));
         }
         st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
-      } else if (g.ekind == EP_DACT) {
+      } else if (EK == EP_DACT) {
         const float4 ap = ld4(g.prev + (long long)pass * g.sprev + off);
         const float aa[4] = {ap.x, ap.y, ap.z, ap.w};
         float keep[4] = {1.f, 1.f, 1.f, 1.f};
@@ -445,7 +509,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
           y[i] = aa[i] > 0.f ? d : d * neg;
         }
         st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
-      } else if (g.ekind == EP_STORE) {
+      } else if (EK == EP_STORE) {
         float* dst = g.Y + (long long)pass * g.sY + off;
         float4 o = make_float4(y[0] * scale, y[1] * scale, y[2] * scale, y[3] * scale);
         if (g.accumulate) {
@@ -453,7 +517,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
           o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
         }
         st4(dst, o);
-      } else if (g.ekind == EP_REPARAM_BWD) {
+      } else if (EK == EP_REPARAM_BWD) {
         // y = dL/dz_enc for latent feature n.  dmu = dz + kl_coef*mu ; dlogvar = dz*eps*0.5*exp(0.5 lv)
         // + kl_coef*0.5*(exp(lv)-1)   
         const float4 mu = ld4(g.mu + off), lv = ld4(g.lv + off), e = ld4(g.eps + off);
@@ -494,7 +558,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_mn_kernel(const GemmArgs g)
 constexpr int DW_MC = 32;          // batch rows per staged chunk
 constexpr int DW_LDS = DW_MC + 4;  // padded row (conflict-free 128-bit reads across rows)
 
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_dw_kernel(const DwArgs g, int nsplit) {
+template <int PK, int QK>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_dw_kernel(const DwArgs g, int nsplit) {
   extern __shared__ __align__(16) float dyn_smem[];
   float* Ps = dyn_smem;                            // [2][64][DW_LDS]
   float* Qs = Ps + 2 * 64 * DW_LDS;                // [2][64][DW_LDS]
@@ -507,8 +572,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_dw_kernel(const DwArgs g, i
   const int mbeg = split * g.rows_per_cta;
   const int mend = min(g.M, mbeg + g.rows_per_cta);
 
-  operand_consts(g.p, pass, g.Bg, g.bn_eps, cs_p);
-  operand_consts(g.q, pass, g.Bg, g.bn_eps, cs_q);
+  operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p);
+  operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q);
   // BatchNorm affine gradients are exactly the backward batch sums (appendix A.2): dbeta = sum dy,
   // dgamma = sum dy*xhat.  One CTA per pass adds them to the gradient buffer.
   if (g.add_affine && g.dgamma && blockIdx.x == 0 && blockIdx.y == 0 && split == 0) {
@@ -531,33 +596,27 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_dw_kernel(const DwArgs g, i
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
   const bool do_bias = (g.db != nullptr || g.label_col >= 0) && blockIdx.x == 0 && tk == 0;
 
-  float4 rp[2], rq[2];
-  auto gload = [&](int mb) {
+  struct Regs { Raw p[2], q[2]; };
+  auto gload = [&](int mb, Regs& r) {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int row = l_row + 32 * t;
-      int mm = mb + l_m;
       // rows beyond this CTA's slice must not contribute: clamp through M = mend
-      rp[t] = load_operand(g.p, cs_p, pass, n0 + row, mm, mend, g.ld, g.slope);
-      rq[t] = load_operand(g.q, cs_q, pass, k0 + row, mm, mend, g.ld, g.slope);
+      load_raw<PK>(g.p, pass, n0 + row, mb + l_m, mend, g.ld, r.p[t]);
+      load_raw<QK>(g.q, pass, k0 + row, mb + l_m, mend, g.ld, r.q[t]);
     }
   };
-  auto sstore = [&](int buf) {
+  auto sstore = [&](int buf, int mb, const Regs& r) {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int row = l_row + 32 * t;
-      st4(Ps + ((size_t)buf * 64 + row) * DW_LDS + l_m, rp[t]);
-      st4(Qs + ((size_t)buf * 64 + row) * DW_LDS + l_m, rq[t]);
+      st4(Ps + ((size_t)buf * 64 + row) * DW_LDS + l_m,
+          finish_operand<PK>(g.p, cs_p, pass, n0 + row, mb + l_m, mend, g.slope, r.p[t]));
+      st4(Qs + ((size_t)buf * 64 + row) * DW_LDS + l_m,
+          finish_operand<QK>(g.q, cs_q, pass, k0 + row, mb + l_m, mend, g.slope, r.q[t]));
     }
   };
-
-  const int nchunks = (mend - mbeg + DW_MC - 1) / DW_MC;
-  gload(mbeg);
-  sstore(0);
-  __syncthreads();
-  for (int c = 0; c < nchunks; ++c) {
-    const int cur = c & 1;
-    if (c + 1 < nchunks) gload(mbeg + (c + 1) * DW_MC);
+  auto compute = [&](int cur) {
     const float* P = Ps + (size_t)cur * 64 * DW_LDS;
     const float* Q = Qs + (size_t)cur * 64 * DW_LDS;
 #pragma unroll
@@ -581,7 +640,18 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_dw_kernel(const DwArgs g, i
         for (int i = 0; i < 4; ++i) bsum[i] += (p[i].x + p[i].y) + (p[i].z + p[i].w);
       }
     }
-    if (c + 1 < nchunks) sstore(cur ^ 1);
+  };
+
+  const int nchunks = (mend - mbeg + DW_MC - 1) / DW_MC;
+  Regs rr;
+  gload(mbeg, rr);
+  sstore(0, mbeg, rr);
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1;
+    if (c + 1 < nchunks) gload(mbeg + (c + 1) * DW_MC, rr);
+    compute(cur);
+    if (c + 1 < nchunks) sstore(cur ^ 1, mbeg + (c + 1) * DW_MC, rr);
     __syncthreads();
   }
 
@@ -605,11 +675,69 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_dw_kernel(const DwArgs g, i
 inline size_t gemm_mn_smem(const GemmArgs& g) {
   size_t f = operand_const_floats(g.a);
   if (g.ekind == EP_DBN) f += 4 * (size_t)g.prev_bn.C;
+  f = (f + 3) & ~(size_t)3;        // 16-byte aligned
+  f += 4 * (size_t)TBN * RED_LD;   // split-K partial tiles
   return f * sizeof(float);
 }
 inline size_t gemm_dw_smem(const DwArgs& g) {
   size_t f = 4 * 64 * DW_LDS + operand_const_floats(g.p) + operand_const_floats(g.q);
   return f * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host dispatch: one small straight-line kernel per (operand kind, epilogue kind) that the steps use
+// ------------------------------------------------------------------------------------------------
+template <bool WT, int AK, int EK>
+inline cudaError_t launch_mn_inst(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_mn_kernel<WT, AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_mn_kernel<WT, AK, EK><<<grid, GEMM_THREADS, smem, st>>>(g);
+  return cudaGetLastError();
+}
+
+inline cudaError_t dispatch_mn(bool wt, const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t st) {
+#define CVG_MN(W, A, E) \
+  if (wt == W && g.a.kind == A && g.ekind == E) return launch_mn_inst<W, A, E>(g, grid, smem, st);
+  CVG_MN(true, OP_PLAIN, EP_LINEAR)
+  CVG_MN(true, OP_BN_ACT, EP_LINEAR)
+  CVG_MN(true, OP_REPARAM, EP_LINEAR)
+  CVG_MN(false, OP_PLAIN, EP_DACT)
+  CVG_MN(false, OP_CONST, EP_DACT)
+  CVG_MN(false, OP_PLAIN, EP_STORE)
+  CVG_MN(false, OP_PLAIN, EP_DBN)
+  CVG_MN(false, OP_BN_BWD, EP_DBN)
+  CVG_MN(false, OP_BN_BWD, EP_REPARAM_BWD)
+#undef CVG_MN
+  return cudaErrorInvalidValue;
+}
+
+template <int PK, int QK>
+inline cudaError_t launch_dw_inst(const DwArgs& g, int nsplit, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<PK, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_dw_kernel<PK, QK><<<grid, GEMM_THREADS, smem, st>>>(g, nsplit);
+  return cudaGetLastError();
+}
+
+inline cudaError_t dispatch_dw(const DwArgs& g, int nsplit, dim3 grid, size_t smem, cudaStream_t st) {
+#define CVG_DW(P, Q) \
+  if (g.p.kind == P && g.q.kind == Q) return launch_dw_inst<P, Q>(g, nsplit, grid, smem, st);
+  CVG_DW(OP_PLAIN, OP_PLAIN)
+  CVG_DW(OP_CONST, OP_PLAIN)
+  CVG_DW(OP_PLAIN, OP_BN_ACT)
+  CVG_DW(OP_BN_BWD, OP_BN_ACT)
+  CVG_DW(OP_BN_BWD, OP_REPARAM)
+  CVG_DW(OP_BN_BWD, OP_PLAIN)
+#undef CVG_DW
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace cvg

@@ -108,10 +108,12 @@ int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
   dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, zp);
   const size_t smem = gemm_mn_smem(g);
   prof_begin(e, wt ? 0 : 1, 2.0 * g.M * (double)g.N * g.R * zp, st);
-  if (wt) gemm_mn_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(g);
-  else gemm_mn_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(g);
+  const cudaError_t err = dispatch_mn(wt, g, grid, smem, st);
   prof_end(e, st);
-  CVG_LAUNCH_CHECK();
+  if (err != cudaSuccess)
+    CVG_FAIL(std::string("gemm_mn launch (a.kind ") + std::to_string(g.a.kind) + ", ekind " + std::to_string(g.ekind) +
+             "): " + cudaGetErrorString(err));
+  e.launches++;
   return 0;
 }
 
@@ -129,9 +131,12 @@ int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
   g.rows_per_cta = rows;
   dim3 grid(kt, nt, g.npass * nsplit);
   prof_begin(e, 2, 2.0 * g.M * (double)g.N * g.K * g.npass, st);
-  gemm_dw_kernel<<<grid, GEMM_THREADS, gemm_dw_smem(g), st>>>(g, nsplit);
+  const cudaError_t err = dispatch_dw(g, nsplit, grid, gemm_dw_smem(g), st);
   prof_end(e, st);
-  CVG_LAUNCH_CHECK();
+  if (err != cudaSuccess)
+    CVG_FAIL(std::string("gemm_dw launch (p.kind ") + std::to_string(g.p.kind) + ", q.kind " + std::to_string(g.q.kind) +
+             "): " + cudaGetErrorString(err));
+  e.launches++;
   return 0;
 }
 

@@ -114,7 +114,7 @@ def compare_grads(eng, orc, net_names, grads, report):
             report.append((f"grad {name}/{key}", ok, worst, mx, float(g_ref.abs().max())))
 
 
-def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS):
+def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=ATOL_FRAC):
     st = orc.state()
     for name in nets:
         i = NETS.index(name)
@@ -127,7 +127,7 @@ def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS):
             if ONE_HOT_FIRST.get(name) == key and loose_prebn_atol:
                 extra = torch.zeros(ref.shape)
                 extra[:, ref.shape[1] - orc.label_num:] = loose_prebn_atol
-            ok, worst, mx = close(got, ref, atol_abs=extra)
+            ok, worst, mx = close(got, ref, atol_abs=extra, atol_frac=atol_frac)
             report.append((f"state {name}/{key}", ok, worst, mx, float(ref.abs().max())))
 
 

@@ -64,7 +64,10 @@ def test_two_label_visits_trajectory():
                 step += 1
     report = []
     # 6 generator steps of lr 2e-4 on round-off gradients: allow |delta| up to 6 * lr on those biases
-    P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5)
+    # 26 Adam steps: every step turns relative gradient differences of ~1e-6 into parameter differences of up
+    # to ~lr * 1e-2 on small-gradient entries, so the per-tensor floor is 2e-3 of the tensor's scale here
+    # (single steps are held to 1e-3 in test_step_losses_and_gradients)
+    P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5, atol_frac=2e-3)
     P.assert_report(report, "parameters after two label visits")
     assert eng.get_adam_step(2) == 10 and eng.get_adam_step(3) == 10 and eng.get_adam_step(0) == 6
     eng.close()
