@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcvaegan_b200.so")
 
 NET_ENCODER, NET_GENERATOR, NET_DISCRIMINATOR, NET_CLASSIFIER = 0, 1, 2, 3
 NET_NAMES = ("encoder", "generator", "discriminator", "classifier")
-STEP_NO_UPDATE, STEP_LOCAL_BN = 1, 2
+STEP_NO_UPDATE, STEP_LOCAL_BN, VISIT_LAMBDA_ZERO = 1, 2, 4
 GRAD_TAIL = 16
 
 
@@ -63,6 +63,8 @@ SIGNATURES = {
     "cvg_step_d": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _I, _P, _P]),
     "cvg_step_c": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _I, _P, _P]),
     "cvg_step_g": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _F, _I, _P, _P]),
+    "cvg_visit": (_I, [_P, _I, _I, _I64, _P, _I64, _P, _I, _I, _I, _I, _P, _P]),
+    "cvg_ctl_set": (_I, [_P, _U64, _U64, _I, _F, _I, _P]),
     "cvg_adam": (_I, [_P, _I, _P]),
     "cvg_sample_rows": (_I, [_P, _P, _I64, _I64, _I64, _I, _U64, _U64, _P, _P, _P]),
     "cvg_generate": (_I, [_P, _I, _I64, _P, _U64, _U64, _I, _P, _P]),

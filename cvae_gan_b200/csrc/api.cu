@@ -51,6 +51,12 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
     delete h;
     return 1;
   }
+  set_all_kernel_attributes();
+  if (cudaGetLastError() != cudaSuccess) {
+    cvg::set_error("cudaFuncSetAttribute failed");
+    delete h;
+    return 1;
+  }
   *out = h;
   return 0;
 }
@@ -107,12 +113,17 @@ int cvg_bind_workspace(CvgHandle* h, void* workspace, int64_t bytes, void* strea
 int cvg_set_adam_step(CvgHandle* h, int net, int64_t t) {
   H_OR_FAIL(h);
   if (net < 0 || net >= CVG_NUM_NETS) CVG_FAIL("bad net id");
-  h->e.adam_t[net] = t;
+  if (!h->e.ws_base) CVG_FAIL("workspace not bound");
+  long long v = (long long)t;
+  CVG_CUDA(cudaMemcpy(&h->e.ws.ctl->adam_t[net], &v, sizeof(v), cudaMemcpyHostToDevice));
   return 0;
 }
 int64_t cvg_get_adam_step(const CvgHandle* h, int net) {
   if (!h || net < 0 || net >= CVG_NUM_NETS) return -1;
-  return h->e.adam_t[net];
+  if (!h->e.ws_base) return -1;
+  long long v = -1;
+  if (cudaMemcpy(&v, &h->e.ws.ctl->adam_t[net], sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
 }
 
 int cvg_comm_unique_id(void* out128) {
@@ -130,21 +141,46 @@ int cvg_step_d(CvgHandle* h, const float* x_real, int label, int B, const CvgNoi
   H_OR_FAIL(h);
   if (!x_real) CVG_FAIL("null x_real");
   if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
-  return step_d(h->e, x_real, label, B, noise, seed, counter, flags, loss_out, (cudaStream_t)stream);
+  StepRng rng;
+  rng.seed = seed; rng.counter = counter;
+  return step_d(h->e, x_real, label, B, noise, rng, flags, loss_out, (cudaStream_t)stream);
 }
 int cvg_step_c(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
                uint64_t counter, int flags, float* loss_out, void* stream) {
   H_OR_FAIL(h);
   if (!x_real) CVG_FAIL("null x_real");
   if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
-  return step_c(h->e, x_real, label, B, noise, seed, counter, flags, loss_out, (cudaStream_t)stream);
+  StepRng rng;
+  rng.seed = seed; rng.counter = counter;
+  return step_c(h->e, x_real, label, B, noise, rng, flags, loss_out, (cudaStream_t)stream);
 }
 int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
                uint64_t counter, float lambda_class_now, int flags, float* loss_out, void* stream) {
   H_OR_FAIL(h);
   if (!x_real) CVG_FAIL("null x_real");
   if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
-  return step_g(h->e, x_real, label, B, noise, seed, counter, lambda_class_now, flags, loss_out, (cudaStream_t)stream);
+  StepRng rng;
+  rng.seed = seed; rng.counter = counter;
+  rng.lambda_class = lambda_class_now; rng.lambda_nonzero = lambda_class_now != 0.f;
+  return step_g(h->e, x_real, label, B, noise, rng, flags, loss_out, (cudaStream_t)stream);
+}
+
+int cvg_visit(CvgHandle* h, int label, int B_local, int64_t B_global, const float* class_rows, int64_t n_rows,
+              const float* x_batches, int d_loop, int c_loop, int g_loop, int flags, float* loss_out, void* stream) {
+  H_OR_FAIL(h);
+  if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
+  if (d_loop < 0 || c_loop < 0 || g_loop < 0) CVG_FAIL("cvg_visit: negative loop count");
+  return visit(h->e, label, B_local, B_global, class_rows, n_rows, x_batches, d_loop, c_loop, g_loop, flags, loss_out,
+               (cudaStream_t)stream);
+}
+
+int cvg_ctl_set(CvgHandle* h, uint64_t seed, uint64_t counter, int set_rng, float lambda_class, int set_lambda, void* stream) {
+  H_OR_FAIL(h);
+  if (!h->e.ws_base) CVG_FAIL("workspace not bound");
+  ctl_set_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->e.ws.ctl, seed, counter, set_rng, lambda_class, set_lambda);
+  CVG_CUDA(cudaGetLastError());
+  h->e.launches++;
+  return 0;
 }
 
 int cvg_adam(CvgHandle* h, int net_mask, void* stream) {
@@ -158,7 +194,7 @@ int cvg_sample_rows(CvgHandle* h, const float* class_rows, int64_t n, int64_t B_
   if (!class_rows || !x_out || n < 1 || B_local < 1 || draw_offset < 0 || draw_offset + B_local > B_global)
     CVG_FAIL("cvg_sample_rows: bad argument");
   sample_rows_kernel<<<(B_local + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      class_rows, n, B_global, draw_offset, B_local, h->e.F, seed, counter, x_out, (long long*)idx_out);
+      class_rows, n, B_global, draw_offset, B_local, h->e.F, seed, counter, nullptr, 0, x_out, (long long*)idx_out);
   CVG_CUDA(cudaGetLastError());
   h->e.launches++;
   return 0;

@@ -62,6 +62,9 @@ struct Workspace {
   double* e_bst = nullptr;
   // generation scratch
   unsigned long long* gen_count = nullptr;
+  // device-resident step control block + staging for device-side sampling
+  StepCtl* ctl = nullptr;
+  float* x_stage = nullptr;        // [rows][F] row-major batch drawn by sample_rows_kernel
 };
 
 struct ProfRec {
@@ -78,7 +81,6 @@ struct Engine {
   int eh[3]{}, gh[3]{}, dh[3]{}, ch[3]{};
   NetLayout lay[4];
   NetBuffers buf[4];
-  int64_t adam_t[4] = {0, 0, 0, 0};
   Workspace ws;
   void* ws_base = nullptr;
   int64_t ws_bytes = 0;
@@ -102,12 +104,23 @@ int64_t workspace_bytes(const Engine& e);
 int carve_workspace(Engine& e, void* base, int64_t bytes);
 
 // train.cu
-int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed, uint64_t counter,
-           int flags, float* loss_out, cudaStream_t st);
-int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed, uint64_t counter,
-           int flags, float* loss_out, cudaStream_t st);
-int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed, uint64_t counter,
-           float lambda_class, int flags, float* loss_out, cudaStream_t st);
+// How a step obtains its Philox key/counter and lambda_class: the C-ABI step calls write them into the control
+// block first (set = true); a label visit leaves the block alone and addresses counter + off.
+struct StepRng {
+  bool set = true;
+  uint64_t seed = 0, counter = 0, off = 0;
+  float lambda_class = 0.f;
+  bool lambda_nonzero = true;
+};
+int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, const StepRng& rng, int flags,
+           float* loss_out, cudaStream_t st);
+int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, const StepRng& rng, int flags,
+           float* loss_out, cudaStream_t st);
+int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* noise, const StepRng& rng, int flags,
+           float* loss_out, cudaStream_t st);
+int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows, int64_t n_rows, const float* x_batches,
+          int d_loop, int c_loop, int g_loop, int flags, float* loss_out, cudaStream_t st);
+void set_all_kernel_attributes();
 int run_adam(Engine& e, int net_mask, cudaStream_t st);
 int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st);
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st);

@@ -689,12 +689,6 @@ inline size_t gemm_dw_smem(const DwArgs& g) {
 // ------------------------------------------------------------------------------------------------
 template <bool WT, int AK, int EK>
 inline cudaError_t launch_mn_inst(const GemmArgs& g, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_mn_kernel<WT, AK, EK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   gemm_mn_kernel<WT, AK, EK><<<grid, GEMM_THREADS, smem, st>>>(g);
   return cudaGetLastError();
 }
@@ -717,12 +711,6 @@ inline cudaError_t dispatch_mn(bool wt, const GemmArgs& g, dim3 grid, size_t sme
 
 template <int PK, int QK>
 inline cudaError_t launch_dw_inst(const DwArgs& g, int nsplit, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_dw_kernel<PK, QK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   gemm_dw_kernel<PK, QK><<<grid, GEMM_THREADS, smem, st>>>(g, nsplit);
   return cudaGetLastError();
 }

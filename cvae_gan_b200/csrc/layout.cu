@@ -222,6 +222,8 @@ static size_t carve(const Engine& e, Workspace& w, void* base) {
     w.e_bst = w.e_fst + (size_t)3 * 2 * STAT_C;
   }
   w.gen_count = c.take<unsigned long long>(4);
+  w.ctl = c.take<StepCtl>(1);
+  w.x_stage = c.take<float>((size_t)rows * F);
   return c.off + 256;
 }
 

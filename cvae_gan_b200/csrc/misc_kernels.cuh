@@ -6,6 +6,33 @@
 namespace cvg {
 
 // ------------------------------------------------------------------------------------------------
+// device-resident control block: everything that changes from step to step lives HERE, not in kernel
+// arguments, so that a whole label visit can be captured in a CUDA graph once and replayed
+// ------------------------------------------------------------------------------------------------
+struct StepCtl {
+  unsigned long long seed;      // Philox key
+  unsigned long long counter;   // Philox step counter (advanced by ctl_bump_kernel)
+  long long adam_t[4];          // torch.optim.Adam state['step'] per network
+  float lambda_class;           // current_lambda_class of this epoch (cvae_gan.py:198-204)
+  float pad;
+};
+
+__global__ void ctl_set_kernel(StepCtl* c, unsigned long long seed, unsigned long long counter, int set_rng,
+                               float lambda_class, int set_lambda) {
+  if (threadIdx.x == 0) {
+    if (set_rng) { c->seed = seed; c->counter = counter; }
+    if (set_lambda) c->lambda_class = lambda_class;
+  }
+}
+__global__ void ctl_bump_kernel(StepCtl* c, unsigned long long dcounter, int adam_mask) {
+  if (threadIdx.x == 0) {
+    c->counter += dcounter;
+    for (int n = 0; n < 4; ++n)
+      if (adam_mask & (1 << n)) c->adam_t[n] += 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // accumulator slots (doubles, zeroed at the start of every step)
 // ------------------------------------------------------------------------------------------------
 enum {
@@ -161,7 +188,8 @@ struct CeArgs {
   int M, ld, K, npass, label;
   const float* logits; long long sl;   // [K][ld]
   float* dlogits; long long sd;        // [K][ld]
-  float coef;                          // 1/Bg (classifier step) or lambda_class/Bg (generator step)
+  float coef;                          // 1/Bg; multiplied by ctl->lambda_class when `ctl` is set (generator step)
+  const StepCtl* ctl;
   double* loss;                        // [npass] accumulators
 };
 
@@ -178,9 +206,10 @@ __global__ void ce_kernel(const CeArgs g) {
     const float lse = logf(s);
     nll = -(double)(l[(size_t)g.label * g.ld] - mx - lse);
     float* d = g.dlogits + (long long)pass * g.sd + m;
+    const float coef = g.ctl ? g.coef * g.ctl->lambda_class : g.coef;
     for (int k = 0; k < g.K; ++k) {
       const float p = expf(l[(size_t)k * g.ld] - mx - lse);
-      d[(size_t)k * g.ld] = (p - (k == g.label ? 1.f : 0.f)) * g.coef;
+      d[(size_t)k * g.ld] = (p - (k == g.label ? 1.f : 0.f)) * coef;
     }
   }
   nll = warp_sum_d(nll);
@@ -381,7 +410,8 @@ __global__ void __launch_bounds__(256) sn_grad_kernel(const SnGradArgs g, const 
 struct AdamSeg {
   float* p; float* g; float* m; float* v;
   long long n;
-  float lr, bc1, bc2_sqrt;
+  float lr;
+  const long long* t_prev;     // device: number of steps taken so far (this launch applies step t_prev + 1)
 };
 struct AdamArgs {
   AdamSeg seg[2];
@@ -392,7 +422,15 @@ struct AdamArgs {
 
 __global__ void adam_kernel(const AdamArgs a) {
   const AdamSeg s = a.seg[blockIdx.y];
-  const float step_size = s.lr / s.bc1;
+  // bias corrections in double like torch's Python scalars: step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t)
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(*s.t_prev + 1);
+    sh[0] = (float)((double)s.lr / (1.0 - pow((double)a.b1, t)));
+    sh[1] = (float)sqrt(1.0 - pow((double)a.b2, t));
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2_sqrt = sh[1];
   const float w = 1.0f - a.b1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s.n; i += (long long)gridDim.x * blockDim.x) {
     const float g = s.g[i];
@@ -400,7 +438,7 @@ __global__ void adam_kernel(const AdamArgs a) {
     // exp_avg.lerp_(grad, 1 - beta1)  (torch lerp: weight < 0.5 ? a + w (b - a) : b - (b - a)(1 - w))
     m = (w < 0.5f) ? m + w * (g - m) : g - (g - m) * (1.0f - w);
     v = v * a.b2 + (1.0f - a.b2) * g * g;
-    const float denom = sqrtf(v) / s.bc2_sqrt + a.eps;
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
     s.p[i] = s.p[i] - step_size * (m / denom);
     s.m[i] = m;
     s.v[i] = v;
@@ -447,7 +485,9 @@ struct FillArgs {
   FillJob job[6];
   int njobs;
   int M, ld;
-  uint64_t seed, counter, row_base;
+  uint64_t seed, counter, row_base;   // used when ctl == nullptr (generation path)
+  const StepCtl* ctl = nullptr;       // training: seed = ctl->seed, counter = ctl->counter + counter_off
+  uint64_t counter_off = 0;
   float keep_prob;
 };
 
@@ -456,6 +496,8 @@ __global__ void fill_noise_kernel(const FillArgs a) {
   const int ngroups = (j.nfeat + 3) >> 2;
   const long long total = (long long)j.npass * ngroups * a.M;
   const uint32_t keep_thr = (uint32_t)((double)a.keep_prob * 4294967296.0);
+  const uint64_t seed = a.ctl ? a.ctl->seed : a.seed;
+  const uint64_t counter = a.ctl ? a.ctl->counter + a.counter_off : a.counter;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(t % a.M);
     const int fg = (int)((t / a.M) % ngroups);
@@ -472,7 +514,7 @@ __global__ void fill_noise_kernel(const FillArgs a) {
         }
       }
     } else {
-      const U4 r = philox_at(a.seed, a.counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
+      const U4 r = philox_at(seed, counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
       if (j.kind == 0) {
         box_muller(r.x, r.y, vals[0], vals[1]);
         box_muller(r.z, r.w, vals[2], vals[3]);
@@ -527,9 +569,12 @@ __device__ __forceinline__ uint64_t feistel(uint64_t x, int half, const uint32_t
 }
 
 __global__ void sample_rows_kernel(const float* rows, long long n, long long B, long long draw_offset, int B_local,
-                                   int F, uint64_t seed, uint64_t counter, float* x_out, long long* idx_out) {
+                                   int F, uint64_t seed_arg, uint64_t counter_arg, const StepCtl* ctl,
+                                   uint64_t counter_off, float* x_out, long long* idx_out) {
   const int il = blockIdx.x * blockDim.x + threadIdx.x;
   if (il >= B_local) return;
+  const uint64_t seed = ctl ? ctl->seed : seed_arg;
+  const uint64_t counter = ctl ? ctl->counter + counter_off : counter_arg;
   const long long i = draw_offset + il;      // index of this draw in the global batch
   long long r;
   if (n == B) {

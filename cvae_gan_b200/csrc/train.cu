@@ -708,21 +708,19 @@ int run_adam(Engine& e, int net_mask, cudaStream_t st) {
   for (int net = 0; net < 4; ++net) {
     if (!(net_mask & (1 << net))) continue;
     if (a.nseg == 2) CVG_FAIL("cvg_adam: at most two networks per call");
-    const int64_t t = ++e.adam_t[net];
     AdamSeg& s = a.seg[a.nseg++];
     s.p = e.buf[net].params; s.g = e.buf[net].grads; s.m = e.buf[net].m; s.v = e.buf[net].v;
     s.n = e.lay[net].n_param;
-    const double bc1 = 1.0 - pow((double)e.cfg.adam_beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)e.cfg.adam_beta2, (double)t);
-    s.lr = (float)((double)net_lr(e, net) / bc1);   // torch: step_size = lr / bias_correction1 (in double)
-    s.bc1 = 1.0f;
-    s.bc2_sqrt = (float)sqrt(bc2);
+    s.lr = net_lr(e, net);
+    s.t_prev = &e.ws.ctl->adam_t[net];
     if (s.n > nmax) nmax = s.n;
   }
   if (a.nseg == 0) return 0;
   int blocks = (int)((nmax + 255) / 256);
   if (blocks > 2 * e.num_sms) blocks = 2 * e.num_sms;
   adam_kernel<<<dim3(blocks, a.nseg), 256, 0, st>>>(a);
+  CVG_LAUNCH_CHECK();
+  ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 0ull, net_mask);   // state['step'] += 1
   CVG_LAUNCH_CHECK();
   return 0;
 }
@@ -755,12 +753,20 @@ static int check_step(Engine& e, int B) {
   return 0;
 }
 
+static int begin_step(Engine& e, const StepRng& rng, bool with_lambda, cudaStream_t st) {
+  if (!rng.set) return 0;
+  ctl_set_kernel<<<1, 32, 0, st>>>(e.ws.ctl, rng.seed, rng.counter, 1, rng.lambda_class, with_lambda ? 1 : 0);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // step D (cvae_gan.py:104-128)
 // ------------------------------------------------------------------------------------------------
-int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, uint64_t seed, uint64_t counter,
-           int flags, float* loss_out, cudaStream_t st) {
+int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
+           float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
+  CVG_TRY(begin_step(e, rng, false, st));
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
   const bool local_bn = flags & CVG_STEP_LOCAL_BN;
@@ -770,7 +776,8 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
   CVG_CUDA(cudaMemsetAsync(w.sn_G, 0, sizeof(float) * 2 * e.lay[D].n_param, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = seed; f.counter = counter; f.row_base = (uint64_t)e.rank * B;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
+  f.ctl = w.ctl; f.counter_off = rng.off;
   f.keep_prob = 1.0f - e.cfg.dropout_p;
   add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
   add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 2, RS_DMASK1);
@@ -813,9 +820,10 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
 // ------------------------------------------------------------------------------------------------
 // step C (cvae_gan.py:131-157)
 // ------------------------------------------------------------------------------------------------
-int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, uint64_t seed, uint64_t counter,
-           int flags, float* loss_out, cudaStream_t st) {
+int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
+           float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
+  CVG_TRY(begin_step(e, rng, false, st));
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
   const bool local_bn = flags & CVG_STEP_LOCAL_BN;
@@ -824,7 +832,8 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   const int C = CVG_NET_CLASSIFIER;
   CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = seed; f.counter = counter; f.row_base = (uint64_t)e.rank * B;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
+  f.ctl = w.ctl; f.counter_off = rng.off;
   f.keep_prob = 1.0f - e.cfg.dropout_p;
   add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
   add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 2, RS_CMASK1);
@@ -839,6 +848,7 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   c.logits = w.c_logit; c.sl = (long long)e.K * ld;
   c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
   c.coef = 1.0f / Bg;
+  c.ctl = nullptr;
   c.loss = w.loss + L_CE0;
   ce_kernel<<<dim3((B + 127) / 128, 2), 128, 0, st>>>(c);
   CVG_LAUNCH_CHECK();
@@ -849,9 +859,10 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
 // ------------------------------------------------------------------------------------------------
 // step E+G (cvae_gan.py:160-216)
 // ------------------------------------------------------------------------------------------------
-int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, uint64_t seed, uint64_t counter,
-           float lambda_class, int flags, float* loss_out, cudaStream_t st) {
+int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
+           float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
+  CVG_TRY(begin_step(e, rng, true, st));
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
   const bool local_bn = flags & CVG_STEP_LOCAL_BN;
@@ -860,7 +871,8 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   const int E = CVG_NET_ENCODER, G = CVG_NET_GENERATOR;
   CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = seed; f.counter = counter; f.row_base = (uint64_t)e.rank * B;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
+  f.ctl = w.ctl; f.counter_off = rng.off;
   f.keep_prob = 1.0f - e.cfg.dropout_p;
   add_job(f, w.z, nz ? nz->eps : nullptr, 0, e.Z, 1, RS_EPS);                     // slot 0: eps
   add_job(f, w.z + (size_t)e.Z * ld, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);      // slot 1: z_prior
@@ -882,7 +894,8 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
   c.logits = w.c_logit; c.sl = (long long)e.K * ld;
   c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
-  c.coef = lambda_class / Bg;
+  c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
+  c.ctl = w.ctl;
   c.loss = w.loss + L_CE0;
   ce_kernel<<<dim3((B + 127) / 128, 1), 128, 0, st>>>(c);
   CVG_LAUNCH_CHECK();
@@ -890,7 +903,7 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   // backward to x_fake: adv = -mean D(x_fake) (cvae_gan.py:189), then the classification term
   const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
   CVG_TRY(bwd_critic(e, x_fake, 0, 1, label, B, seedv, false, true, st));
-  if (lambda_class != 0.f) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, st));
+  if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, st));
 
   // generator output gradients: recon MSE on pass 0, dx on pass 1, through the sigmoid
   SeedArgs s;
@@ -929,6 +942,62 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_TRY(bwd_bn_net(e, eb, B, Bg_bn, 0.f, local_bn, st));
 
   return finish_step(e, (1 << E) | (1 << G), 2, B, flags, loss_out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one label visit (cvae_gan.py:102-216): d_loop critic steps, c_loop classifier steps, g_loop encoder /
+// generator steps, each on a freshly drawn batch.  Everything that varies between visits (Philox
+// counter, Adam step counts, lambda_class) is read from the device control block, so the sequence can be
+// captured into a CUDA graph once per (label, lambda_class != 0) and replayed.
+// ------------------------------------------------------------------------------------------------
+int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows, int64_t n_rows, const float* x_batches,
+          int d_loop, int c_loop, int g_loop, int flags, float* loss_out, cudaStream_t st) {
+  CVG_TRY(check_step(e, B));
+  if (!x_batches && (!class_rows || n_rows < 1)) CVG_FAIL("cvg_visit: need class_rows or x_batches");
+  if (B_global != (int64_t)B * e.world) CVG_FAIL("cvg_visit: B_global must be B_local * world_size");
+  int i = 0;
+  for (int kind = 0; kind < 3; ++kind) {
+    const int reps = kind == 0 ? d_loop : (kind == 1 ? c_loop : g_loop);
+    for (int r = 0; r < reps; ++r, ++i) {
+      const float* x = nullptr;
+      if (x_batches) {
+        x = x_batches + (size_t)i * B * e.F;
+      } else {
+        sample_rows_kernel<<<(B + 127) / 128, 128, 0, st>>>(class_rows, n_rows, B_global, (long long)e.rank * B, B, e.F,
+                                                           0, 0, e.ws.ctl, 0, e.ws.x_stage, nullptr);
+        CVG_LAUNCH_CHECK();
+        x = e.ws.x_stage;
+      }
+      StepRng rng;
+      rng.set = false;
+      rng.off = 1;                                   // sampling used counter + 0
+      rng.lambda_nonzero = !(flags & CVG_VISIT_LAMBDA_ZERO);
+      float* lo = loss_out ? loss_out + 4 * i : nullptr;
+      const int sf = flags & (CVG_STEP_LOCAL_BN | CVG_STEP_NO_UPDATE);
+      if (kind == 0) CVG_TRY(step_d(e, x, label, B, nullptr, rng, sf, lo, st));
+      else if (kind == 1) CVG_TRY(step_c(e, x, label, B, nullptr, rng, sf, lo, st));
+      else CVG_TRY(step_g(e, x, label, B, nullptr, rng, sf, lo, st));
+      ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 2ull, 0);    // two counter values per step: draw + noise
+      CVG_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
+void set_all_kernel_attributes() {
+  // cudaFuncSetAttribute is done once, eagerly, so that nothing but launches happens during graph capture
+  GemmArgs g;
+  DwArgs d;
+  (void)g; (void)d;
+#define CVG_MN_ATTR(W, A, E) cudaFuncSetAttribute(gemm_mn_kernel<W, A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  CVG_MN_ATTR(true, OP_PLAIN, EP_LINEAR) CVG_MN_ATTR(true, OP_BN_ACT, EP_LINEAR) CVG_MN_ATTR(true, OP_REPARAM, EP_LINEAR)
+  CVG_MN_ATTR(false, OP_PLAIN, EP_DACT) CVG_MN_ATTR(false, OP_CONST, EP_DACT) CVG_MN_ATTR(false, OP_PLAIN, EP_STORE)
+  CVG_MN_ATTR(false, OP_PLAIN, EP_DBN) CVG_MN_ATTR(false, OP_BN_BWD, EP_DBN) CVG_MN_ATTR(false, OP_BN_BWD, EP_REPARAM_BWD)
+#undef CVG_MN_ATTR
+#define CVG_DW_ATTR(P, Q) cudaFuncSetAttribute(gemm_dw_kernel<P, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  CVG_DW_ATTR(OP_PLAIN, OP_PLAIN) CVG_DW_ATTR(OP_CONST, OP_PLAIN) CVG_DW_ATTR(OP_PLAIN, OP_BN_ACT)
+  CVG_DW_ATTR(OP_BN_BWD, OP_BN_ACT) CVG_DW_ATTR(OP_BN_BWD, OP_REPARAM) CVG_DW_ATTR(OP_BN_BWD, OP_PLAIN)
+#undef CVG_DW_ATTR
 }
 
 }  // namespace cvg

@@ -21,7 +21,7 @@ import torch
 from . import config as _config
 from . import datasets as _datasets
 from . import models
-from ._lib import NET_CLASSIFIER, NET_DISCRIMINATOR, NET_ENCODER, NET_GENERATOR
+from ._lib import NET_CLASSIFIER, NET_DISCRIMINATOR, NET_ENCODER, NET_GENERATOR, VISIT_LAMBDA_ZERO
 from .engine import Engine, patience_scan
 
 
@@ -77,6 +77,7 @@ class CVAEGAN:
         self._counter = 0          # one Philox counter value per optimiser step / sampling call
         self._gen_rows = 0         # rows of the generation noise stream consumed so far
         self._bn_calls = {NET_ENCODER: 0, NET_GENERATOR: 0}
+        self.use_cuda_graphs = True   # False: same kernels launched eagerly (debugging aid; identical numerics)
 
     # ------------------------------------------------------------------------------------------------
     def _next(self) -> int:
@@ -106,26 +107,38 @@ class CVAEGAN:
             eng.grads[net].zero_()
             eng.set_adam_step(net, 0)
         lam = gc.cvae_gan_config['lambda_class']
-        g_loss = torch.zeros(4, dtype=torch.float32, device=eng.device)
-        scratch = torch.zeros(4, dtype=torch.float32, device=eng.device)
+        loops = (int(gc.d_loop_num), int(gc.c_loop_num), int(gc.g_loop_num))
+        n_steps = sum(loops)
+        batch = int(gc.batch_size)
+        losses = torch.zeros(n_steps, 4, dtype=torch.float32, device=eng.device)
+        # Philox key + starting counter go to the device control block; every step advances it there
+        eng.ctl_set(seed=self._seed, counter=self._counter)
+        graphs = {}
         for e in range(gc.epochs):
+            lam_e = lambda_class_at(e, lam)
+            eng.ctl_set(lambda_class=lam_e)
+            flags = VISIT_LAMBDA_ZERO if lam_e == 0.0 else 0
             for target_label in self.samples.keys():
-                for _ in range(gc.d_loop_num):
-                    x = self._get_target_samples(target_label, gc.batch_size)
-                    eng.step_d(x, target_label, seed=self._seed, counter=self._next(), loss_out=scratch)
-                    self._bn_calls[NET_GENERATOR] += 1
-                for _ in range(gc.c_loop_num):
-                    x = self._get_target_samples(target_label, gc.batch_size)
-                    eng.step_c(x, target_label, seed=self._seed, counter=self._next(), loss_out=scratch)
-                    self._bn_calls[NET_GENERATOR] += 1
-                for _ in range(gc.g_loop_num):
-                    x = self._get_target_samples(target_label, gc.batch_size)
-                    eng.step_g(x, target_label, lambda_class_at(e, lam), seed=self._seed, counter=self._next(),
-                               loss_out=g_loss)
-                    self._bn_calls[NET_GENERATOR] += 2
-                    self._bn_calls[NET_ENCODER] += 1
+                key = (target_label, flags, batch, loops)
+                if self.use_cuda_graphs:
+                    g = graphs.get(key)
+                    if g is None:
+                        # a label visit is ~400 kernel launches of a few microseconds each: captured once per
+                        # (label, lambda_class != 0) and replayed, the host cost per visit is one graph launch
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            eng.visit(target_label, batch, class_rows=self.samples[target_label], loops=loops,
+                                      flags=flags, loss_out=losses)
+                        graphs[key] = g
+                    g.replay()
+                else:
+                    eng.visit(target_label, batch, class_rows=self.samples[target_label], loops=loops, flags=flags,
+                              loss_out=losses)
+                self._counter += 2 * n_steps
+                self._bn_calls[NET_GENERATOR] += loops[0] + loops[1] + 2 * loops[2]
+                self._bn_calls[NET_ENCODER] += loops[2]
             # one read-back per epoch: the last label's last generator step (cvae_gan.py:219-222)
-            recon, kl, adv, cls = g_loss.tolist()
+            recon, kl, adv, cls = losses[n_steps - 1].tolist()
             self.loss_history['recon_loss'].append(recon)
             self.loss_history['kl_loss'].append(kl)
             self.loss_history['adv_loss'].append(adv)
@@ -133,6 +146,8 @@ class CVAEGAN:
             if e % 50 == 0:
                 print(f"CVAE-GAN训练轮次: {e}/{gc.epochs}, 重构损失: {recon:.4f}, KL损失: {kl:.4f}, "
                       f"对抗损失: {adv:.4f}, 分类损失: {cls:.4f}")
+        torch.cuda.synchronize(eng.device)
+        graphs.clear()
         self._sync_bn_counters()
         for m in (self.encoder, self.generator, self.discriminator, self.classifier):
             m.eval()

@@ -179,6 +179,25 @@ class Engine:
                                   float(lambda_class), flags, _ptr(out), _stream()))
         return out
 
+    def ctl_set(self, seed=None, counter=None, lambda_class=None):
+        """Write the device control block (Philox key/counter and/or this epoch's lambda_class)."""
+        set_rng = seed is not None
+        set_l = lambda_class is not None
+        check(self.lib.cvg_ctl_set(self.h, int(seed or 0), int(counter or 0), 1 if set_rng else 0,
+                                   float(lambda_class or 0.0), 1 if set_l else 0, _stream()))
+
+    def visit(self, label: int, batch_global: int, class_rows=None, x_batches=None, loops=(5, 5, 3), flags=0,
+              loss_out=None):
+        """One label visit (capturable in a CUDA graph): loops = (d_loop, c_loop, g_loop)."""
+        b_local = batch_global // self.world_size
+        n = sum(loops)
+        if loss_out is None:
+            loss_out = torch.zeros(n, 4, dtype=torch.float32, device=self.device)
+        check(self.lib.cvg_visit(self.h, int(label), b_local, int(batch_global), _ptr(class_rows),
+                                 0 if class_rows is None else class_rows.size(0), _ptr(x_batches),
+                                 int(loops[0]), int(loops[1]), int(loops[2]), int(flags), _ptr(loss_out), _stream()))
+        return loss_out
+
     def adam(self, net_mask: int):
         check(self.lib.cvg_adam(self.h, int(net_mask), _stream()))
 

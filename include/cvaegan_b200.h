@@ -36,7 +36,8 @@ enum { CVG_NET_ENCODER = 0, CVG_NET_GENERATOR = 1, CVG_NET_DISCRIMINATOR = 2, CV
 /* flags for the step functions */
 enum {
   CVG_STEP_NO_UPDATE = 1,  /* compute losses + gradients, skip Adam (gradients stay in the grad buffers) */
-  CVG_STEP_LOCAL_BN  = 2   /* data parallel only: per-rank BatchNorm statistics (DEVIATES from the reference) */
+  CVG_STEP_LOCAL_BN  = 2,  /* data parallel only: per-rank BatchNorm statistics (DEVIATES from the reference) */
+  CVG_VISIT_LAMBDA_ZERO = 4 /* cvg_visit: the caller guarantees lambda_class == 0 (epochs < 200): skip the classifier backward */
 };
 
 /* Mirrors /root/reference/src/config/gan_config.py:1-21 plus the torch defaults the models rely on. */
@@ -126,6 +127,20 @@ int cvg_step_c(CvgHandle* h, const float* x_real, int label, int B, const CvgNoi
                uint64_t counter, int flags, float* loss_out, void* stream);
 int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
                uint64_t counter, float lambda_class_now, int flags, float* loss_out, void* stream);
+
+/* One label visit of the training loop (cvae_gan.py:102-216): d_loop critic steps, c_loop classifier steps and
+ * g_loop encoder/generator steps, each on a freshly drawn batch - either drawn on the device from class_rows
+ * [n_rows, F] (_get_target_samples) or taken from x_batches [d_loop+c_loop+g_loop, B_local, F] when that is
+ * non-NULL.  Philox seed/counter, the Adam step counts and lambda_class are read from a device-resident control
+ * block (cvg_ctl_set), nothing dynamic is passed by value: the call can be captured in a CUDA graph (stream
+ * capture on `stream`) once per (label, lambda_class != 0) and replayed.  loss_out: device float
+ * [d_loop+c_loop+g_loop][4], one row per step in the layout of the step functions. */
+int cvg_visit(CvgHandle* h, int label, int B_local, int64_t B_global, const float* class_rows, int64_t n_rows,
+              const float* x_batches, int d_loop, int c_loop, int g_loop, int flags, float* loss_out, void* stream);
+
+/* Writes the control block on `stream`: Philox key + step counter (if set_rng) and the epoch's lambda_class
+ * (if set_lambda).  The step functions below do this themselves from their arguments. */
+int cvg_ctl_set(CvgHandle* h, uint64_t seed, uint64_t counter, int set_rng, float lambda_class, int set_lambda, void* stream);
 
 /* torch.optim.Adam.step for the networks in net_mask (bit i = net i), using the bound grad buffers.
  * The step functions call this themselves unless CVG_STEP_NO_UPDATE is set. */
