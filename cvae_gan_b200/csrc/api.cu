@@ -52,6 +52,11 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
     return 1;
   }
   set_all_kernel_attributes();
+  tc_set_kernel_attributes();
+  {
+    const char* off = getenv("CVG_DISABLE_TC");
+    e.use_tc = tc_supported(e) && !(off && off[0] == '1');
+  }
   if (cudaGetLastError() != cudaSuccess) {
     cvg::set_error("cudaFuncSetAttribute failed");
     delete h;

@@ -65,6 +65,9 @@ struct Workspace {
   // device-resident step control block + staging for device-side sampling
   StepCtl* ctl = nullptr;
   float* x_stage = nullptr;        // [rows][F] row-major batch drawn by sample_rows_kernel
+  // tensor-core path: pre-split weights in shared-memory operand order + per-feature epilogue constants
+  float* tc_w = nullptr;
+  float* tc_c = nullptr;
 };
 
 struct ProfRec {
@@ -88,6 +91,7 @@ struct Engine {
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
   int num_sms = 148;
+  bool use_tc = true;      // tensor-core chains (CVG_DISABLE_TC=1 forces the FFMA layer kernels)
 
   float* P(int net, int64_t off) const { return buf[net].params + off; }
   float* G(int net, int64_t off) const { return buf[net].grads + off; }
@@ -133,6 +137,18 @@ int generate_filter(Engine& e, int label, int64_t n, float thr, const float* z, 
                     uint8_t* keep_out, cudaStream_t st);
 int classifier_forward(Engine& e, const float* x, int64_t n, float* logits_out, cudaStream_t st);
 int encoder_forward(Engine& e, const float* x, int label, int64_t n, float* mu_out, float* lv_out, cudaStream_t st);
+
+// eval_tc.cu: fused eval-mode chains on tcgen05 (no CPU or library fallback; unsupported widths use the FFMA kernels)
+bool tc_supported(const Engine& e);
+int64_t tc_prep_floats(const Engine& e);
+int64_t tc_const_floats();
+void tc_set_kernel_attributes();
+int tc_generate(Engine& e, int label, int64_t n, const float* z, uint64_t seed, uint64_t row_offset, float* x_out, cudaStream_t st);
+int tc_generate_filter(Engine& e, int label, int64_t n, float thr, const float* z, uint64_t seed, uint64_t row_offset, float* x_out,
+                       int64_t* idx_out, int64_t capacity, unsigned long long* count_out, float* logits_out, uint8_t* keep_out,
+                       cudaStream_t st);
+int tc_classifier_forward(Engine& e, const float* x, int64_t n, float* logits_out, cudaStream_t st);
+int tc_encoder_forward(Engine& e, const float* x, int label, int64_t n, float* mu_out, float* lv_out, cudaStream_t st);
 
 // shared launch helpers (train.cu)
 int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st);

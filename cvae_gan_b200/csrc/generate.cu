@@ -42,6 +42,7 @@ int generate(Engine& e, int label, int64_t n, const float* z, uint64_t seed, uin
   if (label < 0 || label >= e.K) CVG_FAIL("label out of range");
   if (train_mode && n > e.ws.rows_cap) CVG_FAIL("train-mode generation needs n <= max_batch (batch statistics)");
   if (train_mode && n < 2) CVG_FAIL("BatchNorm in train mode needs more than 1 row");
+  if (!train_mode && e.use_tc) return tc_generate(e, label, n, z, seed, row_offset, x_out, st);
   const int cap = e.ws.rows_cap;
   for (int64_t done = 0; done < n; done += cap) {
     const int rows = (int)((n - done) < cap ? (n - done) : cap);
@@ -59,6 +60,8 @@ int generate_filter(Engine& e, int label, int64_t n, float thr, const float* z, 
                     uint8_t* keep_out, cudaStream_t st) {
   if (!e.ws_base) CVG_FAIL("workspace not bound");
   if (label < 0 || label >= e.K) CVG_FAIL("label out of range");
+  if (e.use_tc)
+    return tc_generate_filter(e, label, n, thr, z, seed, row_offset, x_out, idx_out, capacity, count_out, logits_out, keep_out, st);
   const int cap = e.ws.rows_cap;
   for (int64_t done = 0; done < n; done += cap) {
     const int rows = (int)((n - done) < cap ? (n - done) : cap);
@@ -76,6 +79,7 @@ int generate_filter(Engine& e, int label, int64_t n, float thr, const float* z, 
 
 int classifier_forward(Engine& e, const float* x, int64_t n, float* logits_out, cudaStream_t st) {
   if (!e.ws_base) CVG_FAIL("workspace not bound");
+  if (e.use_tc) return tc_classifier_forward(e, x, n, logits_out, st);
   const int cap = e.ws.rows_cap;
   for (int64_t done = 0; done < n; done += cap) {
     const int rows = (int)((n - done) < cap ? (n - done) : cap);
@@ -91,6 +95,7 @@ int classifier_forward(Engine& e, const float* x, int64_t n, float* logits_out, 
 int encoder_forward(Engine& e, const float* x, int label, int64_t n, float* mu_out, float* lv_out, cudaStream_t st) {
   if (!e.ws_base) CVG_FAIL("workspace not bound");
   if (label < 0 || label >= e.K) CVG_FAIL("label out of range");
+  if (e.use_tc) return tc_encoder_forward(e, x, label, n, mu_out, lv_out, st);
   const int cap = e.ws.rows_cap;
   for (int64_t done = 0; done < n; done += cap) {
     const int rows = (int)((n - done) < cap ? (n - done) : cap);

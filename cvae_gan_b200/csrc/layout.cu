@@ -224,6 +224,8 @@ static size_t carve(const Engine& e, Workspace& w, void* base) {
   w.gen_count = c.take<unsigned long long>(4);
   w.ctl = c.take<StepCtl>(1);
   w.x_stage = c.take<float>((size_t)rows * F);
+  w.tc_w = c.take<float>((size_t)tc_prep_floats(e));
+  w.tc_c = c.take<float>((size_t)tc_const_floats());
   return c.off + 256;
 }
 

@@ -3,4 +3,5 @@
 #include "layout.cu"
 #include "train.cu"
 #include "generate.cu"
+#include "eval_tc.cu"
 #include "api.cu"
