@@ -402,6 +402,16 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
 
     ms = timed(gen_filter, iters, 3)
     accepted = int(eng.count_buf.item())
+    dbg = None
+    if os.environ.get("CVG_TC_DBG") == "1":       # development: per-role cycle split of the fused kernel
+        cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+        check(eng.lib.cvg_debug_tc_counters(eng.h, _ptr(cnt)))
+        gen_filter()
+        torch.cuda.synchronize()
+        check(eng.lib.cvg_debug_tc_counters(eng.h, None))
+        tiles = (n + 63) // 64
+        dbg = {k: v / tiles for k, v in zip(("issuer_wait_act", "issuer_wait_weights", "issuer_wait_stage", "issuer_total",
+                                              "epi_wait_acc", "epi_input", "epi_total", "issue", "L0", "L1", "L2", "L3", "L4", "L5", "L6", "L7"), cnt.tolist())}
 
     def gen_filter_e2e():
         gen_filter()
@@ -418,7 +428,7 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
     out = {
         "metric": "filtered_synth_samples_per_s", "value": accepted_all / (ms * 1e-3), "unit": "accepted rows/s",
         "generated_rows_per_s": gen_rows_s, "acceptance_rate": accepted_all / (n * world), "rows_per_gpu": n,
-        "ms_per_pass": ms, "label": label, "threshold": thr,
+        "ms_per_pass": ms, "label": label, "threshold": thr, "cycles_per_tile": dbg,
         "e2e": {"value": accepted_all / (ms_e2e * 1e-3), "generated_rows_per_s": n * world / (ms_e2e * 1e-3),
                 "unit": "accepted rows/s", "ms_per_pass": ms_e2e, "d2h_bytes_per_pass": accepted * (F_ * 4) + 8,
                 "api": "cvg_generate_filter + count read-back + accepted rows copied to pinned host memory"},

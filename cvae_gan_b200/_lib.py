@@ -75,6 +75,7 @@ SIGNATURES = {
     "cvg_encoder_forward": (_I, [_P, _P, _I, _I64, _P, _P, _P]),
     "cvg_patience_scan": (_I, [_P, _I64, _I64, _I, _I, C.POINTER(_I64), C.POINTER(_I64)]),
     "cvg_debug_read": (_I, [_P, C.c_char_p, _I, _I, _P, C.POINTER(C.c_int), _P]),
+    "cvg_debug_tc_counters": (_I, [_P, _P]),
     "cvg_profile_enable": (_I, [_P, _I]),
     "cvg_profile_read": (_I, [_P, _I, C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cvg_launch_count": (_I64, [_P]),

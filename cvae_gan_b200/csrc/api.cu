@@ -317,6 +317,12 @@ int cvg_debug_read(CvgHandle* h, const char* name, int pass, int rows, float* ds
   return 0;
 }
 
+int cvg_debug_tc_counters(CvgHandle* h, long long* dev_counters) {
+  H_OR_FAIL(h);
+  h->e.tc_dbg = dev_counters;
+  return 0;
+}
+
 int cvg_profile_enable(CvgHandle* h, int enable) {
   H_OR_FAIL(h);
   Engine& e = h->e;

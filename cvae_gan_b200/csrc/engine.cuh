@@ -91,6 +91,7 @@ struct Engine {
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
   int num_sms = 148;
+  long long* tc_dbg = nullptr;   // development: device cycle counters of tc_eval_kernel (cvg_debug_tc_counters)
   bool use_tc = true;      // tensor-core chains (CVG_DISABLE_TC=1 forces the FFMA layer kernels)
 
   float* P(int net, int64_t off) const { return buf[net].params + off; }

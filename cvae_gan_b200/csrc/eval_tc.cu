@@ -14,7 +14,8 @@
 //                     4-byte scattered stores are bank-conflict free.
 //   * accumulators: fp32 in TMEM (feature = lane, row = column); the epilogue reads them with tcgen05.ld, applies
 //     bias / BatchNorm(eval) / LayerNorm / activation and writes the next layer's operand in place.
-//   * warp roles: warps 0-3 = epilogue (128 threads = 128 TMEM lanes), warp 4 = weight producer + MMA issuer.
+//   * warp roles: warps 0-7 = epilogue (two warps per 32-lane TMEM quadrant, 32 of the 64 rows each), warp 8 = weight
+//     producer + MMA issuer.
 //   * z comes from Philox keyed by the GLOBAL row index (same stream as fill_noise_kernel), the filter decision is
 //     filter_decide() (bit-exact torch softmax semantics), accepted rows are compacted with one atomic per tile.
 #include "engine.cuh"
@@ -41,7 +42,9 @@ constexpr int TC_LBO_B = TC_ROWS * 16 + 16;          // bytes between 4-k groups
 constexpr int TC_BBYTES = (TC_MAXK / 4) * TC_LBO_B;  // one plane (hi or lo)
 constexpr int TC_STAGE_BYTES = 2 * TC_KC * 128 * 4;  // hi + lo chunk of a 128-row weight tile
 constexpr int TC_MAXF = 64;                          // widest generator output kept for compaction
-constexpr int TC_THREADS = 160;
+constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, 32 of the 64 rows each
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = TC_EPI_THREADS + 32;
 constexpr int TC_LN_PITCH = TC_ROWS + 1;
 
 enum { TEPI_BN_LRELU = 0, TEPI_RELU = 1, TEPI_LN_RELU = 2, TEPI_SIGMOID_X = 3, TEPI_LOGITS = 4, TEPI_OUT = 5 };
@@ -82,6 +85,7 @@ struct TcEvalArgs {
   float* x_out; long long* idx_out; long long capacity; unsigned long long* count;
   float* logits_out; uint8_t* keep_out;
   float slope, ln_eps;
+  long long* dbg;       // optional cycle counters (development)
 };
 
 struct TcPrepArgs {
@@ -153,13 +157,15 @@ struct TcSmem {
   unsigned long long base;
 };
 
-__device__ __forceinline__ void b_store(uint8_t* b_hi, uint8_t* b_lo, int f, int m, float y) {
-  const uint32_t off = (uint32_t)(f >> 2) * TC_LBO_B + (uint32_t)m * 16 + (uint32_t)(f & 3) * 4;
+__device__ __forceinline__ void b_store(uint8_t* b_hi, uint8_t* b_lo, uint32_t off, float y) {
   float hi, lo;
   split_tf32(y, hi, lo);
   *reinterpret_cast<float*>(b_hi + off) = hi;
   *reinterpret_cast<float*>(b_lo + off) = lo;
 }
+
+#define TC_CLK(var) \
+  if (prof) var = clock64();
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_constant__ TcEvalArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -168,27 +174,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
   uint8_t* stages = smem + 2 * TC_BBYTES;
   float* xs = reinterpret_cast<float*>(stages + TC_STAGES * TC_STAGE_BYTES);   // [TC_MAXF][64] generator outputs
   float* lg = xs + TC_MAXF * TC_ROWS;                                           // [32][64] logits
-  float* red = lg + FILTER_MAXK * TC_ROWS;                                      // [6][64] LayerNorm scratch
-  TcSmem* S = reinterpret_cast<TcSmem*>(red + 6 * TC_ROWS);
+  float* red = lg + FILTER_MAXK * TC_ROWS;                                      // [10][64] LayerNorm scratch
+  TcSmem* S = reinterpret_cast<TcSmem*>(red + 10 * TC_ROWS);
   float* ln_scratch = reinterpret_cast<float*>(b_hi + (TC_MAXK / 8) * TC_LBO_B);  // upper half of the hi plane
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const long long ntiles = (a.n + TC_ROWS - 1) / TC_ROWS;
+  const bool prof = a.dbg != nullptr;
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
     mbar_init(&S->acc_full, 1);
-    mbar_init(&S->act_ready, 128);
+    mbar_init(&S->act_ready, TC_EPI_THREADS);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(&S->tmem_slot, 128);
+  if (warp == TC_EPI_WARPS) tmem_alloc(&S->tmem_slot, 128);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = S->tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, S->tmem_slot, 0);   // warp-uniform for the compiler
 
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     // ===================== weight producer + MMA issuer =====================
+    long long t_act = 0, t_full = 0, t_empty = 0, t_all = 0, c0 = 0, c1 = 0, t_issue = 0, t_lay[TC_MAX_LAYERS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    TC_CLK(t_all);
     int cpt = 0;
     for (int l = 0; l < a.nl; ++l) cpt += a.L[l].n_mtiles * a.L[l].n_kchunks;
     long long my_tiles = 0;
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
       const int kc_len = min(TC_KC, Lr.K - lkc * TC_KC);
       const uint32_t bytes = 2u * kc_len * Lr.M * 4u;
       const float* src = a.wprep + Lr.w_off + (size_t)lmt * Lr.K * Lr.M * 2 + (size_t)lkc * TC_KC * Lr.M * 2;
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(&S->full[s], bytes);
         bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, src, bytes, &S->full[s]);
       }
@@ -211,57 +220,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
     };
     for (int i = 0; i < TC_STAGES && g_load < total; ++i) issue_load();
     unsigned long long n_act = 0;
+    const uint32_t b_hi_a = smem_u32(b_hi), b_lo_a = smem_u32(b_lo), st_a = smem_u32(stages);
     for (long long t = 0; t < my_tiles; ++t) {
       for (int l = 0; l < a.nl; ++l) {
         const TcLayer& Lr = a.L[l];
+        TC_CLK(c0);
         mbar_wait(&S->act_ready, (uint32_t)(n_act & 1));
+        TC_CLK(c1);
+        t_act += c1 - c0;
         ++n_act;
         tc_fence_after_sync();
         const uint32_t idesc = idesc_tf32(Lr.M, TC_ROWS, 0, 0);
+        const uint32_t a_lbo = (uint32_t)Lr.M * 16u;
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
           for (int kc = 0; kc < Lr.n_kchunks; ++kc) {
             if (g >= 2 && g_load < total) {   // refill the stage chunk g-2 used: chunk g-1's MMAs stay in flight
+              TC_CLK(c0);
               mbar_wait(&S->empty[(g - 2) % TC_STAGES], (uint32_t)(((g - 2) / TC_STAGES) & 1));
+              TC_CLK(c1);
+              t_empty += c1 - c0;
               issue_load();
             }
             const int s = (int)(g % TC_STAGES);
+            TC_CLK(c0);
             mbar_wait(&S->full[s], (uint32_t)((g / TC_STAGES) & 1));
+            TC_CLK(c1);
+            t_full += c1 - c0;
             tc_fence_after_sync();
-            if (lane == 0) {
+            TC_CLK(c0);
+            if (elect_one()) {
               const int kc_len = min(TC_KC, Lr.K - kc * TC_KC);
-              const uint32_t a_hi = smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+              const uint32_t a_hi = st_a + (uint32_t)s * TC_STAGE_BYTES;
               const uint32_t a_lo = a_hi + (uint32_t)kc_len * Lr.M * 4u;
-              const uint32_t a_lbo = (uint32_t)Lr.M * 16u;
-              const uint32_t bh = smem_u32(b_hi) + (uint32_t)(kc * TC_KC / 4) * TC_LBO_B;
-              const uint32_t bl = smem_u32(b_lo) + (uint32_t)(kc * TC_KC / 4) * TC_LBO_B;
+              const uint32_t boff = (uint32_t)(kc * TC_KC / 4) * TC_LBO_B;
+              uint64_t dah = smem_desc(a_hi, a_lbo, 128), dal = smem_desc(a_lo, a_lbo, 128);
+              uint64_t dbh = smem_desc(b_hi_a + boff, TC_LBO_B, 128), dbl = smem_desc(b_lo_a + boff, TC_LBO_B, 128);
               const uint32_t d = tmem + (uint32_t)mt * TC_ROWS;
+              const uint64_t a_step = (uint64_t)((2 * a_lbo) >> 4), b_step = (uint64_t)((2 * TC_LBO_B) >> 4);
               for (int ks = 0; ks < kc_len / 8; ++ks) {
-                const uint64_t dah = smem_desc(a_hi + ks * 2 * a_lbo, a_lbo, 128);
-                const uint64_t dal = smem_desc(a_lo + ks * 2 * a_lbo, a_lbo, 128);
-                const uint64_t dbh = smem_desc(bh + ks * 2 * TC_LBO_B, TC_LBO_B, 128);
-                const uint64_t dbl = smem_desc(bl + ks * 2 * TC_LBO_B, TC_LBO_B, 128);
                 mma_tf32(d, dal, dbh, idesc, !(kc == 0 && ks == 0));   // small terms first
                 mma_tf32(d, dah, dbl, idesc, true);
                 mma_tf32(d, dah, dbh, idesc, true);
+                dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
               }
               mma_commit(&S->empty[s]);
               if (mt == Lr.n_mtiles - 1 && kc == Lr.n_kchunks - 1) mma_commit(&S->acc_full);
             }
             __syncwarp();
+            TC_CLK(c1);
+            t_issue += c1 - c0;
+            t_lay[l] += c1 - c0;
             ++g;
           }
         }
       }
     }
+    if (prof && lane == 0) {
+      t_all = clock64() - t_all;
+      atomicAdd((unsigned long long*)a.dbg + 0, (unsigned long long)t_act);
+      atomicAdd((unsigned long long*)a.dbg + 1, (unsigned long long)t_full);
+      atomicAdd((unsigned long long*)a.dbg + 2, (unsigned long long)t_empty);
+      atomicAdd((unsigned long long*)a.dbg + 3, (unsigned long long)t_all);
+      atomicAdd((unsigned long long*)a.dbg + 7, (unsigned long long)t_issue);
+      for (int l = 0; l < a.nl; ++l) atomicAdd((unsigned long long*)a.dbg + 8 + l, (unsigned long long)t_lay[l]);
+    }
   } else {
-    // ===================== epilogue warps (thread = output feature = TMEM lane) =====================
+    // ============== epilogue warps: thread = (output feature = TMEM lane, half of the 64 rows) ==============
+    long long t_acc = 0, t_in = 0, t_all = 0, c0 = 0, c1 = 0;
+    TC_CLK(t_all);
     unsigned long long n_acc = 0;
     const int in_groups = a.L[0].K / 4;
+    const int q = warp & 3, h = warp >> 2;      // TMEM lane quadrant, column half
+    const int mbase = h * 32;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = tile * TC_ROWS;
       const int nrows = (int)min((long long)TC_ROWS, a.n - row0);
+      TC_CLK(c0);
       // ---- layer-0 operand: z (Philox or injected) or x rows, 4 consecutive features of one row per item ----
-      for (int i = tid; i < TC_ROWS * in_groups; i += 128) {
+      for (int i = tid; i < TC_ROWS * in_groups; i += TC_EPI_THREADS) {
         const int m = i % TC_ROWS, fg = i / TC_ROWS;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (m < nrows) {
@@ -285,101 +321,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&S->act_ready);
+      TC_CLK(c1);
+      t_in += c1 - c0;
 
       for (int l = 0; l < a.nl; ++l) {
         const TcLayer& Lr = a.L[l];
         const int next_K = (l + 1 < a.nl) ? a.L[l + 1].K : 0;
+        TC_CLK(c0);
         mbar_wait(&S->acc_full, (uint32_t)(n_acc & 1));
+        TC_CLK(c1);
+        t_acc += c1 - c0;
         ++n_acc;
         tc_fence_after_sync();
-        const int f_local = (Lr.M == 128) ? tid : (warp * 16 + lane);
+        const int f_local = (Lr.M == 128) ? (q * 32 + lane) : (q * 16 + lane);
         const bool lane_ok = (Lr.M == 128) || (lane < 16);
         const float* cst = a.consts + Lr.c_off;
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
-          float v[TC_ROWS];
-          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)mt * TC_ROWS;
+          float v[32];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * TC_ROWS + mbase);
           tmem_ld32(taddr, v);
-          tmem_ld32(taddr + 32, v + 32);
           tmem_wait_ld();
           const int f = mt * Lr.M + f_local;
           const bool valid = lane_ok && f < Lr.N;
-          const float c0 = valid ? cst[f] : 0.f, c1 = valid ? cst[Lr.Npad + f] : 0.f;
-          const float c2 = valid ? cst[2 * Lr.Npad + f] : 0.f, c3 = valid ? cst[3 * Lr.Npad + f] : 0.f;
+          const float c0f = valid ? cst[f] : 0.f, c1f = valid ? cst[Lr.Npad + f] : 0.f;
+          const float c2f = valid ? cst[2 * Lr.Npad + f] : 0.f, c3f = valid ? cst[3 * Lr.Npad + f] : 0.f;
+          const uint32_t boff = (uint32_t)(f >> 2) * TC_LBO_B + (uint32_t)(f & 3) * 4 + (uint32_t)mbase * 16;
           if (Lr.epi == TEPI_BN_LRELU) {
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < TC_ROWS; ++m) {
-                float y = fmaf((v[m] + c0) - c1, c2, c3);
+              for (int m = 0; m < 32; ++m) {
+                float y = fmaf((v[m] + c0f) - c1f, c2f, c3f);
                 y = y > 0.f ? y : y * a.slope;
-                b_store(b_hi, b_lo, f, m, y);
+                b_store(b_hi, b_lo, boff + m * 16, y);
               }
             }
           } else if (Lr.epi == TEPI_RELU) {
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < TC_ROWS; ++m) b_store(b_hi, b_lo, f, m, fmaxf(v[m] + c0, 0.f));
+              for (int m = 0; m < 32; ++m) b_store(b_hi, b_lo, boff + m * 16, fmaxf(v[m] + c0f, 0.f));
             }
           } else if (Lr.epi == TEPI_SIGMOID_X) {
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < TC_ROWS; ++m) {
-                const float y = 1.0f / (1.0f + expf(-(v[m] + c0)));
-                xs[f * TC_ROWS + m] = y;
-                if (next_K) b_store(b_hi, b_lo, f, m, y);
-                if (a.x_all && m < nrows) a.x_all[(size_t)(row0 + m) * a.F + f] = y;
+              for (int m = 0; m < 32; ++m) {
+                const float y = 1.0f / (1.0f + expf(-(v[m] + c0f)));
+                xs[f * TC_ROWS + mbase + m] = y;
+                if (next_K) b_store(b_hi, b_lo, boff + m * 16, y);
+                if (a.x_all && mbase + m < nrows) a.x_all[(size_t)(row0 + mbase + m) * a.F + f] = y;
               }
             }
           } else if (Lr.epi == TEPI_LOGITS) {
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < TC_ROWS; ++m) lg[f * TC_ROWS + m] = v[m] + c0;
+              for (int m = 0; m < 32; ++m) lg[f * TC_ROWS + mbase + m] = v[m] + c0f;
             }
           } else if (Lr.epi == TEPI_OUT) {
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < TC_ROWS; ++m)
-                if (m < nrows) {
-                  if (f < a.out_split) a.out_plain[(size_t)(row0 + m) * a.out_ld + f] = v[m] + c0;
-                  else a.out_plain2[(size_t)(row0 + m) * a.out_ld + (f - a.out_split)] = v[m] + c0;
+              for (int m = 0; m < 32; ++m)
+                if (mbase + m < nrows) {
+                  if (f < a.out_split) a.out_plain[(size_t)(row0 + mbase + m) * a.out_ld + f] = v[m] + c0f;
+                  else a.out_plain2[(size_t)(row0 + mbase + m) * a.out_ld + (f - a.out_split)] = v[m] + c0f;
                 }
             }
           } else {   // TEPI_LN_RELU (one 128-feature tile): LayerNorm over the features of each row, two-pass variance
 #pragma unroll
-            for (int m = 0; m < TC_ROWS; ++m) {
-              v[m] += c0;
-              if (valid) ln_scratch[f * TC_LN_PITCH + m] = v[m];
+            for (int m = 0; m < 32; ++m) {
+              v[m] += c0f;
+              if (valid) ln_scratch[f * TC_LN_PITCH + mbase + m] = v[m];
             }
-            named_bar(1, 128);
-            const int m_r = tid & 63, half = tid >> 6, nh = Lr.N / 2;
+            named_bar(1, TC_EPI_THREADS);
+            const int m_r = tid & 63, part = tid >> 6, nq = Lr.N / 4;
             float s = 0.f;
-            for (int q = 0; q < nh; ++q) s += ln_scratch[(half * nh + q) * TC_LN_PITCH + m_r];
-            red[half * TC_ROWS + m_r] = s;
-            named_bar(1, 128);
-            const float mean = (red[m_r] + red[TC_ROWS + m_r]) / (float)Lr.N;
+            for (int j = 0; j < nq; ++j) s += ln_scratch[(part * nq + j) * TC_LN_PITCH + m_r];
+            red[part * TC_ROWS + m_r] = s;
+            named_bar(1, TC_EPI_THREADS);
+            const float mean = ((red[m_r] + red[TC_ROWS + m_r]) + (red[2 * TC_ROWS + m_r] + red[3 * TC_ROWS + m_r])) / (float)Lr.N;
             float q2 = 0.f;
-            for (int q = 0; q < nh; ++q) {
-              const float dlt = ln_scratch[(half * nh + q) * TC_LN_PITCH + m_r] - mean;
+            for (int j = 0; j < nq; ++j) {
+              const float dlt = ln_scratch[(part * nq + j) * TC_LN_PITCH + m_r] - mean;
               q2 = fmaf(dlt, dlt, q2);
             }
-            red[(2 + half) * TC_ROWS + m_r] = q2;
-            named_bar(1, 128);
-            if (half == 0) {
-              red[4 * TC_ROWS + m_r] = mean;
-              red[5 * TC_ROWS + m_r] = 1.0f / sqrtf((red[2 * TC_ROWS + m_r] + red[3 * TC_ROWS + m_r]) / (float)Lr.N + a.ln_eps);
+            red[(4 + part) * TC_ROWS + m_r] = q2;
+            named_bar(1, TC_EPI_THREADS);
+            if (part == 0) {
+              const float var =
+                  ((red[4 * TC_ROWS + m_r] + red[5 * TC_ROWS + m_r]) + (red[6 * TC_ROWS + m_r] + red[7 * TC_ROWS + m_r])) / (float)Lr.N;
+              red[8 * TC_ROWS + m_r] = mean;
+              red[9 * TC_ROWS + m_r] = 1.0f / sqrtf(var + a.ln_eps);
             }
-            named_bar(1, 128);
+            named_bar(1, TC_EPI_THREADS);
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < TC_ROWS; ++m) {
-                const float nrm = (v[m] - red[4 * TC_ROWS + m]) * red[5 * TC_ROWS + m] * c2 + c3;
-                b_store(b_hi, b_lo, f, m, fmaxf(nrm, 0.f));
+              for (int m = 0; m < 32; ++m) {
+                const float nrm = (v[m] - red[8 * TC_ROWS + mbase + m]) * red[9 * TC_ROWS + mbase + m] * c2f + c3f;
+                b_store(b_hi, b_lo, boff + m * 16, fmaxf(nrm, 0.f));
               }
             }
           }
           // zero padding of the next layer's contraction range (N not a multiple of 8)
           if (lane_ok && f >= Lr.N && f < next_K) {
 #pragma unroll
-            for (int m = 0; m < TC_ROWS; ++m) b_store(b_hi, b_lo, f, m, 0.f);
+            for (int m = 0; m < 32; ++m) b_store(b_hi, b_lo, boff + m * 16, 0.f);
           }
         }
         tc_fence_before_sync();
@@ -391,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
 
       // ---- filter decision + compaction (cvae_gan.py:366-370): thread = row ----
       if (a.do_filter) {
-        named_bar(1, 128);
+        named_bar(1, TC_EPI_THREADS);
         if (tid < TC_ROWS) {
           const int m = tid;
           bool keep = false;
@@ -418,12 +461,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
           }
         }
       }
-      named_bar(1, 128);   // xs / lg / red are reused by the next tile
+      named_bar(1, TC_EPI_THREADS);   // xs / lg / red are reused by the next tile
+    }
+    if (prof && tid == 0) {
+      t_all = clock64() - t_all;
+      atomicAdd((unsigned long long*)a.dbg + 4, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)a.dbg + 5, (unsigned long long)t_in);
+      atomicAdd((unsigned long long*)a.dbg + 6, (unsigned long long)t_all);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == TC_EPI_WARPS) tmem_dealloc(tmem, 128);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -431,7 +480,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 static size_t tc_eval_smem() {
   return 2 * (size_t)TC_BBYTES + (size_t)TC_STAGES * TC_STAGE_BYTES +
-         sizeof(float) * ((size_t)TC_MAXF * TC_ROWS + (size_t)FILTER_MAXK * TC_ROWS + 6 * TC_ROWS) + sizeof(TcSmem) + 64;
+         sizeof(float) * ((size_t)TC_MAXF * TC_ROWS + (size_t)FILTER_MAXK * TC_ROWS + 10 * TC_ROWS) + sizeof(TcSmem) + 64;
 }
 
 void tc_set_kernel_attributes() {
@@ -504,6 +553,7 @@ static int tc_run(Engine& e, ChainBuilder& cb, TcEvalArgs& a, cudaStream_t st) {
   a.ln_eps = e.cfg.ln_eps;
   a.F = e.F;
   a.Kc = e.K;
+  a.dbg = e.tc_dbg;
   const long long ntiles = (a.n + TC_ROWS - 1) / TC_ROWS;
   const int grid = (int)(ntiles < e.num_sms ? ntiles : e.num_sms);
   tc_eval_kernel<<<grid, TC_THREADS, tc_eval_smem(), st>>>(a);

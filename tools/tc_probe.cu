@@ -30,9 +30,9 @@ struct OpLayout {
 __host__ __device__ inline OpLayout op_layout(int rows, int K, int mn_major, int var) {
   OpLayout o;
   if (!mn_major) {
-    if (var == 0) { o.sbo = 128; o.lbo = rows * 16; } else { o.lbo = 128; o.sbo = (K / 4) * 128; }
+    if (var == 0) { o.sbo = 128; o.lbo = rows * 16; } else if (var == 2) { o.sbo = 128; o.lbo = rows * 16 + 16; } else if (var == 3) { o.sbo = 128; o.lbo = rows * 16 + 128; } else { o.lbo = 128; o.sbo = (K / 4) * 128; }
     o.kstep = 2 * o.lbo;
-    o.bytes = (var == 0) ? (K / 4) * o.lbo : (rows / 8) * o.sbo;
+    o.bytes = (var != 1) ? (K / 4) * o.lbo : (rows / 8) * o.sbo;
   } else {
     if (var == 0) { o.lbo = 128; o.sbo = (K / 8) * 128 + 16; } else { o.sbo = 128; o.lbo = (rows / 4) * 128; }
     o.kstep = o.lbo;
@@ -47,9 +47,10 @@ __host__ __device__ inline uint32_t op_offset(const OpLayout& o, int mn_major, i
 
 // A: [M][K] row-major in global, B: [K][N] row-major in global (= feature-major activations)
 __global__ void __launch_bounds__(128) probe_kernel(Case c, const float* A, const float* B, float* D /*[128][N] raw TMEM dump*/,
-                                                    long long* cycles, int repeat) {
+                                                    long long* cycles, int repeat, int commit_every = 0, int two_acc = 0) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const OpLayout la = op_layout(c.M, c.K, c.a_mn, c.a_var), lb = op_layout(c.N, c.K, c.b_mn, c.b_var);
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(128) probe_kernel(Case c, const float* A, cons
   }
   if (tid == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
@@ -101,13 +103,15 @@ __global__ void __launch_bounds__(128) probe_kernel(Case c, const float* A, cons
       for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t dah = dah0 + (uint64_t)(ks * ka), dal = dal0 + (uint64_t)(ks * ka);
         const uint64_t dbh = dbh0 + (uint64_t)(ks * kb), dbl = dbl0 + (uint64_t)(ks * kb);
+        const uint32_t dd = tmem + ((two_acc && (ks & 1)) ? 256u - (uint32_t)c.N : 0u);
         if (c.nsplit == 3) {
-          mma_tf32(tmem, dal, dbh, idesc, acc);
-          mma_tf32(tmem, dah, dbl, idesc, true);
+          mma_tf32(dd, dal, dbh, idesc, acc);
+          mma_tf32(dd, dah, dbl, idesc, true);
           acc = true;
         }
-        mma_tf32(tmem, dah, dbh, idesc, acc);
+        mma_tf32(dd, dah, dbh, idesc, acc);
         acc = true;
+        if (commit_every && ((ks + 1) % commit_every) == 0) mma_commit(&bar2);
       }
     }
     mma_commit(&bar);
@@ -167,6 +171,9 @@ int main() {
   cases.push_back({128, 256, 64, 0, 0, 0, 0, 0, 0, 3});
   cases.push_back({128, 16, 16, 0, 0, 0, 0, 0, 0, 3});
   cases.push_back({128, 64, 64, 0, 0, 0, 1, 0, 0, 3});
+  cases.push_back({128, 64, 64, 0, 0, 0, 2, 0, 0, 3});
+  cases.push_back({128, 64, 64, 0, 0, 0, 3, 0, 0, 3});
+  cases.push_back({64, 64, 64, 0, 0, 0, 2, 0, 0, 3});
   // field-interpretation checks (LBO/SBO swapped) go last: a wrong descriptor may fault
   std::vector<Case> swapped;
   swapped.push_back({128, 64, 32, 0, 1, 0, 0, 1, 0, 1});
@@ -228,9 +235,10 @@ int main() {
 
   // issue-rate: back-to-back MMAs, K = 64 (8 k-steps) x repeat
   for (int N : {16, 32, 64, 128, 256}) {
-    for (int split : {1, 3}) {
-      Case c{128, N, 64, 0, 0, 0, 0, 0, 0, split};
-      const OpLayout la = op_layout(c.M, c.K, 0, 0), lb = op_layout(c.N, c.K, 0, 0);
+    for (int bvar : {0, 1, 2, 3}) {
+      const int split = 3;
+      Case c{128, N, 64, 0, 0, 0, bvar, 0, 0, split};
+      const OpLayout la = op_layout(c.M, c.K, 0, 0), lb = op_layout(c.N, c.K, 0, bvar);
       const size_t smem = 2 * ((la.bytes + 127) & ~127u) + 2 * ((lb.bytes + 127) & ~127u) + 256;
       const int repeat = 64;
       probe_kernel<<<1, 128, smem>>>(c, dA, dB, dD, dcyc, repeat);
@@ -242,8 +250,21 @@ int main() {
       long long cyc;
       cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
       const int nmma = repeat * 8 * split;
-      printf("timing M128 N%3d split%d: %lld cycles for %d MMAs = %.1f cyc/MMA (floor %d)\n", N, split, cyc, nmma,
+      printf("timing M128 N%3d b_var%d: %lld cycles for %d MMAs = %.1f cyc/MMA (floor %d)\n", N, bvar, cyc, nmma,
              (double)cyc / nmma, 128 * N / 256);
+    }
+  }
+  for (int ce : {0, 1, 2, 4, 8}) {
+    for (int two : {0, 1}) {
+      Case c{128, 64, 64, 0, 0, 0, 0, 0, 0, 3};
+      const OpLayout la = op_layout(c.M, c.K, 0, 0), lb = op_layout(c.N, c.K, 0, 0);
+      const size_t smem = 2 * ((la.bytes + 127) & ~127u) + 2 * ((lb.bytes + 127) & ~127u) + 256;
+      probe_kernel<<<1, 128, smem>>>(c, dA, dB, dD, dcyc, 64, ce, two);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("commit test: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+      long long cyc;
+      cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
+      printf("commit every %d k-steps (3 MMAs each), two_acc %d: %.1f cyc/MMA\n", ce, two, (double)cyc / (64 * 8 * 3));
     }
   }
   if (run_cases(swapped)) return 1;
