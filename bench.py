@@ -451,11 +451,15 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
 
     ms_f = timed(standalone, 10, 3)
     acc_f = int(eng.count_buf.item())
-    byts = m * (4 * F_ + 4 * K_) + acc_f * (4 * F_ + 8)
-    out["roofline_filter"] = {"bound": "hbm", "kernel": "filter_compact_kernel", "achieved": byts / (ms_f * 1e-3) / 1e9,
+    # bytes the kernel must move: logits of every row, x of ACCEPTED rows only (read + written) and their indices
+    byts = m * (4 * K_) + acc_f * (4 * F_ + 4 * F_ + 8)
+    byts_survey = m * (4 * F_ + 4 * K_) + acc_f * (4 * F_ + 8)
+    out["roofline_filter"] = {"bound": "hbm", "kernel": "filter_compact_stream_kernel", "achieved": byts / (ms_f * 1e-3) / 1e9,
                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byts / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"],
-                              "rows": m, "acceptance_rate": acc_f / m, "bytes_per_row_model": "4F + 4K + a(4F + 8)",
-                              "rows_per_s": m / (ms_f * 1e-3), "traffic": None}
+                              "rows": m, "acceptance_rate": acc_f / m, "bytes_per_row_model": "4K + a(4F + 4F + 8): x of rejected rows is never read",
+                              "survey_model_gbs": byts_survey / (ms_f * 1e-3) / 1e9, "survey_model": "4F + 4K + a(4F + 8)",
+                              "survey_model_frac": byts_survey / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"],
+                              "rows_per_s": m / (ms_f * 1e-3), "ms": ms_f, "traffic": None}
     return out
 
 

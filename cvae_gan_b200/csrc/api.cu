@@ -20,6 +20,42 @@ struct CvgHandle {
     return 1;                             \
   }
 
+
+// filter_compact_stream_kernel is instantiated for class counts 1..FC_MAX_KC; wider heads use the generic kernel
+constexpr int FC_MAX_KC = 12;
+template <int KC>
+struct FcDispatch {
+  static int attrs() {
+    CVG_CUDA(cudaFuncSetAttribute(filter_compact_stream_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    CVG_CUDA(cudaFuncSetAttribute(filter_compact_stream_kernel<KC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    return FcDispatch<KC - 1>::attrs();
+  }
+  static int launch(int K, unsigned grid, size_t smem, cudaStream_t st, const float* x, const float* logits, long long n, int F,
+                    int label, float thr, uint64_t row_offset, int nsub, float* x_out, long long* idx_out, long long capacity,
+                    unsigned long long* count) {
+    if (K == KC) {
+      filter_compact_stream_kernel<KC><<<grid, FC_THREADS, smem, st>>>(x, logits, n, F, KC, label, thr, row_offset, nsub, x_out,
+                                                                       idx_out, capacity, count);
+      return 0;
+    }
+    return FcDispatch<KC - 1>::launch(K, grid, smem, st, x, logits, n, F, label, thr, row_offset, nsub, x_out, idx_out, capacity, count);
+  }
+};
+template <>
+struct FcDispatch<0> {
+  static int attrs() { return 0; }
+  static int launch(int, unsigned, size_t, cudaStream_t, const float*, const float*, long long, int, int, float, uint64_t, int, float*,
+                    long long*, long long, unsigned long long*) {
+    CVG_FAIL("cvg_filter_compact: unsupported class count");
+  }
+};
+static int fc_set_attributes() { return FcDispatch<FC_MAX_KC>::attrs(); }
+static int fc_launch(int K, unsigned grid, size_t smem, cudaStream_t st, const float* x, const float* logits, long long n, int F,
+                     int label, float thr, uint64_t row_offset, int nsub, float* x_out, long long* idx_out, long long capacity,
+                     unsigned long long* count) {
+  return FcDispatch<FC_MAX_KC>::launch(K, grid, smem, st, x, logits, n, F, label, thr, row_offset, nsub, x_out, idx_out, capacity, count);
+}
+
 extern "C" {
 
 const char* cvg_last_error(void) { return cvg::last_error(); }
@@ -236,8 +272,38 @@ int cvg_filter_compact(const float* x, const float* logits, int64_t n, int F, in
   if (!x || !logits || !count_out || n < 0) CVG_FAIL("cvg_filter_compact: bad argument");
   if (K < 1 || K > FILTER_MAXK) CVG_FAIL("cvg_filter_compact: K must be in [1, 32]");
   if (n == 0) return 0;
-  filter_compact_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, logits, n, 0, F, K, label, thr, row_offset, x_out, (long long*)idx_out, capacity, count_out, nullptr, nullptr);
+  if (K > FC_MAX_KC) {
+    filter_compact_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, logits, n, 0, F, K, label, thr, row_offset, x_out, (long long*)idx_out, capacity, count_out, nullptr, nullptr);
+  } else {
+    const size_t smem = (size_t)FC_SUB_ROWS * K * sizeof(float);      // K <= 32 -> at most 128 KB
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      CVG_CUDA(cudaGetDevice(&dev));
+      CVG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      CVG_TRY(fc_set_attributes());
+    }
+    // few CTAs (one same-address atomic each), one full wave of 6 per SM (__launch_bounds__); sub-blocks are grid-strided over the CTAs.
+    // A launch covers at most grid * FC_MAXSUB sub-blocks; longer streams take several launches.
+    const long long slots = (long long)sms * 6;
+    long long done = 0;
+    while (done < n) {
+      const long long left = n - done;
+      const long long nblk1k = (left + FC_SUB_ROWS - 1) / FC_SUB_ROWS;
+      const long long grid = nblk1k < slots ? nblk1k : slots;
+      long long nsub = (nblk1k + grid - 1) / grid;
+      long long rows_now = left;
+      if (nsub > FC_MAXSUB) {
+        nsub = FC_MAXSUB;
+        rows_now = grid * nsub * FC_SUB_ROWS;
+      }
+      CVG_TRY(fc_launch(K, (unsigned)grid, smem, (cudaStream_t)stream, x + done * F, logits + done * K, rows_now, F, label, thr,
+                        row_offset + (uint64_t)done, (int)nsub, x_out, (long long*)idx_out, capacity, count_out));
+      CVG_CUDA(cudaGetLastError());
+      done += rows_now;
+    }
+  }
   CVG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -605,33 +605,72 @@ __global__ void sample_rows_kernel(const float* rows, long long n, long long B, 
 // ------------------------------------------------------------------------------------------------
 constexpr int FILTER_MAXK = 32;
 
-template <typename LoadLogit>
-__device__ __forceinline__ bool filter_decide(LoadLogit ld, int K, int label, float thr) {
-  float e[FILTER_MAXK];
-  int P = 1;
-  while (P < K) P <<= 1;
+// P = next_pow2(K) known at compile time: everything stays in registers.  The decision is EXACTLY
+//   p = e / sum (IEEE division);  (m, i) = max(p) with the first index on ties;  keep = m > thr && i == label
+// but only p[label] is divided out unconditionally: IEEE division by a common positive divisor is monotonic, so
+// p[k] can only tie with or beat p[label] when e[k] is within a few ulps of e[label] or above it, and only those
+// (rare) candidates are divided and compared exactly.
+template <int P, int KC = 0, typename LoadLogit>
+__device__ __forceinline__ bool filter_decide_p(LoadLogit ld, int K_rt, int label, float thr) {
+  const int K = KC > 0 ? KC : K_rt;     // KC > 0: class count known at compile time (no predicated-off work)
+  float e[P];
   float mx = -INFINITY;
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) { e[k] = ld(k); mx = fmaxf(mx, e[k]); }
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    e[k] = (k < K) ? ld(k) : -INFINITY;
+    if (k < K) mx = fmaxf(mx, e[k]);
+  }
   bool nan = false;
-#pragma unroll 1
+  float el = ld(label);      // (re-read instead of indexing e[]: a dynamic index would push the array to local memory)
+  // exact early-out: the largest exponential is expf(0) = 1; when the label's logit trails the maximum by more than
+  // 2e-6 its exponential is below 1 / 1.000001, i.e. it is "clearly behind" in the sense used below
+  if (mx - el > 2e-6f) return false;
+#pragma unroll
   for (int k = 0; k < P; ++k) {
     if (k < K) { nan |= (e[k] != e[k]); e[k] = expf(e[k] - mx); } else e[k] = 0.f;
   }
-  // butterfly sum: offsets P/2, P/4, ..., 1 (value on lane 0)
-  float s[FILTER_MAXK];
+  el = expf(el - mx);
+  float s[P];
+#pragma unroll
   for (int k = 0; k < P; ++k) s[k] = e[k];
+#pragma unroll
   for (int o = P >> 1; o > 0; o >>= 1)
+#pragma unroll
     for (int k = 0; k < o; ++k) s[k] = s[k] + s[k + o];
   const float sum = s[0];
-  float best = -INFINITY;
-  int arg = 0;
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    const float p = e[k] / sum;
-    if (p > best) { best = p; arg = k; }
+  if (nan) return false;
+  // cheap screen: some other class clearly ahead of the label -> the label cannot be the arg max
+  const float lo = el * 0.999999f;    // "within ~8 ulps below e[label]"
+  bool close = false, lost = false;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if (k < K && k != label) {
+      if (e[k] > el * 1.000001f) lost = true;
+      else if (e[k] >= lo) close = true;
+    }
   }
-  return !nan && (best > thr) && (arg == label);
+  if (lost) return false;
+  const float pl = el / sum;
+  if (!(pl > thr)) return false;
+  if (!close) return true;
+  bool win = true;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if (k < K && k != label && e[k] >= lo) {
+      const float pk = e[k] / sum;
+      if (pk > pl || (pk == pl && k < label)) win = false;
+    }
+  }
+  return win;
+}
+
+template <typename LoadLogit>
+__device__ __forceinline__ bool filter_decide(LoadLogit ld, int K, int label, float thr) {
+  if (K <= 2) return filter_decide_p<2>(ld, K, label, thr);
+  if (K <= 4) return filter_decide_p<4>(ld, K, label, thr);
+  if (K <= 8) return filter_decide_p<8>(ld, K, label, thr);
+  if (K <= 16) return filter_decide_p<16>(ld, K, label, thr);
+  return filter_decide_p<32>(ld, K, label, thr);
 }
 
 __global__ void filter_logits_kernel(const float* logits, long long n, int K, int label, float thr, uint8_t* keep) {
@@ -676,6 +715,136 @@ __global__ void __launch_bounds__(256) filter_compact_kernel(const float* x, con
     if (pos < capacity) {
       for (int f = 0; f < F; ++f) x_out[pos * F + f] = FM ? x[(size_t)f * ld + i] : x[i * F + f];
       if (idx_out) idx_out[pos] = (long long)(row_offset + (uint64_t)i);
+    }
+  }
+}
+
+
+// Standalone filter over MATERIALISED row-major tensors (the memory-bound kernel of SURVEY.md 8d).  One CTA takes
+// `nsub` consecutive sub-blocks of 1024 rows.  Pass 1: each logits sub-block is fetched with coalesced 16-byte
+// streaming loads into shared memory, every thread decides 4 rows from shared memory, and the warp ballots are kept
+// in shared memory.  ONE atomic per CTA then orders its accepted rows (same-address atomics serialise in L2, so
+// there must be few of them).  Pass 2 reads ONLY the accepted rows of x and copies them out - x of a rejected row
+// is never touched: the traffic is 4K + a (4F read + 4F + 8 written) bytes per row, below SURVEY's 4F + 4K +
+// a (4F + 8).
+constexpr int FC_THREADS = 256;
+constexpr int FC_MAXJ = 4;                          // rows per thread per sub-block
+constexpr int FC_SUB_ROWS = FC_MAXJ * FC_THREADS;   // 1024
+constexpr int FC_MAXSUB = 32;                        // sub-blocks per CTA (grid-strided)
+
+__host__ __device__ constexpr int fc_pow2(int k) { return k <= 2 ? 2 : k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32; }
+
+// KC = number of classes (compile time)
+template <int KC>
+__global__ void __launch_bounds__(FC_THREADS, (KC <= 8) ? 6 : 2) filter_compact_stream_kernel(const float* __restrict__ x,
+                                                                           const float* __restrict__ logits, long long n,
+                                                                           int F, int K, int label, float thr,
+                                                                           uint64_t row_offset, int nsub,
+                                                                           float* __restrict__ x_out,
+                                                                           long long* __restrict__ idx_out,
+                                                                           long long capacity, unsigned long long* count) {
+  extern __shared__ __align__(16) float fc_sl[];      // [1024][K] logits of the current sub-block
+  __shared__ unsigned bals[FC_MAXSUB][FC_MAXJ][FC_THREADS / 32];
+  __shared__ int pref[FC_MAXSUB * FC_MAXJ * (FC_THREADS / 32)];
+  __shared__ int wsum[FC_THREADS / 32];
+  __shared__ unsigned long long base;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool vec2 = (F & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out)) & 7) == 0;
+  // ---- pass 1: decisions ----
+  for (int sb = 0; sb < nsub; ++sb) {
+    const long long row0 = ((long long)sb * gridDim.x + blockIdx.x) * FC_SUB_ROWS;
+    const int rows = (int)max(0ll, min((long long)FC_SUB_ROWS, n - row0));
+    if (rows > 0) {
+      const float* src = logits + row0 * K;
+      const long long nfl = (long long)rows * K;
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const long long n4 = nfl >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(fc_sl);
+        // batches of 4 independent 16-byte loads per thread (memory-level parallelism), then the stores
+        for (long long i0 = 0; i0 < n4; i0 += 4 * FC_THREADS) {
+          float4 t[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const long long i = i0 + q * FC_THREADS + tid;
+            if (i < n4) t[q] = __ldcs(s4 + i);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const long long i = i0 + q * FC_THREADS + tid;
+            if (i < n4) d4[i] = t[q];
+          }
+        }
+        for (long long i = (n4 << 2) + tid; i < nfl; i += FC_THREADS) fc_sl[i] = __ldcs(src + i);
+      } else {
+        for (long long i = tid; i < nfl; i += FC_THREADS) fc_sl[i] = __ldcs(src + i);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < FC_MAXJ; ++j) {
+      const int r = j * FC_THREADS + tid;
+      bool keep = false;
+      if (r < rows) keep = filter_decide_p<fc_pow2(KC), KC>([&](int k) { return fc_sl[r * KC + k]; }, KC, label, thr);
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) {
+        bals[sb][j][w] = bal;
+        pref[(sb * FC_MAXJ + j) * (FC_THREADS / 32) + w] = __popc(bal);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- exclusive scan of the per-(sub-block, j, warp) counts; one atomic per CTA ----
+  {
+    const int nent = nsub * FC_MAXJ * (FC_THREADS / 32);           // <= 1024
+    const int per = (nent + FC_THREADS - 1) / FC_THREADS;          // <= 4 consecutive entries per thread
+    int loc[4] = {0, 0, 0, 0}, s = 0;
+    for (int i = 0; i < per; ++i) {
+      const int e = tid * per + i;
+      loc[i] = e < nent ? pref[e] : 0;
+      s += loc[i];
+    }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int q = 0; q < w; ++q) woff += wsum[q];
+    int run = woff + incl - s;
+    for (int i = 0; i < per; ++i) {
+      const int e = tid * per + i;
+      if (e < nent) pref[e] = run;
+      run += loc[i];
+    }
+    if (tid == FC_THREADS - 1) base = run ? atomicAdd(count, (unsigned long long)run) : 0ull;
+    __syncthreads();
+  }
+  // ---- pass 2: copy the accepted rows ----
+  for (int sb = 0; sb < nsub; ++sb) {
+    const long long row0 = ((long long)sb * gridDim.x + blockIdx.x) * FC_SUB_ROWS;
+#pragma unroll
+    for (int j = 0; j < FC_MAXJ; ++j) {
+      const unsigned bal = bals[sb][j][w];
+      if ((bal >> lane) & 1u) {
+        const long long r = row0 + j * FC_THREADS + tid;
+        const long long pos = (long long)base + pref[(sb * FC_MAXJ + j) * (FC_THREADS / 32) + w] + __popc(bal & ((1u << lane) - 1u));
+        if (pos < capacity) {
+          const float* src = x + r * F;
+          float* dst = x_out + pos * F;
+          if (vec2) {
+            const float2* s2 = reinterpret_cast<const float2*>(src);
+            float2* d2 = reinterpret_cast<float2*>(dst);
+            for (int f = 0; f < (F >> 1); ++f) d2[f] = __ldcs(s2 + f);
+          } else {
+            for (int f = 0; f < F; ++f) dst[f] = __ldcs(src + f);
+          }
+          if (idx_out) idx_out[pos] = (long long)(row_offset + (uint64_t)r);
+        }
+      }
     }
   }
 }
