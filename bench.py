@@ -168,6 +168,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _finish(eng, world):
+    """Leave the process without running communicator destructors: with several ranks, tearing down the library's NCCL
+    communicator and torch's process group in arbitrary order has been seen to block for minutes after the result line
+    was printed.  Every rank has finished its GPU work here (barrier), so exiting is safe."""
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    eng.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
@@ -201,7 +217,7 @@ def run_ours(args):
         r = run_filter_leg(eng, dev, world, rank, peaks())
         if rank == 0:
             print(json.dumps(r), flush=True)
-        eng.close()
+        _finish(eng, world)
         return
     tabs = synth_class_tables(dev, ROWS_PER_CLASS, seed=0)
     seed = 1234
@@ -280,7 +296,7 @@ def run_ours(args):
         ms = timed(visit_resident, args.steps, warm)
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms / args.steps, "launches": eng.launch_count()}), flush=True)
-        eng.close()
+        _finish(eng, world)
         return
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -350,9 +366,7 @@ def run_ours(args):
         if filt:
             line["filter"] = filt
         print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(eng, world)
 
 
 

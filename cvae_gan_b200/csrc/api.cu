@@ -104,6 +104,7 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
 
 void cvg_destroy(CvgHandle* h) {
   if (!h) return;
+  nvl_destroy(h->e);
   comm_destroy(h->e);
   delete h;
 }
@@ -175,6 +176,17 @@ int cvg_comm_init(CvgHandle* h, const void* id128, int rank, int world_size) {
   H_OR_FAIL(h);
   if (world_size != h->e.cfg.world_size || rank != h->e.cfg.rank) CVG_FAIL("rank/world_size differ from cvg_create");
   return comm_init(h->e, id128, rank, world_size);
+}
+
+int cvg_nvl_local_handle(CvgHandle* h, void* out64) {
+  H_OR_FAIL(h);
+  if (!out64) CVG_FAIL("null argument");
+  return nvl_local_handle(h->e, out64);
+}
+int cvg_nvl_attach(CvgHandle* h, const void* handles) {
+  H_OR_FAIL(h);
+  if (!handles) CVG_FAIL("null argument");
+  return nvl_attach(h->e, handles);
 }
 
 int cvg_step_d(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "misc_kernels.cuh"
+#include "comm_nvl.cuh"
 
 typedef struct ncclComm* ncclComm_t;
 
@@ -90,6 +91,7 @@ struct Engine {
   int64_t launches = 0;
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
+  NvlState nvl;            // NVLink peer-memory all-reduce for the latency-bound exchanges (comm_nvl.cuh)
   int num_sms = 148;
   long long* tc_dbg = nullptr;   // development: device cycle counters of tc_eval_kernel (cvg_debug_tc_counters)
   bool use_tc = true;      // tensor-core chains (CVG_DISABLE_TC=1 forces the FFMA layer kernels)
@@ -127,6 +129,9 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
           int d_loop, int c_loop, int g_loop, int flags, float* loss_out, cudaStream_t st);
 void set_all_kernel_attributes();
 int run_adam(Engine& e, int net_mask, cudaStream_t st);
+int nvl_local_handle(Engine& e, void* out64);
+int nvl_attach(Engine& e, const void* handles);
+void nvl_destroy(Engine& e);
 int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st);
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st);
 

@@ -62,8 +62,76 @@ void comm_destroy(Engine& e) {
   e.comm = nullptr;
 }
 
+// ------------------------------------------------------------------------------------------------
+// NVLink peer-memory all-reduce (comm_nvl.cuh): staging buffer creation, CUDA IPC attach, launch
+// ------------------------------------------------------------------------------------------------
+int nvl_local_handle(Engine& e, void* out64) {
+  if (e.world <= 1 || e.world > NVL_MAX_WORLD) CVG_FAIL("cvg_nvl_local_handle: world_size must be in [2, 8]");
+  if (e.nvl.local) CVG_FAIL("cvg_nvl_local_handle: already created");
+  size_t slot = (size_t)2 * 2 * STAT_C * sizeof(double);            // BatchNorm moments [2 passes][2][STAT_C]
+  for (int net = 0; net < 4; ++net) {
+    const size_t b = (size_t)(e.lay[net].n_param + CVG_GRAD_TAIL) * sizeof(float);
+    if (b > slot) slot = b;
+  }
+  slot = (slot + 255) & ~(size_t)255;
+  const size_t total = nvl_total_bytes(e.world, slot);
+  CVG_CUDA(cudaMalloc(&e.nvl.local, total));     // communication staging only (never tensor memory)
+  CVG_CUDA(cudaMemset(e.nvl.local, 0, total));
+  CVG_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CVG_CUDA(cudaIpcGetMemHandle(&h, e.nvl.local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  memcpy(out64, &h, 64);
+  e.nvl.total_bytes = total;
+  NvlDev& d = e.nvl.dev;
+  d.world = e.world;
+  d.rank = e.rank;
+  d.slot_bytes = slot;
+  d.peer[e.rank] = (unsigned char*)e.nvl.local;
+  unsigned char* tail = (unsigned char*)e.nvl.local + 2 * (size_t)e.world * slot + 2 * (size_t)e.world * NVL_MAX_CTAS * sizeof(unsigned int);
+  d.epoch = (unsigned long long*)tail;
+  d.done = (unsigned int*)(tail + 64);
+  return 0;
+}
+
+int nvl_attach(Engine& e, const void* handles) {
+  if (!e.nvl.local) CVG_FAIL("cvg_nvl_attach: call cvg_nvl_local_handle first");
+  for (int p = 0; p < e.world; ++p) {
+    if (p == e.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)p * 64, 64);
+    void* ptr = nullptr;
+    CVG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    e.nvl.dev.peer[p] = (unsigned char*)ptr;
+    e.nvl.opened[p] = true;
+  }
+  e.nvl.on = true;
+  return 0;
+}
+
+void nvl_destroy(Engine& e) {
+  for (int p = 0; p < NVL_MAX_WORLD; ++p)
+    if (e.nvl.opened[p]) { cudaIpcCloseMemHandle(e.nvl.dev.peer[p]); e.nvl.opened[p] = false; }
+  if (e.nvl.local) cudaFree(e.nvl.local);
+  e.nvl.local = nullptr;
+  e.nvl.on = false;
+}
+
+template <typename T>
+static int nvl_all_reduce(Engine& e, T* p, int64_t n, cudaStream_t st) {
+  const size_t bytes = (size_t)n * sizeof(T);
+  int grid = (int)((bytes + 16383) / 16384);
+  if (grid < 1) grid = 1;
+  if (grid > NVL_MAX_CTAS) grid = NVL_MAX_CTAS;
+  nvl_allreduce_kernel<T><<<grid, NVL_THREADS, 0, st>>>(e.nvl.dev, p, (long long)n);
+  CVG_CUDA(cudaGetLastError());
+  e.launches++;
+  return 0;
+}
+
 int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st) {
   if (e.world <= 1) return 0;
+  if (e.nvl.on && (size_t)n * sizeof(float) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<float>(e, p, n, st);
   if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
   int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e.comm, st);
   if (r != 0) CVG_FAIL("ncclAllReduce(f32) failed");
@@ -71,6 +139,7 @@ int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st) {
 }
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st) {
   if (e.world <= 1) return 0;
+  if (e.nvl.on && (size_t)n * sizeof(double) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<double>(e, p, n, st);
   if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
   int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, e.comm, st);
   if (r != 0) CVG_FAIL("ncclAllReduce(f64) failed");

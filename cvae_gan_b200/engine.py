@@ -102,6 +102,17 @@ class Engine:
         dist.broadcast(uid, src=0)
         raw = bytes(uid.cpu().tolist())
         check(self.lib.cvg_comm_init(self.h, raw, self.rank, self.world_size))
+        # latency-bound exchanges over NVLink peer memory (CUDA IPC) instead of NCCL; CVG_DISABLE_NVL=1 keeps NCCL
+        import os
+        if dist.get_backend() == "nccl" and self.world_size <= 8 and os.environ.get("CVG_DISABLE_NVL") != "1":
+            hbuf = (C.c_uint8 * 64)()
+            check(self.lib.cvg_nvl_local_handle(self.h, hbuf))
+            mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=self.device)
+            allh = [torch.empty_like(mine) for _ in range(self.world_size)]
+            dist.all_gather(allh, mine)
+            raw_h = b"".join(bytes(t.cpu().tolist()) for t in allh)
+            check(self.lib.cvg_nvl_attach(self.h, raw_h))
+            dist.barrier()
 
     # ---- named views ---------------------------------------------------------------------------------
     def view(self, net: int, key: str, which: str = "params") -> torch.Tensor:

@@ -111,6 +111,13 @@ int64_t cvg_get_adam_step(const CvgHandle* h, int net);
 int cvg_comm_unique_id(void* out128);
 int cvg_comm_init(CvgHandle* h, const void* id128, int rank, int world_size);
 
+/* Optional, after cvg_comm_init on a single node with NVLink peer access: the latency-bound exchanges (BatchNorm
+ * moments, flat gradients) then use a one-shot all-reduce over peer memory instead of NCCL.  Every rank calls
+ * cvg_nvl_local_handle (creates its staging buffer, returns a 64-byte CUDA IPC handle), the host all-gathers the
+ * handles in rank order (world_size x 64 bytes), every rank calls cvg_nvl_attach, then the host runs a barrier. */
+int cvg_nvl_local_handle(CvgHandle* h, void* out64);
+int cvg_nvl_attach(CvgHandle* h, const void* handles);
+
 /* The three optimiser steps of one label visit.
  *   x_real   [B, F] row-major device pointer: the batch _get_target_samples returned (cvae_gan.py:108)
  *   label    the visit's target label
