@@ -134,6 +134,7 @@ int nvl_attach(Engine& e, const void* handles);
 void nvl_destroy(Engine& e);
 int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st);
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st);
+int comm_all_reduce_stats(Engine& e, double* p, int npass, int C, cudaStream_t st);
 
 // generate.cu
 int generate(Engine& e, int label, int64_t n, const float* z, uint64_t seed, uint64_t row_offset, int train_mode,

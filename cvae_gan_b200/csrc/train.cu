@@ -73,7 +73,7 @@ int nvl_local_handle(Engine& e, void* out64) {
     const size_t b = (size_t)(e.lay[net].n_param + CVG_GRAD_TAIL) * sizeof(float);
     if (b > slot) slot = b;
   }
-  slot = (slot + 255) & ~(size_t)255;
+  slot = 2 * ((slot + 255) & ~(size_t)255);      // LL packets: 8 bytes on the wire per 4-byte word
   const size_t total = nvl_total_bytes(e.world, slot);
   CVG_CUDA(cudaMalloc(&e.nvl.local, total));     // communication staging only (never tensor memory)
   CVG_CUDA(cudaMemset(e.nvl.local, 0, total));
@@ -117,21 +117,29 @@ void nvl_destroy(Engine& e) {
   e.nvl.on = false;
 }
 
+// `nseg` segments of `seg_len` elements, `seg_stride` apart
 template <typename T>
-static int nvl_all_reduce(Engine& e, T* p, int64_t n, cudaStream_t st) {
-  const size_t bytes = (size_t)n * sizeof(T);
-  int grid = (int)((bytes + 16383) / 16384);
+static int nvl_all_reduce(Engine& e, T* p, int64_t seg_len, int64_t seg_stride, int nseg, cudaStream_t st) {
+  const long long n = seg_len * nseg;
+  int grid = (int)((n + NVL_THREADS - 1) / NVL_THREADS);     // one element per thread where possible
   if (grid < 1) grid = 1;
   if (grid > NVL_MAX_CTAS) grid = NVL_MAX_CTAS;
-  nvl_allreduce_kernel<T><<<grid, NVL_THREADS, 0, st>>>(e.nvl.dev, p, (long long)n);
+  nvl_allreduce_kernel<T><<<grid, NVL_THREADS, 0, st>>>(e.nvl.dev, p, seg_len, seg_stride, nseg);
   CVG_CUDA(cudaGetLastError());
   e.launches++;
   return 0;
 }
 
+// BatchNorm moments: per pass a slot of 2 * STAT_C doubles holding [sum (C)][sum of squares (C)] contiguously
+int comm_all_reduce_stats(Engine& e, double* p, int npass, int C, cudaStream_t st) {
+  if (e.world <= 1) return 0;
+  if (e.nvl.on) return nvl_all_reduce<double>(e, p, 2 * C, 2 * STAT_C, npass, st);
+  return comm_all_reduce_f64(e, p, (int64_t)npass * 2 * STAT_C, st);
+}
+
 int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st) {
   if (e.world <= 1) return 0;
-  if (e.nvl.on && (size_t)n * sizeof(float) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<float>(e, p, n, st);
+  if (e.nvl.on && 2 * (size_t)n * sizeof(float) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<float>(e, p, n, n, 1, st);
   if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
   int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e.comm, st);
   if (r != 0) CVG_FAIL("ncclAllReduce(f32) failed");
@@ -139,7 +147,7 @@ int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st) {
 }
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st) {
   if (e.world <= 1) return 0;
-  if (e.nvl.on && (size_t)n * sizeof(double) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<double>(e, p, n, st);
+  if (e.nvl.on && 2 * (size_t)n * sizeof(double) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<double>(e, p, n, n, 1, st);
   if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
   int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, e.comm, st);
   if (r != 0) CVG_FAIL("ncclAllReduce(f64) failed");
@@ -258,9 +266,9 @@ static DwArgs base_dw(const Engine& e, int M, float Bg_bn, int npass) {
   return g;
 }
 
-static int sync_stats(Engine& e, double* p, int npass, bool local_bn, cudaStream_t st) {
+static int sync_stats(Engine& e, double* p, int npass, int C, bool local_bn, cudaStream_t st) {
   if (e.world <= 1 || local_bn) return 0;
-  return comm_all_reduce_f64(e, p, (int64_t)npass * 2 * STAT_C, st);
+  return comm_all_reduce_stats(e, p, npass, C, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,7 +352,7 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
       g.sY = (long long)e.F * ld;
     }
     CVG_TRY(launch_mn(e, true, g, st));
-    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 2, local_bn, st));
+    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 2, p.out, local_bn, st));
   }
   return 0;
 }
@@ -387,7 +395,7 @@ int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn
       }
     }
     CVG_TRY(launch_mn(e, true, g, st));
-    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 1, local_bn, st));
+    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 1, p.out, local_bn, st));
   }
   return 0;
 }
@@ -708,7 +716,7 @@ static int bwd_bn_net(Engine& e, const BnNetBwd& b, int M, float Bg_bn, float kl
       g.ostats = bst_of(e, net, l - 1);
       g.sostats = 2 * STAT_C;
       CVG_TRY(launch_mn(e, false, g, st));
-      CVG_TRY(sync_stats(e, bst_of(e, net, l - 1), b.npass, local_bn, st));
+      CVG_TRY(sync_stats(e, bst_of(e, net, l - 1), b.npass, pp.out, local_bn, st));
     } else if (b.want_first_dx) {
       GemmArgs g = base_args(e, M, Bg_bn, b.npass);
       g.only_pass = 0;
