@@ -14,8 +14,8 @@
 //                     4-byte scattered stores are bank-conflict free.
 //   * accumulators: fp32 in TMEM (feature = lane, row = column); the epilogue reads them with tcgen05.ld, applies
 //     bias / BatchNorm(eval) / LayerNorm / activation and writes the next layer's operand in place.
-//   * warp roles: warps 0-7 = epilogue (two warps per 32-lane TMEM quadrant, 32 of the 64 rows each), warp 8 = weight
-//     producer + MMA issuer.
+//   * warp roles: warps 0-7 = epilogue (two warps per 32-lane TMEM quadrant, 32 of the 64 rows each), warp 8 = MMA
+//     issuer, warp 9 = weight producer (bulk copies).
 //   * z comes from Philox keyed by the GLOBAL row index (same stream as fill_noise_kernel), the filter decision is
 //     filter_decide() (bit-exact torch softmax semantics), accepted rows are compacted with one atomic per tile.
 #include "engine.cuh"
@@ -44,7 +44,7 @@ constexpr int TC_STAGE_BYTES = 2 * TC_KC * 128 * 4;  // hi + lo chunk of a 128-r
 constexpr int TC_MAXF = 64;                          // widest generator output kept for compaction
 constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane quadrant, 32 of the 64 rows each
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_THREADS = TC_EPI_THREADS + 32;
+constexpr int TC_THREADS = TC_EPI_THREADS + 64;      // + MMA issuer warp + weight producer warp
 constexpr int TC_LN_PITCH = TC_ROWS + 1;
 
 enum { TEPI_BN_LRELU = 0, TEPI_RELU = 1, TEPI_LN_RELU = 2, TEPI_SIGMOID_X = 3, TEPI_LOGITS = 4, TEPI_OUT = 5 };
@@ -195,30 +195,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
   const uint32_t tmem = __shfl_sync(0xffffffffu, S->tmem_slot, 0);   // warp-uniform for the compiler
 
   if (warp == TC_EPI_WARPS) {
-    // ===================== weight producer + MMA issuer =====================
+    // ===================== MMA issuer =====================
     long long t_act = 0, t_full = 0, t_empty = 0, t_all = 0, c0 = 0, c1 = 0, t_issue = 0, t_lay[TC_MAX_LAYERS] = {0, 0, 0, 0, 0, 0, 0, 0};
     TC_CLK(t_all);
-    int cpt = 0;
-    for (int l = 0; l < a.nl; ++l) cpt += a.L[l].n_mtiles * a.L[l].n_kchunks;
     long long my_tiles = 0;
     if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
-    const unsigned long long total = (unsigned long long)my_tiles * cpt;
-    unsigned long long g_load = 0, g = 0;
-    int ll = 0, lmt = 0, lkc = 0;      // load iterator
-    auto issue_load = [&]() {
-      const TcLayer& Lr = a.L[ll];
-      const int s = (int)(g_load % TC_STAGES);
-      const int kc_len = min(TC_KC, Lr.K - lkc * TC_KC);
-      const uint32_t bytes = 2u * kc_len * Lr.M * 4u;
-      const float* src = a.wprep + Lr.w_off + (size_t)lmt * Lr.K * Lr.M * 2 + (size_t)lkc * TC_KC * Lr.M * 2;
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&S->full[s], bytes);
-        bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, src, bytes, &S->full[s]);
-      }
-      ++g_load;
-      if (++lkc == Lr.n_kchunks) { lkc = 0; if (++lmt == Lr.n_mtiles) { lmt = 0; if (++ll == a.nl) ll = 0; } }
-    };
-    for (int i = 0; i < TC_STAGES && g_load < total; ++i) issue_load();
+    unsigned long long g = 0;
     unsigned long long n_act = 0;
     const uint32_t b_hi_a = smem_u32(b_hi), b_lo_a = smem_u32(b_lo), st_a = smem_u32(stages);
     for (long long t = 0; t < my_tiles; ++t) {
@@ -234,13 +216,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
         const uint32_t a_lbo = (uint32_t)Lr.M * 16u;
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
           for (int kc = 0; kc < Lr.n_kchunks; ++kc) {
-            if (g >= 2 && g_load < total) {   // refill the stage chunk g-2 used: chunk g-1's MMAs stay in flight
-              TC_CLK(c0);
-              mbar_wait(&S->empty[(g - 2) % TC_STAGES], (uint32_t)(((g - 2) / TC_STAGES) & 1));
-              TC_CLK(c1);
-              t_empty += c1 - c0;
-              issue_load();
-            }
             const int s = (int)(g % TC_STAGES);
             TC_CLK(c0);
             mbar_wait(&S->full[s], (uint32_t)((g / TC_STAGES) & 1));
@@ -263,7 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
                 mma_tf32(d, dah, dbh, idesc, true);
                 dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
               }
-              mma_commit(&S->empty[s]);
+              mma_commit(&S->empty[s]);     // frees the weight stage for the producer warp
               if (mt == Lr.n_mtiles - 1 && kc == Lr.n_kchunks - 1) mma_commit(&S->acc_full);
             }
             __syncwarp();
@@ -283,6 +258,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
       atomicAdd((unsigned long long*)a.dbg + 3, (unsigned long long)t_all);
       atomicAdd((unsigned long long*)a.dbg + 7, (unsigned long long)t_issue);
       for (int l = 0; l < a.nl; ++l) atomicAdd((unsigned long long*)a.dbg + 8 + l, (unsigned long long)t_lay[l]);
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ===================== weight producer: the chunk sequence of a tile is static, it just runs ahead =====================
+    int cpt = 0;
+    for (int l = 0; l < a.nl; ++l) cpt += a.L[l].n_mtiles * a.L[l].n_kchunks;
+    long long my_tiles = 0;
+    if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
+    const unsigned long long total = (unsigned long long)my_tiles * cpt;
+    int ll = 0, lmt = 0, lkc = 0;
+    for (unsigned long long gl = 0; gl < total; ++gl) {
+      const int s = (int)(gl % TC_STAGES);
+      if (gl >= TC_STAGES) mbar_wait(&S->empty[s], (uint32_t)(((gl / TC_STAGES) - 1) & 1));
+      const TcLayer& Lr = a.L[ll];
+      const int kc_len = min(TC_KC, Lr.K - lkc * TC_KC);
+      const uint32_t bytes = 2u * kc_len * Lr.M * 4u;
+      const float* src = a.wprep + Lr.w_off + (size_t)lmt * Lr.K * Lr.M * 2 + (size_t)lkc * TC_KC * Lr.M * 2;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&S->full[s], bytes);
+        bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, src, bytes, &S->full[s]);
+      }
+      __syncwarp();
+      if (++lkc == Lr.n_kchunks) { lkc = 0; if (++lmt == Lr.n_mtiles) { lmt = 0; if (++ll == a.nl) ll = 0; } }
     }
   } else {
     // ============== epilogue warps: thread = (output feature = TMEM lane, half of the 64 rows) ==============
@@ -327,15 +324,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
       for (int l = 0; l < a.nl; ++l) {
         const TcLayer& Lr = a.L[l];
         const int next_K = (l + 1 < a.nl) ? a.L[l + 1].K : 0;
+        const int f_local = (Lr.M == 128) ? (q * 32 + lane) : (q * 16 + lane);
+        const bool lane_ok = (Lr.M == 128) || (lane < 16);
+        const float* cst = a.consts + Lr.c_off;
+        // per-feature constants of both m-tiles are fetched while the MMAs are still running
+        float cpre[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int f = mt * Lr.M + f_local;
+          const bool v = mt < Lr.n_mtiles && lane_ok && f < Lr.N;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cpre[mt][j] = v ? __ldg(cst + j * Lr.Npad + f) : 0.f;
+        }
         TC_CLK(c0);
         mbar_wait(&S->acc_full, (uint32_t)(n_acc & 1));
         TC_CLK(c1);
         t_acc += c1 - c0;
         ++n_acc;
         tc_fence_after_sync();
-        const int f_local = (Lr.M == 128) ? (q * 32 + lane) : (q * 16 + lane);
-        const bool lane_ok = (Lr.M == 128) || (lane < 16);
-        const float* cst = a.consts + Lr.c_off;
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
           float v[32];
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * TC_ROWS + mbase);
@@ -343,8 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
           tmem_wait_ld();
           const int f = mt * Lr.M + f_local;
           const bool valid = lane_ok && f < Lr.N;
-          const float c0f = valid ? cst[f] : 0.f, c1f = valid ? cst[Lr.Npad + f] : 0.f;
-          const float c2f = valid ? cst[2 * Lr.Npad + f] : 0.f, c3f = valid ? cst[3 * Lr.Npad + f] : 0.f;
+          const float c0f = cpre[mt & 1][0], c1f = cpre[mt & 1][1], c2f = cpre[mt & 1][2], c3f = cpre[mt & 1][3];
           const uint32_t boff = (uint32_t)(f >> 2) * TC_LBO_B + (uint32_t)(f & 3) * 4 + (uint32_t)mbase * 16;
           if (Lr.epi == TEPI_BN_LRELU) {
             if (valid) {
