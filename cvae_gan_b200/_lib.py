@@ -65,6 +65,7 @@ SIGNATURES = {
     "cvg_step_d": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _I, _P, _P]),
     "cvg_step_c": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _I, _P, _P]),
     "cvg_step_g": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _F, _I, _P, _P]),
+    "cvg_step_classifier": (_I, [_P, _P, _P, _I, C.POINTER(CvgNoise), _U64, _U64, _F, _F, _F, _F, _I, _P, _P]),
     "cvg_visit": (_I, [_P, _I, _I, _I64, _P, _I64, _P, _I, _I, _I, _I, _P, _P]),
     "cvg_ctl_set": (_I, [_P, _U64, _U64, _I, _F, _I, _P]),
     "cvg_adam": (_I, [_P, _I, _P]),

@@ -2,7 +2,7 @@
 Unlike the reference, importing this package has no filesystem side effects."""
 import torch
 
-from . import gan_config  # noqa: F401
+from . import classifier_config, gan_config  # noqa: F401
 
 seed = 0
 

@@ -218,6 +218,17 @@ int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoi
   return step_g(h->e, x_real, label, B, noise, rng, flags, loss_out, (cudaStream_t)stream);
 }
 
+int cvg_step_classifier(CvgHandle* h, const float* x, const int64_t* labels, int B, const CvgNoise* noise, uint64_t seed,
+                        uint64_t counter, float lr, float beta1, float beta2, float eps, int flags, float* loss_out,
+                        void* stream) {
+  H_OR_FAIL(h);
+  if (!x || !labels) CVG_FAIL("cvg_step_classifier: null argument");
+  StepRng rng;
+  rng.seed = seed; rng.counter = counter;
+  AdamOverride ov{lr, beta1, beta2, eps};
+  return step_classifier(h->e, x, (const long long*)labels, B, noise, rng, ov, flags, loss_out, (cudaStream_t)stream);
+}
+
 int cvg_visit(CvgHandle* h, int label, int B_local, int64_t B_global, const float* class_rows, int64_t n_rows,
               const float* x_batches, int d_loop, int c_loop, int g_loop, int flags, float* loss_out, void* stream) {
   H_OR_FAIL(h);

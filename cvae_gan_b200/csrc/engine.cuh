@@ -128,7 +128,12 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* noi
 int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows, int64_t n_rows, const float* x_batches,
           int d_loop, int c_loop, int g_loop, int flags, float* loss_out, cudaStream_t st);
 void set_all_kernel_attributes();
-int run_adam(Engine& e, int net_mask, cudaStream_t st);
+struct AdamOverride {
+  float lr, beta1, beta2, eps;
+};
+int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov = nullptr);
+int step_classifier(Engine& e, const float* x, const long long* labels, int B, const CvgNoise* noise, const StepRng& rng,
+                    const AdamOverride& ov, int flags, float* loss_out, cudaStream_t st);
 int nvl_local_handle(Engine& e, void* out64);
 int nvl_attach(Engine& e, const void* handles);
 void nvl_destroy(Engine& e);

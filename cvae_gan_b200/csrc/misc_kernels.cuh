@@ -191,6 +191,7 @@ struct CeArgs {
   float coef;                          // 1/Bg; multiplied by ctl->lambda_class when `ctl` is set (generator step)
   const StepCtl* ctl;
   double* loss;                        // [npass] accumulators
+  const long long* labels = nullptr;   // per-row targets (downstream Classifier.fit); null -> the shared `label`
 };
 
 __global__ void ce_kernel(const CeArgs g) {
@@ -204,12 +205,13 @@ __global__ void ce_kernel(const CeArgs g) {
     float s = 0.f;
     for (int k = 0; k < g.K; ++k) s += expf(l[(size_t)k * g.ld] - mx);
     const float lse = logf(s);
-    nll = -(double)(l[(size_t)g.label * g.ld] - mx - lse);
+    const int tgt = g.labels ? (int)g.labels[m] : g.label;
+    nll = -(double)(l[(size_t)tgt * g.ld] - mx - lse);
     float* d = g.dlogits + (long long)pass * g.sd + m;
     const float coef = g.ctl ? g.coef * g.ctl->lambda_class : g.coef;
     for (int k = 0; k < g.K; ++k) {
       const float p = expf(l[(size_t)k * g.ld] - mx - lse);
-      d[(size_t)k * g.ld] = (p - (k == g.label ? 1.f : 0.f)) * coef;
+      d[(size_t)k * g.ld] = (p - (k == tgt ? 1.f : 0.f)) * coef;
     }
   }
   nll = warp_sum_d(nll);

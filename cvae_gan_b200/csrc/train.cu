@@ -774,12 +774,12 @@ static float net_lr(const Engine& e, int net) {
   return e.cfg.g_lr;
 }
 
-int run_adam(Engine& e, int net_mask, cudaStream_t st) {
+int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov) {
   AdamArgs a;
   a.nseg = 0;
-  a.b1 = e.cfg.adam_beta1;
-  a.b2 = e.cfg.adam_beta2;
-  a.eps = e.cfg.adam_eps;
+  a.b1 = ov ? ov->beta1 : e.cfg.adam_beta1;
+  a.b2 = ov ? ov->beta2 : e.cfg.adam_beta2;
+  a.eps = ov ? ov->eps : e.cfg.adam_eps;
   a.clear_grad = 1;
   long long nmax = 0;
   for (int net = 0; net < 4; ++net) {
@@ -788,7 +788,7 @@ int run_adam(Engine& e, int net_mask, cudaStream_t st) {
     AdamSeg& s = a.seg[a.nseg++];
     s.p = e.buf[net].params; s.g = e.buf[net].grads; s.m = e.buf[net].m; s.v = e.buf[net].v;
     s.n = e.lay[net].n_param;
-    s.lr = net_lr(e, net);
+    s.lr = ov ? ov->lr : net_lr(e, net);
     s.t_prev = &e.ws.ctl->adam_t[net];
     if (s.n > nmax) nmax = s.n;
   }
@@ -803,7 +803,8 @@ int run_adam(Engine& e, int net_mask, cudaStream_t st) {
 }
 
 // pack local loss sums into the first net's gradient tail, all-reduce gradients (+tail), Adam, unpack
-static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, float* loss_out, cudaStream_t st) {
+static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, float* loss_out, cudaStream_t st,
+                       const AdamOverride* ov = nullptr) {
   int first = -1;
   for (int net = 0; net < 4; ++net)
     if (net_mask & (1 << net)) { first = net; break; }
@@ -817,7 +818,7 @@ static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, floa
     unpack_loss_kernel<<<1, 32, 0, st>>>(tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, 1, tail);
     CVG_LAUNCH_CHECK();
   }
-  if (!(flags & CVG_STEP_NO_UPDATE)) CVG_TRY(run_adam(e, net_mask, st));
+  if (!(flags & CVG_STEP_NO_UPDATE)) CVG_TRY(run_adam(e, net_mask, st, ov));
   return 0;
 }
 
@@ -931,6 +932,42 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_LAUNCH_CHECK();
   CVG_TRY(bwd_classifier(e, w.xT, sx, 2, B, true, false, false, st));
   return finish_step(e, 1 << C, 1, B, flags, loss_out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// downstream fine-tuning step of the classifier network (classifier.py:24-45): logits = C(x) in train mode (dropout),
+// loss = mean cross_entropy(logits, labels) with PER-ROW labels, Adam with the caller's hyper-parameters
+// ------------------------------------------------------------------------------------------------
+int step_classifier(Engine& e, const float* x, const long long* labels, int B, const CvgNoise* nz, const StepRng& rng,
+                    const AdamOverride& ov, int flags, float* loss_out, cudaStream_t st) {
+  if (!e.ws_base) CVG_FAIL("workspace not bound");
+  if (B < 1 || B > e.ws.rows_cap) CVG_FAIL("batch size exceeds max_batch");
+  CVG_TRY(begin_step(e, rng, false, st));
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const int C = CVG_NET_CLASSIFIER;
+  const float Bg = (float)B * (float)e.world;
+  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  FillArgs f;
+  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
+  f.ctl = w.ctl; f.counter_off = rng.off;
+  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
+  add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
+  CVG_TRY(launch_fill(e, f, st));
+  CVG_TRY(stage_x(e, x, B, st));
+  CVG_TRY(fwd_classifier(e, w.xT, 0, 1, true, B, st));
+  CeArgs c;
+  c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = 0; c.labels = labels;
+  c.logits = w.c_logit; c.sl = (long long)e.K * ld;
+  c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
+  c.coef = 1.0f / Bg;
+  c.ctl = nullptr;
+  c.loss = w.loss + L_CE0;
+  ce_kernel<<<dim3((B + 127) / 128, 1), 128, 0, st>>>(c);
+  CVG_LAUNCH_CHECK();
+  CVG_TRY(bwd_classifier(e, w.xT, 0, 1, B, true, false, false, st));
+  return finish_step(e, 1 << C, 1, B, flags, loss_out, st, &ov);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -182,6 +182,24 @@ class Engine:
                                   flags, _ptr(out), _stream()))
         return out
 
+    def step_classifier(self, x, labels, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, noise=None, seed=0, counter=0, flags=0,
+                        loss_out=None):
+        """One fine-tuning step of the classifier on (x[B,F], labels[B]) - classifier.py:34-44."""
+        x = self._x(x)
+        labels = labels.to(self.device, torch.int64).contiguous()
+        keep = [x, labels]
+        out = self.loss_buf if loss_out is None else loss_out
+        check(self.lib.cvg_step_classifier(self.h, _ptr(x), _ptr(labels), x.size(0), self._noise(noise, keep), seed, counter,
+                                           float(lr), float(betas[0]), float(betas[1]), float(eps), flags, _ptr(out),
+                                           _stream()))
+        return out
+
+    def reset_adam(self, net: int):
+        """Fresh torch.optim.Adam state for one network (zero moments, step 0)."""
+        self.adam_m[net].zero_()
+        self.adam_v[net].zero_()
+        self.set_adam_step(net, 0)
+
     def step_g(self, x_real, label: int, lambda_class: float, noise=None, seed=0, counter=0, flags=0, loss_out=None):
         x = self._x(x_real)
         keep = [x]

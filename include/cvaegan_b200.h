@@ -135,6 +135,16 @@ int cvg_step_c(CvgHandle* h, const float* x_real, int label, int B, const CvgNoi
 int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
                uint64_t counter, float lambda_class_now, int flags, float* loss_out, void* stream);
 
+/* One optimiser step of the DOWNSTREAM classifier fine-tuning (/root/reference/src/classifier.py:24-45, used by
+ * scripts/train_cvae_gan.py:143-165 on the augmented set): logits = C(x) in train mode, loss = mean
+ * cross_entropy(logits, labels) with per-row labels (device int64[B], values in [0, label_num)), backward, Adam with the
+ * caller's hyper-parameters (classifier_config.lr = 1e-3, torch defaults 0.9 / 0.999 / 1e-8) on the classifier's
+ * Adam state (reset it with cvg_set_adam_step + zeroed moment buffers for a fresh optimiser).  Only c_mask1 / c_mask2
+ * ([1, B, H]) of `noise` are used.  loss_out: device float[4] = {loss, loss, 0, 0}. */
+int cvg_step_classifier(CvgHandle* h, const float* x, const int64_t* labels, int B, const CvgNoise* noise, uint64_t seed,
+                        uint64_t counter, float lr, float beta1, float beta2, float eps, int flags, float* loss_out,
+                        void* stream);
+
 /* One label visit of the training loop (cvae_gan.py:102-216): d_loop critic steps, c_loop classifier steps and
  * g_loop encoder/generator steps, each on a freshly drawn batch - either drawn on the device from class_rows
  * [n_rows, F] (_get_target_samples) or taken from x_batches [d_loop+c_loop+g_loop, B_local, F] when that is

@@ -1,0 +1,98 @@
+"""Downstream classifier fine-tuning on the CUDA engine (cvg_step_classifier, cvae_gan_b200/classifier.py) against the
+oracle restatement of /root/reference/src/classifier.py (itself pinned to the unmodified reference by ref_clf.npz)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import classifier_oracle as CO  # noqa: E402
+from oracle import cvae_gan_oracle as O  # noqa: E402
+from tests import parity as P  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+STEP_NO_UPDATE = 1
+
+
+def _masks(B, g):
+    m1 = (torch.rand(1, B, 256, generator=g) < 0.7).to(torch.uint8)
+    m2 = (torch.rand(1, B, 128, generator=g) < 0.7).to(torch.uint8)
+    inj = O.InjectedNoise()
+    inj.push("c_mask1", m1[0].float())
+    inj.push("c_mask2", m2[0].float())
+    return inj, {"c_mask1": m1.cuda(), "c_mask2": m2.cuda()}
+
+
+@pytest.mark.parametrize("F_,K,B", [(10, 5, 64), (10, 5, 37), (30, 5, 64)])
+def test_classifier_step_loss_grads_and_adam(F_, K, B):
+    orc, eng, g = P.make_pair(F_, K, 64, seed=70 + B)
+    sd = {k: v.detach().clone() for k, v in orc.sd["classifier"].items()}
+    x = torch.rand(B, F_, generator=g)
+    y = torch.randint(0, K, (B,), generator=g)
+    # gradients (no update)
+    inj, dev = _masks(B, g)
+    loss_ref, grads = CO.classifier_step(sd, x, y, inj, None)
+    out = eng.step_classifier(x.cuda(), y.cuda(), noise=dev, flags=STEP_NO_UPDATE)
+    assert abs(float(out[0]) - loss_ref) <= 1e-3 * abs(loss_ref) + 1e-6
+    for key, g_ref in zip(CO.KEYS, grads):
+        ok, worst, mx = P.close(eng.view(3, key, "grads"), g_ref, atol_abs=1e-9)
+        assert ok, (key, worst, mx)
+    # three updates with a fresh Adam(lr 1e-3, betas 0.9 / 0.999)
+    eng.zero_grads()
+    eng.reset_adam(3)
+    adam = O.OracleAdam([sd[k] for k in CO.KEYS], 1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for _ in range(3):
+        xb = torch.rand(B, F_, generator=g)
+        yb = torch.randint(0, K, (B,), generator=g)
+        inj, dev = _masks(B, g)
+        CO.classifier_step(sd, xb, yb, inj, adam)
+        eng.step_classifier(xb.cuda(), yb.cuda(), lr=1e-3, noise=dev)
+    for key in CO.KEYS:
+        ok, worst, mx = P.close(eng.view(3, key), sd[key])
+        assert ok, (key, worst, mx)
+    assert eng.get_adam_step(3) == 3
+    eng.close()
+
+
+def test_classifier_fit_f1_within_half_a_point(golden_dir):
+    """Classifier.fit / .test through the product class: macro F1 within 0.5 points of the CPU restatement trained with the
+    same recipe (different dropout streams, so the comparison is statistical - north_star tolerance)."""
+    import cvae_gan_b200 as pkg
+    gz = np.load(os.path.join(golden_dir, "ref_clf.npz"))
+    F_, K = int(gz["meta"][0]), int(gz["meta"][1])
+    from sklearn.datasets import make_blobs
+    from sklearn.preprocessing import minmax_scale
+    x, y = make_blobs(n_samples=[500, 400, 200, 120, 300], n_features=F_, centers=None, cluster_std=1.5, random_state=11)
+    x = minmax_scale(x).astype(np.float32)
+    perm = np.random.RandomState(1).permutation(len(y))
+    x, y = torch.from_numpy(x[perm]), torch.from_numpy(y[perm].astype(np.int64))
+    xtr, ytr, xte, yte = x[:1000], y[:1000], x[1000:], y[1000:]
+    epochs, lr, bs = 12, 1e-3, 64
+    # CPU restatement from the golden start state
+    sd = {k[len("init/"):]: torch.from_numpy(gz[k]).clone() for k in gz.files if k.startswith("init/")}
+    torch.manual_seed(5)
+    CO.fit(sd, xtr, ytr, epochs, lr, bs)
+    m_ref, _ = CO.macro_metrics(yte, CO.predict(sd, xte), K)
+    # product path
+    pkg.datasets.feature_num, pkg.datasets.label_num = F_, K
+    pkg.datasets.tr_samples, pkg.datasets.tr_labels = xtr, ytr
+    pkg.datasets.te_samples, pkg.datasets.te_labels = xte, yte
+    cc = pkg.config.classifier_config
+    old = (cc.epochs, cc.lr, cc.batch_size)
+    cc.epochs, cc.lr, cc.batch_size = epochs, lr, bs
+    try:
+        torch.manual_seed(5)
+        clf = pkg.Classifier("t")
+        clf.model.load_state_dict({k[len("init/"):]: torch.from_numpy(gz[k]) for k in gz.files if k.startswith("init/")})
+        clf.fit(pkg.datasets.TrDataset())
+        clf.test(pkg.datasets.TeDataset())
+    finally:
+        cc.epochs, cc.lr, cc.batch_size = old
+    assert abs(clf.metrics["F1"] - m_ref["F1"]) <= 0.005, (clf.metrics, m_ref)
+    assert clf.confusion_matrix.sum() == len(yte)
+    clf.binary_test(pkg.datasets.TeDataset())
+    assert 0.0 <= clf.metrics["F1"] <= 1.0

@@ -136,3 +136,26 @@ def test_patience_scan_equals_literal_loop():
             if k == 0:
                 patience -= 1
         assert O.patience_scan(keep, num) == (pos, result)
+
+
+# ---------------------------------------------------------------------------------------------------
+# downstream classifier (classifier.py): oracle/classifier_oracle.py against the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+def test_classifier_fit_and_test_match_reference(golden_dir):
+    import os
+    import numpy as np
+    from oracle import classifier_oracle as CO
+    gz = np.load(os.path.join(golden_dir, "ref_clf.npz"))
+    F_, K, epochs, bs, seed = [int(v) for v in gz["meta"]]
+    sd = {k[len("init/"):]: torch.from_numpy(gz[k]).clone() for k in gz.files if k.startswith("init/")}
+    xtr, ytr = torch.from_numpy(gz["xtr"]), torch.from_numpy(gz["ytr"])
+    xte, yte = torch.from_numpy(gz["xte"]), torch.from_numpy(gz["yte"])
+    torch.set_num_threads(1)
+    torch.manual_seed(seed)
+    CO.fit(sd, xtr, ytr, epochs, float(gz["lr"][0]), bs)
+    for k in sd:
+        ref = torch.from_numpy(gz["final/" + k])
+        assert torch.allclose(sd[k], ref, rtol=2e-4, atol=2e-6), (k, float((sd[k] - ref).abs().max()))
+    m, cm = CO.macro_metrics(yte, CO.predict(sd, xte), K)
+    assert np.array_equal(cm.numpy().astype(np.int64), gz["confusion"])
+    assert np.allclose([m["Precision"], m["Recall"], m["F1"]], gz["metrics"], atol=1e-12)
