@@ -753,12 +753,20 @@ __global__ void __launch_bounds__(FC_THREADS, (KC <= 8) ? 6 : 2) filter_compact_
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const bool vec2 = (F & 1) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out)) & 7) == 0;
   // ---- pass 1: decisions ----
+  // A cheap exact screen first (a row whose label logit trails the maximum by more than 2e-6 cannot win, see
+  // filter_decide_p); the survivors are compacted into a shared list and only they pay for the softmax arithmetic -
+  // without the compaction a warp runs the expensive path as soon as ONE of its 32 rows survives.
+  __shared__ unsigned short surv[FC_SUB_ROWS];
+  __shared__ unsigned int bitmap[FC_SUB_ROWS / 32];
+  __shared__ int nsurv;
   for (int sb = 0; sb < nsub; ++sb) {
     const long long row0 = ((long long)sb * gridDim.x + blockIdx.x) * FC_SUB_ROWS;
     const int rows = (int)max(0ll, min((long long)FC_SUB_ROWS, n - row0));
+    if (tid < FC_SUB_ROWS / 32) bitmap[tid] = 0u;
+    if (tid == 0) nsurv = 0;
     if (rows > 0) {
-      const float* src = logits + row0 * K;
-      const long long nfl = (long long)rows * K;
+      const float* src = logits + row0 * KC;
+      const long long nfl = (long long)rows * KC;
       if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const long long n4 = nfl >> 2;
         const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -786,10 +794,31 @@ __global__ void __launch_bounds__(FC_THREADS, (KC <= 8) ? 6 : 2) filter_compact_
 #pragma unroll
     for (int j = 0; j < FC_MAXJ; ++j) {
       const int r = j * FC_THREADS + tid;
-      bool keep = false;
-      if (r < rows) keep = filter_decide_p<fc_pow2(KC), KC>([&](int k) { return fc_sl[r * KC + k]; }, KC, label, thr);
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (lane == 0) {
+      bool cand = false;
+      if (r < rows) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) mx = fmaxf(mx, fc_sl[r * KC + k]);
+        cand = !(mx - fc_sl[r * KC + label] > 2e-6f);      // NaNs stay candidates; the full decision rejects them
+      }
+      const unsigned cb = __ballot_sync(0xffffffffu, cand);
+      int wbase = 0;
+      if (lane == 0 && cb) wbase = atomicAdd(&nsurv, __popc(cb));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (cand) surv[wbase + __popc(cb & ((1u << lane) - 1u))] = (unsigned short)r;
+    }
+    __syncthreads();
+    for (int i = tid; i < nsurv; i += FC_THREADS) {
+      const int r = surv[i];
+      if (filter_decide_p<fc_pow2(KC), KC>([&](int k) { return fc_sl[r * KC + k]; }, KC, label, thr))
+        atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+    }
+    __syncthreads();
+    // row j * 256 + tid sits in bit `lane` of bitmap word j * 8 + w: exactly the ballot layout
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < FC_MAXJ; ++j) {
+        const unsigned bal = bitmap[j * (FC_THREADS / 32) + w];
         bals[sb][j][w] = bal;
         pref[(sb * FC_MAXJ + j) * (FC_THREADS / 32) + w] = __popc(bal);
       }
@@ -840,9 +869,26 @@ __global__ void __launch_bounds__(FC_THREADS, (KC <= 8) ? 6 : 2) filter_compact_
           if (vec2) {
             const float2* s2 = reinterpret_cast<const float2*>(src);
             float2* d2 = reinterpret_cast<float2*>(dst);
-            for (int f = 0; f < (F >> 1); ++f) d2[f] = __ldcs(s2 + f);
+            // all loads of a batch are in flight before the first store (a row costs one memory round trip, not F/2)
+            for (int f0 = 0; f0 < (F >> 1); f0 += 8) {
+              float2 t[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (f0 + q < (F >> 1)) t[q] = __ldcs(s2 + f0 + q);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (f0 + q < (F >> 1)) d2[f0 + q] = t[q];
+            }
           } else {
-            for (int f = 0; f < F; ++f) dst[f] = __ldcs(src + f);
+            for (int f0 = 0; f0 < F; f0 += 8) {
+              float t[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (f0 + q < F) t[q] = __ldcs(src + f0 + q);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (f0 + q < F) dst[f0 + q] = t[q];
+            }
           }
           if (idx_out) idx_out[pos] = (long long)(row_offset + (uint64_t)r);
         }

@@ -41,7 +41,8 @@ if what == "filter" and len(sys.argv) > 3:
         x_out = torch.empty(n, F_, device=dev); idx_out = torch.empty(n, dtype=torch.int64, device=dev)
         e0.record()
         for _ in range(10):
+            eng.count_buf.zero_()
             check(eng.lib.cvg_filter_compact(_ptr(x), _ptr(lg), n, F_, K_, 0, float(thr), 0, _ptr(x_out), _ptr(idx_out), n, _ptr(eng.count_buf), _stream()))
         e1.record()
         torch.cuda.synchronize()
-        print("thr", thr, "ms", e0.elapsed_time(e1) / 10, "accepted/10", int(eng.count_buf.item()) // 13)
+        print("thr", thr, "ms", e0.elapsed_time(e1) / 10, "accepted", int(eng.count_buf.item()))
