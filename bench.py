@@ -431,14 +431,14 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
     accepted = int(eng.count_buf.item())
     dbg = None
     if os.environ.get("CVG_TC_DBG") == "1":       # development: per-role cycle split of the fused kernel
-        cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(32, dtype=torch.int64, device=dev)
         check(eng.lib.cvg_debug_tc_counters(eng.h, _ptr(cnt)))
         gen_filter()
         torch.cuda.synchronize()
         check(eng.lib.cvg_debug_tc_counters(eng.h, None))
         tiles = (n + 63) // 64
         dbg = {k: v / tiles for k, v in zip(("issuer_wait_act", "issuer_wait_weights", "issuer_wait_stage", "issuer_total",
-                                              "epi_wait_acc", "epi_input", "epi_total", "issue", "L0", "L1", "L2", "L3", "L4", "L5", "L6", "L7"), cnt.tolist())}
+                                              "epi_wait_acc", "epi_input", "epi_total", "issue", "L0", "L1", "L2", "L3", "L4", "L5", "L6", "L7", "epi_tmem_ld", "epi_fence", "E0", "E1", "E2", "E3", "E4", "E5", "E6", "E7"), cnt.tolist())}
 
     def gen_filter_e2e():
         gen_filter()

@@ -46,6 +46,7 @@ constexpr int TC_EPI_WARPS = 8;                       // two warps per TMEM lane
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = TC_EPI_THREADS + 64;      // + MMA issuer warp + weight producer warp
 constexpr int TC_LN_PITCH = TC_ROWS + 1;
+constexpr int TC_XS_PITCH = TC_ROWS + 1;            // generator outputs [F][pitch] kept for the compaction
 
 enum { TEPI_BN_LRELU = 0, TEPI_RELU = 1, TEPI_LN_RELU = 2, TEPI_SIGMOID_X = 3, TEPI_LOGITS = 4, TEPI_OUT = 5 };
 
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
   uint8_t* b_lo = smem + TC_BBYTES;
   uint8_t* stages = smem + 2 * TC_BBYTES;
   float* xs = reinterpret_cast<float*>(stages + TC_STAGES * TC_STAGE_BYTES);   // [TC_MAXF][64] generator outputs
-  float* lg = xs + TC_MAXF * TC_ROWS;                                           // [32][64] logits
+  float* lg = xs + TC_MAXF * TC_XS_PITCH;                                         // [32][64] logits
   float* red = lg + FILTER_MAXK * TC_ROWS;                                      // [10][64] LayerNorm scratch
   TcSmem* S = reinterpret_cast<TcSmem*>(red + 10 * TC_ROWS);
   float* ln_scratch = reinterpret_cast<float*>(b_hi + (TC_MAXK / 8) * TC_LBO_B);  // upper half of the hi plane
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
     if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - 1 - blockIdx.x) / gridDim.x + 1;
     unsigned long long g = 0;
     unsigned long long n_act = 0;
+    bool peeked = false;
     const uint32_t b_hi_a = smem_u32(b_hi), b_lo_a = smem_u32(b_lo), st_a = smem_u32(stages);
     for (long long t = 0; t < my_tiles; ++t) {
       for (int l = 0; l < a.nl; ++l) {
@@ -218,10 +220,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
           for (int kc = 0; kc < Lr.n_kchunks; ++kc) {
             const int s = (int)(g % TC_STAGES);
             TC_CLK(c0);
-            mbar_wait(&S->full[s], (uint32_t)((g / TC_STAGES) & 1));
+            if (!peeked) mbar_wait(&S->full[s], (uint32_t)((g / TC_STAGES) & 1));
             TC_CLK(c1);
             t_full += c1 - c0;
             tc_fence_after_sync();
+            // probe the NEXT chunk's barrier now: the probe's latency hides behind the MMA issue below
+            const bool peek_next = mbar_test_wait(&S->full[(g + 1) % TC_STAGES], (uint32_t)(((g + 1) / TC_STAGES) & 1));
             TC_CLK(c0);
             if (elect_one()) {
               const int kc_len = min(TC_KC, Lr.K - kc * TC_KC);
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
             TC_CLK(c1);
             t_issue += c1 - c0;
             t_lay[l] += c1 - c0;
+            peeked = peek_next;
             ++g;
           }
         }
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
     }
   } else {
     // ============== epilogue warps: thread = (output feature = TMEM lane, half of the 64 rows) ==============
-    long long t_acc = 0, t_in = 0, t_all = 0, c0 = 0, c1 = 0;
+    long long t_acc = 0, t_in = 0, t_all = 0, c0 = 0, c1 = 0, t_ld = 0, t_fence = 0, t_epi_l[TC_MAX_LAYERS] = {0, 0, 0, 0, 0, 0, 0, 0};
     TC_CLK(t_all);
     unsigned long long n_acc = 0;
     const int in_groups = a.L[0].K / 4;
@@ -342,11 +347,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
         t_acc += c1 - c0;
         ++n_acc;
         tc_fence_after_sync();
+        long long e0 = 0, e1 = 0;
+        TC_CLK(e0);
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
           float v[32];
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * TC_ROWS + mbase);
+          TC_CLK(c0);
           tmem_ld32(taddr, v);
           tmem_wait_ld();
+          TC_CLK(c1);
+          t_ld += c1 - c0;
           const int f = mt * Lr.M + f_local;
           const bool valid = lane_ok && f < Lr.N;
           const float c0f = cpre[mt & 1][0], c1f = cpre[mt & 1][1], c2f = cpre[mt & 1][2], c3f = cpre[mt & 1][3];
@@ -366,13 +376,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
               for (int m = 0; m < 32; ++m) b_store(b_hi, b_lo, boff + m * 16, fmaxf(v[m] + c0f, 0.f));
             }
           } else if (Lr.epi == TEPI_SIGMOID_X) {
+            // few output features (F): the owning lanes only park the pre-activations, then ALL epilogue threads share
+            // the sigmoid / split / stores (otherwise F lanes of one warp serialise 64 rows each)
             if (valid) {
 #pragma unroll
-              for (int m = 0; m < 32; ++m) {
-                const float y = 1.0f / (1.0f + expf(-(v[m] + c0f)));
-                xs[f * TC_ROWS + mbase + m] = y;
-                if (next_K) b_store(b_hi, b_lo, boff + m * 16, y);
-                if (a.x_all && mbase + m < nrows) a.x_all[(size_t)(row0 + mbase + m) * a.F + f] = y;
+              for (int m = 0; m < 32; ++m) xs[f * TC_XS_PITCH + mbase + m] = v[m] + c0f;
+            }
+            named_bar(1, TC_EPI_THREADS);
+            for (int i = tid; i < Lr.N * TC_ROWS; i += TC_EPI_THREADS) {
+              const int ff = i / TC_ROWS, m = i - ff * TC_ROWS;
+              const float y = 1.0f / (1.0f + expf(-xs[ff * TC_XS_PITCH + m]));
+              xs[ff * TC_XS_PITCH + m] = y;
+              if (next_K) b_store(b_hi, b_lo, (uint32_t)(ff >> 2) * TC_LBO_B + (uint32_t)(ff & 3) * 4 + (uint32_t)m * 16, y);
+            }
+            if (a.x_all) {
+              named_bar(1, TC_EPI_THREADS);
+              for (int i = tid; i < nrows * Lr.N; i += TC_EPI_THREADS) {      // row-major order: coalesced stores
+                const int m = i / Lr.N, ff = i - m * Lr.N;
+                a.x_all[(size_t)(row0 + m) * a.F + ff] = xs[ff * TC_XS_PITCH + m];
               }
             }
           } else if (Lr.epi == TEPI_LOGITS) {
@@ -398,14 +419,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
             named_bar(1, TC_EPI_THREADS);
             const int m_r = tid & 63, part = tid >> 6, nq = Lr.N / 4;
             float s = 0.f;
-            for (int j = 0; j < nq; ++j) s += ln_scratch[(part * nq + j) * TC_LN_PITCH + m_r];
+            {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};           // independent partial sums: the loads pipeline
+              const float* col = ln_scratch + (size_t)part * nq * TC_LN_PITCH + m_r;
+#pragma unroll 4
+              for (int j = 0; j < nq; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s4[u] += col[(j + u) * TC_LN_PITCH];
+              }
+              s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            }
             red[part * TC_ROWS + m_r] = s;
             named_bar(1, TC_EPI_THREADS);
             const float mean = ((red[m_r] + red[TC_ROWS + m_r]) + (red[2 * TC_ROWS + m_r] + red[3 * TC_ROWS + m_r])) / (float)Lr.N;
             float q2 = 0.f;
-            for (int j = 0; j < nq; ++j) {
-              const float dlt = ln_scratch[(part * nq + j) * TC_LN_PITCH + m_r] - mean;
-              q2 = fmaf(dlt, dlt, q2);
+            {
+              float q4[4] = {0.f, 0.f, 0.f, 0.f};
+              const float* col = ln_scratch + (size_t)part * nq * TC_LN_PITCH + m_r;
+#pragma unroll 4
+              for (int j = 0; j < nq; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float dlt = col[(j + u) * TC_LN_PITCH] - mean;
+                  q4[u] = fmaf(dlt, dlt, q4[u]);
+                }
+              }
+              q2 = (q4[0] + q4[1]) + (q4[2] + q4[3]);
             }
             red[(4 + part) * TC_ROWS + m_r] = q2;
             named_bar(1, TC_EPI_THREADS);
@@ -430,11 +469,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
             for (int m = 0; m < 32; ++m) b_store(b_hi, b_lo, boff + m * 16, 0.f);
           }
         }
+        TC_CLK(c0);
         tc_fence_before_sync();
         if (l + 1 < a.nl) {
           fence_proxy_async_smem();
           mbar_arrive(&S->act_ready);
         }
+        TC_CLK(e1);
+        t_fence += e1 - c0;
+        t_epi_l[l] += e1 - e0;
       }
 
       // ---- filter decision + compaction (cvae_gan.py:366-370): thread = row ----
@@ -460,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
           if (keep) {
             const long long pos = (long long)S->base + (warp ? S->warp_cnt[0] : 0) + __popc(bal & ((1u << lane) - 1u));
             if (pos < a.capacity) {
-              for (int f = 0; f < a.F; ++f) a.x_out[pos * a.F + f] = xs[f * TC_ROWS + m];
+              for (int f = 0; f < a.F; ++f) a.x_out[pos * a.F + f] = xs[f * TC_XS_PITCH + m];
               if (a.idx_out) a.idx_out[pos] = (long long)(a.row_offset + (unsigned long long)(row0 + m));
             }
           }
@@ -473,6 +516,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
       atomicAdd((unsigned long long*)a.dbg + 4, (unsigned long long)t_acc);
       atomicAdd((unsigned long long*)a.dbg + 5, (unsigned long long)t_in);
       atomicAdd((unsigned long long*)a.dbg + 6, (unsigned long long)t_all);
+      atomicAdd((unsigned long long*)a.dbg + 16, (unsigned long long)t_ld);
+      atomicAdd((unsigned long long*)a.dbg + 17, (unsigned long long)t_fence);
+      for (int l = 0; l < a.nl; ++l) atomicAdd((unsigned long long*)a.dbg + 18 + l, (unsigned long long)t_epi_l[l]);
     }
   }
   tc_fence_before_sync();
@@ -485,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 static size_t tc_eval_smem() {
   return 2 * (size_t)TC_BBYTES + (size_t)TC_STAGES * TC_STAGE_BYTES +
-         sizeof(float) * ((size_t)TC_MAXF * TC_ROWS + (size_t)FILTER_MAXK * TC_ROWS + 10 * TC_ROWS) + sizeof(TcSmem) + 64;
+         sizeof(float) * ((size_t)TC_MAXF * TC_XS_PITCH + (size_t)FILTER_MAXK * TC_ROWS + 10 * TC_ROWS) + sizeof(TcSmem) + 64;
 }
 
 void tc_set_kernel_attributes() {
