@@ -351,7 +351,8 @@ def run_ours(args):
             "config": {"workload": "CVAE-GAN training, Car-Hacking shape F=10 K=5 Z=128, fp32, batch 4096 per GPU "
                                    "(BASELINE.json configs[1]); step = one label visit = 5 D + 5 C + 3 E/G optimiser steps",
                        "global_batch": Bg, "batch_per_gpu": B, "opt_steps_per_step": OPT_STEPS,
-                       "launch": "one CUDA graph per label visit", "parallelism": f"dp{world}", "l2": "inputs larger than L2: 200 MB class tables, random row gather per step",
+                       "launch": "one CUDA graph per label visit", "parallelism": f"dp{world}",
+                       "exchange": ("none" if world == 1 else ("nvlink peer-memory LL all-reduce" if getattr(eng, "nvl", False) else "nccl")), "l2": "inputs larger than L2: 200 MB class tables, random row gather per step",
                        "losses_finite": ok},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": OPT_STEPS * B * F_ * 4,
                     "d2h_bytes_per_step": OPT_STEPS * 16, "ms_per_step": ms_e2e / args.steps,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "cvg_comm_init": (_I, [_P, _P, _I, _I]),
     "cvg_nvl_local_handle": (_I, [_P, _P]),
     "cvg_nvl_attach": (_I, [_P, _P]),
+    "cvg_nvl_disable": (_I, [_P]),
     "cvg_step_d": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _I, _P, _P]),
     "cvg_step_c": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _I, _P, _P]),
     "cvg_step_g": (_I, [_P, _P, _I, _I, C.POINTER(CvgNoise), _U64, _U64, _F, _I, _P, _P]),

@@ -189,6 +189,12 @@ int cvg_nvl_attach(CvgHandle* h, const void* handles) {
   return nvl_attach(h->e, handles);
 }
 
+int cvg_nvl_disable(CvgHandle* h) {
+  H_OR_FAIL(h);
+  nvl_destroy(h->e);
+  return 0;
+}
+
 int cvg_step_d(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
                uint64_t counter, int flags, float* loss_out, void* stream) {
   H_OR_FAIL(h);

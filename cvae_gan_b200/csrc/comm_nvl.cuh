@@ -11,7 +11,8 @@
 //   * parity double buffering is enough: a rank can only start exchange ep + 2 after it finished ep + 1, which needed
 //     every peer's ep + 1 flags, which a peer writes after it has finished reading the slots of ep.
 // The exchange number lives in device memory (advanced by the last CTA of each launch), so the launches are
-// CUDA-graph capturable.  A peer that never arrives makes the wait trap after ~4 s instead of hanging the GPU.
+// CUDA-graph capturable.  A peer that never arrives makes the wait trap after ~60 s instead of hanging the GPU
+// (ranks legitimately drift by seconds around graph instantiation and host-side work).
 #pragma once
 #include "common.cuh"
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(NVL_THREADS) nvl_allreduce_kernel(const NvlDev
           if (ok) pending &= ~(1u << q);
         }
       }
-      if (pending && clock64() - t0 > 8000000000ll) __trap();   // ~4 s: a peer never arrived
+      if (pending && clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never arrived
     }
     T s = 0;
 #pragma unroll

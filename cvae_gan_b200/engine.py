@@ -73,6 +73,7 @@ class Engine:
         check(self.lib.cvg_bind_workspace(h, C.c_void_p(base), nbytes, _stream()))
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.count_buf = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.nvl = False
         if self.world_size > 1:
             self._init_comm()
 
@@ -105,13 +106,23 @@ class Engine:
         # latency-bound exchanges over NVLink peer memory (CUDA IPC) instead of NCCL; CVG_DISABLE_NVL=1 keeps NCCL
         import os
         if dist.get_backend() == "nccl" and self.world_size <= 8 and os.environ.get("CVG_DISABLE_NVL") != "1":
+            # every rank must take the same decision: all-reduce the success flags of both stages (MIN)
             hbuf = (C.c_uint8 * 64)()
-            check(self.lib.cvg_nvl_local_handle(self.h, hbuf))
-            mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=self.device)
-            allh = [torch.empty_like(mine) for _ in range(self.world_size)]
-            dist.all_gather(allh, mine)
-            raw_h = b"".join(bytes(t.cpu().tolist()) for t in allh)
-            check(self.lib.cvg_nvl_attach(self.h, raw_h))
+            ok = self.lib.cvg_nvl_local_handle(self.h, hbuf) == 0
+            flag = torch.tensor([1 if ok else 0], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=self.device)
+                allh = [torch.empty_like(mine) for _ in range(self.world_size)]
+                dist.all_gather(allh, mine)
+                raw_h = b"".join(bytes(t.cpu().tolist()) for t in allh)
+                ok = self.lib.cvg_nvl_attach(self.h, raw_h) == 0
+                flag = torch.tensor([1 if ok else 0], device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) != 1:
+                    # no peer access between some pair of GPUs: every rank stays on NCCL
+                    check(self.lib.cvg_nvl_disable(self.h))
+            self.nvl = bool(int(flag.item()) == 1)
             dist.barrier()
 
     # ---- named views ---------------------------------------------------------------------------------

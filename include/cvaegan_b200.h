@@ -117,6 +117,8 @@ int cvg_comm_init(CvgHandle* h, const void* id128, int rank, int world_size);
  * handles in rank order (world_size x 64 bytes), every rank calls cvg_nvl_attach, then the host runs a barrier. */
 int cvg_nvl_local_handle(CvgHandle* h, void* out64);
 int cvg_nvl_attach(CvgHandle* h, const void* handles);
+/* Back to NCCL for the exchanges (all ranks together, e.g. when one rank could not map a peer). */
+int cvg_nvl_disable(CvgHandle* h);
 
 /* The three optimiser steps of one label visit.
  *   x_real   [B, F] row-major device pointer: the batch _get_target_samples returned (cvae_gan.py:108)

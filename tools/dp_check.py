@@ -85,15 +85,17 @@ def main():
         for v in list(range(VISITS)) + list(range(10)):
             one.visit(v % K_, Bg, class_rows=tabs[v % K_], loss_out=loss1)
         torch.cuda.synchronize()
-        worst = 0.0
+        worst, worst_key = 0.0, ""
         for net in range(4):
             ref = one.export_state(net)
             for k, t in states[net].items():
                 if not t.is_floating_point() or k in SKIP:
                     continue
                 d = (t - ref[k]).abs().max().item() / (ref[k].abs().max().item() + 1e-12)
-                worst = max(worst, d)
-        print(f"max relative deviation of any tensor vs the single-GPU run on the global batch: {worst:.3e}", flush=True)
+                if d > worst:
+                    worst, worst_key = d, f"{net}/{k}"
+
+        print(f"max relative deviation of any tensor vs the single-GPU run on the global batch: {worst:.3e} ({worst_key})", flush=True)
         print("losses dp :", [round(x, 5) for x in loss[-1].tolist()], flush=True)
         print("losses one:", [round(x, 5) for x in loss1[-1].tolist()], flush=True)
         print("DP_CHECK", "OK" if (flag.item() == 1 and worst < 5e-3) else "FAIL", flush=True)
