@@ -526,6 +526,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
   if (warp == TC_EPI_WARPS) tmem_dealloc(tmem, 128);
 }
 
+}  // namespace cvg
+
+#include "eval_tc128.cuh"
+
+namespace cvg {
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -536,6 +542,14 @@ static size_t tc_eval_smem() {
 
 void tc_set_kernel_attributes() {
   cudaFuncSetAttribute(tc_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_eval_smem());
+  cudaFuncSetAttribute(tc_eval128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_eval128_smem());
+}
+
+// 128-row tiles (eval_tc128.cuh) need F and K small enough for their side buffers; CVG_TC_ROWS64=1 forces 64-row tiles
+static bool tc_use_128(const Engine& e) {
+  const char* v = getenv("CVG_TC_ROWS64");        // read per call: tests toggle it
+  const bool forced64 = v && v[0] == '1';
+  return !forced64 && e.F <= TC128_MAXF && e.K <= TC128_MAXKC;
 }
 
 // Which networks the tensor-core chain supports: every hidden width a multiple of 64 and <= 256.
@@ -605,9 +619,15 @@ static int tc_run(Engine& e, ChainBuilder& cb, TcEvalArgs& a, cudaStream_t st) {
   a.F = e.F;
   a.Kc = e.K;
   a.dbg = e.tc_dbg;
-  const long long ntiles = (a.n + TC_ROWS - 1) / TC_ROWS;
-  const int grid = (int)(ntiles < e.num_sms ? ntiles : e.num_sms);
-  tc_eval_kernel<<<grid, TC_THREADS, tc_eval_smem(), st>>>(a);
+  if (tc_use_128(e)) {
+    const long long ntiles = (a.n + TC128_ROWS - 1) / TC128_ROWS;
+    const int grid = (int)(ntiles < e.num_sms ? ntiles : e.num_sms);
+    tc_eval128_kernel<<<grid, TC_THREADS, tc_eval128_smem(), st>>>(a);
+  } else {
+    const long long ntiles = (a.n + TC_ROWS - 1) / TC_ROWS;
+    const int grid = (int)(ntiles < e.num_sms ? ntiles : e.num_sms);
+    tc_eval_kernel<<<grid, TC_THREADS, tc_eval_smem(), st>>>(a);
+  }
   CVG_LAUNCH_CHECK();
   return 0;
 }
