@@ -33,6 +33,9 @@ namespace cvg {
 
 using namespace tc;
 
+#ifndef CVG_TC_DEFAULT_MODE
+#define CVG_TC_DEFAULT_MODE 1
+#endif
 constexpr int TC_MAX_LAYERS = 8;
 constexpr int TC_ROWS = 64;                          // batch rows per tile (MMA N)
 constexpr int TC_KC = 16;                            // contraction values per weight chunk
@@ -529,6 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval_kernel(const __grid_con
 }  // namespace cvg
 
 #include "eval_tc128.cuh"
+#include "eval_tcpp.cuh"
 
 namespace cvg {
 
@@ -543,19 +547,27 @@ static size_t tc_eval_smem() {
 void tc_set_kernel_attributes() {
   cudaFuncSetAttribute(tc_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_eval_smem());
   cudaFuncSetAttribute(tc_eval128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_eval128_smem());
+  cudaFuncSetAttribute(tc_eval_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_eval_pp_smem());
 }
 
-// 128-row tiles (eval_tc128.cuh) need F and K small enough for their side buffers; CVG_TC_ROWS64=1 forces 64-row tiles
-static bool tc_use_128(const Engine& e) {
-  const char* v = getenv("CVG_TC_ROWS64");        // read per call: tests toggle it
-  const bool forced64 = v && v[0] == '1';
-  return !forced64 && e.F <= TC128_MAXF && e.K <= TC128_MAXKC;
+// Kernel variant: 0 = 64-row tiles (any supported shape), 1 = 128-row tiles, 2 = two 64-row tiles in flight (ping-pong).
+// 1 and 2 need F <= 32 and K <= 16 for their side buffers.  CVG_TC_MODE = 64 | 128 | pp overrides (read per call:
+// tests toggle it); CVG_TC_ROWS64=1 is the older spelling of CVG_TC_MODE=64.
+static int tc_mode(const Engine& e) {
+  const bool small = e.F <= TC128_MAXF && e.K <= TC128_MAXKC;
+  const char* r64 = getenv("CVG_TC_ROWS64");
+  const char* m = getenv("CVG_TC_MODE");
+  if ((r64 && r64[0] == '1') || !small) return 0;
+  if (m && !strcmp(m, "64")) return 0;
+  if (m && !strcmp(m, "128")) return 1;
+  if (m && !strcmp(m, "pp")) return 2;
+  return CVG_TC_DEFAULT_MODE;
 }
 
 // Which networks the tensor-core chain supports: every hidden width a multiple of 64 and <= 256.
 bool tc_supported(const Engine& e) {
   auto ok = [](const int* h) { return h[0] <= 256 && h[1] <= 256 && h[2] <= 256 && h[0] % 64 == 0 && h[1] % 64 == 0 && h[2] % 64 == 0; };
-  return ok(e.eh) && ok(e.gh) && ok(e.dh) && ok(e.ch) && e.F <= TC_MAXF && e.Z % 8 == 0 && e.Z <= TC_MAXK && 2 * e.Z <= 256 &&
+  return ok(e.eh) && ok(e.gh) && ok(e.dh) && ok(e.ch) && e.F <= TC_MAXF && e.Z % 8 == 0 && e.Z <= TC128_MAXK && 2 * e.Z <= 256 &&
          e.K <= FILTER_MAXK && e.ch[1] % 2 == 0;
 }
 
@@ -619,7 +631,12 @@ static int tc_run(Engine& e, ChainBuilder& cb, TcEvalArgs& a, cudaStream_t st) {
   a.F = e.F;
   a.Kc = e.K;
   a.dbg = e.tc_dbg;
-  if (tc_use_128(e)) {
+  const int mode = tc_mode(e);
+  if (mode == 2) {
+    const long long npairs = ((a.n + TCPP_ROWS - 1) / TCPP_ROWS + 1) / 2;
+    const int grid = (int)(npairs < e.num_sms ? npairs : e.num_sms);
+    tc_eval_pp_kernel<<<grid, TC_THREADS, tc_eval_pp_smem(), st>>>(a);
+  } else if (mode == 1) {
     const long long ntiles = (a.n + TC128_ROWS - 1) / TC128_ROWS;
     const int grid = (int)(ntiles < e.num_sms ? ntiles : e.num_sms);
     tc_eval128_kernel<<<grid, TC_THREADS, tc_eval128_smem(), st>>>(a);

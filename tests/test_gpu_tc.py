@@ -29,15 +29,12 @@ def _pair_engines(F_, K, seed):
     return orc, eng_tc, eng_ff, g
 
 
-@pytest.mark.parametrize("rows64", [False, True])
+@pytest.mark.parametrize("mode", ["128", "64", "pp"])
 @pytest.mark.parametrize("F_,K,n", [(10, 5, 1), (10, 5, 63), (10, 5, 65), (10, 5, 129), (10, 5, 1000), (30, 5, 333), (7, 3, 200),
                                     (16, 9, 129)])
-def test_tc_chain_matches_ffma_and_oracle(F_, K, n, rows64, monkeypatch):
-    """rows64: the 64-row-tile kernel (used when F > 32 or K > 16) instead of the 128-row-tile kernel."""
-    if rows64:
-        monkeypatch.setenv("CVG_TC_ROWS64", "1")
-    else:
-        monkeypatch.delenv("CVG_TC_ROWS64", raising=False)
+def test_tc_chain_matches_ffma_and_oracle(F_, K, n, mode, monkeypatch):
+    """mode: 128-row tiles, 64-row tiles (used when F > 32 or K > 16), or two 64-row tiles in flight (ping-pong)."""
+    monkeypatch.setenv("CVG_TC_MODE", mode)
     orc, eng_tc, eng_ff, g = _pair_engines(F_, K, seed=50 + F_ + K)
     label = K - 1
     z = torch.randn(n, 128, generator=g)
