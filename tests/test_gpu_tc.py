@@ -31,7 +31,7 @@ def _pair_engines(F_, K, seed):
 
 @pytest.mark.parametrize("mode", ["128", "64", "pp"])
 @pytest.mark.parametrize("F_,K,n", [(10, 5, 1), (10, 5, 63), (10, 5, 65), (10, 5, 129), (10, 5, 1000), (30, 5, 333), (7, 3, 200),
-                                    (16, 9, 129)])
+                                    (16, 9, 129), (40, 20, 70)])
 def test_tc_chain_matches_ffma_and_oracle(F_, K, n, mode, monkeypatch):
     """mode: 128-row tiles, 64-row tiles (used when F > 32 or K > 16), or two 64-row tiles in flight (ping-pong)."""
     monkeypatch.setenv("CVG_TC_MODE", mode)
@@ -65,6 +65,17 @@ def test_tc_chain_matches_ffma_and_oracle(F_, K, n, mode, monkeypatch):
     assert (mt - mf).abs().max().item() < 5e-5 and (vt - vf).abs().max().item() < 5e-5
     eng_tc.close()
     eng_ff.close()
+
+
+def test_tc_empty_and_wide_inputs():
+    """n = 0 is a no-op; F > 32 / K > 16 take the 64-row kernel whatever CVG_TC_MODE says."""
+    _, eng, g = P.make_pair(40, 20, 64, seed=62)
+    assert eng.generate(3, 0).shape == (0, 40)
+    xg, idx, cnt, _, _ = eng.generate_filter(3, 0, 0.1)
+    assert int(cnt.item()) == 0
+    x = torch.rand(5, 40, generator=g).cuda()
+    assert eng.classifier_forward(x).shape == (5, 20)
+    eng.close()
 
 
 def test_tc_philox_rows_do_not_depend_on_tiling():
