@@ -38,6 +38,15 @@ OPT_STEPS = D_LOOP + C_LOOP + G_LOOP
 FLOP_PER_SAMPLE = 873_945
 
 
+def ncu_traffic():
+    """DRAM bytes per launch from the committed ncu captures (profiles/r1_traffic.json), or {}."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -324,7 +333,7 @@ def run_ours(args):
     total_gemm_ms = sum(v[2] for v in prof.values())
     roofline = {
         "bound": "tensor", "kernel": top, "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " bf16 dense (sustained)",
+        "frac": achieved / pk["bf16_tflops_sustained"], "traffic": ncu_traffic().get(top, {}).get("bytes"), "peak_source": pk["source"] + " bf16 dense (sustained)",
         "note": "fp32 SIMT FFMA kernels (exact-fp32 parity path); peak quoted is the measured bf16 tensor peak as the "
                 "contract requires - the fp32 CUDA-core ceiling of a B200 is ~74 TFLOP/s nominal",
         "launches_profiled": n_l, "avg_launch_us": 1e3 * t_ms / max(n_l, 1),
@@ -461,7 +470,8 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
         "e2e": {"value": accepted_all / (ms_e2e * 1e-3), "generated_rows_per_s": n * world / (ms_e2e * 1e-3),
                 "unit": "accepted rows/s", "ms_per_pass": ms_e2e, "d2h_bytes_per_pass": accepted * (F_ * 4) + 8,
                 "api": "cvg_generate_filter + count read-back + accepted rows copied to pinned host memory"},
-        "roofline_fused": {"bound": "tensor", "kernel": "tc_eval_kernel (tcgen05 kind::tf32, 3xTF32)",
+        "roofline_fused": {"bound": "tensor", "kernel": "tc_eval128_kernel (tcgen05 kind::tf32, 3xTF32, 128-row tiles)",
+                           "traffic": ncu_traffic().get("tc_eval128_kernel", {}).get("bytes"),
                            "achieved": gen_rows_s / world * GEN_FLOP_PER_ROW / 1e12, "peak": pk["bf16_tflops"],
                            "unit": "TFLOP/s", "frac": gen_rows_s / world * GEN_FLOP_PER_ROW / 1e12 / pk["bf16_tflops"],
                            "note": "algorithmic fp32 FLOP; each costs 3 tf32 MMAs (fp32-accurate split), tf32 peak is half the "
@@ -488,7 +498,8 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
                               "rows": m, "acceptance_rate": acc_f / m, "bytes_per_row_model": "4K + a(4F + 4F + 8): x of rejected rows is never read",
                               "survey_model_gbs": byts_survey / (ms_f * 1e-3) / 1e9, "survey_model": "4F + 4K + a(4F + 8)",
                               "survey_model_frac": byts_survey / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"],
-                              "rows_per_s": m / (ms_f * 1e-3), "ms": ms_f, "traffic": None}
+                              "rows_per_s": m / (ms_f * 1e-3), "ms": ms_f,
+                              "traffic": ncu_traffic().get("filter_compact_stream_kernel", {}).get("bytes")}
     return out
 
 
