@@ -5,8 +5,9 @@
 //   * operands live in shared memory in the NO-SWIZZLE canonical core-matrix layouts
 //       K-major  (the contraction index is contiguous in the source):  core matrix = 8 rows x 16 bytes
 //           byte offset(row, k)  = (row / 8) * SBO + (row % 8) * 16 + (k / 4) * LBO + (k % 4) * 4
-//       MN-major (the row index is contiguous in the source):          core matrix = 8 k x 16 bytes
-//           byte offset(row, k)  = (row / 4) * SBO + (row % 4) * 4 + (k / 8) * LBO + (k % 8) * 16
+//     (MN-major tf32 operands are NOT accepted in the no-swizzle / 32B / 128B layouts on this part - only
+//     SWIZZLE_128B_BASE32B responds, tools/tc_probe2.cu - so every operand here is K-major; GEMMs that would need the
+//     other orientation get a transposed copy of the weights instead)
 //   * one tf32 MMA consumes 8 contraction values; fp32 accuracy comes from the 3xTF32 split
 //       x = hi + lo, hi = rna_tf32(x), lo = x - hi :   x*w ~= lo*w_hi + hi*w_lo + hi*w_hi
 //   * accumulators are fp32 in TMEM, row i of the 128-row tile in lane i, column j in column j.

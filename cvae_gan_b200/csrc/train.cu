@@ -360,7 +360,6 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
 int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn, cudaStream_t st) {
   const int net = CVG_NET_ENCODER;
   const Workspace& w = e.ws;
-  const size_t ld = w.ld;
   for (int l = 0; l < 4; ++l) {
     const LinearP& p = lin(e, net, l);
     GemmArgs g = base_args(e, M, Bg, 1);
@@ -846,7 +845,6 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_TRY(check_step(e, B));
   CVG_TRY(begin_step(e, rng, false, st));
   const Workspace& w = e.ws;
-  const size_t ld = w.ld;
   const bool local_bn = flags & CVG_STEP_LOCAL_BN;
   const float Bg = (float)B * (float)e.world;
   const float Bg_bn = local_bn ? (float)B : Bg;
@@ -1100,9 +1098,6 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
 
 void set_all_kernel_attributes() {
   // cudaFuncSetAttribute is done once, eagerly, so that nothing but launches happens during graph capture
-  GemmArgs g;
-  DwArgs d;
-  (void)g; (void)d;
 #define CVG_MN_ATTR(W, A, E) cudaFuncSetAttribute(gemm_mn_kernel<W, A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   CVG_MN_ATTR(true, OP_PLAIN, EP_LINEAR) CVG_MN_ATTR(true, OP_BN_ACT, EP_LINEAR) CVG_MN_ATTR(true, OP_REPARAM, EP_LINEAR)
   CVG_MN_ATTR(false, OP_PLAIN, EP_DACT) CVG_MN_ATTR(false, OP_CONST, EP_DACT) CVG_MN_ATTR(false, OP_PLAIN, EP_STORE)
