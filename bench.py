@@ -447,9 +447,9 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
         gen_filter()
         torch.cuda.synchronize()
         check(eng.lib.cvg_debug_tc_counters(eng.h, None))
-        tiles = (n + 63) // 64
+        tiles = (n + 127) // 128 if os.environ.get("CVG_TC_MODE", "128") == "128" else (n + 63) // 64
         dbg = {k: v / tiles for k, v in zip(("issuer_wait_act", "issuer_wait_weights", "issuer_wait_stage", "issuer_total",
-                                              "epi_wait_acc", "epi_input", "epi_total", "issue", "L0", "L1", "L2", "L3", "L4", "L5", "L6", "L7", "epi_tmem_ld", "epi_fence", "E0", "E1", "E2", "E3", "E4", "E5", "E6", "E7"), cnt.tolist())}
+                                              "epi_wait_acc", "epi_input", "epi_total", "issue", "L0", "L1", "L2", "L3", "L4", "L5", "L6", "L7", "epi_tmem_ld(64) / plane_free wait(128)", "epi_fence", "E0", "E1", "E2", "E3", "E4", "E5", "E6", "E7"), cnt.tolist())}
 
     def gen_filter_e2e():
         gen_filter()

@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
     // ===================== MMA issuer =====================
     unsigned long long g = 0, n_act = 0;
     bool peeked = false;
+    const bool prof = a.dbg != nullptr;
+    long long t_act = 0, t_full = 0, t_issue = 0, t_all = 0, c0 = 0, c1 = 0;
+    TC_CLK(t_all);
     const uint32_t b_hi_a = smem_u32(b_hi), b_lo_a = smem_u32(b_lo), st_a = smem_u32(stages);
     for (long long t = 0; t < my_tiles; ++t) {
       for (int l = 0; l < a.nl; ++l) {
@@ -113,7 +116,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
         const uint32_t a_lbo = (uint32_t)Lr.M * 16u;
         const uint32_t acc0 = split_in ? 256u : 0u;               // third accumulator for a split consumer
         const int half_chunks = TC128_MAXK / TC_KC;
+        TC_CLK(c0);
         mbar_wait(&S->act_ready, (uint32_t)(n_act & 1));
+        TC_CLK(c1);
+        t_act += c1 - c0;
         ++n_act;
         tc_fence_after_sync();
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
@@ -122,14 +128,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
               // planes may be overwritten once the K-half-0 MMAs have completed; then wait for K-half 1
               if (elect_one()) mma_commit(&S->plane_free);
               __syncwarp();
+              TC_CLK(c0);
               mbar_wait(&S->act_ready, (uint32_t)(n_act & 1));
+              TC_CLK(c1);
+              t_act += c1 - c0;
               ++n_act;
               tc_fence_after_sync();
             }
             const int s = (int)(g % TC_STAGES);
+            TC_CLK(c0);
             if (!peeked) mbar_wait(&S->full[s], (uint32_t)((g / TC_STAGES) & 1));
+            TC_CLK(c1);
+            t_full += c1 - c0;
             tc_fence_after_sync();
             const bool peek_next = mbar_test_wait(&S->full[(g + 1) % TC_STAGES], (uint32_t)(((g + 1) / TC_STAGES) & 1));
+            TC_CLK(c0);
             if (elect_one()) {
               const int kc_len = min(TC_KC, Lr.K - kc * TC_KC);
               const uint32_t a_hi = st_a + (uint32_t)s * TC_STAGE_BYTES;
@@ -149,11 +162,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
               if (mt == Lr.n_mtiles - 1 && kc == Lr.n_kchunks - 1) mma_commit(&S->acc_full);
             }
             __syncwarp();
+            TC_CLK(c1);
+            t_issue += c1 - c0;
             peeked = peek_next;
             ++g;
           }
         }
       }
+    }
+    if (prof && lane == 0) {
+      t_all = clock64() - t_all;
+      atomicAdd((unsigned long long*)a.dbg + 0, (unsigned long long)t_act);
+      atomicAdd((unsigned long long*)a.dbg + 1, (unsigned long long)t_full);
+      atomicAdd((unsigned long long*)a.dbg + 3, (unsigned long long)t_all);
+      atomicAdd((unsigned long long*)a.dbg + 7, (unsigned long long)t_issue);
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== weight producer =====================
@@ -178,12 +200,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
   } else {
     // ============== epilogue warps: thread = (output feature = TMEM lane, 64 of the 128 rows) ==============
     unsigned long long n_acc = 0, n_pf = 0;
+    const bool prof = a.dbg != nullptr;
+    long long t_acc = 0, t_in = 0, t_all = 0, t_pf = 0, c0 = 0, c1 = 0, e0 = 0, e1 = 0, t_epi_l[TC_MAX_LAYERS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    TC_CLK(t_all);
     const int in_groups = a.L[0].K / 4;
     const int q = warp & 3, h = warp >> 2;
     const int mbase = h * 64;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long row0 = tile * TC128_ROWS;
       const int nrows = (int)min((long long)TC128_ROWS, a.n - row0);
+      TC_CLK(c0);
       for (int i = tid; i < TC128_ROWS * in_groups; i += TC_EPI_THREADS) {
         const int m = i % TC128_ROWS, fg = i / TC128_ROWS;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -208,6 +234,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&S->act_ready);
+      TC_CLK(c1);
+      t_in += c1 - c0;
 
       for (int l = 0; l < a.nl; ++l) {
         const TcLayer& Lr = a.L[l];
@@ -226,16 +254,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 4; ++j) cpre[mt][j] = vv ? __ldg(cst + j * Lr.Npad + f) : 0.f;
         }
+        TC_CLK(c0);
         mbar_wait(&S->acc_full, (uint32_t)(n_acc & 1));
+        TC_CLK(c1);
+        t_acc += c1 - c0;
         ++n_acc;
         tc_fence_after_sync();
+        TC_CLK(e0);
         for (int mt = 0; mt < Lr.n_mtiles; ++mt) {
           if (split_out && mt == 1) {
             // m-tile 0 went to the planes; the consumer's K-half-0 MMAs must finish before they are overwritten
             tc_fence_before_sync();
             fence_proxy_async_smem();
             mbar_arrive(&S->act_ready);
+            TC_CLK(c0);
             mbar_wait(&S->plane_free, (uint32_t)(n_pf & 1));
+            TC_CLK(c1);
+            t_pf += c1 - c0;
             ++n_pf;
             tc_fence_after_sync();
           }
@@ -342,6 +377,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
           fence_proxy_async_smem();
           mbar_arrive(&S->act_ready);
         }
+        TC_CLK(e1);
+        t_epi_l[l] += e1 - e0;
       }
 
       if (a.do_filter) {
@@ -374,6 +411,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_eval128_kernel(const __grid_
         }
       }
       named_bar(1, TC_EPI_THREADS);
+    }
+    if (prof && tid == 0) {
+      t_all = clock64() - t_all;
+      atomicAdd((unsigned long long*)a.dbg + 4, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)a.dbg + 5, (unsigned long long)t_in);
+      atomicAdd((unsigned long long*)a.dbg + 6, (unsigned long long)t_all);
+      atomicAdd((unsigned long long*)a.dbg + 16, (unsigned long long)t_pf);
+      for (int l = 0; l < a.nl; ++l) atomicAdd((unsigned long long*)a.dbg + 18 + l, (unsigned long long)t_epi_l[l]);
     }
   }
   tc_fence_before_sync();

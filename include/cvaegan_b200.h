@@ -223,7 +223,7 @@ int cvg_debug_read(CvgHandle* h, const char* name, int pass, int rows, float* ds
 
 /* Development hook: when dev_counters (device int64[32]) is non-NULL the tensor-core chain kernel adds its per-role
  * cycle counts to it ([0] issuer waiting for activations, [1] for weights, [2] for free stages, [3] issuer total,
- * [4] epilogue waiting for accumulators, [5] input generation, [6] epilogue total, [7] MMA issue, [8..15] issue per layer, [16] TMEM loads, [17] fences + arrive, [18..25] epilogue per layer).  NULL switches it off. */
+ * [4] epilogue waiting for accumulators, [5] input generation, [6] epilogue total, [7] MMA issue, [8..15] issue per layer, [16] TMEM loads (64-row kernel) or plane_free waits (128-row kernel), [17] fences + arrive, [18..25] epilogue per layer).  NULL switches it off. */
 int cvg_debug_tc_counters(CvgHandle* h, long long* dev_counters);
 
 /* Measurement hook for bench.py: when enabled, every GEMM launch is bracketed by CUDA events on its
