@@ -6,9 +6,11 @@ scripts/train_cvae_gan.py:143-165.
 labels, backward, Adam(lr = classifier_config.lr, torch default betas) with a FRESH optimiser state, exactly what
 `Adam(params=self.model.parameters(), lr=...)` gives the reference) whenever `self.model` is a classifier attached to
 an engine - i.e. after `clf.model = gan.classifier` (train_cvae_gan.py:145).  Batches follow the reference's
-`DataLoader(dataset, batch_size, shuffle=True)`: a new permutation per epoch drawn from torch's CPU generator in the
-same way `RandomSampler` does, last partial batch included.  Dropout masks come from the engine's Philox stream, so
-the trajectory matches the reference statistically, not bit for bit (tests compare F1).
+`DataLoader(dataset, batch_size, shuffle=True)`: a new permutation per epoch from a generator seeded out of torch's
+default CPU generator (the mechanism of `RandomSampler`), last partial batch included.  Dropout masks come from the
+engine's Philox stream, whereas the reference's dropout draws interleave with the sampler's on the same generator -
+so the trajectory matches the reference statistically, not bit for bit (tests compare F1; the bit-level replay of the
+reference's own sequence lives in oracle/classifier_oracle.py).
 """
 from __future__ import annotations
 

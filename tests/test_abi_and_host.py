@@ -130,3 +130,36 @@ def test_oracle_models_equal_mirror_forward():
         mu, lv = mods["encoder"](x, torch.full((16,), 4))
         omu, olv = O.encoder_forward(orc.sd["encoder"], x, 4, False)
         assert torch.allclose(mu, omu, atol=1e-6) and torch.allclose(lv, olv, atol=1e-6)
+
+
+def test_pipeline_minmax_and_pickle_format(tmp_path):
+    """Driver plumbing (scripts/train_cvae_gan.py:19-43, 131-140) on the CPU: joint min-max scaling equals sklearn's
+    minmax_scale on the concatenation, the result is shifted to a zero minimum, and the pickle is the 4-tuple of numpy
+    arrays the reference's tools read."""
+    import pickle
+    import numpy as np
+    from sklearn.preprocessing import minmax_scale
+    from cvae_gan_b200 import datasets as ds
+    from cvae_gan_b200 import pipeline
+    g = torch.Generator().manual_seed(3)
+    tr = torch.randn(50, 6, generator=g) * 7 + 3
+    te = torch.randn(20, 6, generator=g) * 7 + 3
+    tr[:, 2] = 1.5
+    te[:, 2] = 1.5                                   # constant column
+    saved = (ds.tr_samples, ds.tr_labels, ds.te_samples, ds.te_labels, ds.feature_num, ds.label_num)
+    try:
+        ds.tr_samples, ds.te_samples = tr.clone(), te.clone()
+        ds.tr_labels = torch.arange(50) % 4
+        ds.te_labels = torch.arange(20) % 4
+        pipeline.minmax_scale_(ds, device="cpu")
+        ref = minmax_scale(torch.cat([tr, te]).numpy())
+        ref = ref - ref.min()
+        assert np.allclose(torch.cat([ds.tr_samples, ds.te_samples]).numpy(), ref, atol=1e-6)
+        assert ds.feature_num == 6 and ds.label_num == 4
+        out = str(tmp_path / "d.pkl")
+        pipeline.dump_dataset(out, ds)
+        with open(out, "rb") as f:
+            a, b, c, d = pickle.load(f)
+        assert a.shape == (50, 6) and b.shape == (50,) and c.shape == (20, 6) and d.shape == (20,)
+    finally:
+        ds.tr_samples, ds.tr_labels, ds.te_samples, ds.te_labels, ds.feature_num, ds.label_num = saved
