@@ -114,7 +114,25 @@ def compare_grads(eng, orc, net_names, grads, report):
             report.append((f"grad {name}/{key}", ok, worst, mx, float(g_ref.abs().max())))
 
 
-def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=ATOL_FRAC):
+def close_mostly(a, b, rtol, atol_frac, atol_abs, outlier_frac, hard_atol):
+    """Like `close`, but a fraction `outlier_frac` of the entries may miss the tolerance as long as every entry is within
+    `hard_atol`.  For multi-step trajectories: the weight-gradient kernels accumulate with float atomics (order varies
+    from run to run), and Adam turns a round-off-sized gradient whose sign flips into a full +-lr step - a handful of
+    near-zero-gradient entries can then random-walk by up to (number of steps) * lr in either implementation."""
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    scale = float(b.abs().max()) if b.numel() else 0.0
+    tol = rtol * b.abs() + atol_frac * scale + atol_abs
+    err = (a - b).abs()
+    bad = (err > tol)
+    n_bad = int(bad.sum())
+    mx = float(err.max()) if b.numel() else 0.0
+    ok = n_bad <= outlier_frac * max(b.numel(), 1) and mx <= hard_atol + float((rtol * b.abs()).max() if b.numel() else 0.0)
+    worst = float((err / (tol + 1e-30)).max()) if b.numel() else 0.0
+    return ok, worst, mx
+
+
+def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=ATOL_FRAC, outlier_frac=0.0, hard_atol=0.0):
     st = orc.state()
     for name in nets:
         i = NETS.index(name)
@@ -127,7 +145,10 @@ def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=A
             if ONE_HOT_FIRST.get(name) == key and loose_prebn_atol:
                 extra = torch.zeros(ref.shape)
                 extra[:, ref.shape[1] - orc.label_num:] = loose_prebn_atol
-            ok, worst, mx = close(got, ref, atol_abs=extra, atol_frac=atol_frac)
+            if outlier_frac > 0.0:
+                ok, worst, mx = close_mostly(got, ref, RTOL, atol_frac, extra, outlier_frac, hard_atol)
+            else:
+                ok, worst, mx = close(got, ref, atol_abs=extra, atol_frac=atol_frac)
             report.append((f"state {name}/{key}", ok, worst, mx, float(ref.abs().max())))
 
 

