@@ -152,6 +152,50 @@ def time_cpu_port(visits: int, warm: int, batch: int, threads: int, rows_per_cla
     return OPT_STEPS * batch * visits / dt, dt / visits
 
 
+def time_cpu_filter_port(threads: int, budget_s: float = 6.0):
+    """The reference's generation + classifier-confidence filter on the host cores (oracle port), two ways:
+    `generate_qualified_samples` as written (chunks of <= 10 rows, cvae_gan.py:347-378) and one vectorised
+    generate -> classify -> filter call.  Returns generated rows/s of both."""
+    import torch
+    from oracle import cvae_gan_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    orc = O.OracleCVAEGAN(F_, K_, O.OracleConfig(batch_size=64)).init_like_reference(g)
+    for k in orc.training:
+        orc.training[k] = False                       # after fit() every network is in eval mode (cvae_gan.py:233-236)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        probe = orc.classify_eval(orc.generate_samples(0, 2000)).argmax(1)
+    label = int(torch.bincount(probe, minlength=K_).argmax())   # a label this (untrained) classifier does accept at thr 0
+
+    class Counting(O.TorchNoise):
+        rows = 0
+
+        def randn(self, rows, cols, tag=""):
+            Counting.rows += rows
+            return super().randn(rows, cols, tag)
+
+    noise = Counting()
+    t0 = time.perf_counter()
+    asked = 0
+    while time.perf_counter() - t0 < budget_s / 2:
+        orc.generate_qualified_samples(label, 2000, thr=0.0, noise=noise)
+        asked += 2000
+    dt_chunk = time.perf_counter() - t0
+    chunked = Counting.rows / dt_chunk
+    n_vec = 200_000
+    z = torch.randn(n_vec, Z_)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < budget_s / 2:
+        orc.generate_filter_stream(label, z, 0.0)
+        reps += 1
+    vec = reps * n_vec / (time.perf_counter() - t0)
+    return {"chunked_generated_rows_per_s": chunked, "vectorised_generated_rows_per_s": vec, "label": label, "threshold": 0.0,
+            "sample": f"oracle port on {threads} threads: generate_qualified_samples in chunks of 10 for {dt_chunk:.1f} s "
+                      f"({Counting.rows} rows), and {reps} vectorised passes over {n_vec} rows"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -372,6 +416,10 @@ def run_ours(args):
             "roofline": roofline,
         }
         if cpu:
+            try:
+                cpu["filter"] = time_cpu_filter_port(cores)
+            except Exception as ex:          # the baseline is informative; never lose the bench line over it
+                cpu["filter"] = {"error": str(ex)[:200]}
             line["cpu_baseline"] = cpu
         if filt:
             line["filter"] = filt
