@@ -445,17 +445,16 @@ def run_filter_leg(eng, dev, world, rank, pk, iters=3):
     # the generator / classifier of this run are freshly trained on synthetic blobs: probe which label the classifier
     # accepts at all (100 k rows per label), lowering the threshold if nothing passes at the reference's 0.5 (a classifier
     # a few hundred steps old is barely more confident than 1/K)
-    if world == 1 or True:
-        best = (0.0, 0, 0.5)
-        for t in (0.5, 0.35, 0.25, 0.21, 0.0):
-            for lab in range(K_):
-                _, _, cnt, _, _ = eng.generate_filter(lab, 100_000, t, seed=99, row_offset=0, capacity=1)
-                a = float(cnt.item()) / 100_000
-                if a > best[0]:
-                    best = (a, lab, t)
-            if best[0] >= 0.01:
-                break
-        label, thr = best[1], best[2]
+    best = (0.0, 0, 0.5)
+    for t in (0.5, 0.35, 0.25, 0.21, 0.0):
+        for lab in range(K_):
+            _, _, cnt, _, _ = eng.generate_filter(lab, 100_000, t, seed=99, row_offset=0, capacity=1)
+            a = float(cnt.item()) / 100_000
+            if a > best[0]:
+                best = (a, lab, t)
+        if best[0] >= 0.01:
+            break
+    label, thr = best[1], best[2]
     row_offset = rank * n
     x_out = torch.empty(n, F_, device=dev)
     idx_out = torch.empty(n, dtype=torch.int64, device=dev)
