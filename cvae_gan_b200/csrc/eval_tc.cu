@@ -18,6 +18,11 @@
 //     issuer, warp 9 = weight producer (bulk copies).
 //   * z comes from Philox keyed by the GLOBAL row index (same stream as fill_noise_kernel), the filter decision is
 //     filter_decide() (bit-exact torch softmax semantics), accepted rows are compacted with one atomic per tile.
+//
+// Three tile variants share the layer tables, the prep kernel and the host code below (tc_mode()):
+//   tc_eval_kernel      (this file)       64-row tiles, planes hold a whole 256-wide layer; any supported shape
+//   tc_eval128_kernel   (eval_tc128.cuh)  128-row tiles, extra accumulators in TMEM, split-K hand-off; the default
+//   tc_eval_pp_kernel   (eval_tcpp.cuh)   two 64-row tiles in flight (experimental, CVG_TC_MODE=pp)
 #include "engine.cuh"
 #include "tc05.cuh"
 
