@@ -83,6 +83,9 @@ SIGNATURES = {
     "cvg_profile_enable": (_I, [_P, _I]),
     "cvg_profile_read": (_I, [_P, _I, C.POINTER(_I64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cvg_launch_count": (_I64, [_P]),
+    "cvg_debug_set": (_I, [_P, C.c_char_p, _I]),
+    "cvg_debug_get": (_I, [_P, C.c_char_p, C.POINTER(_I)]),
+    "cvg_debug_mk_cycles": (_I, [_P, _P, _I, C.POINTER(_I)]),
 }
 
 _lib = None

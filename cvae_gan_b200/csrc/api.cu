@@ -92,6 +92,14 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
   {
     const char* off = getenv("CVG_DISABLE_TC");
     e.use_tc = tc_supported(e) && !(off && off[0] == '1');
+    // training steps: ONE persistent tcgen05 kernel per step / label visit (mega.cuh).  CVG_TRAIN_MODE=ffma keeps the
+    // stand-alone FP32-FMA layer kernels (the A/B reference); widths the program kernel does not cover use them too.
+    const char* tm = getenv("CVG_TRAIN_MODE");
+    e.mk.enabled = mk_supported(e) && !(tm && !strcmp(tm, "ffma"));
+    const char* coop = getenv("CVG_MK_COOP");
+    e.mk.coop = !(coop && coop[0] == '0');
+    const char* ab = getenv("CVG_MK_ALLBAR");
+    e.mk.allbar = ab && ab[0] == '1';
   }
   if (cudaGetLastError() != cudaSuccess) {
     cvg::set_error("cudaFuncSetAttribute failed");
@@ -106,6 +114,7 @@ void cvg_destroy(CvgHandle* h) {
   if (!h) return;
   nvl_destroy(h->e);
   comm_destroy(h->e);
+  mk_destroy(h->e);
   delete h;
 }
 
@@ -450,5 +459,42 @@ int cvg_profile_read(CvgHandle* h, int kernel_class, int64_t* launches, double* 
 }
 
 int64_t cvg_launch_count(const CvgHandle* h) { return h ? h->e.launches : -1; }
+
+int cvg_debug_set(CvgHandle* h, const char* key, int value) {
+  H_OR_FAIL(h);
+  if (!key) CVG_FAIL("null key");
+  Engine& e = h->e;
+  const std::string k(key);
+  if (k == "train_mode") {            // 0: stand-alone FFMA kernels, 1: step-program kernel (tcgen05)
+    if (value && !mk_supported(e)) CVG_FAIL("cvg_debug_set: the step-program kernel does not cover these layer widths");
+    e.mk.enabled = value != 0;
+  } else if (k == "mk_max_ops") e.mk.max_ops = value;
+  else if (k == "mk_allbar") e.mk.allbar = value != 0;
+  else if (k == "mk_coop") e.mk.coop = value != 0;
+  else CVG_FAIL("cvg_debug_set: unknown key");
+  return 0;
+}
+
+int cvg_debug_get(const CvgHandle* h, const char* key, int* value) {
+  H_OR_FAIL(h);
+  if (!key || !value) CVG_FAIL("null argument");
+  const Engine& e = h->e;
+  const std::string k(key);
+  if (k == "train_mode") *value = e.mk.enabled ? 1 : 0;
+  else if (k == "mk_last_nops") *value = e.mk.last_nops;
+  else if (k == "mk_supported") *value = mk_supported(e) ? 1 : 0;
+  else CVG_FAIL("cvg_debug_get: unknown key");
+  return 0;
+}
+
+int cvg_debug_mk_cycles(CvgHandle* h, long long* out, int capacity, int* count) {
+  H_OR_FAIL(h);
+  Engine& e = h->e;
+  if (!e.ws_base) CVG_FAIL("workspace not bound");
+  const int n = e.mk.last_nops < capacity ? e.mk.last_nops : capacity;
+  if (count) *count = n;
+  if (out && n > 0) CVG_CUDA(cudaMemcpy(out, e.ws.mk_dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 }  // extern "C"

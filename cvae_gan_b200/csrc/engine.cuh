@@ -69,6 +69,48 @@ struct Workspace {
   // tensor-core path: pre-split weights in shared-memory operand order + per-feature epilogue constants
   float* tc_w = nullptr;
   float* tc_c = nullptr;
+  // step-program kernel (mega.cuh): weight-gradient partial slots, grid-barrier counter, materialised z_enc slot
+  float* dw_scratch = nullptr;
+  long long dw_scratch_floats = 0;
+  unsigned int* mk_bar = nullptr;
+  float* z_eps = nullptr;          // [Z][ld] reparameterisation noise of the E+G step when the program kernel runs it
+  long long* mk_dbg = nullptr;     // per-op cycle counters of the last program (development)
+};
+
+// ---- step-program recorder (mega.cu) ---------------------------------------------------------------------------------
+struct MkSlot {
+  void* dev = nullptr;
+  void* host = nullptr;            // pinned mirror (a captured graph re-reads it at every replay)
+  size_t bytes = 0;
+  unsigned long long hash = 0;
+  cudaEvent_t ev = nullptr;        // completion of the last upload from `host`
+  bool in_graph = false;           // uploaded during stream capture: never recycled
+  unsigned long long last_use = 0;
+};
+struct MkPendingRed {
+  unsigned char bytes[160];
+  int items;
+};
+struct MkState {
+  bool enabled = true;             // CVG_TRAIN_MODE=ffma (or an unsupported shape) keeps the stand-alone FFMA kernels
+  bool coop = true;                // cooperative launch (CVG_MK_COOP=0: plain launch of one CTA per SM)
+  bool allbar = false;             // CVG_MK_ALLBAR=1: a grid barrier before every op (debugging)
+  int max_ops = -1;                // development: truncate every program after this many ops
+  bool recording = false;
+  bool par_next = false;
+  std::vector<unsigned char> ops;  // mk::OpRec records
+  int nops = 0;
+  int phase_items = 0;
+  long long scratch_off = 0;
+  int n_exchanges = 0;
+  int adam_inc[4] = {0, 0, 0, 0};
+  unsigned long long dcounter = 0;
+  std::vector<MkPendingRed> pending_red;
+  const float* src_rows = nullptr;   // inside a visit program: class table the next step draws its batch from
+  long long src_n = 0, src_Bg = 0, src_off = 0;
+  std::vector<MkSlot> slots;
+  unsigned long long clock = 0;
+  int last_nops = 0;
 };
 
 struct ProfRec {
@@ -95,6 +137,7 @@ struct Engine {
   int num_sms = 148;
   long long* tc_dbg = nullptr;   // development: device cycle counters of tc_eval_kernel (cvg_debug_tc_counters)
   bool use_tc = true;      // tensor-core chains (CVG_DISABLE_TC=1 forces the FFMA layer kernels)
+  MkState mk;              // training steps as ONE persistent tcgen05 kernel per step / label visit (mega.cuh)
 
   float* P(int net, int64_t off) const { return buf[net].params + off; }
   float* G(int net, int64_t off) const { return buf[net].grads + off; }
@@ -140,6 +183,17 @@ void nvl_destroy(Engine& e);
 int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st);
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st);
 int comm_all_reduce_stats(Engine& e, double* p, int npass, int C, cudaStream_t st);
+
+// mega.cu: step programs
+bool mk_supported(const Engine& e);
+void mk_set_kernel_attributes();
+void mk_destroy(Engine& e);
+int mk_begin(Engine& e);                                   // start recording (no-op when the program kernel is off)
+int mk_flush(Engine& e, cudaStream_t st);                  // finish + upload + launch the recorded program
+int mk_push(Engine& e, int kind, const void* payload, size_t bytes, int items, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0,
+            const void* extra = nullptr, size_t extra_bytes = 0);
+int mk_push_dw(Engine& e, const DwArgs& g);                // weight-gradient op + its deferred deterministic reduction
+int mk_emit_dwred(Engine& e);                              // emits the pending reductions (one phase)
 
 // generate.cu
 int generate(Engine& e, int label, int64_t n, const float* z, uint64_t seed, uint64_t row_offset, int train_mode,

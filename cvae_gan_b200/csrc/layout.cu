@@ -226,6 +226,23 @@ static size_t carve(const Engine& e, Workspace& w, void* base) {
   w.x_stage = c.take<float>((size_t)rows * F);
   w.tc_w = c.take<float>((size_t)tc_prep_floats(e));
   w.tc_c = c.take<float>((size_t)tc_const_floats());
+  // step-program kernel: 32 row slices of every weight gradient of the E+G step (the largest) fit
+  {
+    long long per = 0;
+    for (int net = 0; net < 4; ++net) {
+      long long t = 0;
+      for (int i = 0; i < e.lay[net].nlin; ++i) {
+        const LinearP& p = e.lay[net].lin[i];
+        t += (long long)p.out * (((p.in + 15) & ~15) + 1);
+      }
+      per += t * (net == CVG_NET_GENERATOR || net == CVG_NET_DISCRIMINATOR ? 2 : 1);
+    }
+    w.dw_scratch_floats = 32 * per;
+  }
+  w.dw_scratch = c.take<float>((size_t)w.dw_scratch_floats);
+  w.mk_bar = c.take<unsigned int>(64);
+  w.z_eps = c.take<float>((size_t)Z * ld);
+  w.mk_dbg = c.take<long long>(2048);
   return c.off + 256;
 }
 

@@ -1,0 +1,1400 @@
+// cvaegan_b200 - the training "step program" kernel (sm_100a): ONE persistent cooperative kernel executes a whole
+// optimiser step - or a whole label visit of 13 steps - of cvae_gan.py:104-216.
+//
+//   * The host records the step as a PROGRAM of ops (train.cu emits the same GemmArgs / DwArgs / LnArgs ... records
+//     it used to launch one kernel each for); one CTA per SM walks the program, takes the work items of every op
+//     round-robin, and a grid barrier replaces each kernel boundary (~1.5 us instead of a launch + drain + ramp).
+//   * Every GEMM (forward, input-gradient, weight-gradient) runs on the 5th-generation tensor cores:
+//     tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-level accuracy), accumulators in TMEM, both operands staged
+//     into shared memory in the K-major no-swizzle core-matrix layout of tc05.cuh by all 512 threads - the operand
+//     transforms (BatchNorm + LeakyReLU of the producing layer, BatchNorm backward) are applied in registers on the
+//     way, so normalised activations never exist in memory.  Orientation: D[feature][row] (forward / input gradient:
+//     MMA M = 128 output features, N = 64 or 128 batch rows) and D[out][in] (weight gradient: M = 128, N = in-features,
+//     K = batch rows).  A two-stage ring lets the asynchronous MMAs of chunk c overlap the staging of chunk c + 1.
+//   * Weight gradients are DETERMINISTIC: every (layer tile, row slice) writes its partial to a scratch slot and a
+//     reduce op sums the slots in a fixed order (no float atomics).
+//   * Data parallel: the BatchNorm-moment and gradient exchanges are ops of the same program (LL packets over NVLink
+//     peer memory, comm_nvl.cuh) - no extra launches.
+//
+// Activations stay in the feature-major workspace of gemm.cuh ([features][ld], L2 resident), so every op has the
+// same inputs and outputs as the stand-alone kernel it replaces: the FFMA kernels remain as the A/B reference
+// (CVG_TRAIN_MODE=ffma) and tests compare the two paths buffer by buffer.
+#pragma once
+#include "engine.cuh"
+#include "tc05.cuh"
+
+namespace cvg {
+namespace mk {
+using namespace tc;
+
+constexpr int THREADS = 512;
+constexpr int KC = 32;                        // contraction values per pipeline stage
+constexpr int KG = KC / 4;                    // groups of 4 contraction values (one 16-byte core-matrix row)
+constexpr int LBO_A = 128 * 16 + 16;          // bytes between k-groups of the A operand (128 rows, padded: conflict-free stores)
+constexpr int A_PLANE = KG * LBO_A;
+constexpr int B_MAXN = 256;                   // widest MMA N
+constexpr int LBO_B_MAX = B_MAXN * 16 + 16;
+constexpr int B_PLANE = KG * LBO_B_MAX;
+constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // hi + lo planes of both operands
+constexpr int NSTAGE = 2;
+constexpr int CS_FLOATS = 2560;               // per-feature constants of the operand transforms / epilogues (C <= 256)
+constexpr int RED_DOUBLES = 1024;
+constexpr int TMEM_COLS = 256;
+constexpr int OP_BYTES = 512;
+constexpr int MAX_C = 256;                    // widest BatchNorm layer the program kernel handles
+
+enum {
+  K_MN = 1, K_DW, K_DWRED, K_FILL, K_STAGE, K_SN_POWER, K_SN_DOT, K_SN_GRAD, K_LN_FWD, K_LN_BWD, K_CE, K_SEED, K_ZERO,
+  K_PACK, K_UNPACK, K_ADAM, K_CTL_SET, K_FINISH, K_NVL_F32, K_NVL_F64, K_REPARAM
+};
+
+struct alignas(16) OpRec {
+  int kind;
+  int bar_before;     // grid barrier before this op (it reads what earlier ops wrote)
+  int items;          // independent work items
+  int first;          // offset of the op's items within its phase (rotates the CTA assignment)
+  int aux[4];
+  unsigned char payload[OP_BYTES - 32];
+};
+static_assert(sizeof(OpRec) == OP_BYTES, "op record size");
+
+// ---- payloads that have no stand-alone kernel argument struct -------------------------------------------------------
+struct DwRedArgs {
+  const float* part; const float* bpart;     // [nz][N][Kp], [nz][N]
+  int nz, nsplit, npass;
+  int N, K, Kp;
+  float* dW; long long sdW; int ldw, wcol0;
+  float* db; int label_col;
+  float* dgamma; float* dbeta; const double* bstats; long long sb; int C; int add_affine;
+};
+struct StageArgs {            // _get_target_samples (optional) + transpose to the feature-major workspace
+  const float* src;           // row-major [.][F]: the batch itself, or the class table when sampling
+  long long n_rows;           // > 0: draw rows from the class table (cvae_gan.py:247-260)
+  long long B_global, draw_offset;
+  int M, F, ld;
+  const StepCtl* ctl; unsigned long long counter_off;
+  float* xT;
+};
+struct ZeroArgs { void* p; long long bytes; };
+struct PackArgs { const double* acc; float* tail; };
+struct UnpackArgs { const float* tail; float* out; int kind; float Bg, F; float* tail_w; };
+struct CtlSetArgs { StepCtl* ctl; unsigned long long seed, counter; int set_rng; float lambda_class; int set_lambda; };
+struct FinishArgs { StepCtl* ctl; unsigned long long dcounter; int adam_inc[4]; int n_exchanges; };
+struct NvlArgs { void* data; long long seg_len, seg_stride; int nseg; int exchange; };   // exchange: index within the program
+struct ReparamArgs { const float* mu; const float* lv; const float* eps; float* out; int M, ld, Z; };
+struct AdamOp { AdamArgs a; int t_off[2]; };
+
+struct Params {
+  const OpRec* ops;
+  int nops;
+  unsigned int* bar_counter;     // zeroed by the host before every launch
+  NvlDev nvl;                    // world == 0: no peer exchanges in this program
+  long long* dbg;                // optional per-op cycle counters [nops] (CTA 0)
+};
+
+struct Ctrl {
+  uint64_t bar[NSTAGE];
+  uint32_t tmem_slot;
+  uint32_t pad;
+  unsigned long long nvl_epoch0;
+};
+
+constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + CS_FLOATS * 4 + RED_DOUBLES * 8 + OP_BYTES + sizeof(Ctrl) + 64;
+
+struct Ctx {
+  uint8_t* stages;
+  float* cs;
+  double* red;
+  uint64_t* bar;
+  uint32_t tmem;
+  int n_commit[NSTAGE];
+  int tid, warp, lane;
+};
+
+// ---- loads of data that other CTAs produced earlier in the SAME launch: L2 only (L1 is not coherent) ---------------
+__device__ __forceinline__ float ldg1(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ double ldgd(const double* p) { return __ldcg(p); }
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all CTAs of the (cooperative, co-resident) grid; a CTA that never arrives makes the others trap instead of hanging
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(counter) < target) {
+      if (clock64() - t0 > 20000000000ll) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ---- BatchNorm constants (same arithmetic as gemm.cuh, statistics read through L2) -----------------------------------
+__device__ __forceinline__ void mk_bn_mean_rstd(const BnRef& bn, int pass, int c, float Bg, float eps, float& mean, float& rstd) {
+  float var;
+  if (bn.eval) {
+    mean = ldg1(bn.rmean + c);
+    var = ldg1(bn.rvar + c);
+  } else {
+    const double* s = bn.fstats + (long long)pass * bn.sf;
+    const double inv = 1.0 / (double)Bg;
+    const double m = ldgd(s + c) * inv;
+    double v = ldgd(s + bn.C + c) * inv - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+  }
+  rstd = 1.0f / sqrtf(var + eps);
+}
+
+__device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs) {
+  if (o.kind == OP_BN_ACT) {
+    const int C = o.bn.C;
+    for (int c = threadIdx.x; c < C; c += THREADS) {
+      float mean, rstd;
+      mk_bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd);
+      cs[c] = ldg1(o.bn.gamma + c) * rstd;
+      cs[C + c] = ldg1(o.bn.beta + c);
+      cs[2 * C + c] = mean;
+    }
+  } else if (o.kind == OP_BN_BWD) {
+    const int C = o.bn.C;
+    const double* bs = o.bn.bstats + (long long)pass * o.bn.sb;
+    for (int c = threadIdx.x; c < C; c += THREADS) {
+      float mean, rstd;
+      mk_bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd);
+      cs[c] = ldg1(o.bn.gamma + c) * rstd;
+      cs[C + c] = (float)(ldgd(bs + c) / (double)Bg);
+      cs[2 * C + c] = (float)(ldgd(bs + C + c) / (double)Bg);
+      cs[3 * C + c] = mean;
+      cs[4 * C + c] = rstd;
+    }
+  }
+}
+
+__device__ __forceinline__ void mk_bn_update_running(const BnRef& bn, int npass, float Bg, float momentum) {
+  for (int c = threadIdx.x; c < bn.C; c += THREADS) {
+    float rm = ldg1(bn.rmean + c), rv = ldg1(bn.rvar + c);
+    for (int p = 0; p < npass; ++p) {
+      const double* s = bn.fstats + (long long)p * bn.sf;
+      const double m = ldgd(s + c) / (double)Bg;
+      double v = ldgd(s + bn.C + c) / (double)Bg - m * m;
+      if (v < 0.0) v = 0.0;
+      const double unb = v * ((double)Bg / ((double)Bg - 1.0));
+      rm = (1.0f - momentum) * rm + momentum * (float)m;
+      rv = (1.0f - momentum) * rv + momentum * (float)unb;
+    }
+    bn.rmean[c] = rm;
+    bn.rvar[c] = rv;
+  }
+}
+
+// ---- operand element access -------------------------------------------------------------------------------------------
+// raw values of ONE element (feature row r, batch row m) of an operand; the transform is applied later, right before the
+// value goes to shared memory, so the loads of the next chunk stay in flight across the MMAs of this one
+struct Raw1 { float a, b; };
+__device__ __forceinline__ void mk_load1(const Operand& o, int pass, int r, int m, int M, int ld, Raw1& w) {
+  w.a = 0.f; w.b = 0.f;
+  if (r >= o.rows || m >= M || o.kind == OP_CONST) return;
+  const size_t off = (size_t)r * ld + m;
+  w.a = ldg1(o.p + (long long)pass * o.sp + off);
+  if (o.kind == OP_BN_BWD) w.b = ldg1(o.h + (long long)pass * o.sh + off);
+}
+__device__ __forceinline__ float mk_finish1(const Operand& o, const float* cs, int r, int m, int M, float slope, const Raw1& w) {
+  if (r >= o.rows || m >= M) return 0.f;
+  switch (o.kind) {
+    case OP_BN_ACT: {
+      const int C = o.bn.C;
+      return act_lrelu(fmaf(w.a - cs[2 * C + r], cs[r], cs[C + r]), slope);
+    }
+    case OP_BN_BWD: {
+      const int C = o.bn.C;
+      return cs[r] * (w.a - cs[C + r] - (w.b - cs[3 * C + r]) * cs[4 * C + r] * cs[2 * C + r]);
+    }
+    case OP_CONST:
+      return o.cst;
+    default:
+      return w.a;
+  }
+}
+// 4 consecutive batch rows of one feature row (weight-gradient operands: the contraction runs over batch rows)
+struct Raw4 { float4 a, b; };
+__device__ __forceinline__ void mk_load4(const Operand& o, int pass, int r, int m, int M, int ld, Raw4& w) {
+  w.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  w.b = w.a;
+  if (r >= o.rows || m >= M || o.kind == OP_CONST) return;
+  const size_t off = (size_t)r * ld + m;
+  w.a = ldg4(o.p + (long long)pass * o.sp + off);
+  if (o.kind == OP_BN_BWD) w.b = ldg4(o.h + (long long)pass * o.sh + off);
+}
+__device__ __forceinline__ float4 mk_finish4(const Operand& o, const float* cs, int r, int m, int M, float slope, const Raw4& w) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r >= o.rows || m >= M) return v;
+  switch (o.kind) {
+    case OP_BN_ACT: {
+      const int C = o.bn.C;
+      const float sc = cs[r], sh = cs[C + r], mean = cs[2 * C + r];
+      v.x = act_lrelu(fmaf(w.a.x - mean, sc, sh), slope);
+      v.y = act_lrelu(fmaf(w.a.y - mean, sc, sh), slope);
+      v.z = act_lrelu(fmaf(w.a.z - mean, sc, sh), slope);
+      v.w = act_lrelu(fmaf(w.a.w - mean, sc, sh), slope);
+    } break;
+    case OP_BN_BWD: {
+      const int C = o.bn.C;
+      const float c1 = cs[r], c2 = cs[C + r], c3 = cs[2 * C + r], mean = cs[3 * C + r], rstd = cs[4 * C + r];
+      v.x = c1 * (w.a.x - c2 - (w.b.x - mean) * rstd * c3);
+      v.y = c1 * (w.a.y - c2 - (w.b.y - mean) * rstd * c3);
+      v.z = c1 * (w.a.z - c2 - (w.b.z - mean) * rstd * c3);
+      v.w = c1 * (w.a.w - c2 - (w.b.w - mean) * rstd * c3);
+    } break;
+    case OP_CONST:
+      v = make_float4(o.cst, o.cst, o.cst, o.cst);
+      break;
+    default:
+      v = w.a;
+      break;
+  }
+  if (m + 3 >= M) {
+    if (m + 1 >= M) v.y = 0.f;
+    if (m + 2 >= M) v.z = 0.f;
+    if (m + 3 >= M) v.w = 0.f;
+  }
+  return v;
+}
+
+// hi / lo planes of one operand value group: 16-byte stores
+__device__ __forceinline__ void st_split4(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t off, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x);
+  split_tf32(v.y, h.y, l.y);
+  split_tf32(v.z, h.z, l.z);
+  split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4*>(hi_plane + off) = h;
+  *reinterpret_cast<float4*>(lo_plane + off) = l;
+}
+
+__device__ __forceinline__ void stage_ptrs(const Ctx& c, int s, uint8_t*& a_hi, uint8_t*& a_lo, uint8_t*& b_hi, uint8_t*& b_lo) {
+  uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
+  a_hi = base;
+  a_lo = base + A_PLANE;
+  b_hi = base + 2 * A_PLANE;
+  b_lo = base + 2 * A_PLANE + B_PLANE;
+}
+
+// MMAs of one staged chunk: nks steps of 8 contraction values, three tf32 MMAs each (small terms first); one commit
+__device__ __forceinline__ void issue_chunk(const Ctx& c, int s, int nks, int n_mma, uint32_t lbo_b, bool first_chunk) {
+  if (c.warp == 0) {
+    tc_fence_after_sync();
+    if (elect_one()) {
+      const uint32_t base = smem_u32(c.stages + (size_t)s * STAGE_BYTES);
+      uint64_t dah = smem_desc(base, LBO_A, 128), dal = smem_desc(base + A_PLANE, LBO_A, 128);
+      uint64_t dbh = smem_desc(base + 2 * A_PLANE, lbo_b, 128), dbl = smem_desc(base + 2 * A_PLANE + B_PLANE, lbo_b, 128);
+      const uint32_t idesc = idesc_tf32(128, n_mma, 0, 0);
+      const uint64_t a_step = (uint64_t)((2 * LBO_A) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
+      for (int ks = 0; ks < nks; ++ks) {
+        mma_tf32(c.tmem, dal, dbh, idesc, !(first_chunk && ks == 0));
+        mma_tf32(c.tmem, dah, dbl, idesc, true);
+        mma_tf32(c.tmem, dah, dbh, idesc, true);
+        dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
+      }
+      mma_commit(&c.bar[s]);
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void wait_stage(Ctx& c, int s) {
+  if (c.n_commit[s] > 0) mbar_wait(&c.bar[s], (uint32_t)((c.n_commit[s] - 1) & 1));
+}
+
+// ======================================================================================================================
+// forward / input-gradient GEMM item:  D[n][m] = sum_r A[n][r] * B[m][r]
+//   wt  : A = W[n][r] (forward)          !wt : A = W[r][n] (input gradient)
+//   B = operand g.a (feature-major [r][m] in memory, transformed), m = batch rows of this tile
+// ======================================================================================================================
+struct MnRegs {
+  float4 a[2];        // raw weights (already in operand order)
+  Raw1 b[2][4];
+};
+
+__device__ __forceinline__ void mn_load(const GemmArgs& g, bool wt, int Nt, int pass, int n0, int m0, int chunk, int tid, MnRegs& rg) {
+  const int r0 = chunk * KC;
+  const bool wvec = ((g.ldw | g.wcol0) & 3) == 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * THREADS;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wt) {
+      const int k4 = idx & 7, n = n0 + (idx >> 3), r = r0 + k4 * 4;
+      if (n < g.N && r < g.R) {
+        const float* src = g.W + (size_t)n * g.ldw + g.wcol0 + r;
+        if (wvec && r + 3 < g.R) {
+          w = ldg4(src);
+        } else {
+          w.x = ldg1(src);
+          if (r + 1 < g.R) w.y = ldg1(src + 1);
+          if (r + 2 < g.R) w.z = ldg1(src + 2);
+          if (r + 3 < g.R) w.w = ldg1(src + 3);
+        }
+      }
+    } else {
+      const int n = n0 + (idx & 127), k4 = idx >> 7, r = r0 + k4 * 4;
+      if (n < g.N) {
+        const float* src = g.W + (size_t)r * g.ldw + g.wcol0 + n;
+        if (r < g.R) w.x = ldg1(src);
+        if (r + 1 < g.R) w.y = ldg1(src + (size_t)g.ldw);
+        if (r + 2 < g.R) w.z = ldg1(src + 2 * (size_t)g.ldw);
+        if (r + 3 < g.R) w.w = ldg1(src + 3 * (size_t)g.ldw);
+      }
+    }
+    rg.a[j] = w;
+  }
+  const int nb = (Nt * KG) / THREADS;   // 1 (64 rows) or 2 (128 rows)
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (j < nb) {
+      const int idx = tid + j * THREADS;
+      const int m = m0 + idx % Nt, r = r0 + (idx / Nt) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mk_load1(g.a, pass, r + i, m, g.M, g.ld, rg.b[j][i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void mn_store(const Ctx& c, const GemmArgs& g, bool wt, int Nt, int m0, int chunk, int s, int nk4,
+                                         const float* cs_a, const MnRegs& rg) {
+  uint8_t *a_hi, *a_lo, *b_hi, *b_lo;
+  stage_ptrs(c, s, a_hi, a_lo, b_hi, b_lo);
+  const int r0 = chunk * KC;
+  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = c.tid + j * THREADS;
+    int k4, n;
+    if (wt) { k4 = idx & 7; n = idx >> 3; } else { n = idx & 127; k4 = idx >> 7; }
+    if (k4 < nk4) st_split4(a_hi, a_lo, (uint32_t)k4 * LBO_A + (uint32_t)n * 16u, rg.a[j]);
+  }
+  const int nb = (Nt * KG) / THREADS;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (j < nb) {
+      const int idx = c.tid + j * THREADS;
+      const int ml = idx % Nt, k4 = idx / Nt, m = m0 + ml, r = r0 + k4 * 4;
+      if (k4 < nk4) {
+        float4 v;
+        v.x = mk_finish1(g.a, cs_a, r, m, g.M, g.slope, rg.b[j][0]);
+        v.y = mk_finish1(g.a, cs_a, r + 1, m, g.M, g.slope, rg.b[j][1]);
+        v.z = mk_finish1(g.a, cs_a, r + 2, m, g.M, g.slope, rg.b[j][2]);
+        v.w = mk_finish1(g.a, cs_a, r + 3, m, g.M, g.slope, rg.b[j][3]);
+        st_split4(b_hi, b_lo, (uint32_t)k4 * lbo_b + (uint32_t)ml * 16u, v);
+      }
+    }
+  }
+}
+
+__device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
+  const int ntm = (g.M + Nt - 1) / Nt;
+  const int nmt = (g.N + 127) / 128;
+  const int rt = item % ntm;
+  const int t2 = item / ntm;
+  const int mt = t2 % nmt;
+  const int pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
+  const int m0 = rt * Nt, n0 = mt * 128;
+  float* cs_a = c.cs;
+  float* cs_e = c.cs + operand_const_floats(g.a);
+  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
+  const int nchunks = (g.R + KC - 1) / KC;
+
+  MnRegs rg;
+  mn_load(g, wt, Nt, pass, n0, m0, 0, c.tid, rg);     // in flight while the constants are prepared
+
+  mk_operand_consts(g.a, pass, g.Bg, g.bn_eps, cs_a);
+  if (g.ekind == EP_DBN) {
+    const int C = g.prev_bn.C;
+    for (int ch = c.tid; ch < C; ch += THREADS) {
+      float mean, rstd;
+      mk_bn_mean_rstd(g.prev_bn, pass, ch, g.Bg, g.bn_eps, mean, rstd);
+      cs_e[ch] = ldg1(g.prev_bn.gamma + ch) * rstd;
+      cs_e[C + ch] = ldg1(g.prev_bn.beta + ch);
+      cs_e[2 * C + ch] = mean;
+      cs_e[3 * C + ch] = rstd;
+    }
+  }
+  if (g.a.kind == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum);
+  __syncthreads();
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int s = ch & 1;
+    const int klen = min(KC, g.R - ch * KC);
+    const int nks = (klen + 7) >> 3;
+    if (ch >= NSTAGE) wait_stage(c, s);             // the MMAs that read this stage two chunks ago have completed
+    mn_store(c, g, wt, Nt, m0, ch, s, 2 * nks, cs_a, rg);
+    if (ch + 1 < nchunks) mn_load(g, wt, Nt, pass, n0, m0, ch + 1, c.tid, rg);
+    fence_proxy_async_smem();
+    __syncthreads();
+    issue_chunk(c, s, nks, Nt, lbo_b, ch == 0);
+    c.n_commit[s]++;
+  }
+  wait_stage(c, 0);
+  if (nchunks > 1) wait_stage(c, 1);
+  tc_fence_after_sync();
+
+  // ---- epilogue: thread = (output feature = TMEM lane, 16-row column blocks) ----------------------------------------
+  const int q = c.warp & 3, cgp = c.warp >> 2;
+  const int n = n0 + q * 32 + c.lane;
+  const bool nvalid = n < g.N;
+  const float scale = g.scale ? ldg1(g.scale + pass) : 1.0f;
+  double s1 = 0.0, s2 = 0.0, tot = 0.0, klsum = 0.0;
+  float bias = 0.f;
+  float e_sc = 0.f, e_sh = 0.f, e_mean = 0.f, e_rstd = 0.f;
+  if (nvalid) {
+    if (g.ekind == EP_LINEAR) {
+      bias = g.bias ? ldg1(g.bias + n) : 0.f;
+      if (g.wlabel) bias += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
+    } else if (g.ekind == EP_DBN) {
+      const int C = g.prev_bn.C;
+      e_sc = cs_e[n]; e_sh = cs_e[C + n]; e_mean = cs_e[2 * C + n]; e_rstd = cs_e[3 * C + n];
+    }
+  }
+  const int nhb = Nt / 64;
+  for (int hb = 0; hb < nhb; ++hb) {
+    const int col = cgp * (Nt / 4) + hb * 16;
+    float v[16];
+    tmem_ld16(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      const int m = m0 + col + gq * 4;
+      if (!nvalid || m >= g.M) continue;
+      float y[4] = {v[gq * 4], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]};
+      const bool rowv[4] = {true, m + 1 < g.M, m + 2 < g.M, m + 3 < g.M};
+      const size_t off = (size_t)n * g.ld + m;
+      if (g.ekind == EP_LINEAR) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = fmaf(y[i], scale, bias);
+        if (g.kl_acc) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rowv[i]) klsum += (n < g.kl_split) ? 0.5 * (double)y[i] * (double)y[i] : -0.5 * (1.0 + (double)y[i] - (double)expf(y[i]));
+        }
+        if (g.ostats) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rowv[i]) { s1 += (double)y[i]; s2 += (double)y[i] * (double)y[i]; }
+        }
+        if (g.act == ACT_LRELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = act_lrelu(y[i], g.slope);
+        } else if (g.act == ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
+        } else if (g.act == ACT_SIGMOID) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = 1.0f / (1.0f + expf(-y[i]));
+        }
+        if (g.mask) {
+          const uchar4 mk = __ldcg(reinterpret_cast<const uchar4*>(g.mask + (long long)pass * g.smask + off));
+          y[0] = mk.x ? y[0] * g.keep_inv : 0.f;
+          y[1] = mk.y ? y[1] * g.keep_inv : 0.f;
+          y[2] = mk.z ? y[2] * g.keep_inv : 0.f;
+          y[3] = mk.w ? y[3] * g.keep_inv : 0.f;
+        }
+        if (g.osum) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (rowv[i]) tot += (double)y[i];
+        }
+        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (g.ekind == EP_DBN) {
+        const float4 h = ldg4(g.prev + (long long)pass * g.sprev + off);
+        const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pre = fmaf(hh[i] - e_mean, e_sc, e_sh);
+          const float dy = rowv[i] ? (pre > 0.f ? y[i] : y[i] * g.slope) : 0.f;
+          y[i] = dy;
+          s1 += (double)dy;
+          s2 += (double)(dy * ((hh[i] - e_mean) * e_rstd));
+        }
+        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (g.ekind == EP_DACT) {
+        const float4 ap = ldg4(g.prev + (long long)pass * g.sprev + off);
+        const float aa[4] = {ap.x, ap.y, ap.z, ap.w};
+        float keep[4] = {1.f, 1.f, 1.f, 1.f};
+        if (g.mask) {
+          const uchar4 mk = __ldcg(reinterpret_cast<const uchar4*>(g.mask + (long long)pass * g.smask + off));
+          keep[0] = mk.x ? g.keep_inv : 0.f;
+          keep[1] = mk.y ? g.keep_inv : 0.f;
+          keep[2] = mk.z ? g.keep_inv : 0.f;
+          keep[3] = mk.w ? g.keep_inv : 0.f;
+        }
+        const float neg = (g.act == ACT_LRELU) ? g.slope : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d = y[i] * scale * keep[i];
+          y[i] = aa[i] > 0.f ? d : d * neg;
+        }
+        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (g.ekind == EP_STORE) {
+        float* dst = g.Y + (long long)pass * g.sY + off;
+        float4 o = make_float4(y[0] * scale, y[1] * scale, y[2] * scale, y[3] * scale);
+        if (g.accumulate) {
+          const float4 old = ldg4(dst);
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
+        st4(dst, o);
+      } else if (g.ekind == EP_REPARAM_BWD) {
+        const float4 mu = ldg4(g.mu + off), lv = ldg4(g.lv + off), ee4 = ldg4(g.eps + off);
+        const float mm[4] = {mu.x, mu.y, mu.z, mu.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w}, ee[4] = {ee4.x, ee4.y, ee4.z, ee4.w};
+        float dmu[4], dlv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dmu[i] = rowv[i] ? y[i] + g.kl_coef * mm[i] : 0.f;
+          dlv[i] = rowv[i] ? y[i] * ee[i] * 0.5f * expf(0.5f * ll[i]) + g.kl_coef * 0.5f * (expf(ll[i]) - 1.0f) : 0.f;
+        }
+        st4(g.Y + off, make_float4(dmu[0], dmu[1], dmu[2], dmu[3]));
+        st4(g.Y + (size_t)(g.N + n) * g.ld + m, make_float4(dlv[0], dlv[1], dlv[2], dlv[3]));
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  if (g.ostats) {
+    // the four column groups of a feature meet in shared memory: one atomic pair per (feature, tile)
+    const int slot = (cgp * 128 + q * 32 + c.lane) * 2;
+    c.red[slot] = s1;
+    c.red[slot + 1] = s2;
+    __syncthreads();
+    if (cgp == 0 && nvalid) {
+      const int b = (q * 32 + c.lane) * 2;
+      const double t1 = (c.red[b] + c.red[256 + b]) + (c.red[512 + b] + c.red[768 + b]);
+      const double t2 = (c.red[b + 1] + c.red[256 + b + 1]) + (c.red[512 + b + 1] + c.red[768 + b + 1]);
+      double* st = g.ostats + (long long)pass * g.sostats;
+      atomicAdd(st + n, t1);
+      atomicAdd(st + g.N + n, t2);
+    }
+  }
+  if (g.osum) {
+    tot = warp_sum_d(tot);
+    if (c.lane == 0 && tot != 0.0) atomicAdd(g.osum + pass, tot);
+  }
+  if (g.kl_acc) {
+    klsum = warp_sum_d(klsum);
+    if (c.lane == 0 && klsum != 0.0) atomicAdd(g.kl_acc, klsum);
+  }
+  __syncthreads();     // TMEM drained, constants and the reduction scratch free for the next item
+}
+
+// ======================================================================================================================
+// weight-gradient GEMM item:  part[z][n][k] = sum_{m in slice} P[n][m] * Q[k][m]      (+ bias partial sum_m P[n][m])
+// ======================================================================================================================
+struct DwRegs {
+  Raw4 p[2];
+  Raw4 q[4];
+};
+
+__device__ __forceinline__ void dw_load(const DwArgs& g, int pass, int n0, int npad, int mb, int mend, int tid, DwRegs& rg) {
+  const int rgp = tid & 7;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int f = (tid >> 3) + j * (THREADS / 8);
+    mk_load4(g.p, pass, n0 + f, mb + rgp * 4, mend, g.ld, rg.p[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int f = (tid >> 3) + j * (THREADS / 8);
+    if (f < npad) mk_load4(g.q, pass, f, mb + rgp * 4, mend, g.ld, rg.q[j]);
+  }
+}
+
+__device__ __forceinline__ void dw_store(const Ctx& c, const DwArgs& g, int n0, int npad, int mb, int mend, int s, const float* cs_p,
+                                         const float* cs_q, const DwRegs& rg, float* bsum) {
+  uint8_t *a_hi, *a_lo, *b_hi, *b_lo;
+  stage_ptrs(c, s, a_hi, a_lo, b_hi, b_lo);
+  const int rgp = c.tid & 7;
+  const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int f = (c.tid >> 3) + j * (THREADS / 8);
+    const float4 v = mk_finish4(g.p, cs_p, n0 + f, mb + rgp * 4, mend, g.slope, rg.p[j]);
+    bsum[j] += (v.x + v.y) + (v.z + v.w);
+    st_split4(a_hi, a_lo, (uint32_t)rgp * LBO_A + (uint32_t)f * 16u, v);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int f = (c.tid >> 3) + j * (THREADS / 8);
+    if (f < npad) {
+      const float4 v = mk_finish4(g.q, cs_q, f, mb + rgp * 4, mend, g.slope, rg.q[j]);
+      st_split4(b_hi, b_lo, (uint32_t)rgp * lbo_b + (uint32_t)f * 16u, v);
+    }
+  }
+}
+
+// aux: [0] = nsplit, scratch pointers in the op header
+struct DwScratch { float* part; float* bpart; int nsplit; int kp; };
+
+__device__ void dw_item(Ctx& c, const DwArgs& g, const DwScratch& sc, int item) {
+  const int nnt = (g.N + 127) / 128;
+  const int nt = item % nnt;
+  const int z = item / nnt;
+  const int pass = z / sc.nsplit, split = z % sc.nsplit;
+  const int n0 = nt * 128;
+  const int mbeg = split * g.rows_per_cta;
+  const int mend = min(g.M, mbeg + g.rows_per_cta);
+  const int npad = (g.K + 15) & ~15;
+  const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
+  float* cs_p = c.cs;
+  float* cs_q = c.cs + operand_const_floats(g.p);
+  const int nchunks = mend > mbeg ? (mend - mbeg + KC - 1) / KC : 0;
+
+  DwRegs rg;
+  if (nchunks > 0) dw_load(g, pass, n0, npad, mbeg, mend, c.tid, rg);
+  mk_operand_consts(g.p, pass, g.Bg, g.bn_eps, cs_p);
+  mk_operand_consts(g.q, pass, g.Bg, g.bn_eps, cs_q);
+  __syncthreads();
+
+  float bsum[2] = {0.f, 0.f};
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int s = ch & 1;
+    const int mb = mbeg + ch * KC;
+    const int nks = (min(KC, mend - mb) + 7) >> 3;
+    if (ch >= NSTAGE) wait_stage(c, s);
+    dw_store(c, g, n0, npad, mb, mend, s, cs_p, cs_q, rg, bsum);
+    if (ch + 1 < nchunks) dw_load(g, pass, n0, npad, mb + KC, mend, c.tid, rg);
+    fence_proxy_async_smem();
+    __syncthreads();
+    issue_chunk(c, s, nks, npad, lbo_b, ch == 0);
+    c.n_commit[s]++;
+  }
+  if (nchunks > 0) wait_stage(c, 0);
+  if (nchunks > 1) wait_stage(c, 1);
+  tc_fence_after_sync();
+
+  // ---- epilogue: the partial tile goes to its scratch slot (row pitch kp), 16 columns per TMEM load ---------------------
+  const int q = c.warp & 3, cgp = c.warp >> 2;
+  const int n = n0 + q * 32 + c.lane;
+  float* prow = sc.part + ((size_t)z * g.N + n) * sc.kp;
+  for (int b = cgp; b < npad / 16; b += 4) {
+    float v[16];
+    if (nchunks > 0) {
+      tmem_ld16(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 16), v);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+    if (n < g.N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st4(prow + b * 16 + i * 4, make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]));
+    }
+  }
+  // bias partial: the 8 lanes that staged the 8 row groups of a feature
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float b = bsum[j];
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    b += __shfl_xor_sync(0xffffffffu, b, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 4);
+    const int f = n0 + (c.tid >> 3) + j * (THREADS / 8);
+    if ((c.tid & 7) == 0 && f < g.N) sc.bpart[(size_t)z * g.N + f] = b;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+}
+
+// sums the row-slice partials in a fixed order and adds them to the gradient buffer (deterministic)
+__device__ void dwred_item(const DwRedArgs& a, int item) {
+  const int per_item = 4 * THREADS;
+  const int ndest = a.sdW != 0 ? a.npass : 1;
+  const int zper = a.sdW != 0 ? a.nsplit : a.nz;
+  const long long nel = (long long)a.N * a.K;
+  for (int d = 0; d < ndest; ++d) {
+    float* dW = a.dW + (long long)d * a.sdW;
+    for (long long e = (long long)item * per_item + threadIdx.x; e < min(nel, (long long)(item + 1) * per_item); e += THREADS) {
+      const int n = (int)(e / a.K), k = (int)(e % a.K);
+      float s = 0.f;
+      for (int z = d * zper; z < (d + 1) * zper; ++z) s += ldg1(a.part + ((size_t)z * a.N + n) * a.Kp + k);
+      float* dst = dW + (size_t)n * a.ldw + a.wcol0 + k;
+      *dst = ldg1(dst) + s;
+    }
+    if (item == 0 && a.label_col >= 0) {
+      for (int n = threadIdx.x; n < a.N; n += THREADS) {
+        float s = 0.f;
+        for (int z = d * zper; z < (d + 1) * zper; ++z) s += ldg1(a.bpart + (size_t)z * a.N + n);
+        float* dst = dW + (size_t)n * a.ldw + a.label_col;
+        *dst = ldg1(dst) + s;
+      }
+    }
+  }
+  if (item == 0) {
+    if (a.db) {
+      for (int n = threadIdx.x; n < a.N; n += THREADS) {
+        float s = 0.f;
+        for (int z = 0; z < a.nz; ++z) s += ldg1(a.bpart + (size_t)z * a.N + n);
+        a.db[n] = ldg1(a.db + n) + s;
+      }
+    }
+    if (a.add_affine && a.dgamma) {
+      for (int p = 0; p < a.npass; ++p) {
+        const double* bs = a.bstats + (long long)p * a.sb;
+        for (int ch = threadIdx.x; ch < a.C; ch += THREADS) {
+          a.dbeta[ch] = ldg1(a.dbeta + ch) + (float)ldgd(bs + ch);
+          a.dgamma[ch] = ldg1(a.dgamma + ch) + (float)ldgd(bs + a.C + ch);
+        }
+      }
+    }
+  }
+}
+
+// ======================================================================================================================
+// row-wise / element-wise ops: the bodies of misc_kernels.cuh re-cut for 512-thread CTAs and grid-strided work items
+// ======================================================================================================================
+constexpr int FILL_VB = 64;       // work items per fill job
+constexpr int ADAM_VB = 96;       // work items per Adam segment
+constexpr int NVL_VB = 8;         // work items per exchange (each thread pushes / polls its own elements)
+
+__device__ void fill_item(const FillArgs& a, int item) {
+  const FillJob j = a.job[item / FILL_VB];
+  const int vb = item % FILL_VB;
+  const int ngroups = (j.nfeat + 3) >> 2;
+  const long long total = (long long)j.npass * ngroups * a.M;
+  const uint32_t keep_thr = (uint32_t)((double)a.keep_prob * 4294967296.0);
+  const uint64_t seed = a.ctl ? __ldcg(&a.ctl->seed) : a.seed;
+  const uint64_t counter = a.ctl ? __ldcg(&a.ctl->counter) + a.counter_off : a.counter;
+  for (long long t = (long long)vb * THREADS + threadIdx.x; t < total; t += (long long)FILL_VB * THREADS) {
+    const int m = (int)(t % a.M);
+    const int fg = (int)((t / a.M) % ngroups);
+    const int pass = (int)(t / ((long long)a.M * ngroups));
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+    uint8_t bits[4] = {0, 0, 0, 0};
+    if (j.injected) {
+      for (int i = 0; i < 4; ++i) {
+        const int f = fg * 4 + i;
+        if (f < j.nfeat) {
+          const size_t src = ((size_t)pass * a.M + m) * j.nfeat + f;
+          if (j.kind == 0) vals[i] = ((const float*)j.injected)[src];
+          else bits[i] = ((const uint8_t*)j.injected)[src] ? 1 : 0;
+        }
+      }
+    } else {
+      const U4 r = philox_at(seed, counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
+      if (j.kind == 0) {
+        box_muller(r.x, r.y, vals[0], vals[1]);
+        box_muller(r.z, r.w, vals[2], vals[3]);
+      } else {
+        bits[0] = r.x < keep_thr; bits[1] = r.y < keep_thr; bits[2] = r.z < keep_thr; bits[3] = r.w < keep_thr;
+      }
+    }
+    for (int i = 0; i < 4; ++i) {
+      const int f = fg * 4 + i;
+      if (f < j.nfeat) {
+        const size_t dst = ((size_t)pass * j.nfeat + f) * a.ld + m;
+        if (j.kind == 0) ((float*)j.out)[dst] = vals[i];
+        else ((uint8_t*)j.out)[dst] = bits[i];
+      }
+    }
+  }
+}
+
+// cvae_gan.py:247-260 (optional) + transpose of the batch to the feature-major workspace: thread = batch row
+__device__ void stage_item(const StageArgs& a, int item) {
+  const int il = item * THREADS + threadIdx.x;
+  if (il >= a.M) return;
+  long long r = il;
+  if (a.n_rows > 0) {
+    const uint64_t seed = __ldcg(&a.ctl->seed);
+    const uint64_t counter = __ldcg(&a.ctl->counter) + a.counter_off;
+    const long long n = a.n_rows, B = a.B_global;
+    const long long i = a.draw_offset + il;
+    if (n == B) {
+      r = i;
+    } else if (n < B) {
+      const U4 u = philox_at(seed, counter, RS_SAMPLE, 0, (uint64_t)i, 0);
+      const uint64_t w = ((uint64_t)u.x << 32) | u.y;
+      r = (long long)(w % (uint64_t)n);
+    } else {
+      int bits = 1;
+      while ((1ll << bits) < n) ++bits;
+      const int half = (bits + 1) >> 1;
+      uint32_t keys[6];
+      const U4 k0 = philox_at(seed, counter, RS_SAMPLE, 1, 0, 0), k1 = philox_at(seed, counter, RS_SAMPLE, 1, 1, 0);
+      keys[0] = k0.x; keys[1] = k0.y; keys[2] = k0.z; keys[3] = k0.w; keys[4] = k1.x; keys[5] = k1.y;
+      uint64_t x = (uint64_t)i;
+      do { x = feistel(x, half, keys); } while (x >= (uint64_t)n);
+      r = (long long)x;
+    }
+  }
+  for (int f = 0; f < a.F; ++f) a.xT[(size_t)f * a.ld + il] = a.src[(size_t)r * a.F + f];
+}
+
+__device__ void reparam_item(const ReparamArgs& a, int item) {
+  const long long idx = (long long)item * THREADS + threadIdx.x;
+  if (idx >= (long long)a.Z * a.ld) return;
+  const int m = (int)(idx % a.ld);
+  float v = 0.f;
+  if (m < a.M) v = ldg1(a.mu + idx) + ldg1(a.eps + idx) * expf(0.5f * ldg1(a.lv + idx));
+  a.out[idx] = v;
+}
+
+// LayerNorm forward: 64 batch rows per item; warp = (row half, feature group), lane = row
+__device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] */) {
+  const int nrb = (g.M + 63) / 64;
+  const int pass = item / nrb, rb = item % nrb;
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7, hf = threadIdx.x >> 8;
+  const int m = rb * 64 + hf * 32 + lane;
+  const bool valid = m < g.M;
+  const int fpt = (g.C + 7) / 8;
+  const int c0 = w * fpt;
+  const float* h = g.h + (long long)pass * g.sh + (valid ? m : 0);
+  float* rd = red + hf * 256;
+  float v[LN_MAXF];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int cc = c0 + i;
+    v[i] = (i < fpt && cc < g.C && valid) ? ldg1(h + (size_t)cc * g.ld) : 0.f;
+    s += v[i];
+  }
+  rd[w * 32 + lane] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += rd[k * 32 + lane];
+  const float mean = tot / (float)g.C;
+  __syncthreads();
+  float qv = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int cc = c0 + i;
+    if (i < fpt && cc < g.C) { const float d = v[i] - mean; qv = fmaf(d, d, qv); }
+  }
+  rd[w * 32 + lane] = qv;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += rd[k * 32 + lane];
+  const float rstd = 1.0f / sqrtf(tot / (float)g.C + g.eps);
+  if (valid) {
+    float* a = g.a + (long long)pass * g.sa + m;
+    const uint8_t* mk = g.mask ? g.mask + (long long)pass * g.smask + m : nullptr;
+#pragma unroll
+    for (int i = 0; i < LN_MAXF; ++i) {
+      const int cc = c0 + i;
+      if (i < fpt && cc < g.C) {
+        float nv = (v[i] - mean) * rstd * ldg1(g.g + cc) + ldg1(g.b + cc);
+        nv = fmaxf(nv, 0.f);
+        if (mk) nv = __ldcg(mk + (size_t)cc * g.ld) ? nv * g.keep_inv : 0.f;
+        a[(size_t)cc * g.ld] = nv;
+      }
+    }
+    if (g.rs && w == 0) {
+      float* rs = g.rs + (long long)pass * g.srs;
+      rs[m] = mean;
+      rs[g.ld + m] = rstd;
+    }
+  }
+  __syncthreads();
+}
+
+// LayerNorm backward; the affine gradients of an item go to a scratch slot (summed in order by the last... see host)
+__device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8][32] */) {
+  const int nrb = (g.M + 63) / 64;
+  const int pass = item / nrb, rb = item % nrb;
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7, hf = threadIdx.x >> 8;
+  const int m = rb * 64 + hf * 32 + lane;
+  const bool valid = m < g.M;
+  const int mm = valid ? m : 0;
+  const int fpt = (g.C + 7) / 8;
+  const int c0 = w * fpt;
+  const float* h = g.h + (long long)pass * g.sh + mm;
+  float* dn = g.dn + (long long)pass * g.sdn + mm;
+  const float* rs = g.rs + (long long)pass * g.srs;
+  const float mean = ldg1(rs + mm), rstd = ldg1(rs + g.ld + mm);
+  float* r1 = red + hf * 512;
+  float* r2 = r1 + 256;
+  float xh[LN_MAXF], d[LN_MAXF];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int cc = c0 + i;
+    const bool on = i < fpt && cc < g.C && valid;
+    xh[i] = on ? (ldg1(h + (size_t)cc * g.ld) - mean) * rstd : 0.f;
+    d[i] = on ? ldg1(dn + (size_t)cc * g.ld) : 0.f;
+    const float dx = on ? d[i] * ldg1(g.g + cc) : 0.f;
+    s1 += dx;
+    s2 = fmaf(dx, xh[i], s2);
+  }
+  r1[w * 32 + lane] = s1;
+  r2[w * 32 + lane] = s2;
+  __syncthreads();
+  s1 = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1 += r1[k * 32 + lane]; s2 += r2[k * 32 + lane]; }
+  s1 /= (float)g.C;
+  s2 /= (float)g.C;
+#pragma unroll
+  for (int i = 0; i < LN_MAXF; ++i) {
+    const int cc = c0 + i;
+    const bool on = i < fpt && cc < g.C;       // warp-uniform
+    if (!on) continue;
+    if (valid) dn[(size_t)cc * g.ld] = rstd * (d[i] * ldg1(g.g + cc) - s1 - xh[i] * s2);
+    if (g.dg) {
+      const float a = warp_sum(d[i] * xh[i]), b = warp_sum(d[i]);
+      if (lane == 0) {
+        atomicAdd(g.dg + cc, a);
+        atomicAdd(g.db + cc, b);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ void ce_item(const CeArgs& g, int item) {
+  const int nrb = (g.M + THREADS - 1) / THREADS;
+  const int pass = item / nrb;
+  const int m = (item % nrb) * THREADS + threadIdx.x;
+  double nll = 0.0;
+  if (m < g.M) {
+    const float* l = g.logits + (long long)pass * g.sl + m;
+    float mx = -INFINITY;
+    for (int k = 0; k < g.K; ++k) mx = fmaxf(mx, ldg1(l + (size_t)k * g.ld));
+    float s = 0.f;
+    for (int k = 0; k < g.K; ++k) s += expf(ldg1(l + (size_t)k * g.ld) - mx);
+    const float lse = logf(s);
+    const int tgt = g.labels ? (int)g.labels[m] : g.label;
+    nll = -(double)(ldg1(l + (size_t)tgt * g.ld) - mx - lse);
+    float* d = g.dlogits + (long long)pass * g.sd + m;
+    const float coef = g.ctl ? g.coef * __ldcg(&g.ctl->lambda_class) : g.coef;
+    for (int k = 0; k < g.K; ++k) {
+      const float p = expf(ldg1(l + (size_t)k * g.ld) - mx - lse);
+      d[(size_t)k * g.ld] = (p - (k == tgt ? 1.f : 0.f)) * coef;
+    }
+  }
+  nll = warp_sum_d(nll);
+  if ((threadIdx.x & 31) == 0 && nll != 0.0) atomicAdd(g.loss + pass, nll);
+}
+
+__device__ void seed_item(const SeedArgs& g, int item) {
+  const int nblk = (int)(((long long)g.F * g.ld + THREADS - 1) / THREADS);
+  const int pass = item / nblk;
+  const int idx = (item % nblk) * THREADS + threadIdx.x;
+  const int f = idx / g.ld, m = idx % g.ld;
+  double sq = 0.0;
+  if (f < g.F) {
+    const size_t off = (size_t)f * g.ld + m;
+    float d = 0.f;
+    if (m < g.M) {
+      const float o = ldg1(g.out + (long long)pass * g.sout + off);
+      float dout;
+      if (pass == 0) {
+        const float diff = o - ldg1(g.x + off);
+        sq = (double)diff * (double)diff;
+        dout = g.coef_recon * 2.0f * diff;
+      } else {
+        dout = ldg1(g.dx + off);
+      }
+      d = dout * (1.0f - o) * o;
+    }
+    g.dpre[(long long)pass * g.sdpre + off] = d;
+  }
+  if (pass == 0) {
+    sq = warp_sum_d(sq);
+    if ((threadIdx.x & 31) == 0 && sq != 0.0) atomicAdd(g.recon_acc, sq);
+  }
+}
+
+// spectral norm power iteration of one critic layer (item = layer), `npass` consecutive forwards; sm: 3 * 1024 + 512 floats
+__device__ void sn_power_item(const SnArgs& g, int item, float* sm, double* red) {
+  float* su = sm;
+  float* sv = sm + SN_MAXDIM;
+  float* stt = sm + 2 * SN_MAXDIM;
+  float* part = sm + 3 * SN_MAXDIM;
+  const SnLayer L = g.L[item];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = THREADS >> 5;
+  for (int i = tid; i < L.rows; i += THREADS) su[i] = ldg1(L.u + i);
+  for (int i = tid; i < L.cols; i += THREADS) sv[i] = ldg1(L.v + i);
+  __syncthreads();
+  int cp = 1;
+  while (cp < L.cols) cp <<= 1;
+  if (cp > THREADS) cp = THREADS;
+  const int ng = THREADS / cp, kq = tid % cp, gq = tid / cp;
+  for (int p = 0; p < g.npass; ++p) {
+    if (g.do_power) {
+      for (int n = w; n < L.rows; n += nw) {
+        float s = 0.f;
+        for (int k = lane; k < L.cols; k += 32) s = fmaf(ldg1(L.W + (size_t)n * L.cols + k), sv[k], s);
+        s = warp_sum(s);
+        if (lane == 0) stt[n] = s;
+      }
+      __syncthreads();
+      double q = 0.0;
+      for (int i = tid; i < L.rows; i += THREADS) q += (double)stt[i] * stt[i];
+      q = block_sum_d(q, red);
+      float nrm = fmaxf((float)sqrt(q), g.eps);
+      for (int i = tid; i < L.rows; i += THREADS) su[i] = stt[i] / nrm;
+      __syncthreads();
+      for (int k0 = 0; k0 < L.cols; k0 += cp) {
+        const int k = k0 + kq;
+        float s = 0.f;
+        if (k < L.cols)
+          for (int n = gq; n < L.rows; n += ng) s = fmaf(ldg1(L.W + (size_t)n * L.cols + k), su[n], s);
+        part[tid] = s;
+        __syncthreads();
+        if (gq == 0 && k < L.cols) {
+          float t = 0.f;
+          for (int j = 0; j < ng; ++j) t += part[j * cp + kq];
+          stt[k] = t;
+        }
+        __syncthreads();
+      }
+      q = 0.0;
+      for (int i = tid; i < L.cols; i += THREADS) q += (double)stt[i] * stt[i];
+      q = block_sum_d(q, red);
+      nrm = fmaxf((float)sqrt(q), g.eps);
+      for (int i = tid; i < L.cols; i += THREADS) sv[i] = stt[i] / nrm;
+      __syncthreads();
+    }
+    double sg = 0.0;
+    for (int n = w; n < L.rows; n += nw) {
+      float s = 0.f;
+      for (int k = lane; k < L.cols; k += 32) s = fmaf(ldg1(L.W + (size_t)n * L.cols + k), sv[k], s);
+      s = warp_sum(s);
+      if (lane == 0) sg += (double)s * su[n];
+    }
+    sg = block_sum_d(sg, red);
+    if (tid == 0) {
+      g.sigma[p * 4 + item] = (float)sg;
+      g.inv_sigma[item * 2 + p] = 1.0f / (float)sg;
+    }
+    float* us = g.u_snap + (long long)p * g.ssnap + L.snap_off;
+    float* vs = g.v_snap + (long long)p * g.ssnap + L.snap_off;
+    for (int i = tid; i < L.rows; i += THREADS) us[i] = su[i];
+    for (int i = tid; i < L.cols; i += THREADS) vs[i] = sv[i];
+    __syncthreads();
+  }
+  if (g.do_power) {
+    for (int i = tid; i < L.rows; i += THREADS) L.u[i] = su[i];
+    for (int i = tid; i < L.cols; i += THREADS) L.v[i] = sv[i];
+  }
+  __syncthreads();
+}
+
+constexpr int SN_DOT_VB = 8;
+__device__ void sn_dot_item(const SnGradArgs& g, double* dots, int item, double* red) {
+  const int vb = item % SN_DOT_VB, l = (item / SN_DOT_VB) % 4, p = item / (SN_DOT_VB * 4);
+  const SnLayer L = g.L[l];
+  const int n_el = L.rows * L.cols;
+  const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
+  double d = 0.0;
+  for (int i = vb * THREADS + threadIdx.x; i < n_el; i += SN_DOT_VB * THREADS) d += (double)ldg1(G + i) * (double)ldg1(L.W + i);
+  d = block_sum_d(d, red);
+  if (threadIdx.x == 0 && d != 0.0) atomicAdd(dots + l * 2 + p, d);
+  __syncthreads();
+}
+
+constexpr int SN_GRAD_VB = 16;
+__device__ void sn_grad_item(const SnGradArgs& g, const double* dots, int item) {
+  const int vb = item % SN_GRAD_VB, l = item / SN_GRAD_VB;
+  const SnLayer L = g.L[l];
+  const int n_el = L.rows * L.cols;
+  for (int i = vb * THREADS + threadIdx.x; i < n_el; i += SN_GRAD_VB * THREADS) {
+    const int n = i / L.cols, k = i % L.cols;
+    float acc = 0.f;
+    for (int p = 0; p < g.npass; ++p) {
+      const float is = ldg1(g.inv_sigma + l * 2 + p);
+      const float* G = g.Gp + (long long)p * g.sG + g.w_off[l];
+      const float u = ldg1(g.u_snap + (long long)p * g.ssnap + L.snap_off + n);
+      const float v = ldg1(g.v_snap + (long long)p * g.ssnap + L.snap_off + k);
+      acc += ldg1(G + i) * is - (float)(ldgd(dots + l * 2 + p) * (double)is * (double)is) * u * v;
+    }
+    float* dst = g.grad + g.w_off[l] + i;
+    *dst = ldg1(dst) + acc;
+  }
+  if (l == 3 && vb == 0 && threadIdx.x == 0 && g.last_bias_grad) *g.last_bias_grad = ldg1(g.last_bias_grad) + g.last_bias_value;
+}
+
+__device__ void adam_item(const AdamOp& op, int item) {
+  __shared__ float sh[2];
+  const AdamArgs& a = op.a;
+  const int si = item / ADAM_VB, vb = item % ADAM_VB;
+  const AdamSeg s = a.seg[si];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double t = (double)(__ldcg(s.t_prev) + 1 + op.t_off[si]);
+    sh[0] = (float)((double)s.lr / (1.0 - pow((double)a.b1, t)));
+    sh[1] = (float)sqrt(1.0 - pow((double)a.b2, t));
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2_sqrt = sh[1];
+  const float w = 1.0f - a.b1;
+  for (long long i = (long long)vb * THREADS + threadIdx.x; i < s.n; i += (long long)ADAM_VB * THREADS) {
+    const float g = ldg1(s.g + i);
+    float m = ldg1(s.m + i), v = ldg1(s.v + i);
+    m = (w < 0.5f) ? m + w * (g - m) : g - (g - m) * (1.0f - w);
+    v = v * a.b2 + (1.0f - a.b2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+    s.p[i] = ldg1(s.p + i) - step_size * (m / denom);
+    s.m[i] = m;
+    s.v[i] = v;
+    if (a.clear_grad) s.g[i] = 0.f;
+  }
+}
+
+__device__ void zero_item(const ZeroArgs& a, int item) {
+  const long long n16 = a.bytes >> 4;
+  uint4* p = reinterpret_cast<uint4*>(a.p);
+  const long long per = (long long)THREADS * 8;
+  for (long long i = (long long)item * per + threadIdx.x; i < min(n16, (long long)(item + 1) * per); i += THREADS) p[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (item == 0 && threadIdx.x < (a.bytes & 15)) reinterpret_cast<unsigned char*>(a.p)[(n16 << 4) + threadIdx.x] = 0;
+}
+
+// one exchange of the LL all-reduce of comm_nvl.cuh; ep = exchange number on every rank
+template <typename T>
+__device__ void nvl_item(const NvlDev& d, const NvlArgs& a, unsigned long long ep, int item) {
+  constexpr int W = sizeof(T) / 4;
+  T* data = reinterpret_cast<T*>(a.data);
+  const unsigned int ep32 = (unsigned int)ep;
+  const int par = (int)(ep & 1ull);
+  const long long n = a.seg_len * a.nseg;
+  const long long stride = (long long)NVL_VB * THREADS;
+  for (long long e = (long long)item * THREADS + threadIdx.x; e < n; e += stride) {
+    const long long sg = e / a.seg_len, off = e - sg * a.seg_len;
+    const T x = __ldcg(data + sg * a.seg_stride + off);
+    unsigned int w[W];
+    memcpy(w, &x, sizeof(T));
+    for (int p = 0; p < d.world; ++p) {
+      unsigned char* dst = d.peer[p] + nvl_slot_off(d, par, d.rank) + (unsigned long long)e * (W * 8);
+#pragma unroll
+      for (int k = 0; k < W; ++k) ll_store(dst + k * 8, w[k], ep32);
+    }
+  }
+  const unsigned char* base = d.peer[d.rank];
+  const long long t0 = clock64();
+  for (long long e = (long long)item * THREADS + threadIdx.x; e < n; e += stride) {
+    unsigned int w[NVL_MAX_WORLD][W];
+    unsigned int pending = (1u << d.world) - 1u;
+    while (pending) {
+#pragma unroll
+      for (int q = 0; q < NVL_MAX_WORLD; ++q) {
+        if (q < d.world && ((pending >> q) & 1u)) {
+          const unsigned char* src = base + nvl_slot_off(d, par, q) + (unsigned long long)e * (W * 8);
+          bool ok = true;
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            unsigned int f;
+            ll_load(src + k * 8, w[q][k], f);
+            ok &= (f == ep32);
+          }
+          if (ok) pending &= ~(1u << q);
+        }
+      }
+      if (pending && clock64() - t0 > 120000000000ll) __trap();
+    }
+    T s = 0;
+#pragma unroll
+    for (int q = 0; q < NVL_MAX_WORLD; ++q) {
+      if (q < d.world) {
+        T x;
+        memcpy(&x, w[q], sizeof(T));
+        s += x;
+      }
+    }
+    const long long sg = e / a.seg_len, off = e - sg * a.seg_len;
+    data[sg * a.seg_stride + off] = s;
+  }
+}
+
+// ======================================================================================================================
+// the program interpreter
+// ======================================================================================================================
+template <typename T>
+__device__ __forceinline__ const T& payload(const OpRec* op) { return *reinterpret_cast<const T*>(op->payload); }
+
+__global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Ctx c;
+  c.stages = smem;
+  c.cs = reinterpret_cast<float*>(smem + (size_t)NSTAGE * STAGE_BYTES);
+  c.red = reinterpret_cast<double*>(c.cs + CS_FLOATS);
+  OpRec* sop = reinterpret_cast<OpRec*>(c.red + RED_DOUBLES);
+  Ctrl* S = reinterpret_cast<Ctrl*>(sop + 1);
+  c.tid = threadIdx.x;
+  c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);
+  c.lane = c.tid & 31;
+  c.n_commit[0] = 0;
+  c.n_commit[1] = 0;
+  if (c.tid == 0) {
+    mbar_init(&S->bar[0], 1);
+    mbar_init(&S->bar[1], 1);
+    fence_mbar_init();
+    S->nvl_epoch0 = P.nvl.world > 1 ? *reinterpret_cast<volatile unsigned long long*>(P.nvl.epoch) : 0ull;
+  }
+  if (c.warp == 0) tmem_alloc(&S->tmem_slot, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  c.tmem = __shfl_sync(0xffffffffu, S->tmem_slot, 0);
+  c.bar = S->bar;
+  const unsigned long long nvl_epoch0 = S->nvl_epoch0;
+  unsigned int target = 0;
+  const int G = (int)gridDim.x;
+  long long t_op = 0;
+
+  for (int oi = 0; oi < P.nops; ++oi) {
+    __syncthreads();
+    if (c.tid < OP_BYTES / 4) reinterpret_cast<uint32_t*>(sop)[c.tid] = reinterpret_cast<const uint32_t*>(P.ops + oi)[c.tid];
+    __syncthreads();
+    if (sop->bar_before) grid_barrier(P.bar_counter, target);
+    if (P.dbg && blockIdx.x == 0 && c.tid == 0) t_op = clock64();
+    const int items = sop->items;
+    const int i0 = (((int)blockIdx.x - sop->first) % G + G) % G;
+    switch (sop->kind) {
+      case K_MN: {
+        const GemmArgs& g = payload<GemmArgs>(sop);
+        for (int it = i0; it < items; it += G) mn_item(c, g, sop->aux[0] != 0, sop->aux[1], it);
+      } break;
+      case K_DW: {
+        const DwArgs& g = payload<DwArgs>(sop);
+        DwScratch sc;
+        memcpy(&sc.part, sop->payload + sizeof(DwArgs), sizeof(float*));
+        memcpy(&sc.bpart, sop->payload + sizeof(DwArgs) + sizeof(float*), sizeof(float*));
+        sc.nsplit = sop->aux[0];
+        sc.kp = sop->aux[1];
+        for (int it = i0; it < items; it += G) dw_item(c, g, sc, it);
+      } break;
+      case K_DWRED: {
+        const DwRedArgs& a = payload<DwRedArgs>(sop);
+        for (int it = i0; it < items; it += G) dwred_item(a, it);
+      } break;
+      case K_FILL: {
+        const FillArgs& a = payload<FillArgs>(sop);
+        for (int it = i0; it < items; it += G) fill_item(a, it);
+      } break;
+      case K_STAGE: {
+        const StageArgs& a = payload<StageArgs>(sop);
+        for (int it = i0; it < items; it += G) stage_item(a, it);
+      } break;
+      case K_REPARAM: {
+        const ReparamArgs& a = payload<ReparamArgs>(sop);
+        for (int it = i0; it < items; it += G) reparam_item(a, it);
+      } break;
+      case K_SN_POWER: {
+        const SnArgs& a = payload<SnArgs>(sop);
+        for (int it = i0; it < items; it += G) sn_power_item(a, it, reinterpret_cast<float*>(c.stages), c.red);
+      } break;
+      case K_SN_DOT: {
+        const SnGradArgs& a = payload<SnGradArgs>(sop);
+        double* dots;
+        memcpy(&dots, sop->payload + sizeof(SnGradArgs), sizeof(double*));
+        for (int it = i0; it < items; it += G) sn_dot_item(a, dots, it, c.red);
+      } break;
+      case K_SN_GRAD: {
+        const SnGradArgs& a = payload<SnGradArgs>(sop);
+        double* dots;
+        memcpy(&dots, sop->payload + sizeof(SnGradArgs), sizeof(double*));
+        for (int it = i0; it < items; it += G) sn_grad_item(a, dots, it);
+      } break;
+      case K_LN_FWD: {
+        const LnArgs& a = payload<LnArgs>(sop);
+        for (int it = i0; it < items; it += G) ln_fwd_item(a, it, c.cs);
+      } break;
+      case K_LN_BWD: {
+        const LnBwdArgs& a = payload<LnBwdArgs>(sop);
+        for (int it = i0; it < items; it += G) ln_bwd_item(a, it, c.cs);
+      } break;
+      case K_CE: {
+        const CeArgs& a = payload<CeArgs>(sop);
+        for (int it = i0; it < items; it += G) ce_item(a, it);
+      } break;
+      case K_SEED: {
+        const SeedArgs& a = payload<SeedArgs>(sop);
+        for (int it = i0; it < items; it += G) seed_item(a, it);
+      } break;
+      case K_ZERO: {
+        const ZeroArgs& a = payload<ZeroArgs>(sop);
+        for (int it = i0; it < items; it += G) zero_item(a, it);
+      } break;
+      case K_ADAM: {
+        const AdamOp& a = payload<AdamOp>(sop);
+        for (int it = i0; it < items; it += G) adam_item(a, it);
+      } break;
+      case K_PACK: {
+        const PackArgs& a = payload<PackArgs>(sop);
+        if (i0 == 0 && c.tid < L_COUNT) a.tail[c.tid] = (float)ldgd(a.acc + c.tid);
+      } break;
+      case K_UNPACK: {
+        const UnpackArgs& a = payload<UnpackArgs>(sop);
+        if (i0 == 0) {
+          if (c.tid == 0) {
+            const float* tail = a.tail;
+            float* out = a.out;
+            const float Bg = a.Bg;
+            if (a.kind == 0) {
+              const float r = ldg1(tail + L_DREAL) / Bg, f = ldg1(tail + L_DFAKE) / Bg;
+              out[0] = -r + f; out[1] = r; out[2] = f; out[3] = 0.f;
+            } else if (a.kind == 1) {
+              const float r = ldg1(tail + L_CE0) / Bg, f = ldg1(tail + L_CE1) / Bg;
+              out[0] = r + f; out[1] = r; out[2] = f; out[3] = 0.f;
+            } else {
+              out[0] = ldg1(tail + L_RECON) / (Bg * a.F);
+              out[1] = ldg1(tail + L_KL) / Bg;
+              out[2] = -ldg1(tail + L_DFAKE) / Bg;
+              out[3] = ldg1(tail + L_CE0) / Bg;
+            }
+          }
+          __syncthreads();
+          if (c.tid < CVG_GRAD_TAIL) a.tail_w[c.tid] = 0.f;
+        }
+      } break;
+      case K_CTL_SET: {
+        const CtlSetArgs& a = payload<CtlSetArgs>(sop);
+        if (i0 == 0 && c.tid == 0) {
+          if (a.set_rng) { a.ctl->seed = a.seed; a.ctl->counter = a.counter; }
+          if (a.set_lambda) a.ctl->lambda_class = a.lambda_class;
+        }
+      } break;
+      case K_FINISH: {
+        const FinishArgs& a = payload<FinishArgs>(sop);
+        if (i0 == 0 && c.tid == 0) {
+          a.ctl->counter = __ldcg(&a.ctl->counter) + a.dcounter;
+          for (int n = 0; n < 4; ++n) a.ctl->adam_t[n] = __ldcg(&a.ctl->adam_t[n]) + a.adam_inc[n];
+          if (P.nvl.world > 1 && a.n_exchanges > 0)
+            *reinterpret_cast<volatile unsigned long long*>(P.nvl.epoch) = nvl_epoch0 + (unsigned long long)a.n_exchanges;
+        }
+      } break;
+      case K_NVL_F32: {
+        const NvlArgs& a = payload<NvlArgs>(sop);
+        for (int it = i0; it < items; it += G) nvl_item<float>(P.nvl, a, nvl_epoch0 + 1ull + (unsigned long long)a.exchange, it);
+      } break;
+      case K_NVL_F64: {
+        const NvlArgs& a = payload<NvlArgs>(sop);
+        for (int it = i0; it < items; it += G) nvl_item<double>(P.nvl, a, nvl_epoch0 + 1ull + (unsigned long long)a.exchange, it);
+      } break;
+      default:
+        break;
+    }
+    if (P.dbg && blockIdx.x == 0 && c.tid == 0) P.dbg[oi] = clock64() - t_op;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (c.warp == 0) tmem_dealloc(c.tmem, TMEM_COLS);
+}
+
+static_assert(sizeof(GemmArgs) <= OP_BYTES - 32, "GemmArgs does not fit an op record");
+static_assert(sizeof(DwArgs) + 2 * sizeof(float*) <= OP_BYTES - 32, "DwArgs does not fit an op record");
+static_assert(sizeof(FillArgs) <= OP_BYTES - 32, "FillArgs does not fit an op record");
+static_assert(sizeof(SnArgs) <= OP_BYTES - 32, "SnArgs does not fit an op record");
+static_assert(sizeof(SnGradArgs) + sizeof(double*) <= OP_BYTES - 32, "SnGradArgs does not fit an op record");
+static_assert(sizeof(AdamOp) <= OP_BYTES - 32, "AdamOp does not fit an op record");
+
+}  // namespace mk
+}  // namespace cvg

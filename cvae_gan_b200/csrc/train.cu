@@ -5,8 +5,12 @@
 #include <math.h>
 
 #include "engine.cuh"
+#include "mega.cuh"
 
 namespace cvg {
+
+// next op has no dependency on the ops of the current phase (step-program kernel only; a stream orders launches anyway)
+#define CVG_PAR(e) do { (e).mk.par_next = true; } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // NCCL, resolved at run time from the libnccl.so.2 that torch already loaded (no link dependency).
@@ -121,6 +125,13 @@ void nvl_destroy(Engine& e) {
 template <typename T>
 static int nvl_all_reduce(Engine& e, T* p, int64_t seg_len, int64_t seg_stride, int nseg, cudaStream_t st) {
   const long long n = seg_len * nseg;
+  if (e.mk.recording) {
+    mk::NvlArgs a;
+    a.data = p; a.seg_len = seg_len; a.seg_stride = seg_stride; a.nseg = nseg;
+    a.exchange = e.mk.n_exchanges++;
+    if ((unsigned long long)n * sizeof(T) * 2 > e.nvl.dev.slot_bytes) CVG_FAIL("step program: exchange larger than the NVLink staging slot");
+    return mk_push(e, sizeof(T) == 8 ? mk::K_NVL_F64 : mk::K_NVL_F32, &a, sizeof(a), mk::NVL_VB);
+  }
   int grid = (int)((n + NVL_THREADS - 1) / NVL_THREADS);     // one element per thread where possible
   if (grid < 1) grid = 1;
   if (grid > NVL_MAX_CTAS) grid = NVL_MAX_CTAS;
@@ -182,6 +193,14 @@ static void prof_end(Engine& e, cudaStream_t st) {
 
 int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
   const int zp = g.only_pass >= 0 ? 1 : g.npass;
+  if (e.mk.recording) {
+    // 64-row tiles while they still fit one wave and a half of CTAs, 128-row tiles (full-rate MMAs) for larger batches
+    const int nmt = (g.N + 127) / 128;
+    int Nt = 64;
+    if ((long long)((g.M + 63) / 64) * nmt * zp > 3 * e.num_sms / 2) Nt = 128;
+    const int items = zp * nmt * ((g.M + Nt - 1) / Nt);
+    return mk_push(e, mk::K_MN, &g, sizeof(g), items, wt ? 1 : 0, Nt);
+  }
   dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, zp);
   const size_t smem = gemm_mn_smem(g);
   prof_begin(e, wt ? 0 : 1, 2.0 * g.M * (double)g.N * g.R * zp, st);
@@ -195,6 +214,7 @@ int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
 }
 
 int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
+  if (e.mk.recording) return mk_push_dw(e, g0);
   DwArgs g = g0;
   const int kt = (g.K + 63) / 64, nt = (g.N + 63) / 64;
   const int target = 2 * e.num_sms;
@@ -276,6 +296,7 @@ static int sync_stats(Engine& e, double* p, int npass, int C, bool local_bn, cud
 // ------------------------------------------------------------------------------------------------
 static int launch_fill(Engine& e, FillArgs& a, cudaStream_t st) {
   if (a.njobs == 0) return 0;
+  if (e.mk.recording) return mk_push(e, mk::K_FILL, &a, sizeof(a), a.njobs * mk::FILL_VB);
   long long mx = 0;
   for (int i = 0; i < a.njobs; ++i) {
     long long t = (long long)a.job[i].npass * ((a.job[i].nfeat + 3) / 4) * a.M;
@@ -299,7 +320,31 @@ static void add_job(FillArgs& a, void* out, const void* inj, int kind, int nfeat
   j.stream = stream;
 }
 
+static int emit_zero(Engine& e, void* p, size_t bytes, cudaStream_t st) {
+  if (e.mk.recording) {
+    mk::ZeroArgs a;
+    a.p = p; a.bytes = (long long)bytes;
+    const int items = (int)((bytes / 16 + mk::THREADS * 8 - 1) / (mk::THREADS * 8));
+    return mk_push(e, mk::K_ZERO, &a, sizeof(a), items < 1 ? 1 : items);
+  }
+  CVG_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+  return 0;
+}
+
 static int stage_x(Engine& e, const float* x_real, int M, cudaStream_t st) {
+  if (e.mk.recording) {
+    // inside a visit program the batch is drawn from the class table right here (cvae_gan.py:247-260)
+    const MkState& src = e.mk;
+    mk::StageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = src.src_rows ? src.src_rows : x_real;
+    a.n_rows = src.src_rows ? src.src_n : 0;
+    a.B_global = src.src_Bg; a.draw_offset = src.src_off;
+    a.M = M; a.F = e.F; a.ld = e.ws.ld;
+    a.ctl = e.ws.ctl; a.counter_off = e.mk.dcounter;
+    a.xT = e.ws.xT;
+    return mk_push(e, mk::K_STAGE, &a, sizeof(a), (M + mk::THREADS - 1) / mk::THREADS);
+  }
   to_feature_major_kernel<<<(M + 127) / 128, 128, 0, st>>>(x_real, nullptr, M, e.F, e.ws.ld, e.ws.xT);
   CVG_LAUNCH_CHECK();
   return 0;
@@ -319,7 +364,7 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
     g.R = (l == 0) ? e.Z : p.in;
     g.N = p.out;
     if (l == 0) {
-      g.a.kind = reparam_pass0 ? OP_REPARAM : OP_PLAIN;
+      g.a.kind = (reparam_pass0 && !e.mk.recording) ? OP_REPARAM : OP_PLAIN;
       g.a.rows = e.Z;
       g.a.p = w.z;
       g.a.sp = (long long)e.Z * ld;
@@ -421,6 +466,7 @@ static int launch_sn(Engine& e, int npass, bool do_power, cudaStream_t st) {
   a.u_snap = e.ws.sn_u;
   a.v_snap = e.ws.sn_v;
   a.ssnap = e.ws.sn_snap;
+  if (e.mk.recording) return mk_push(e, mk::K_SN_POWER, &a, sizeof(a), 4);
   sn_power_kernel<<<4, SN_THREADS, 0, st>>>(a);
   CVG_LAUNCH_CHECK();
   return 0;
@@ -511,8 +557,12 @@ int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool 
       a.mask = train ? w.c_m2 : nullptr; a.smask = (long long)p.out * ld; a.keep_inv = keep_inv;
       a.a = w.c_a2; a.sa = (long long)p.out * ld;
       a.rs = w.c_rs; a.srs = 2 * (long long)ld;
-      ln_fwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
-      CVG_LAUNCH_CHECK();
+      if (e.mk.recording) {
+        CVG_TRY(mk_push(e, mk::K_LN_FWD, &a, sizeof(a), npass * ((M + 63) / 64)));
+      } else {
+        ln_fwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
+        CVG_LAUNCH_CHECK();
+      }
     }
   }
   return 0;
@@ -543,6 +593,7 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
       // OP_CONST carries one value: run the two passes of layer 4 as separate launches
       const int reps = (l == 3 && npass > 1) ? npass : 1;
       for (int r = 0; r < reps; ++r) {
+        if (r > 0) CVG_PAR(e);
         DwArgs d = base_dw(e, M, (float)M, reps > 1 ? 1 : npass);
         d.N = p.out;
         d.K = (l == 0) ? e.F : p.in;
@@ -568,6 +619,7 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
     g.W = e.P(net, p.w);
     g.ldw = p.in;
     g.scale = w.sn_inv_sigma + l * 2;
+    if (want_dw) CVG_PAR(e);      // the input gradient and the weight gradient of a layer read the same dY
     if (l == 0) {
       g.ekind = EP_STORE;
       g.Y = w.dx;
@@ -584,6 +636,7 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
       g.sY = (long long)p.in * ld;
       if (l == 3 && npass > 1) {
         for (int r = 0; r < npass; ++r) {   // per-pass constant seed
+          if (r > 0) CVG_PAR(e);
           GemmArgs gr = g;
           gr.a.cst = seed[r];
           gr.only_pass = r;
@@ -649,6 +702,7 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       if (l == 2) { g.prev = w.c_a2; g.mask = w.c_m2; g.smask = (long long)p.in * ld; g.keep_inv = keep_inv; }
       if (l == 1) { g.prev = w.c_a1; g.mask = w.c_m1; g.smask = (long long)p.in * ld; g.keep_inv = keep_inv; }
     }
+    if (want_dw) CVG_PAR(e);
     CVG_TRY(launch_mn(e, false, g, st));
     if (l == 2) {   // c_g[1] holds dL/dn -> LayerNorm backward in place -> dL/dh2
       const LinearP& p1 = lin(e, net, 1);
@@ -660,8 +714,12 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       a.g = e.P(net, p1.gamma);
       a.dg = want_dw ? e.G(net, p1.gamma) : nullptr;
       a.db = want_dw ? e.G(net, p1.beta) : nullptr;
-      ln_bwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
-      CVG_LAUNCH_CHECK();
+      if (e.mk.recording) {
+        CVG_TRY(mk_push(e, mk::K_LN_BWD, &a, sizeof(a), npass * ((M + 63) / 64)));
+      } else {
+        ln_bwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
+        CVG_LAUNCH_CHECK();
+      }
     }
   }
   return 0;
@@ -727,12 +785,13 @@ static int bwd_bn_net(Engine& e, const BnNetBwd& b, int M, float Bg_bn, float kl
       g.ekind = EP_REPARAM_BWD;
       g.mu = w.e_ml;
       g.lv = w.e_ml + (size_t)e.Z * ld;
-      g.eps = w.z;
+      g.eps = e.mk.recording ? w.z_eps : w.z;
       g.kl_coef = kl_coef;
       g.Y = w.e_dml;
       CVG_TRY(launch_mn(e, false, g, st));
     }
     // ---- dW, db, and the BatchNorm affine gradients of this layer ------------------------------------
+    if (l > 0 || b.want_first_dx) CVG_PAR(e);     // beside the input-gradient op just emitted: both read dY of layer l
     DwArgs d = base_dw(e, M, Bg_bn, b.npass);
     d.N = p.out;
     d.p = dy;
@@ -792,6 +851,15 @@ int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov) {
     if (s.n > nmax) nmax = s.n;
   }
   if (a.nseg == 0) return 0;
+  if (e.mk.recording) {
+    mk::AdamOp op;
+    op.a = a;
+    op.t_off[0] = op.t_off[1] = 0;
+    int si = 0;
+    for (int net = 0; net < 4; ++net)
+      if (net_mask & (1 << net)) { op.t_off[si++] = e.mk.adam_inc[net]; e.mk.adam_inc[net]++; }
+    return mk_push(e, mk::K_ADAM, &op, sizeof(op), a.nseg * mk::ADAM_VB);
+  }
   int blocks = (int)((nmax + 255) / 256);
   if (blocks > 2 * e.num_sms) blocks = 2 * e.num_sms;
   adam_kernel<<<dim3(blocks, a.nseg), 256, 0, st>>>(a);
@@ -808,6 +876,29 @@ static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, floa
   for (int net = 0; net < 4; ++net)
     if (net_mask & (1 << net)) { first = net; break; }
   float* tail = e.buf[first].grads + e.lay[first].n_param;
+  if (e.mk.recording) {
+    const bool had_red = !e.mk.pending_red.empty();
+    CVG_TRY(mk_emit_dwred(e));                 // deterministic sums of the weight-gradient row slices
+    mk::PackArgs pa;
+    pa.acc = e.ws.loss; pa.tail = tail;
+    if (had_red) CVG_PAR(e);                   // beside the reductions: the loss sums were complete phases ago
+    CVG_TRY(mk_push(e, mk::K_PACK, &pa, sizeof(pa), 1));
+    for (int net = 0; net < 4; ++net)
+      if (net_mask & (1 << net))
+        CVG_TRY(comm_all_reduce_f32(e, e.buf[net].grads, e.lay[net].n_param + (net == first ? CVG_GRAD_TAIL : 0), st));
+    bool par = false;
+    if (loss_out) {
+      mk::UnpackArgs ua;
+      ua.tail = tail; ua.out = loss_out; ua.kind = kind; ua.Bg = (float)M * (float)e.world; ua.F = (float)e.F; ua.tail_w = tail;
+      CVG_TRY(mk_push(e, mk::K_UNPACK, &ua, sizeof(ua), 1));
+      par = true;
+    }
+    if (!(flags & CVG_STEP_NO_UPDATE)) {
+      if (par) CVG_PAR(e);
+      CVG_TRY(run_adam(e, net_mask, st, ov));
+    }
+    return 0;
+  }
   pack_loss_kernel<<<1, 32, 0, st>>>(e.ws.loss, tail);
   CVG_LAUNCH_CHECK();
   for (int net = 0; net < 4; ++net)
@@ -830,9 +921,52 @@ static int check_step(Engine& e, int B) {
   return 0;
 }
 
+static bool mk_usable(const Engine& e) { return e.mk.enabled && (e.world == 1 || e.nvl.on); }
+
+// A step called on its own records (and at its end launches) its own program; inside a visit it appends to the visit's.
+struct ProgramScope {
+  Engine& e;
+  bool own = false;
+  explicit ProgramScope(Engine& en) : e(en) {
+    if (mk_usable(e) && !e.mk.recording) { mk_begin(e); own = true; }
+  }
+  int finish(cudaStream_t st) {
+    if (!own) return 0;
+    own = false;
+    return mk_flush(e, st);
+  }
+  ~ProgramScope() { if (own) e.mk.recording = false; }    // error path: drop the half-recorded program
+};
+
 static int begin_step(Engine& e, const StepRng& rng, bool with_lambda, cudaStream_t st) {
   if (!rng.set) return 0;
+  if (e.mk.recording) {
+    // the ops of this program take the Philox key / counter from their own arguments (fill_args); the control block is
+    // still brought up to date for ops that read lambda_class from it and for later calls
+    mk::CtlSetArgs a;
+    a.ctl = e.ws.ctl; a.seed = rng.seed; a.counter = rng.counter; a.set_rng = 1;
+    a.lambda_class = rng.lambda_class; a.set_lambda = with_lambda ? 1 : 0;
+    return mk_push(e, mk::K_CTL_SET, &a, sizeof(a), 1);
+  }
   ctl_set_kernel<<<1, 32, 0, st>>>(e.ws.ctl, rng.seed, rng.counter, 1, rng.lambda_class, with_lambda ? 1 : 0);
+  CVG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Philox addressing of a step's noise (see StepRng)
+static void fill_args(Engine& e, FillArgs& f, const StepRng& rng, int B) {
+  f.njobs = 0; f.M = B; f.ld = e.ws.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
+  f.ctl = e.ws.ctl; f.counter_off = rng.off;
+  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  if (e.mk.recording) {
+    if (rng.set) { f.ctl = nullptr; f.seed = rng.seed; f.counter = rng.counter + rng.off; }
+    else f.counter_off = rng.off + e.mk.dcounter;
+  }
+}
+
+static int emit_ce(Engine& e, const CeArgs& c, int B, int npass, cudaStream_t st) {
+  if (e.mk.recording) return mk_push(e, mk::K_CE, &c, sizeof(c), npass * ((B + mk::THREADS - 1) / mk::THREADS));
+  ce_kernel<<<dim3((B + 127) / 128, npass), 128, 0, st>>>(c);
   CVG_LAUNCH_CHECK();
   return 0;
 }
@@ -843,25 +977,29 @@ static int begin_step(Engine& e, const StepRng& rng, bool with_lambda, cudaStrea
 int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
            float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
+  ProgramScope prog(e);
   CVG_TRY(begin_step(e, rng, false, st));
   const Workspace& w = e.ws;
   const bool local_bn = flags & CVG_STEP_LOCAL_BN;
   const float Bg = (float)B * (float)e.world;
   const float Bg_bn = local_bn ? (float)B : Bg;
   const int D = CVG_NET_DISCRIMINATOR;
-  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
-  CVG_CUDA(cudaMemsetAsync(w.sn_G, 0, sizeof(float) * 2 * e.lay[D].n_param, st));
+  if (rng.set) CVG_PAR(e);
+  CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
+  CVG_PAR(e);
+  CVG_TRY(emit_zero(e, w.sn_G, sizeof(float) * 2 * e.lay[D].n_param, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
-  f.ctl = w.ctl; f.counter_off = rng.off;
-  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  fill_args(e, f, rng, B);
   add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
   add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 2, RS_DMASK1);
   add_job(f, w.d_m2, nz ? nz->d_mask2 : nullptr, 1, e.dh[1], 2, RS_DMASK2);
+  CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
+  CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, st));
   // G(z) under no_grad, still in train mode: batch stats, running stats updated (cvae_gan.py:113-115)
   CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  CVG_PAR(e);                           // the power iterations only touch the critic's weights and u / v
   CVG_TRY(launch_sn(e, 2, true, st));   // D(real) then D(fake): two consecutive power iterations
   const long long sx = w.g_out - w.xT;  // pass 0 reads xT, pass 1 reads g_out (pass slot 0)
   CVG_TRY(fwd_critic(e, w.xT, sx, 2, label, B, w.loss + L_DREAL, st));
@@ -885,12 +1023,20 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
     a.last_bias_grad = e.G(D, lin(e, D, 3).b);
     a.last_bias_value = (float)B * (seedv[0] + seedv[1]);
     double* dots = w.loss + 8;   // 8 zeroed accumulator slots after the loss sums
-    sn_dot_kernel<<<dim3(16, 4, 2), 256, 0, st>>>(a, dots);
-    CVG_LAUNCH_CHECK();
-    sn_grad_kernel<<<dim3(32, 4), 256, 0, st>>>(a, dots);
-    CVG_LAUNCH_CHECK();
+    if (e.mk.recording) {
+      CVG_TRY(mk_emit_dwred(e));   // per-pass raw critic gradients, summed over the row slices in a fixed order
+      CVG_TRY(mk_push(e, mk::K_SN_DOT, &a, sizeof(a), mk::SN_DOT_VB * 4 * 2, 0, 0, 0, 0, &dots, sizeof(dots)));
+      CVG_TRY(mk_push(e, mk::K_SN_GRAD, &a, sizeof(a), mk::SN_GRAD_VB * 4, 0, 0, 0, 0, &dots, sizeof(dots)));
+      CVG_PAR(e);                  // the loss pack that follows is independent of the spectral-norm gradient
+    } else {
+      sn_dot_kernel<<<dim3(16, 4, 2), 256, 0, st>>>(a, dots);
+      CVG_LAUNCH_CHECK();
+      sn_grad_kernel<<<dim3(32, 4), 256, 0, st>>>(a, dots);
+      CVG_LAUNCH_CHECK();
+    }
   }
-  return finish_step(e, 1 << D, 0, B, flags, loss_out, st);
+  CVG_TRY(finish_step(e, 1 << D, 0, B, flags, loss_out, st));
+  return prog.finish(st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -899,6 +1045,7 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
 int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
            float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
+  ProgramScope prog(e);
   CVG_TRY(begin_step(e, rng, false, st));
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
@@ -906,15 +1053,16 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   const float Bg = (float)B * (float)e.world;
   const float Bg_bn = local_bn ? (float)B : Bg;
   const int C = CVG_NET_CLASSIFIER;
-  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  if (rng.set) CVG_PAR(e);
+  CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
-  f.ctl = w.ctl; f.counter_off = rng.off;
-  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  fill_args(e, f, rng, B);
   add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
   add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 2, RS_CMASK1);
   add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 2, RS_CMASK2);
+  CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
+  CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, st));
   CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
   const long long sx = w.g_out - w.xT;
@@ -926,10 +1074,10 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   c.coef = 1.0f / Bg;
   c.ctl = nullptr;
   c.loss = w.loss + L_CE0;
-  ce_kernel<<<dim3((B + 127) / 128, 2), 128, 0, st>>>(c);
-  CVG_LAUNCH_CHECK();
+  CVG_TRY(emit_ce(e, c, B, 2, st));
   CVG_TRY(bwd_classifier(e, w.xT, sx, 2, B, true, false, false, st));
-  return finish_step(e, 1 << C, 1, B, flags, loss_out, st);
+  CVG_TRY(finish_step(e, 1 << C, 1, B, flags, loss_out, st));
+  return prog.finish(st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -940,19 +1088,21 @@ int step_classifier(Engine& e, const float* x, const long long* labels, int B, c
                     const AdamOverride& ov, int flags, float* loss_out, cudaStream_t st) {
   if (!e.ws_base) CVG_FAIL("workspace not bound");
   if (B < 1 || B > e.ws.rows_cap) CVG_FAIL("batch size exceeds max_batch");
+  ProgramScope prog(e);
   CVG_TRY(begin_step(e, rng, false, st));
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
   const int C = CVG_NET_CLASSIFIER;
   const float Bg = (float)B * (float)e.world;
-  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  if (rng.set) CVG_PAR(e);
+  CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
-  f.ctl = w.ctl; f.counter_off = rng.off;
-  f.keep_prob = 1.0f - e.cfg.dropout_p;
+  fill_args(e, f, rng, B);
   add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
   add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
+  CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
+  CVG_PAR(e);
   CVG_TRY(stage_x(e, x, B, st));
   CVG_TRY(fwd_classifier(e, w.xT, 0, 1, true, B, st));
   CeArgs c;
@@ -962,10 +1112,10 @@ int step_classifier(Engine& e, const float* x, const long long* labels, int B, c
   c.coef = 1.0f / Bg;
   c.ctl = nullptr;
   c.loss = w.loss + L_CE0;
-  ce_kernel<<<dim3((B + 127) / 128, 1), 128, 0, st>>>(c);
-  CVG_LAUNCH_CHECK();
+  CVG_TRY(emit_ce(e, c, B, 1, st));
   CVG_TRY(bwd_classifier(e, w.xT, 0, 1, B, true, false, false, st));
-  return finish_step(e, 1 << C, 1, B, flags, loss_out, st, &ov);
+  CVG_TRY(finish_step(e, 1 << C, 1, B, flags, loss_out, st, &ov));
+  return prog.finish(st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -974,6 +1124,7 @@ int step_classifier(Engine& e, const float* x, const long long* labels, int B, c
 int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
            float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
+  ProgramScope prog(e);
   CVG_TRY(begin_step(e, rng, true, st));
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
@@ -981,24 +1132,33 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   const float Bg = (float)B * (float)e.world;
   const float Bg_bn = local_bn ? (float)B : Bg;
   const int E = CVG_NET_ENCODER, G = CVG_NET_GENERATOR;
-  CVG_CUDA(cudaMemsetAsync(w.acc, 0, w.acc_bytes, st));
+  if (rng.set) CVG_PAR(e);
+  CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
   FillArgs f;
-  f.njobs = 0; f.M = B; f.ld = w.ld; f.seed = 0; f.counter = 0; f.row_base = (uint64_t)e.rank * B;
-  f.ctl = w.ctl; f.counter_off = rng.off;
-  f.keep_prob = 1.0f - e.cfg.dropout_p;
-  add_job(f, w.z, nz ? nz->eps : nullptr, 0, e.Z, 1, RS_EPS);                     // slot 0: eps
+  fill_args(e, f, rng, B);
+  // eps: slot 0 of ws.z for the stand-alone kernels (reparameterisation fused into the operand load); the program
+  // kernel keeps eps apart and materialises z_enc into slot 0 (mk::K_REPARAM below)
+  add_job(f, e.mk.recording ? w.z_eps : w.z, nz ? nz->eps : nullptr, 0, e.Z, 1, RS_EPS);
   add_job(f, w.z + (size_t)e.Z * ld, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);      // slot 1: z_prior
   add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 1, RS_DMASK1);
   add_job(f, w.d_m2, nz ? nz->d_mask2 : nullptr, 1, e.dh[1], 1, RS_DMASK2);
   add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
   add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
+  CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
+  CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, st));
 
   // forward: E -> (mu, logvar); G on z_enc (pass 0) and z_prior (pass 1); D and C on x_fake
   CVG_TRY(fwd_encoder(e, true, label, B, Bg_bn, local_bn, st));
+  if (e.mk.recording) {
+    mk::ReparamArgs ra;
+    ra.mu = w.e_ml; ra.lv = w.e_ml + (size_t)e.Z * ld; ra.eps = w.z_eps; ra.out = w.z; ra.M = B; ra.ld = w.ld; ra.Z = e.Z;
+    CVG_TRY(mk_push(e, mk::K_REPARAM, &ra, sizeof(ra), (int)(((long long)e.Z * ld + mk::THREADS - 1) / mk::THREADS)));
+  }
   CVG_TRY(fwd_generator(e, 2, true, true, label, B, Bg_bn, local_bn, st));
   const float* x_fake = w.g_out + (size_t)e.F * ld;
+  CVG_PAR(e);
   CVG_TRY(launch_sn(e, 1, true, st));
   CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, st));
   CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, st));
@@ -1009,8 +1169,7 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
   c.ctl = w.ctl;
   c.loss = w.loss + L_CE0;
-  ce_kernel<<<dim3((B + 127) / 128, 1), 128, 0, st>>>(c);
-  CVG_LAUNCH_CHECK();
+  CVG_TRY(emit_ce(e, c, B, 1, st));
 
   // backward to x_fake: adv = -mean D(x_fake) (cvae_gan.py:189), then the classification term
   const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
@@ -1025,15 +1184,19 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   s.dpre = w.g_dout; s.sdpre = (long long)e.F * ld;
   s.coef_recon = e.cfg.lambda_recon / (Bg * (float)e.F);
   s.recon_acc = w.loss + L_RECON;
-  g_seed_kernel<<<dim3((unsigned)((e.F * ld + 255) / 256), 2), 256, 0, st>>>(s);
-  CVG_LAUNCH_CHECK();
+  if (e.mk.recording) {
+    CVG_TRY(mk_push(e, mk::K_SEED, &s, sizeof(s), 2 * (int)(((long long)e.F * ld + mk::THREADS - 1) / mk::THREADS)));
+  } else {
+    g_seed_kernel<<<dim3((unsigned)((e.F * ld + 255) / 256), 2), 256, 0, st>>>(s);
+    CVG_LAUNCH_CHECK();
+  }
 
   const LinearP& g0 = lin(e, G, 0);
   BnNetBwd gb;
   gb.net = G; gb.npass = 2;
   gb.h = w.g_h; gb.dy = w.g_dy;
   gb.top_dy = w.g_dout; gb.s_top = (long long)e.F * ld;
-  gb.first_in.kind = OP_REPARAM; gb.first_in.rows = e.Z;
+  gb.first_in.kind = e.mk.recording ? OP_PLAIN : OP_REPARAM; gb.first_in.rows = e.Z;
   gb.first_in.p = w.z; gb.first_in.sp = (long long)e.Z * ld;
   gb.first_in.mu = w.e_ml; gb.first_in.lv = w.e_ml + (size_t)e.Z * ld; gb.first_in.eps = w.z;
   gb.first_in.reparam_pass = 0;
@@ -1053,7 +1216,8 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   eb.want_first_dx = false;
   CVG_TRY(bwd_bn_net(e, eb, B, Bg_bn, 0.f, local_bn, st));
 
-  return finish_step(e, (1 << E) | (1 << G), 2, B, flags, loss_out, st);
+  CVG_TRY(finish_step(e, (1 << E) | (1 << G), 2, B, flags, loss_out, st));
+  return prog.finish(st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1067,6 +1231,8 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
   CVG_TRY(check_step(e, B));
   if (!x_batches && (!class_rows || n_rows < 1)) CVG_FAIL("cvg_visit: need class_rows or x_batches");
   if (B_global != (int64_t)B * e.world) CVG_FAIL("cvg_visit: B_global must be B_local * world_size");
+  // step-program kernel: the whole visit is ONE program = one launch (batch draws included)
+  ProgramScope prog(e);
   int i = 0;
   for (int kind = 0; kind < 3; ++kind) {
     const int reps = kind == 0 ? d_loop : (kind == 1 ? c_loop : g_loop);
@@ -1074,6 +1240,9 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       const float* x = nullptr;
       if (x_batches) {
         x = x_batches + (size_t)i * B * e.F;
+      } else if (e.mk.recording) {
+        e.mk.src_rows = class_rows; e.mk.src_n = n_rows; e.mk.src_Bg = B_global; e.mk.src_off = (long long)e.rank * B;
+        x = class_rows;
       } else {
         sample_rows_kernel<<<(B + 127) / 128, 128, 0, st>>>(class_rows, n_rows, B_global, (long long)e.rank * B, B, e.F,
                                                            0, 0, e.ws.ctl, 0, e.ws.x_stage, nullptr);
@@ -1089,14 +1258,20 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       if (kind == 0) CVG_TRY(step_d(e, x, label, B, nullptr, rng, sf, lo, st));
       else if (kind == 1) CVG_TRY(step_c(e, x, label, B, nullptr, rng, sf, lo, st));
       else CVG_TRY(step_g(e, x, label, B, nullptr, rng, sf, lo, st));
-      ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 2ull, 0);    // two counter values per step: draw + noise
-      CVG_LAUNCH_CHECK();
+      e.mk.src_rows = nullptr;
+      if (e.mk.recording) {
+        e.mk.dcounter += 2;                                    // applied once by the program's finish op
+      } else {
+        ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 2ull, 0);    // two counter values per step: draw + noise
+        CVG_LAUNCH_CHECK();
+      }
     }
   }
-  return 0;
+  return prog.finish(st);
 }
 
 void set_all_kernel_attributes() {
+  mk_set_kernel_attributes();
   // cudaFuncSetAttribute is done once, eagerly, so that nothing but launches happens during graph capture
 #define CVG_MN_ATTR(W, A, E) cudaFuncSetAttribute(gemm_mn_kernel<W, A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   CVG_MN_ATTR(true, OP_PLAIN, EP_LINEAR) CVG_MN_ATTR(true, OP_BN_ACT, EP_LINEAR) CVG_MN_ATTR(true, OP_REPARAM, EP_LINEAR)

@@ -334,6 +334,22 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.cvg_launch_count(self.h))
 
+    def debug_set(self, key: str, value: int):
+        """Executor switches: train_mode (1 = step-program tcgen05 kernel, 0 = stand-alone FFMA kernels), mk_max_ops, ..."""
+        check(self.lib.cvg_debug_set(self.h, key.encode(), int(value)))
+
+    def debug_get(self, key: str) -> int:
+        v = C.c_int()
+        check(self.lib.cvg_debug_get(self.h, key.encode(), C.byref(v)))
+        return v.value
+
+    def mk_cycles(self):
+        """Per-op cycle counts of the last step program (CVG_MK_DBG=1)."""
+        n = C.c_int()
+        buf = (C.c_longlong * 2048)()
+        check(self.lib.cvg_debug_mk_cycles(self.h, buf, 2048, C.byref(n)))
+        return list(buf[:n.value])
+
 
 def patience_scan(keep_host: torch.Tensor, num: int, chunk: int = 10, patience: int = 20):
     """Host integer logic of cvae_gan.py:350-376 (see cvg_patience_scan)."""

@@ -236,6 +236,17 @@ int cvg_profile_read(CvgHandle* h, int kernel_class, int64_t* launches, double* 
 /* Number of kernels this handle has launched since creation (bench.py reports it as gpu_launches). */
 int64_t cvg_launch_count(const CvgHandle* h);
 
+/* Training executor switches (tests, A/B runs; the defaults come from the environment at cvg_create).
+ *   "train_mode"  1 = step-program kernel: one persistent tcgen05 kernel per optimiser step / label visit (default),
+ *                 0 = stand-alone FP32-FMA layer kernels (CVG_TRAIN_MODE=ffma)
+ *   "mk_max_ops"  truncate every recorded program after this many ops (-1 = off; bisecting)
+ *   "mk_allbar"   grid barrier before every op       "mk_coop"  cooperative launch on / off
+ * cvg_debug_get: "train_mode", "mk_supported", "mk_last_nops" (ops of the last program incl. the finish op).
+ * cvg_debug_mk_cycles: per-op cycle counts of the last program as seen by CTA 0 (needs CVG_MK_DBG=1). */
+int cvg_debug_set(CvgHandle* h, const char* key, int value);
+int cvg_debug_get(const CvgHandle* h, const char* key, int* value);
+int cvg_debug_mk_cycles(CvgHandle* h, long long* out, int capacity, int* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,8 @@ def _single_thread_cpu():
 # ---------------------------------------------------------------------------------------------------
 # per-step gradients (no update): every parameter gradient of every network, three shapes
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("F_,K,B", [(10, 5, 64), (10, 4, 200), (30, 5, 128), (10, 5, 333)])
+# (10, 5, 4096) is BASELINE.json configs[1] (the benchmarked shape); (10, 4, 4096) is the OTIDS class count of configs[2]
+@pytest.mark.parametrize("F_,K,B", [(10, 5, 64), (10, 4, 200), (30, 5, 128), (10, 5, 333), (10, 5, 4096), (10, 4, 4096)])
 @pytest.mark.parametrize("kind", ["d", "c", "g"])
 def test_step_losses_and_gradients(kind, F_, K, B):
     orc, eng, g = P.make_pair(F_, K, B, seed=5 + B)
@@ -74,6 +75,38 @@ def test_two_label_visits_trajectory():
     P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5, atol_frac=2e-3, outlier_frac=2e-3, hard_atol=10 * 2e-4)
     P.assert_report(report, "parameters after two label visits")
     assert eng.get_adam_step(2) == 10 and eng.get_adam_step(3) == 10 and eng.get_adam_step(0) == 6
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# one full epoch (K = 5 label visits = 65 optimiser steps) at the benchmarked batch 4096 with
+# lambda_class != 0, every step's losses checked, parameters checked at the end
+# ---------------------------------------------------------------------------------------------------
+def test_one_epoch_trajectory_batch4096():
+    F_, K, B = 10, 5, 4096
+    orc, eng, g = P.make_pair(F_, K, B, seed=23)
+    x, y = P.make_data(F_, K, [6000, 4096, 5000, 3000, 8000], seed=4)   # randperm, all-rows and randint branches
+    orc.divide_samples(x, y)
+    step = 0
+    for label in range(K):
+        n = len(orc.samples[label])
+        for kind, reps in (("d", 5), ("c", 5), ("g", 3)):
+            for _ in range(reps):
+                if n > B:
+                    idx = torch.randperm(n, generator=g)[:B]
+                elif n == B:
+                    idx = torch.arange(B)
+                else:
+                    idx = torch.randint(0, n, (B,), generator=g)
+                xb = orc.samples[label][idx].contiguous()
+                ref, got, _ = P.run_step(kind, orc, eng, xb, label, g, lambda_class=0.25, update=True)
+                assert P.losses_close(ref, got, rtol=2e-3, atol=5e-4), (step, kind, ref, got)
+                step += 1
+    assert step == 65
+    report = []
+    P.compare_state(eng, orc, report, loose_prebn_atol=15 * 2e-4 * 1.5, atol_frac=2e-3, outlier_frac=2e-3, hard_atol=25 * 2e-4)
+    P.assert_report(report, "parameters after one epoch at batch 4096")
+    assert eng.get_adam_step(2) == 25 and eng.get_adam_step(3) == 25 and eng.get_adam_step(0) == 15
     eng.close()
 
 
