@@ -491,9 +491,11 @@ int cvg_debug_mk_cycles(CvgHandle* h, long long* out, int capacity, int* count) 
   H_OR_FAIL(h);
   Engine& e = h->e;
   if (!e.ws_base) CVG_FAIL("workspace not bound");
+  // capacity >= 2048 + 64: also returns the GEMM section counters at out[2048 ...]
   const int n = e.mk.last_nops < capacity ? e.mk.last_nops : capacity;
   if (count) *count = n;
   if (out && n > 0) CVG_CUDA(cudaMemcpy(out, e.ws.mk_dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  if (out && capacity >= 2048 + 64) CVG_CUDA(cudaMemcpy(out + 2048, e.ws.mk_dbg + 2048, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -242,7 +242,7 @@ static size_t carve(const Engine& e, Workspace& w, void* base) {
   w.dw_scratch = c.take<float>((size_t)w.dw_scratch_floats);
   w.mk_bar = c.take<unsigned int>(64);
   w.z_eps = c.take<float>((size_t)Z * ld);
-  w.mk_dbg = c.take<long long>(2048);
+  w.mk_dbg = c.take<long long>(2048 + 64);
   return c.off + 256;
 }
 

@@ -13,7 +13,7 @@ using mk::OpRec;
 bool mk_supported(const Engine& e) {
   auto ok = [](const int* h) { return h[0] <= mk::MAX_C && h[1] <= mk::MAX_C && h[2] <= mk::MAX_C; };
   return ok(e.eh) && ok(e.gh) && ok(e.dh) && ok(e.ch) && e.F + e.K <= mk::B_MAXN && e.Z <= mk::B_MAXN && 2 * e.Z <= SN_MAXDIM &&
-         e.ch[1] <= 8 * LN_MAXF;
+         e.ch[1] <= 8 * mk::MK_LN_F;
 }
 
 void mk_set_kernel_attributes() {
@@ -219,6 +219,8 @@ int mk_flush(Engine& e, cudaStream_t st) {
   P.bar_counter = e.ws.mk_bar;
   if (e.world > 1 && e.nvl.on) P.nvl = e.nvl.dev;
   P.dbg = (getenv("CVG_MK_DBG") && m.nops <= 2048) ? e.ws.mk_dbg : nullptr;
+  P.prof = P.dbg ? e.ws.mk_dbg + 2048 : nullptr;
+  if (P.prof) CVG_CUDA(cudaMemsetAsync(P.prof, 0, 64 * sizeof(long long), st));
   m.last_nops = m.nops;
   void* args[1] = {&P};
   cudaError_t err;

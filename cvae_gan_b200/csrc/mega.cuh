@@ -90,6 +90,7 @@ struct Params {
   unsigned int* bar_counter;     // zeroed by the host before every launch
   NvlDev nvl;                    // world == 0: no peer exchanges in this program
   long long* dbg;                // optional per-op cycle counters [nops] (CTA 0)
+  long long* prof;               // optional section counters of the GEMM items (CTA 0, development)
 };
 
 struct Ctrl {
@@ -101,15 +102,20 @@ struct Ctrl {
 
 constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + CS_FLOATS * 4 + RED_DOUBLES * 8 + OP_BYTES + sizeof(Ctrl) + 64;
 
-struct Ctx {
+// Per-CTA pipeline state.  Everything here lives in registers (all users are force-inlined): with ~217 KB of shared
+// memory the L1 has ~10 KB left, so a single spilled word costs an L2 round trip.
+struct Pipe {
   uint8_t* stages;
   float* cs;
   double* red;
   uint64_t* bar;
   uint32_t tmem;
-  int n_commit[NSTAGE];
+  uint32_t ph;          // bit s: parity of the newest commit on stage s; bit 8 + s: stage s has been committed to
   int tid, warp, lane;
+  long long* prof;
 };
+#define MK_T(var) if (c.prof) var = clock64();
+#define MK_ACC(slot, t0, t1) if (c.prof && c.tid == 0) c.prof[slot] += (t1) - (t0);
 
 // ---- loads of data that other CTAs produced earlier in the SAME launch: L2 only (L1 is not coherent) ---------------
 __device__ __forceinline__ float ldg1(const float* p) { return __ldcg(p); }
@@ -156,8 +162,9 @@ __device__ __forceinline__ void mk_bn_mean_rstd(const BnRef& bn, int pass, int c
   rstd = 1.0f / sqrtf(var + eps);
 }
 
+template <int KIND>
 __device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs) {
-  if (o.kind == OP_BN_ACT) {
+  if (KIND == OP_BN_ACT) {
     const int C = o.bn.C;
     for (int c = threadIdx.x; c < C; c += THREADS) {
       float mean, rstd;
@@ -166,7 +173,7 @@ __device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, fl
       cs[C + c] = ldg1(o.bn.beta + c);
       cs[2 * C + c] = mean;
     }
-  } else if (o.kind == OP_BN_BWD) {
+  } else if (KIND == OP_BN_BWD) {
     const int C = o.bn.C;
     const double* bs = o.bn.bstats + (long long)pass * o.bn.sb;
     for (int c = threadIdx.x; c < C; c += THREADS) {
@@ -198,77 +205,13 @@ __device__ __forceinline__ void mk_bn_update_running(const BnRef& bn, int npass,
   }
 }
 
-// ---- operand element access -------------------------------------------------------------------------------------------
-// raw values of ONE element (feature row r, batch row m) of an operand; the transform is applied later, right before the
-// value goes to shared memory, so the loads of the next chunk stay in flight across the MMAs of this one
-struct Raw1 { float a, b; };
-__device__ __forceinline__ void mk_load1(const Operand& o, int pass, int r, int m, int M, int ld, Raw1& w) {
-  w.a = 0.f; w.b = 0.f;
-  if (r >= o.rows || m >= M || o.kind == OP_CONST) return;
-  const size_t off = (size_t)r * ld + m;
-  w.a = ldg1(o.p + (long long)pass * o.sp + off);
-  if (o.kind == OP_BN_BWD) w.b = ldg1(o.h + (long long)pass * o.sh + off);
-}
-__device__ __forceinline__ float mk_finish1(const Operand& o, const float* cs, int r, int m, int M, float slope, const Raw1& w) {
-  if (r >= o.rows || m >= M) return 0.f;
-  switch (o.kind) {
-    case OP_BN_ACT: {
-      const int C = o.bn.C;
-      return act_lrelu(fmaf(w.a - cs[2 * C + r], cs[r], cs[C + r]), slope);
-    }
-    case OP_BN_BWD: {
-      const int C = o.bn.C;
-      return cs[r] * (w.a - cs[C + r] - (w.b - cs[3 * C + r]) * cs[4 * C + r] * cs[2 * C + r]);
-    }
-    case OP_CONST:
-      return o.cst;
-    default:
-      return w.a;
-  }
-}
-// 4 consecutive batch rows of one feature row (weight-gradient operands: the contraction runs over batch rows)
-struct Raw4 { float4 a, b; };
-__device__ __forceinline__ void mk_load4(const Operand& o, int pass, int r, int m, int M, int ld, Raw4& w) {
-  w.a = make_float4(0.f, 0.f, 0.f, 0.f);
-  w.b = w.a;
-  if (r >= o.rows || m >= M || o.kind == OP_CONST) return;
-  const size_t off = (size_t)r * ld + m;
-  w.a = ldg4(o.p + (long long)pass * o.sp + off);
-  if (o.kind == OP_BN_BWD) w.b = ldg4(o.h + (long long)pass * o.sh + off);
-}
-__device__ __forceinline__ float4 mk_finish4(const Operand& o, const float* cs, int r, int m, int M, float slope, const Raw4& w) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r >= o.rows || m >= M) return v;
-  switch (o.kind) {
-    case OP_BN_ACT: {
-      const int C = o.bn.C;
-      const float sc = cs[r], sh = cs[C + r], mean = cs[2 * C + r];
-      v.x = act_lrelu(fmaf(w.a.x - mean, sc, sh), slope);
-      v.y = act_lrelu(fmaf(w.a.y - mean, sc, sh), slope);
-      v.z = act_lrelu(fmaf(w.a.z - mean, sc, sh), slope);
-      v.w = act_lrelu(fmaf(w.a.w - mean, sc, sh), slope);
-    } break;
-    case OP_BN_BWD: {
-      const int C = o.bn.C;
-      const float c1 = cs[r], c2 = cs[C + r], c3 = cs[2 * C + r], mean = cs[3 * C + r], rstd = cs[4 * C + r];
-      v.x = c1 * (w.a.x - c2 - (w.b.x - mean) * rstd * c3);
-      v.y = c1 * (w.a.y - c2 - (w.b.y - mean) * rstd * c3);
-      v.z = c1 * (w.a.z - c2 - (w.b.z - mean) * rstd * c3);
-      v.w = c1 * (w.a.w - c2 - (w.b.w - mean) * rstd * c3);
-    } break;
-    case OP_CONST:
-      v = make_float4(o.cst, o.cst, o.cst, o.cst);
-      break;
-    default:
-      v = w.a;
-      break;
-  }
-  if (m + 3 >= M) {
-    if (m + 1 >= M) v.y = 0.f;
-    if (m + 2 >= M) v.z = 0.f;
-    if (m + 3 >= M) v.w = 0.f;
-  }
-  return v;
+// transform of ONE operand value of feature row r (the constants of the row come from shared memory)
+template <int KIND>
+__device__ __forceinline__ float mk_xform(float a, float b, const float* cs, int C, int r, float slope, float cst) {
+  if (KIND == OP_BN_ACT) return act_lrelu(fmaf(a - cs[2 * C + r], cs[r], cs[C + r]), slope);
+  if (KIND == OP_BN_BWD) return cs[r] * (a - cs[C + r] - (b - cs[3 * C + r]) * cs[4 * C + r] * cs[2 * C + r]);
+  if (KIND == OP_CONST) return cst;
+  return a;
 }
 
 // hi / lo planes of one operand value group: 16-byte stores
@@ -282,28 +225,26 @@ __device__ __forceinline__ void st_split4(uint8_t* hi_plane, uint8_t* lo_plane, 
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
 
-__device__ __forceinline__ void stage_ptrs(const Ctx& c, int s, uint8_t*& a_hi, uint8_t*& a_lo, uint8_t*& b_hi, uint8_t*& b_lo) {
-  uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
-  a_hi = base;
-  a_lo = base + A_PLANE;
-  b_hi = base + 2 * A_PLANE;
-  b_lo = base + 2 * A_PLANE + B_PLANE;
-}
-
-// MMAs of one staged chunk: nks steps of 8 contraction values, three tf32 MMAs each (small terms first); one commit
-__device__ __forceinline__ void issue_chunk(const Ctx& c, int s, int nks, int n_mma, uint32_t lbo_b, bool first_chunk) {
+// MMAs of one staged chunk: nks steps of 8 contraction values, three tf32 MMAs each (small terms first); one commit.
+// Every descriptor input is broadcast from lane 0 so that ptxas keeps the issue loop in uniform registers.
+__device__ __forceinline__ void issue_chunk(const Pipe& c, int s, int nks, int n_mma, uint32_t lbo_b, bool first_chunk) {
   if (c.warp == 0) {
     tc_fence_after_sync();
+    const uint32_t base = __shfl_sync(0xffffffffu, smem_u32(c.stages) + (uint32_t)s * STAGE_BYTES, 0);
+    const uint32_t lbo = __shfl_sync(0xffffffffu, lbo_b, 0);
+    const uint32_t nm = __shfl_sync(0xffffffffu, (uint32_t)n_mma, 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
+    const int steps = __shfl_sync(0xffffffffu, nks, 0);
+    const uint32_t fresh = __shfl_sync(0xffffffffu, first_chunk ? 1u : 0u, 0);
     if (elect_one()) {
-      const uint32_t base = smem_u32(c.stages + (size_t)s * STAGE_BYTES);
       uint64_t dah = smem_desc(base, LBO_A, 128), dal = smem_desc(base + A_PLANE, LBO_A, 128);
-      uint64_t dbh = smem_desc(base + 2 * A_PLANE, lbo_b, 128), dbl = smem_desc(base + 2 * A_PLANE + B_PLANE, lbo_b, 128);
-      const uint32_t idesc = idesc_tf32(128, n_mma, 0, 0);
-      const uint64_t a_step = (uint64_t)((2 * LBO_A) >> 4), b_step = (uint64_t)((2 * lbo_b) >> 4);
-      for (int ks = 0; ks < nks; ++ks) {
-        mma_tf32(c.tmem, dal, dbh, idesc, !(first_chunk && ks == 0));
-        mma_tf32(c.tmem, dah, dbl, idesc, true);
-        mma_tf32(c.tmem, dah, dbh, idesc, true);
+      uint64_t dbh = smem_desc(base + 2 * A_PLANE, lbo, 128), dbl = smem_desc(base + 2 * A_PLANE + B_PLANE, lbo, 128);
+      const uint32_t idesc = idesc_tf32(128, (int)nm, 0, 0);
+      const uint64_t a_step = (uint64_t)((2 * LBO_A) >> 4), b_step = (uint64_t)((2 * lbo) >> 4);
+      for (int ks = 0; ks < steps; ++ks) {
+        mma_tf32(tm, dal, dbh, idesc, !(fresh && ks == 0));
+        mma_tf32(tm, dah, dbl, idesc, true);
+        mma_tf32(tm, dah, dbh, idesc, true);
         dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
       }
       mma_commit(&c.bar[s]);
@@ -312,115 +253,145 @@ __device__ __forceinline__ void issue_chunk(const Ctx& c, int s, int nks, int n_
   }
 }
 
-__device__ __forceinline__ void wait_stage(Ctx& c, int s) {
-  if (c.n_commit[s] > 0) mbar_wait(&c.bar[s], (uint32_t)((c.n_commit[s] - 1) & 1));
+__device__ __forceinline__ void wait_stage(const Pipe& c, int s) {
+  if (c.ph & (256u << s)) mbar_wait(&c.bar[s], (c.ph >> s) & 1u);
+}
+__device__ __forceinline__ void note_commit(Pipe& c, int s) {
+  c.ph = (c.ph & (256u << s)) ? (c.ph ^ (1u << s)) : (c.ph | (256u << s));
 }
 
 // ======================================================================================================================
 // forward / input-gradient GEMM item:  D[n][m] = sum_r A[n][r] * B[m][r]
-//   wt  : A = W[n][r] (forward)          !wt : A = W[r][n] (input gradient)
+//   WT  : A = W[n][r] (forward)          !WT : A = W[r][n] (input gradient)
 //   B = operand g.a (feature-major [r][m] in memory, transformed), m = batch rows of this tile
+// Operand kind (AK) and epilogue (EK) are compile-time; the tile height (64 / 128 rows) is a shift.
 // ======================================================================================================================
-struct MnRegs {
-  float4 a[2];        // raw weights (already in operand order)
-  Raw1 b[2][4];
-};
+template <bool WT, int AK, int EK>
+__device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt_shift, const int item) {
+  const int tid = c.tid;
+  const int M = g.M, ld = g.ld, N = g.N;
+  const int R = min(g.R, g.a.rows);
+  const int Nt = 1 << nt_shift;
+  const int ntm = (M + Nt - 1) >> nt_shift, nmt = (N + 127) >> 7;
+  const int rt = item % ntm, t2 = item / ntm, mt = t2 % nmt;
+  const int pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
+  const int m0 = rt << nt_shift, n0 = mt << 7;
+  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
+  const int nchunks = (R + KC - 1) / KC;
+  const int ldw = g.ldw;
+  const float slope = g.slope;
+  float* cs_a = c.cs;
+  float* cs_e = c.cs + (AK == OP_BN_ACT ? 3 * g.a.bn.C : (AK == OP_BN_BWD ? 5 * g.a.bn.C : 0));
+  const int Ca = (AK == OP_BN_ACT || AK == OP_BN_BWD) ? g.a.bn.C : 0;
+  long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+  MK_T(q0);
 
-__device__ __forceinline__ void mn_load(const GemmArgs& g, bool wt, int Nt, int pass, int n0, int m0, int chunk, int tid, MnRegs& rg) {
-  const int r0 = chunk * KC;
-  const bool wvec = ((g.ldw | g.wcol0) & 3) == 0;
+  // ---- per-thread operand addressing (fixed for the whole item) -----------------------------------------------------
+  const float* pa[2];
+  uint32_t sa[2];
+  int ka[2];
+  bool va[2];
+  const bool wvec = WT && (((ldw | g.wcol0) & 3) == 0);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int idx = tid + j * THREADS;
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (wt) {
-      const int k4 = idx & 7, n = n0 + (idx >> 3), r = r0 + k4 * 4;
-      if (n < g.N && r < g.R) {
-        const float* src = g.W + (size_t)n * g.ldw + g.wcol0 + r;
-        if (wvec && r + 3 < g.R) {
-          w = ldg4(src);
+    const int k4 = WT ? (idx & 7) : (idx >> 7);
+    const int nl = WT ? (idx >> 3) : (idx & 127);
+    ka[j] = k4 * 4;
+    va[j] = n0 + nl < N;
+    sa[j] = (uint32_t)k4 * LBO_A + (uint32_t)nl * 16u;
+    pa[j] = WT ? g.W + (size_t)(n0 + nl) * ldw + g.wcol0 + k4 * 4 : g.W + (size_t)(k4 * 4) * ldw + g.wcol0 + n0 + nl;
+  }
+  const float* pb[2];
+  const float* ph[2];
+  uint32_t sb[2];
+  int kb[2];
+  bool vb[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * THREADS;
+    const int ml = idx & (Nt - 1), k4 = idx >> nt_shift;
+    const int m = m0 + ml;
+    kb[j] = k4 * 4;
+    vb[j] = (k4 < KG) && (m < M);
+    sb[j] = (uint32_t)k4 * lbo_b + (uint32_t)ml * 16u;
+    pb[j] = (AK == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + (size_t)(k4 * 4) * ld + m;
+    ph[j] = (AK == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + (size_t)(k4 * 4) * ld + m : nullptr;
+  }
+  const bool two_b = Nt > 64;      // 128-row tiles: two operand groups per thread
+
+  float4 ra[2];
+  float rb[2][4], rh[2][4];
+  auto load_chunk = [&](int ch) {
+    const int r0 = ch * KC;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = r0 + ka[j];
+      if (va[j] && r < R) {
+        if (WT) {
+          const float* src = pa[j] + r0;
+          if (wvec && r + 3 < R) {
+            w = ldg4(src);
+          } else {
+            w.x = ldg1(src);
+            if (r + 1 < R) w.y = ldg1(src + 1);
+            if (r + 2 < R) w.z = ldg1(src + 2);
+            if (r + 3 < R) w.w = ldg1(src + 3);
+          }
         } else {
+          const float* src = pa[j] + (size_t)r0 * ldw;
           w.x = ldg1(src);
-          if (r + 1 < g.R) w.y = ldg1(src + 1);
-          if (r + 2 < g.R) w.z = ldg1(src + 2);
-          if (r + 3 < g.R) w.w = ldg1(src + 3);
+          if (r + 1 < R) w.y = ldg1(src + (size_t)ldw);
+          if (r + 2 < R) w.z = ldg1(src + 2 * (size_t)ldw);
+          if (r + 3 < R) w.w = ldg1(src + 3 * (size_t)ldw);
         }
       }
-    } else {
-      const int n = n0 + (idx & 127), k4 = idx >> 7, r = r0 + k4 * 4;
-      if (n < g.N) {
-        const float* src = g.W + (size_t)r * g.ldw + g.wcol0 + n;
-        if (r < g.R) w.x = ldg1(src);
-        if (r + 1 < g.R) w.y = ldg1(src + (size_t)g.ldw);
-        if (r + 2 < g.R) w.z = ldg1(src + 2 * (size_t)g.ldw);
-        if (r + 3 < g.R) w.w = ldg1(src + 3 * (size_t)g.ldw);
+      ra[j] = w;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (j == 0 || two_b) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + kb[j] + i;
+          rb[j][i] = 0.f;
+          rh[j][i] = 0.f;
+          if (AK != OP_CONST && vb[j] && r < R) {
+            rb[j][i] = ldg1(pb[j] + (size_t)(r0 + i) * ld);
+            if (AK == OP_BN_BWD) rh[j][i] = ldg1(ph[j] + (size_t)(r0 + i) * ld);
+          }
+        }
       }
     }
-    rg.a[j] = w;
-  }
-  const int nb = (Nt * KG) / THREADS;   // 1 (64 rows) or 2 (128 rows)
+  };
+  auto store_chunk = [&](int ch, int s, int nk4) {
+    uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
+    const int r0 = ch * KC;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    if (j < nb) {
-      const int idx = tid + j * THREADS;
-      const int m = m0 + idx % Nt, r = r0 + (idx / Nt) * 4;
+    for (int j = 0; j < 2; ++j)
+      if ((ka[j] >> 2) < nk4) st_split4(base, base + A_PLANE, sa[j], ra[j]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) mk_load1(g.a, pass, r + i, m, g.M, g.ld, rg.b[j][i]);
-    }
-  }
-}
-
-__device__ __forceinline__ void mn_store(const Ctx& c, const GemmArgs& g, bool wt, int Nt, int m0, int chunk, int s, int nk4,
-                                         const float* cs_a, const MnRegs& rg) {
-  uint8_t *a_hi, *a_lo, *b_hi, *b_lo;
-  stage_ptrs(c, s, a_hi, a_lo, b_hi, b_lo);
-  const int r0 = chunk * KC;
-  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
+    for (int j = 0; j < 2; ++j) {
+      if ((j == 0 || two_b) && (kb[j] >> 2) < nk4) {
+        float v[4];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int idx = c.tid + j * THREADS;
-    int k4, n;
-    if (wt) { k4 = idx & 7; n = idx >> 3; } else { n = idx & 127; k4 = idx >> 7; }
-    if (k4 < nk4) st_split4(a_hi, a_lo, (uint32_t)k4 * LBO_A + (uint32_t)n * 16u, rg.a[j]);
-  }
-  const int nb = (Nt * KG) / THREADS;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    if (j < nb) {
-      const int idx = c.tid + j * THREADS;
-      const int ml = idx % Nt, k4 = idx / Nt, m = m0 + ml, r = r0 + k4 * 4;
-      if (k4 < nk4) {
-        float4 v;
-        v.x = mk_finish1(g.a, cs_a, r, m, g.M, g.slope, rg.b[j][0]);
-        v.y = mk_finish1(g.a, cs_a, r + 1, m, g.M, g.slope, rg.b[j][1]);
-        v.z = mk_finish1(g.a, cs_a, r + 2, m, g.M, g.slope, rg.b[j][2]);
-        v.w = mk_finish1(g.a, cs_a, r + 3, m, g.M, g.slope, rg.b[j][3]);
-        st_split4(b_hi, b_lo, (uint32_t)k4 * lbo_b + (uint32_t)ml * 16u, v);
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + kb[j] + i;
+          v[i] = (vb[j] && r < R) ? mk_xform<AK>(rb[j][i], rh[j][i], cs_a, Ca, r, slope, g.a.cst) : 0.f;
+        }
+        st_split4(base + 2 * A_PLANE, base + 2 * A_PLANE + B_PLANE, sb[j], make_float4(v[0], v[1], v[2], v[3]));
       }
     }
-  }
-}
+  };
 
-__device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
-  const int ntm = (g.M + Nt - 1) / Nt;
-  const int nmt = (g.N + 127) / 128;
-  const int rt = item % ntm;
-  const int t2 = item / ntm;
-  const int mt = t2 % nmt;
-  const int pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
-  const int m0 = rt * Nt, n0 = mt * 128;
-  float* cs_a = c.cs;
-  float* cs_e = c.cs + operand_const_floats(g.a);
-  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
-  const int nchunks = (g.R + KC - 1) / KC;
+  load_chunk(0);     // in flight while the constants are prepared
 
-  MnRegs rg;
-  mn_load(g, wt, Nt, pass, n0, m0, 0, c.tid, rg);     // in flight while the constants are prepared
-
-  mk_operand_consts(g.a, pass, g.Bg, g.bn_eps, cs_a);
-  if (g.ekind == EP_DBN) {
+  // ---- per-feature constants -----------------------------------------------------------------------------------------
+  mk_operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a);
+  if (EK == EP_DBN) {
     const int C = g.prev_bn.C;
-    for (int ch = c.tid; ch < C; ch += THREADS) {
+    for (int ch = tid; ch < C; ch += THREADS) {
       float mean, rstd;
       mk_bn_mean_rstd(g.prev_bn, pass, ch, g.Bg, g.bn_eps, mean, rstd);
       cs_e[ch] = ldg1(g.prev_bn.gamma + ch) * rstd;
@@ -429,56 +400,97 @@ __device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
       cs_e[3 * C + ch] = rstd;
     }
   }
-  if (g.a.kind == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum);
+  if (AK == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum);
+
+  // ---- epilogue addressing + the values it needs from memory, requested now ------------------------------------------
+  const int q = c.warp & 3, cgp = c.warp >> 2;
+  const int n = n0 + q * 32 + c.lane;
+  const bool nvalid = n < N;
+  const int colw = Nt >> 2;                  // columns (batch rows) per column group: 16 or 32
+  float scale = 1.0f, bias = 0.f;
+  if (g.scale) scale = ldg1(g.scale + pass);
+  if (EK == EP_LINEAR && nvalid) {
+    bias = g.bias ? ldg1(g.bias + n) : 0.f;
+    if (g.wlabel) bias += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
+  }
   __syncthreads();
+  MK_T(q1);
+  MK_ACC(0, q0, q1);
 
   for (int ch = 0; ch < nchunks; ++ch) {
     const int s = ch & 1;
-    const int klen = min(KC, g.R - ch * KC);
+    const int klen = min(KC, R - ch * KC);
     const int nks = (klen + 7) >> 3;
+    MK_T(q2);
     if (ch >= NSTAGE) wait_stage(c, s);             // the MMAs that read this stage two chunks ago have completed
-    mn_store(c, g, wt, Nt, m0, ch, s, 2 * nks, cs_a, rg);
-    if (ch + 1 < nchunks) mn_load(g, wt, Nt, pass, n0, m0, ch + 1, c.tid, rg);
+    MK_T(q3);
+    MK_ACC(1, q2, q3);
+    store_chunk(ch, s, 2 * nks);
+    MK_T(q2);
+    MK_ACC(2, q3, q2);
+    if (ch + 1 < nchunks) load_chunk(ch + 1);
     fence_proxy_async_smem();
     __syncthreads();
+    MK_T(q3);
+    MK_ACC(3, q2, q3);
     issue_chunk(c, s, nks, Nt, lbo_b, ch == 0);
-    c.n_commit[s]++;
+    note_commit(c, s);
+    MK_T(q2);
+    MK_ACC(4, q3, q2);
   }
+
+  // ---- epilogue: thread = (output feature = TMEM lane, 16-row column blocks).  The memory operands of the first block
+  // are requested before the MMAs are waited for.
+  float e_sc = 0.f, e_sh = 0.f, e_mean = 0.f, e_rstd = 0.f;
+  if (EK == EP_DBN && nvalid) {
+    const int C = g.prev_bn.C;
+    e_sc = cs_e[n]; e_sh = cs_e[C + n]; e_mean = cs_e[2 * C + n]; e_rstd = cs_e[3 * C + n];
+  }
+  const float keep_inv = g.keep_inv;
+  const uint8_t* mask_p = (EK == EP_LINEAR || EK == EP_DACT) && g.mask ? g.mask + (long long)pass * g.smask : nullptr;
+  const float* prev_p = (EK == EP_DBN || EK == EP_DACT) ? g.prev + (long long)pass * g.sprev : nullptr;
+  float* Yp = g.Y + (long long)pass * g.sY;
+  float4 pv[4];
+  uchar4 mkv[4];
+  auto epi_prefetch = [&](int hb) {
+    const int col = cgp * colw + hb * 16;
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      const int m = m0 + col + gq * 4;
+      pv[gq] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mkv[gq] = make_uchar4(1, 1, 1, 1);
+      if (nvalid && m < M) {
+        const size_t off = (size_t)n * ld + m;
+        if (prev_p) pv[gq] = ldg4(prev_p + off);
+        if (mask_p) mkv[gq] = __ldcg(reinterpret_cast<const uchar4*>(mask_p + off));
+        if (EK == EP_STORE && g.accumulate) pv[gq] = ldg4(Yp + off);
+      }
+    }
+  };
+  epi_prefetch(0);
+  MK_T(q2);
   wait_stage(c, 0);
   if (nchunks > 1) wait_stage(c, 1);
   tc_fence_after_sync();
+  MK_T(q3);
+  MK_ACC(5, q2, q3);
+  if (c.prof && c.tid == 0) { c.prof[8] += nchunks; c.prof[9] += 1; }
 
-  // ---- epilogue: thread = (output feature = TMEM lane, 16-row column blocks) ----------------------------------------
-  const int q = c.warp & 3, cgp = c.warp >> 2;
-  const int n = n0 + q * 32 + c.lane;
-  const bool nvalid = n < g.N;
-  const float scale = g.scale ? ldg1(g.scale + pass) : 1.0f;
   double s1 = 0.0, s2 = 0.0, tot = 0.0, klsum = 0.0;
-  float bias = 0.f;
-  float e_sc = 0.f, e_sh = 0.f, e_mean = 0.f, e_rstd = 0.f;
-  if (nvalid) {
-    if (g.ekind == EP_LINEAR) {
-      bias = g.bias ? ldg1(g.bias + n) : 0.f;
-      if (g.wlabel) bias += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
-    } else if (g.ekind == EP_DBN) {
-      const int C = g.prev_bn.C;
-      e_sc = cs_e[n]; e_sh = cs_e[C + n]; e_mean = cs_e[2 * C + n]; e_rstd = cs_e[3 * C + n];
-    }
-  }
-  const int nhb = Nt / 64;
+  const int nhb = Nt >> 6;
   for (int hb = 0; hb < nhb; ++hb) {
-    const int col = cgp * (Nt / 4) + hb * 16;
+    const int col = cgp * colw + hb * 16;
     float v[16];
     tmem_ld16(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
     tmem_wait_ld();
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) {
       const int m = m0 + col + gq * 4;
-      if (!nvalid || m >= g.M) continue;
+      if (!nvalid || m >= M) continue;
       float y[4] = {v[gq * 4], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]};
-      const bool rowv[4] = {true, m + 1 < g.M, m + 2 < g.M, m + 3 < g.M};
-      const size_t off = (size_t)n * g.ld + m;
-      if (g.ekind == EP_LINEAR) {
+      const bool rowv[4] = {true, m + 1 < M, m + 2 < M, m + 3 < M};
+      const size_t off = (size_t)n * ld + m;
+      if (EK == EP_LINEAR) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = fmaf(y[i], scale, bias);
         if (g.kl_acc) {
@@ -493,7 +505,7 @@ __device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
         }
         if (g.act == ACT_LRELU) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) y[i] = act_lrelu(y[i], g.slope);
+          for (int i = 0; i < 4; ++i) y[i] = act_lrelu(y[i], slope);
         } else if (g.act == ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) y[i] = fmaxf(y[i], 0.f);
@@ -501,58 +513,50 @@ __device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) y[i] = 1.0f / (1.0f + expf(-y[i]));
         }
-        if (g.mask) {
-          const uchar4 mk = __ldcg(reinterpret_cast<const uchar4*>(g.mask + (long long)pass * g.smask + off));
-          y[0] = mk.x ? y[0] * g.keep_inv : 0.f;
-          y[1] = mk.y ? y[1] * g.keep_inv : 0.f;
-          y[2] = mk.z ? y[2] * g.keep_inv : 0.f;
-          y[3] = mk.w ? y[3] * g.keep_inv : 0.f;
+        if (mask_p) {
+          y[0] = mkv[gq].x ? y[0] * keep_inv : 0.f;
+          y[1] = mkv[gq].y ? y[1] * keep_inv : 0.f;
+          y[2] = mkv[gq].z ? y[2] * keep_inv : 0.f;
+          y[3] = mkv[gq].w ? y[3] * keep_inv : 0.f;
         }
         if (g.osum) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (rowv[i]) tot += (double)y[i];
         }
-        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
-      } else if (g.ekind == EP_DBN) {
-        const float4 h = ldg4(g.prev + (long long)pass * g.sprev + off);
-        const float hh[4] = {h.x, h.y, h.z, h.w};
+        st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (EK == EP_DBN) {
+        const float hh[4] = {pv[gq].x, pv[gq].y, pv[gq].z, pv[gq].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float pre = fmaf(hh[i] - e_mean, e_sc, e_sh);
-          const float dy = rowv[i] ? (pre > 0.f ? y[i] : y[i] * g.slope) : 0.f;
+          const float dy = rowv[i] ? (pre > 0.f ? y[i] : y[i] * slope) : 0.f;
           y[i] = dy;
           s1 += (double)dy;
           s2 += (double)(dy * ((hh[i] - e_mean) * e_rstd));
         }
-        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
-      } else if (g.ekind == EP_DACT) {
-        const float4 ap = ldg4(g.prev + (long long)pass * g.sprev + off);
-        const float aa[4] = {ap.x, ap.y, ap.z, ap.w};
+        st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (EK == EP_DACT) {
+        const float aa[4] = {pv[gq].x, pv[gq].y, pv[gq].z, pv[gq].w};
         float keep[4] = {1.f, 1.f, 1.f, 1.f};
-        if (g.mask) {
-          const uchar4 mk = __ldcg(reinterpret_cast<const uchar4*>(g.mask + (long long)pass * g.smask + off));
-          keep[0] = mk.x ? g.keep_inv : 0.f;
-          keep[1] = mk.y ? g.keep_inv : 0.f;
-          keep[2] = mk.z ? g.keep_inv : 0.f;
-          keep[3] = mk.w ? g.keep_inv : 0.f;
+        if (mask_p) {
+          keep[0] = mkv[gq].x ? keep_inv : 0.f;
+          keep[1] = mkv[gq].y ? keep_inv : 0.f;
+          keep[2] = mkv[gq].z ? keep_inv : 0.f;
+          keep[3] = mkv[gq].w ? keep_inv : 0.f;
         }
-        const float neg = (g.act == ACT_LRELU) ? g.slope : 0.f;
+        const float neg = (g.act == ACT_LRELU) ? slope : 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float d = y[i] * scale * keep[i];
           y[i] = aa[i] > 0.f ? d : d * neg;
         }
-        st4(g.Y + (long long)pass * g.sY + off, make_float4(y[0], y[1], y[2], y[3]));
-      } else if (g.ekind == EP_STORE) {
-        float* dst = g.Y + (long long)pass * g.sY + off;
+        st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
+      } else if (EK == EP_STORE) {
         float4 o = make_float4(y[0] * scale, y[1] * scale, y[2] * scale, y[3] * scale);
-        if (g.accumulate) {
-          const float4 old = ldg4(dst);
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        st4(dst, o);
-      } else if (g.ekind == EP_REPARAM_BWD) {
+        if (g.accumulate) { o.x += pv[gq].x; o.y += pv[gq].y; o.z += pv[gq].z; o.w += pv[gq].w; }
+        st4(Yp + off, o);
+      } else if (EK == EP_REPARAM_BWD) {
         const float4 mu = ldg4(g.mu + off), lv = ldg4(g.lv + off), ee4 = ldg4(g.eps + off);
         const float mm[4] = {mu.x, mu.y, mu.z, mu.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w}, ee[4] = {ee4.x, ee4.y, ee4.z, ee4.w};
         float dmu[4], dlv[4];
@@ -562,13 +566,14 @@ __device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
           dlv[i] = rowv[i] ? y[i] * ee[i] * 0.5f * expf(0.5f * ll[i]) + g.kl_coef * 0.5f * (expf(ll[i]) - 1.0f) : 0.f;
         }
         st4(g.Y + off, make_float4(dmu[0], dmu[1], dmu[2], dmu[3]));
-        st4(g.Y + (size_t)(g.N + n) * g.ld + m, make_float4(dlv[0], dlv[1], dlv[2], dlv[3]));
+        st4(g.Y + (size_t)(N + n) * ld + m, make_float4(dlv[0], dlv[1], dlv[2], dlv[3]));
       }
     }
     __syncwarp();
+    if (hb + 1 < nhb) epi_prefetch(hb + 1);
   }
   tc_fence_before_sync();
-  if (g.ostats) {
+  if ((EK == EP_LINEAR || EK == EP_DBN) && g.ostats) {
     // the four column groups of a feature meet in shared memory: one atomic pair per (feature, tile)
     const int slot = (cgp * 128 + q * 32 + c.lane) * 2;
     c.red[slot] = s1;
@@ -577,103 +582,157 @@ __device__ void mn_item(Ctx& c, const GemmArgs& g, bool wt, int Nt, int item) {
     if (cgp == 0 && nvalid) {
       const int b = (q * 32 + c.lane) * 2;
       const double t1 = (c.red[b] + c.red[256 + b]) + (c.red[512 + b] + c.red[768 + b]);
-      const double t2 = (c.red[b + 1] + c.red[256 + b + 1]) + (c.red[512 + b + 1] + c.red[768 + b + 1]);
+      const double t2s = (c.red[b + 1] + c.red[256 + b + 1]) + (c.red[512 + b + 1] + c.red[768 + b + 1]);
       double* st = g.ostats + (long long)pass * g.sostats;
       atomicAdd(st + n, t1);
-      atomicAdd(st + g.N + n, t2);
+      atomicAdd(st + N + n, t2s);
     }
   }
-  if (g.osum) {
+  if (EK == EP_LINEAR && g.osum) {
+    // one atomic per tile (the sums of the 16 warps meet in shared memory first)
     tot = warp_sum_d(tot);
-    if (c.lane == 0 && tot != 0.0) atomicAdd(g.osum + pass, tot);
+    __syncthreads();
+    if (c.lane == 0) c.red[c.warp] = tot;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < THREADS / 32; ++w) t += c.red[w];
+      if (t != 0.0) atomicAdd(g.osum + pass, t);
+    }
   }
-  if (g.kl_acc) {
+  if (EK == EP_LINEAR && g.kl_acc) {
     klsum = warp_sum_d(klsum);
-    if (c.lane == 0 && klsum != 0.0) atomicAdd(g.kl_acc, klsum);
+    __syncthreads();
+    if (c.lane == 0) c.red[c.warp] = klsum;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < THREADS / 32; ++w) t += c.red[w];
+      if (t != 0.0) atomicAdd(g.kl_acc, t);
+    }
   }
   __syncthreads();     // TMEM drained, constants and the reduction scratch free for the next item
+  MK_T(q2);
+  MK_ACC(6, q3, q2);
+}
+
+// run-time kinds -> the instantiations the steps use (same list as dispatch_mn in gemm.cuh)
+__device__ __forceinline__ void mn_dispatch(Pipe& c, const GemmArgs& g, bool wt, int nt_shift, int items, int i0, int G) {
+#define CVG_MK_MN(W, A, E)                                                    \
+  if (wt == W && g.a.kind == A && g.ekind == E) {                             \
+    for (int it = i0; it < items; it += G) mn_item<W, A, E>(c, g, nt_shift, it); \
+    return;                                                                   \
+  }
+  CVG_MK_MN(true, OP_PLAIN, EP_LINEAR)
+  CVG_MK_MN(true, OP_BN_ACT, EP_LINEAR)
+  CVG_MK_MN(false, OP_PLAIN, EP_DACT)
+  CVG_MK_MN(false, OP_CONST, EP_DACT)
+  CVG_MK_MN(false, OP_PLAIN, EP_STORE)
+  CVG_MK_MN(false, OP_PLAIN, EP_DBN)
+  CVG_MK_MN(false, OP_BN_BWD, EP_DBN)
+  CVG_MK_MN(false, OP_BN_BWD, EP_REPARAM_BWD)
+#undef CVG_MK_MN
 }
 
 // ======================================================================================================================
 // weight-gradient GEMM item:  part[z][n][k] = sum_{m in slice} P[n][m] * Q[k][m]      (+ bias partial sum_m P[n][m])
 // ======================================================================================================================
-struct DwRegs {
-  Raw4 p[2];
-  Raw4 q[4];
-};
-
-__device__ __forceinline__ void dw_load(const DwArgs& g, int pass, int n0, int npad, int mb, int mend, int tid, DwRegs& rg) {
-  const int rgp = tid & 7;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int f = (tid >> 3) + j * (THREADS / 8);
-    mk_load4(g.p, pass, n0 + f, mb + rgp * 4, mend, g.ld, rg.p[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int f = (tid >> 3) + j * (THREADS / 8);
-    if (f < npad) mk_load4(g.q, pass, f, mb + rgp * 4, mend, g.ld, rg.q[j]);
-  }
-}
-
-__device__ __forceinline__ void dw_store(const Ctx& c, const DwArgs& g, int n0, int npad, int mb, int mend, int s, const float* cs_p,
-                                         const float* cs_q, const DwRegs& rg, float* bsum) {
-  uint8_t *a_hi, *a_lo, *b_hi, *b_lo;
-  stage_ptrs(c, s, a_hi, a_lo, b_hi, b_lo);
-  const int rgp = c.tid & 7;
-  const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int f = (c.tid >> 3) + j * (THREADS / 8);
-    const float4 v = mk_finish4(g.p, cs_p, n0 + f, mb + rgp * 4, mend, g.slope, rg.p[j]);
-    bsum[j] += (v.x + v.y) + (v.z + v.w);
-    st_split4(a_hi, a_lo, (uint32_t)rgp * LBO_A + (uint32_t)f * 16u, v);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int f = (c.tid >> 3) + j * (THREADS / 8);
-    if (f < npad) {
-      const float4 v = mk_finish4(g.q, cs_q, f, mb + rgp * 4, mend, g.slope, rg.q[j]);
-      st_split4(b_hi, b_lo, (uint32_t)rgp * lbo_b + (uint32_t)f * 16u, v);
-    }
-  }
-}
-
-// aux: [0] = nsplit, scratch pointers in the op header
 struct DwScratch { float* part; float* bpart; int nsplit; int kp; };
 
-__device__ void dw_item(Ctx& c, const DwArgs& g, const DwScratch& sc, int item) {
-  const int nnt = (g.N + 127) / 128;
-  const int nt = item % nnt;
-  const int z = item / nnt;
+template <int PK, int QK>
+__device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratch& sc, const int item) {
+  const int tid = c.tid;
+  const int M = g.M, ld = g.ld, N = g.N, K = g.K;
+  const int nnt = (N + 127) >> 7;
+  const int nt = item % nnt, z = item / nnt;
   const int pass = z / sc.nsplit, split = z % sc.nsplit;
-  const int n0 = nt * 128;
+  const int n0 = nt << 7;
   const int mbeg = split * g.rows_per_cta;
-  const int mend = min(g.M, mbeg + g.rows_per_cta);
-  const int npad = (g.K + 15) & ~15;
+  const int mend = min(M, mbeg + g.rows_per_cta);
+  const int npad = (K + 15) & ~15;
   const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
+  const float slope = g.slope;
   float* cs_p = c.cs;
-  float* cs_q = c.cs + operand_const_floats(g.p);
+  const int Cp = (PK == OP_BN_BWD) ? g.p.bn.C : 0;
+  const int Cq = (QK == OP_BN_ACT) ? g.q.bn.C : 0;
+  float* cs_q = c.cs + 5 * Cp;
   const int nchunks = mend > mbeg ? (mend - mbeg + KC - 1) / KC : 0;
+  const int prows = min(N, g.p.rows), qrows = min(K, g.q.rows);
 
-  DwRegs rg;
-  if (nchunks > 0) dw_load(g, pass, n0, npad, mbeg, mend, c.tid, rg);
-  mk_operand_consts(g.p, pass, g.Bg, g.bn_eps, cs_p);
-  mk_operand_consts(g.q, pass, g.Bg, g.bn_eps, cs_q);
+  // thread -> (feature rows f0 + 64 j, row group rgp): 8 lanes cover the 32 batch rows of a chunk for one feature
+  const int rgp = tid & 7, f0 = tid >> 3;
+  const size_t step64 = (size_t)64 * ld;
+  const float* pp0 = (PK == OP_CONST) ? nullptr : g.p.p + (long long)pass * g.p.sp + (size_t)(n0 + f0) * ld + rgp * 4;
+  const float* ph0 = (PK == OP_BN_BWD) ? g.p.h + (long long)pass * g.p.sh + (size_t)(n0 + f0) * ld + rgp * 4 : nullptr;
+  const float* pq0 = g.q.p + (long long)pass * g.q.sp + (size_t)f0 * ld + rgp * 4;
+
+  float4 rp[2], rph[2], rq[4];
+  auto load_chunk = [&](int mb) {
+    const bool rows_ok = mb + rgp * 4 < mend;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rph[j] = rp[j];
+      if (PK != OP_CONST && n0 + f0 + j * 64 < prows && rows_ok) {
+        rp[j] = ldg4(pp0 + j * step64 + mb);
+        if (PK == OP_BN_BWD) rph[j] = ldg4(ph0 + j * step64 + mb);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      rq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f0 + j * 64 < qrows && rows_ok) rq[j] = ldg4(pq0 + j * step64 + mb);
+    }
+  };
+  float bsum[2] = {0.f, 0.f};
+  auto store_chunk = [&](int mb, int s) {
+    uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
+    const int m = mb + rgp * 4;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = n0 + f0 + j * 64;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < prows && m < mend) {
+        v.x = mk_xform<PK>(rp[j].x, rph[j].x, cs_p, Cp, f, slope, g.p.cst);
+        v.y = (m + 1 < mend) ? mk_xform<PK>(rp[j].y, rph[j].y, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+        v.z = (m + 2 < mend) ? mk_xform<PK>(rp[j].z, rph[j].z, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+        v.w = (m + 3 < mend) ? mk_xform<PK>(rp[j].w, rph[j].w, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+      }
+      bsum[j] += (v.x + v.y) + (v.z + v.w);
+      st_split4(base, base + A_PLANE, (uint32_t)rgp * LBO_A + (uint32_t)(f0 + j * 64) * 16u, v);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = f0 + j * 64;
+      if (f < npad) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < qrows && m < mend) {
+          v.x = mk_xform<QK>(rq[j].x, 0.f, cs_q, Cq, f, slope, 0.f);
+          v.y = (m + 1 < mend) ? mk_xform<QK>(rq[j].y, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+          v.z = (m + 2 < mend) ? mk_xform<QK>(rq[j].z, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+          v.w = (m + 3 < mend) ? mk_xform<QK>(rq[j].w, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+        }
+        st_split4(base + 2 * A_PLANE, base + 2 * A_PLANE + B_PLANE, (uint32_t)rgp * lbo_b + (uint32_t)f * 16u, v);
+      }
+    }
+  };
+
+  if (nchunks > 0) load_chunk(mbeg);
+  mk_operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p);
+  mk_operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q);
   __syncthreads();
 
-  float bsum[2] = {0.f, 0.f};
   for (int ch = 0; ch < nchunks; ++ch) {
     const int s = ch & 1;
     const int mb = mbeg + ch * KC;
     const int nks = (min(KC, mend - mb) + 7) >> 3;
     if (ch >= NSTAGE) wait_stage(c, s);
-    dw_store(c, g, n0, npad, mb, mend, s, cs_p, cs_q, rg, bsum);
-    if (ch + 1 < nchunks) dw_load(g, pass, n0, npad, mb + KC, mend, c.tid, rg);
+    store_chunk(mb, s);
+    if (ch + 1 < nchunks) load_chunk(mb + KC);
     fence_proxy_async_smem();
     __syncthreads();
     issue_chunk(c, s, nks, npad, lbo_b, ch == 0);
-    c.n_commit[s]++;
+    note_commit(c, s);
   }
   if (nchunks > 0) wait_stage(c, 0);
   if (nchunks > 1) wait_stage(c, 1);
@@ -682,7 +741,7 @@ __device__ void dw_item(Ctx& c, const DwArgs& g, const DwScratch& sc, int item) 
   // ---- epilogue: the partial tile goes to its scratch slot (row pitch kp), 16 columns per TMEM load ---------------------
   const int q = c.warp & 3, cgp = c.warp >> 2;
   const int n = n0 + q * 32 + c.lane;
-  float* prow = sc.part + ((size_t)z * g.N + n) * sc.kp;
+  float* prow = sc.part + ((size_t)z * N + n) * sc.kp;
   for (int b = cgp; b < npad / 16; b += 4) {
     float v[16];
     if (nchunks > 0) {
@@ -692,10 +751,11 @@ __device__ void dw_item(Ctx& c, const DwArgs& g, const DwScratch& sc, int item) 
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.f;
     }
-    if (n < g.N) {
+    if (n < N) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) st4(prow + b * 16 + i * 4, make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]));
     }
+    __syncwarp();
   }
   // bias partial: the 8 lanes that staged the 8 row groups of a feature
 #pragma unroll
@@ -704,11 +764,25 @@ __device__ void dw_item(Ctx& c, const DwArgs& g, const DwScratch& sc, int item) 
     b += __shfl_xor_sync(0xffffffffu, b, 1);
     b += __shfl_xor_sync(0xffffffffu, b, 2);
     b += __shfl_xor_sync(0xffffffffu, b, 4);
-    const int f = n0 + (c.tid >> 3) + j * (THREADS / 8);
-    if ((c.tid & 7) == 0 && f < g.N) sc.bpart[(size_t)z * g.N + f] = b;
+    const int f = n0 + f0 + j * 64;
+    if (rgp == 0 && f < N) sc.bpart[(size_t)z * N + f] = b;
   }
   tc_fence_before_sync();
   __syncthreads();
+}
+
+__device__ __forceinline__ void dw_dispatch(Pipe& c, const DwArgs& g, const DwScratch& sc, int items, int i0, int G) {
+#define CVG_MK_DW(P_, Q_)                                                  \
+  if (g.p.kind == P_ && g.q.kind == Q_) {                                  \
+    for (int it = i0; it < items; it += G) dw_item<P_, Q_>(c, g, sc, it);  \
+    return;                                                                \
+  }
+  CVG_MK_DW(OP_PLAIN, OP_PLAIN)
+  CVG_MK_DW(OP_CONST, OP_PLAIN)
+  CVG_MK_DW(OP_PLAIN, OP_BN_ACT)
+  CVG_MK_DW(OP_BN_BWD, OP_BN_ACT)
+  CVG_MK_DW(OP_BN_BWD, OP_PLAIN)
+#undef CVG_MK_DW
 }
 
 // sums the row-slice partials in a fixed order and adds them to the gradient buffer (deterministic)
@@ -758,6 +832,7 @@ __device__ void dwred_item(const DwRedArgs& a, int item) {
 // ======================================================================================================================
 // row-wise / element-wise ops: the bodies of misc_kernels.cuh re-cut for 512-thread CTAs and grid-strided work items
 // ======================================================================================================================
+constexpr int MK_LN_F = 16;      // LayerNorm features per thread (C <= 128)
 constexpr int FILL_VB = 64;       // work items per fill job
 constexpr int ADAM_VB = 96;       // work items per Adam segment
 constexpr int NVL_VB = 8;         // work items per exchange (each thread pushes / polls its own elements)
@@ -856,10 +931,10 @@ __device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] 
   const int c0 = w * fpt;
   const float* h = g.h + (long long)pass * g.sh + (valid ? m : 0);
   float* rd = red + hf * 256;
-  float v[LN_MAXF];
+  float v[MK_LN_F];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MK_LN_F; ++i) {
     const int cc = c0 + i;
     v[i] = (i < fpt && cc < g.C && valid) ? ldg1(h + (size_t)cc * g.ld) : 0.f;
     s += v[i];
@@ -873,7 +948,7 @@ __device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] 
   __syncthreads();
   float qv = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MK_LN_F; ++i) {
     const int cc = c0 + i;
     if (i < fpt && cc < g.C) { const float d = v[i] - mean; qv = fmaf(d, d, qv); }
   }
@@ -887,7 +962,7 @@ __device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] 
     float* a = g.a + (long long)pass * g.sa + m;
     const uint8_t* mk = g.mask ? g.mask + (long long)pass * g.smask + m : nullptr;
 #pragma unroll
-    for (int i = 0; i < LN_MAXF; ++i) {
+    for (int i = 0; i < MK_LN_F; ++i) {
       const int cc = c0 + i;
       if (i < fpt && cc < g.C) {
         float nv = (v[i] - mean) * rstd * ldg1(g.g + cc) + ldg1(g.b + cc);
@@ -921,10 +996,10 @@ __device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8
   const float mean = ldg1(rs + mm), rstd = ldg1(rs + g.ld + mm);
   float* r1 = red + hf * 512;
   float* r2 = r1 + 256;
-  float xh[LN_MAXF], d[LN_MAXF];
+  float xh[MK_LN_F], d[MK_LN_F];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MK_LN_F; ++i) {
     const int cc = c0 + i;
     const bool on = i < fpt && cc < g.C && valid;
     xh[i] = on ? (ldg1(h + (size_t)cc * g.ld) - mean) * rstd : 0.f;
@@ -942,7 +1017,7 @@ __device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8
   s1 /= (float)g.C;
   s2 /= (float)g.C;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MK_LN_F; ++i) {
     const int cc = c0 + i;
     const bool on = i < fpt && cc < g.C;       // warp-uniform
     if (!on) continue;
@@ -1221,7 +1296,7 @@ __device__ __forceinline__ const T& payload(const OpRec* op) { return *reinterpr
 
 __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  Ctx c;
+  Pipe c;
   c.stages = smem;
   c.cs = reinterpret_cast<float*>(smem + (size_t)NSTAGE * STAGE_BYTES);
   c.red = reinterpret_cast<double*>(c.cs + CS_FLOATS);
@@ -1230,8 +1305,8 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   c.tid = threadIdx.x;
   c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);
   c.lane = c.tid & 31;
-  c.n_commit[0] = 0;
-  c.n_commit[1] = 0;
+  c.ph = 0u;
+  c.prof = blockIdx.x == 0 ? P.prof : nullptr;
   if (c.tid == 0) {
     mbar_init(&S->bar[0], 1);
     mbar_init(&S->bar[1], 1);
@@ -1260,7 +1335,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
     switch (sop->kind) {
       case K_MN: {
         const GemmArgs& g = payload<GemmArgs>(sop);
-        for (int it = i0; it < items; it += G) mn_item(c, g, sop->aux[0] != 0, sop->aux[1], it);
+        mn_dispatch(c, g, sop->aux[0] != 0, sop->aux[1] == 128 ? 7 : 6, items, i0, G);
       } break;
       case K_DW: {
         const DwArgs& g = payload<DwArgs>(sop);
@@ -1269,7 +1344,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
         memcpy(&sc.bpart, sop->payload + sizeof(DwArgs) + sizeof(float*), sizeof(float*));
         sc.nsplit = sop->aux[0];
         sc.kp = sop->aux[1];
-        for (int it = i0; it < items; it += G) dw_item(c, g, sc, it);
+        dw_dispatch(c, g, sc, items, i0, G);
       } break;
       case K_DWRED: {
         const DwRedArgs& a = payload<DwRedArgs>(sop);

@@ -939,6 +939,7 @@ struct ProgramScope {
 };
 
 static int begin_step(Engine& e, const StepRng& rng, bool with_lambda, cudaStream_t st) {
+  e.mk.scratch_off = 0;      // the previous step's weight-gradient slices were reduced before its last barrier
   if (!rng.set) return 0;
   if (e.mk.recording) {
     // the ops of this program take the Philox key / counter from their own arguments (fill_args); the control block is

@@ -346,8 +346,9 @@ class Engine:
     def mk_cycles(self):
         """Per-op cycle counts of the last step program (CVG_MK_DBG=1)."""
         n = C.c_int()
-        buf = (C.c_longlong * 2048)()
-        check(self.lib.cvg_debug_mk_cycles(self.h, buf, 2048, C.byref(n)))
+        buf = (C.c_longlong * (2048 + 64))()
+        check(self.lib.cvg_debug_mk_cycles(self.h, buf, 2048 + 64, C.byref(n)))
+        self.mk_sections = list(buf[2048:2048 + 16])
         return list(buf[:n.value])
 
 

@@ -47,11 +47,12 @@ def main():
     update = os.environ.get("AB_UPDATE") == "1"
     tol = 2e-4
     bad = 0
-    for kind in "dcg":
+    for kind in os.environ.get("AB_KINDS", "dcg"):
         orc, ea, g = P.make_pair(F_, K, B, seed=7)
         eb = clone_engine(ea, B)
-        ea.debug_set("train_mode", 0)
-        eb.debug_set("train_mode", 1)
+        ma, mb = (int(v) for v in os.environ.get("AB_MODES", "0,1").split(","))
+        ea.debug_set("train_mode", ma)
+        eb.debug_set("train_mode", mb)
         x, y = P.make_data(F_, K, [B] * K, seed=1)
         xb = x[y == 1][:B].contiguous().cuda()
         inj, dev = P.draw_noise(kind, B, 128, g)
@@ -104,9 +105,31 @@ def main():
             if update:
                 r, sc = rel(eb.params[net], ea.params[net])
                 print(f"   params {P.NETS[net]}: rel {r:9.3e}")
+        if kind == "g" and os.environ.get("AB_CHECK_EDY1"):
+            # float64 recomputation of the encoder's layer-2 input gradient from engine A's own buffers: who is right?
+            for tag, e in (("ffma", ea), ("program", eb)):
+                dy2 = e.debug_read("e_dy2", B).double()
+                h2 = e.debug_read("e_h2", B).double()
+                h1 = e.debug_read("e_h1", B).double()
+                W2 = e.view(0, "encoder.6.weight").double()
+                g2 = e.view(0, "encoder.7.weight").double()
+                g1, b1 = e.view(0, "encoder.4.weight").double(), e.view(0, "encoder.4.bias").double()
+                m2, v2 = h2.mean(0), h2.var(0, unbiased=False)
+                r2 = 1.0 / torch.sqrt(v2 + 1e-5)
+                xh2 = (h2 - m2) * r2
+                v = g2 * r2 * (dy2 - dy2.mean(0) - xh2 * (dy2 * xh2).mean(0))
+                y = v @ W2
+                m1, v1 = h1.mean(0), h1.var(0, unbiased=False)
+                pre1 = (h1 - m1) / torch.sqrt(v1 + 1e-5) * g1 + b1
+                want = torch.where(pre1 > 0, y, 0.2 * y)
+                got = e.debug_read("e_dy1", B).double()
+                r, sc = rel(got, want)
+                print(f"   e_dy1 of {tag} vs float64 recomputation from its own inputs: rel {r:9.3e} scale {sc:9.3e}; "
+                      f"|v| {float(v.abs().max()):.3e} |dy2| {float(dy2.abs().max()):.3e} min var2 {float(v2.min()):.3e}")
         cyc = eb.mk_cycles() if os.environ.get("CVG_MK_DBG") else []
         if cyc:
             print("   op cycles (CTA 0):", cyc)
+            print("   mn sections (CTA 0) [preamble, wait, store, load+sync, issue, final wait, epilogue, -, chunks, items]:", eb.mk_sections)
         ea.close()
         eb.close()
     print("A/B", "FAIL" if bad else "OK", bad)
