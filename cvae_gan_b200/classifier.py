@@ -46,10 +46,8 @@ class Classifier:
 
     @staticmethod
     def _tensors(dataset):
-        if hasattr(dataset, "tensors"):
-            return dataset.tensors()
-        xs, ys = zip(*[dataset[i] for i in range(len(dataset))])
-        return torch.stack(xs), torch.stack(ys)
+        from .cvae_gan import dataset_tensors
+        return dataset_tensors(dataset)
 
     # ---- classifier.py:24-45 -----------------------------------------------------------------------------------
     def fit(self, dataset):
@@ -59,6 +57,8 @@ class Classifier:
         x_all, y_all = self._tensors(dataset)
         x_all = x_all.to(eng.device, torch.float32).contiguous()
         y_all = y_all.to(eng.device, torch.int64).contiguous()
+        if y_all.numel() and (int(y_all.min()) < 0 or int(y_all.max()) >= eng.K):
+            raise ValueError(f"labels must lie in [0, {eng.K}) - got [{int(y_all.min())}, {int(y_all.max())}]")
         n, bs = x_all.size(0), int(cc.batch_size)
         if bs > eng.max_batch:
             raise ValueError(f"classifier batch_size {bs} exceeds the engine's max_batch {eng.max_batch}")

@@ -74,6 +74,8 @@ struct Workspace {
   long long dw_scratch_floats = 0;
   unsigned int* mk_bar = nullptr;
   float* z_eps = nullptr;          // [Z][ld] reparameterisation noise of the E+G step when the program kernel runs it
+  float* mk_wprep = nullptr;       // hi / lo pre-split weight chunks of every layer, both GEMM orientations
+  long long mk_wprep_floats = 0;
   long long* mk_dbg = nullptr;     // per-op cycle counters of the last program (development)
 };
 
@@ -86,6 +88,12 @@ struct MkSlot {
   cudaEvent_t ev = nullptr;        // completion of the last upload from `host`
   bool in_graph = false;           // uploaded during stream capture: never recycled
   unsigned long long last_use = 0;
+};
+struct MkPrepSlot {
+  const float* W = nullptr;
+  int ldw = 0, wcol0 = 0, wt = 0, R = 0, N = 0, net = -1;
+  long long off = 0;               // floats into ws.mk_wprep
+  bool fresh = false;              // prepped in this program and the net has not been updated since
 };
 struct MkPendingRed {
   unsigned char bytes[160];
@@ -106,6 +114,8 @@ struct MkState {
   int adam_inc[4] = {0, 0, 0, 0};
   unsigned long long dcounter = 0;
   std::vector<MkPendingRed> pending_red;
+  std::vector<MkPrepSlot> prep;    // per program: which weight operands have been pre-split, and where
+  long long prep_off = 0;
   const float* src_rows = nullptr;   // inside a visit program: class table the next step draws its batch from
   long long src_n = 0, src_Bg = 0, src_off = 0;
   std::vector<MkSlot> slots;
@@ -192,6 +202,8 @@ int mk_begin(Engine& e);                                   // start recording (n
 int mk_flush(Engine& e, cudaStream_t st);                  // finish + upload + launch the recorded program
 int mk_push(Engine& e, int kind, const void* payload, size_t bytes, int items, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0,
             const void* extra = nullptr, size_t extra_bytes = 0);
+int mk_weight_operand(Engine& e, const GemmArgs& g, bool wt, const float** out, bool* emitted = nullptr);   // pre-split weights (+ prep op when stale)
+void mk_weights_updated(Engine& e, int net_mask);          // Adam recorded for these networks: their pre-split copies are stale
 int mk_push_dw(Engine& e, const DwArgs& g);                // weight-gradient op + its deferred deterministic reduction
 int mk_emit_dwred(Engine& e);                              // emits the pending reductions (one phase)
 

@@ -240,6 +240,18 @@ static size_t carve(const Engine& e, Workspace& w, void* base) {
     w.dw_scratch_floats = 32 * per;
   }
   w.dw_scratch = c.take<float>((size_t)w.dw_scratch_floats);
+  {
+    // pre-split weight chunks (128 rows x 32 k, hi + lo = 8192 floats): both orientations of every Linear; the heads and
+    // first layers are prepped with a narrower contraction, never a wider one
+    long long chunks = 0;
+    for (int net = 0; net < 4; ++net)
+      for (int i = 0; i < e.lay[net].nlin; ++i) {
+        const LinearP& p = e.lay[net].lin[i];
+        chunks += (long long)((p.out + 127) / 128) * ((p.in + 31) / 32) + (long long)((p.in + 127) / 128) * ((p.out + 31) / 32);
+      }
+    w.mk_wprep_floats = chunks * 8192;
+  }
+  w.mk_wprep = c.take<float>((size_t)w.mk_wprep_floats);
   w.mk_bar = c.take<unsigned int>(64);
   w.z_eps = c.take<float>((size_t)Z * ld);
   w.mk_dbg = c.take<long long>(2048 + 64);

@@ -43,7 +43,54 @@ int mk_begin(Engine& e) {
   m.dcounter = 0;
   for (int i = 0; i < 4; ++i) m.adam_inc[i] = 0;
   m.pending_red.clear();
+  m.prep.clear();
+  m.prep_off = 0;
   return 0;
+}
+
+// Pre-split copy of a GEMM's weight operand: found or created; a K_PREP op is emitted when the copy is stale (first use
+// in this program, or the network was updated by Adam since).  The op joins the current phase - it only reads weights,
+// which no op of a step writes before its Adam - and the GEMM's own barrier orders it.
+int mk_weight_operand(Engine& e, const GemmArgs& g, bool wt, const float** out, bool* emitted) {
+  MkState& m = e.mk;
+  if (emitted) *emitted = false;
+  const int R = g.R < g.a.rows ? g.R : g.a.rows;
+  MkPrepSlot* slot = nullptr;
+  for (auto& sl : m.prep)
+    if (sl.W == g.W && sl.wt == (wt ? 1 : 0) && sl.wcol0 == g.wcol0 && sl.R == R && sl.N == g.N && sl.ldw == g.ldw) { slot = &sl; break; }
+  if (!slot) {
+    MkPrepSlot sl;
+    sl.W = g.W; sl.ldw = g.ldw; sl.wcol0 = g.wcol0; sl.wt = wt ? 1 : 0; sl.R = R; sl.N = g.N;
+    for (int net = 0; net < 4; ++net)
+      if (g.W >= e.buf[net].params && g.W < e.buf[net].params + e.lay[net].n_param) sl.net = net;
+    if (sl.net < 0) CVG_FAIL("step program: GEMM weight operand outside the bound parameter buffers");
+    const long long chunks = (long long)((g.N + 127) / 128) * ((R + mk::KC - 1) / mk::KC);
+    sl.off = m.prep_off;
+    m.prep_off += chunks * mk::CHUNK_FLOATS;
+    if (m.prep_off > e.ws.mk_wprep_floats) CVG_FAIL("step program: pre-split weight buffer exhausted");
+    m.prep.push_back(sl);
+    slot = &m.prep.back();
+  }
+  if (!slot->fresh) {
+    mk::PrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = 1;
+    a.e[0].W = slot->W; a.e[0].ldw = slot->ldw; a.e[0].wcol0 = slot->wcol0; a.e[0].wt = slot->wt;
+    a.e[0].R = slot->R; a.e[0].N = slot->N; a.e[0].off = slot->off;
+    a.wprep = e.ws.mk_wprep;
+    const int chunks = ((slot->N + 127) / 128) * ((slot->R + mk::KC - 1) / mk::KC);
+    if (m.nops > 0) m.par_next = true;
+    CVG_TRY(mk_push(e, mk::K_PREP, &a, sizeof(a), chunks));
+    slot->fresh = true;
+    if (emitted) *emitted = true;
+  }
+  *out = e.ws.mk_wprep + slot->off;
+  return 0;
+}
+
+void mk_weights_updated(Engine& e, int net_mask) {
+  for (auto& sl : e.mk.prep)
+    if (net_mask & (1 << sl.net)) sl.fresh = false;
 }
 
 int mk_push(Engine& e, int kind, const void* payload, size_t bytes, int items, int a0, int a1, int a2, int a3, const void* extra,
@@ -219,7 +266,7 @@ int mk_flush(Engine& e, cudaStream_t st) {
   P.bar_counter = e.ws.mk_bar;
   if (e.world > 1 && e.nvl.on) P.nvl = e.nvl.dev;
   P.dbg = (getenv("CVG_MK_DBG") && m.nops <= 2048) ? e.ws.mk_dbg : nullptr;
-  P.prof = P.dbg ? e.ws.mk_dbg + 2048 : nullptr;
+  P.prof = (P.dbg && getenv("CVG_MK_PROF")) ? e.ws.mk_dbg + 2048 : nullptr;
   if (P.prof) CVG_CUDA(cudaMemsetAsync(P.prof, 0, 64 * sizeof(long long), st));
   m.last_nops = m.nops;
   void* args[1] = {&P};

@@ -22,16 +22,23 @@
 #pragma once
 #include "engine.cuh"
 #include "tc05.cuh"
+#include <type_traits>
 
 namespace cvg {
 namespace mk {
 using namespace tc;
 
-constexpr int THREADS = 512;
+constexpr int THREADS = 320;                  // 8 worker warps + MMA issuer warp + weight producer warp
+constexpr int WORKERS = 256;
+constexpr int ISSUER_WARP = 8;
+constexpr int PRODUCER_WARP = 9;
 constexpr int KC = 32;                        // contraction values per pipeline stage
 constexpr int KG = KC / 4;                    // groups of 4 contraction values (one 16-byte core-matrix row)
-constexpr int LBO_A = 128 * 16 + 16;          // bytes between k-groups of the A operand (128 rows, padded: conflict-free stores)
-constexpr int A_PLANE = KG * LBO_A;
+constexpr int LBO_A = 128 * 16;               // bytes between k-groups of a pre-split weight chunk (written by TMA)
+constexpr int LBO_AP = 128 * 16 + 16;         // ... of an A operand staged by threads (weight gradient), padded: conflict-free stores
+constexpr int A_PLANE = KG * LBO_AP;
+constexpr int WPLANE_FLOATS = KG * LBO_A / 4;      // one plane (hi or lo) of a prepped weight chunk: 128 rows x 32 k
+constexpr int CHUNK_FLOATS = 2 * WPLANE_FLOATS;
 constexpr int B_MAXN = 256;                   // widest MMA N
 constexpr int LBO_B_MAX = B_MAXN * 16 + 16;
 constexpr int B_PLANE = KG * LBO_B_MAX;
@@ -45,7 +52,7 @@ constexpr int MAX_C = 256;                    // widest BatchNorm layer the prog
 
 enum {
   K_MN = 1, K_DW, K_DWRED, K_FILL, K_STAGE, K_SN_POWER, K_SN_DOT, K_SN_GRAD, K_LN_FWD, K_LN_BWD, K_CE, K_SEED, K_ZERO,
-  K_PACK, K_UNPACK, K_ADAM, K_CTL_SET, K_FINISH, K_NVL_F32, K_NVL_F64, K_REPARAM
+  K_PACK, K_UNPACK, K_ADAM, K_CTL_SET, K_FINISH, K_NVL_F32, K_NVL_F64, K_REPARAM, K_PREP
 };
 
 struct alignas(16) OpRec {
@@ -94,7 +101,8 @@ struct Params {
 };
 
 struct Ctrl {
-  uint64_t bar[NSTAGE];
+  uint64_t full[NSTAGE];
+  uint64_t done[NSTAGE];
   uint32_t tmem_slot;
   uint32_t pad;
   unsigned long long nvl_epoch0;
@@ -102,20 +110,31 @@ struct Ctrl {
 
 constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + CS_FLOATS * 4 + RED_DOUBLES * 8 + OP_BYTES + sizeof(Ctrl) + 64;
 
-// Per-CTA pipeline state.  Everything here lives in registers (all users are force-inlined): with ~217 KB of shared
+// Per-CTA pipeline state.  Everything here lives in registers (all users are force-inlined): with ~215 KB of shared
 // memory the L1 has ~10 KB left, so a single spilled word costs an L2 round trip.
+//
+// Warp roles inside a GEMM item (the tcgen05 issue loop blocks for as long as the tensor pipe is busy, so it must not
+// sit in a warp that also stages operands):
+//   warps 0-7  workers : stage the activation operand(s) (global -> registers -> transform -> hi/lo split -> shared memory),
+//                        then run the epilogue (TMEM -> registers -> shared-memory transpose -> coalesced global I/O)
+//   warp 8     issuer  : waits for a stage to be full, issues its MMAs, commits them to the stage's "done" barrier
+//   warp 9     producer: streams the pre-split weight chunks of forward / input-gradient GEMMs with 1-D bulk copies (TMA)
+// Stage hand-off is mbarrier-only (full[s]: 256 worker arrivals + the producer's expect_tx; done[s]: tcgen05.commit).
 struct Pipe {
   uint8_t* stages;
   float* cs;
   double* red;
-  uint64_t* bar;
+  uint64_t* full;       // [NSTAGE]
+  uint64_t* done;       // [NSTAGE]
   uint32_t tmem;
-  uint32_t ph;          // bit s: parity of the newest commit on stage s; bit 8 + s: stage s has been committed to
+  uint32_t use0, use1;  // how many times stage 0 / 1 has been filled so far by this CTA (every role counts identically)
   int tid, warp, lane;
   long long* prof;
 };
 #define MK_T(var) if (c.prof) var = clock64();
-#define MK_ACC(slot, t0, t1) if (c.prof && c.tid == 0) c.prof[slot] += (t1) - (t0);
+#define MK_ACC(slot, t0, t1) if (c.prof && c.tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + (slot), (unsigned long long)((t1) - (t0)));
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- loads of data that other CTAs produced earlier in the SAME launch: L2 only (L1 is not coherent) ---------------
 __device__ __forceinline__ float ldg1(const float* p) { return __ldcg(p); }
@@ -144,7 +163,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// ---- BatchNorm constants (same arithmetic as gemm.cuh, statistics read through L2) -----------------------------------
+// ---- BatchNorm constants (same arithmetic as gemm.cuh, statistics read through L2); worker threads only -------------
 __device__ __forceinline__ void mk_bn_mean_rstd(const BnRef& bn, int pass, int c, float Bg, float eps, float& mean, float& rstd) {
   float var;
   if (bn.eval) {
@@ -163,10 +182,10 @@ __device__ __forceinline__ void mk_bn_mean_rstd(const BnRef& bn, int pass, int c
 }
 
 template <int KIND>
-__device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs) {
+__device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs, int tid) {
   if (KIND == OP_BN_ACT) {
     const int C = o.bn.C;
-    for (int c = threadIdx.x; c < C; c += THREADS) {
+    for (int c = tid; c < C; c += WORKERS) {
       float mean, rstd;
       mk_bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd);
       cs[c] = ldg1(o.bn.gamma + c) * rstd;
@@ -176,7 +195,7 @@ __device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, fl
   } else if (KIND == OP_BN_BWD) {
     const int C = o.bn.C;
     const double* bs = o.bn.bstats + (long long)pass * o.bn.sb;
-    for (int c = threadIdx.x; c < C; c += THREADS) {
+    for (int c = tid; c < C; c += WORKERS) {
       float mean, rstd;
       mk_bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd);
       cs[c] = ldg1(o.bn.gamma + c) * rstd;
@@ -188,8 +207,8 @@ __device__ __forceinline__ void mk_operand_consts(const Operand& o, int pass, fl
   }
 }
 
-__device__ __forceinline__ void mk_bn_update_running(const BnRef& bn, int npass, float Bg, float momentum) {
-  for (int c = threadIdx.x; c < bn.C; c += THREADS) {
+__device__ __forceinline__ void mk_bn_update_running(const BnRef& bn, int npass, float Bg, float momentum, int tid) {
+  for (int c = tid; c < bn.C; c += WORKERS) {
     float rm = ldg1(bn.rmean + c), rv = ldg1(bn.rvar + c);
     for (int p = 0; p < npass; ++p) {
       const double* s = bn.fstats + (long long)p * bn.sf;
@@ -213,6 +232,37 @@ __device__ __forceinline__ float mk_xform(float a, float b, const float* cs, int
   if (KIND == OP_CONST) return cst;
   return a;
 }
+// ... of FOUR consecutive feature rows r .. r + 3 (r % 4 == 0) of one batch row: the constants come as 16-byte loads.
+// Values beyond the contraction length were loaded as zeros; BatchNorm kinds always have R == C (a multiple of 4).
+template <int KIND>
+__device__ __forceinline__ float4 mk_xform4(const float* a, const float* b, const float* cs, int C, int r, int R, float slope, float cst) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r >= R) return v;
+  if (KIND == OP_BN_ACT) {
+    const float4 sc = *reinterpret_cast<const float4*>(cs + r), sh = *reinterpret_cast<const float4*>(cs + C + r);
+    const float4 mn = *reinterpret_cast<const float4*>(cs + 2 * C + r);
+    v.x = act_lrelu(fmaf(a[0] - mn.x, sc.x, sh.x), slope);
+    v.y = act_lrelu(fmaf(a[1] - mn.y, sc.y, sh.y), slope);
+    v.z = act_lrelu(fmaf(a[2] - mn.z, sc.z, sh.z), slope);
+    v.w = act_lrelu(fmaf(a[3] - mn.w, sc.w, sh.w), slope);
+  } else if (KIND == OP_BN_BWD) {
+    const float4 c1 = *reinterpret_cast<const float4*>(cs + r), c2 = *reinterpret_cast<const float4*>(cs + C + r);
+    const float4 c3 = *reinterpret_cast<const float4*>(cs + 2 * C + r), mn = *reinterpret_cast<const float4*>(cs + 3 * C + r);
+    const float4 rs = *reinterpret_cast<const float4*>(cs + 4 * C + r);
+    v.x = c1.x * (a[0] - c2.x - (b[0] - mn.x) * rs.x * c3.x);
+    v.y = c1.y * (a[1] - c2.y - (b[1] - mn.y) * rs.y * c3.y);
+    v.z = c1.z * (a[2] - c2.z - (b[2] - mn.z) * rs.z * c3.z);
+    v.w = c1.w * (a[3] - c2.w - (b[3] - mn.w) * rs.w * c3.w);
+  } else if (KIND == OP_CONST) {
+    v.x = cst;
+    v.y = r + 1 < R ? cst : 0.f;
+    v.z = r + 2 < R ? cst : 0.f;
+    v.w = r + 3 < R ? cst : 0.f;
+  } else {
+    v = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  return v;
+}
 
 // hi / lo planes of one operand value group: 16-byte stores
 __device__ __forceinline__ void st_split4(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t off, float4 v) {
@@ -225,173 +275,176 @@ __device__ __forceinline__ void st_split4(uint8_t* hi_plane, uint8_t* lo_plane, 
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
 
-// MMAs of one staged chunk: nks steps of 8 contraction values, three tf32 MMAs each (small terms first); one commit.
-// Every descriptor input is broadcast from lane 0 so that ptxas keeps the issue loop in uniform registers.
-__device__ __forceinline__ void issue_chunk(const Pipe& c, int s, int nks, int n_mma, uint32_t lbo_b, bool first_chunk) {
-  if (c.warp == 0) {
-    tc_fence_after_sync();
-    const uint32_t base = __shfl_sync(0xffffffffu, smem_u32(c.stages) + (uint32_t)s * STAGE_BYTES, 0);
-    const uint32_t lbo = __shfl_sync(0xffffffffu, lbo_b, 0);
-    const uint32_t nm = __shfl_sync(0xffffffffu, (uint32_t)n_mma, 0);
-    const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
-    const int steps = __shfl_sync(0xffffffffu, nks, 0);
-    const uint32_t fresh = __shfl_sync(0xffffffffu, first_chunk ? 1u : 0u, 0);
-    if (elect_one()) {
-      uint64_t dah = smem_desc(base, LBO_A, 128), dal = smem_desc(base + A_PLANE, LBO_A, 128);
-      uint64_t dbh = smem_desc(base + 2 * A_PLANE, lbo, 128), dbl = smem_desc(base + 2 * A_PLANE + B_PLANE, lbo, 128);
-      const uint32_t idesc = idesc_tf32(128, (int)nm, 0, 0);
-      const uint64_t a_step = (uint64_t)((2 * LBO_A) >> 4), b_step = (uint64_t)((2 * lbo) >> 4);
-      for (int ks = 0; ks < steps; ++ks) {
-        mma_tf32(tm, dal, dbh, idesc, !(fresh && ks == 0));
-        mma_tf32(tm, dah, dbl, idesc, true);
-        mma_tf32(tm, dah, dbh, idesc, true);
-        dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
-      }
-      mma_commit(&c.bar[s]);
-    }
-    __syncwarp();
-  }
+// ---- stage bookkeeping: every role calls next_use() once per chunk, so the parities agree without communication --------
+__device__ __forceinline__ uint32_t next_use(Pipe& c, int s) {       // returns the 1-based use index of stage s
+  if (s == 0) return ++c.use0;
+  return ++c.use1;
+}
+// workers / producer: the MMAs of the previous use of this stage have finished reading it
+__device__ __forceinline__ void wait_stage_free(const Pipe& c, int s, uint32_t k) {
+  if (k > 1) mbar_wait(&c.done[s], (k - 2) & 1u);
+}
+// workers, end of an item: the MMAs of the newest use have completed (accumulator final)
+__device__ __forceinline__ void wait_stage_done(const Pipe& c, int s) {
+  const uint32_t k = s == 0 ? c.use0 : c.use1;
+  if (k > 0) mbar_wait(&c.done[s], (k - 1) & 1u);
 }
 
-__device__ __forceinline__ void wait_stage(const Pipe& c, int s) {
-  if (c.ph & (256u << s)) mbar_wait(&c.bar[s], (c.ph >> s) & 1u);
+// issuer warp: MMAs of one staged chunk - nks steps of 8 contraction values, three tf32 MMAs each (small terms first)
+__device__ __forceinline__ void issue_chunk(const Pipe& c, int s, uint32_t k, int nks, int n_mma, uint32_t lbo_a, uint32_t lbo_b,
+                                            bool first_chunk) {
+  mbar_wait(&c.full[s], (k - 1) & 1u);
+  tc_fence_after_sync();
+  const uint32_t base = __shfl_sync(0xffffffffu, smem_u32(c.stages) + (uint32_t)s * STAGE_BYTES, 0);
+  const uint32_t lbb = __shfl_sync(0xffffffffu, lbo_b, 0);
+  const uint32_t lba = __shfl_sync(0xffffffffu, lbo_a, 0);
+  const uint32_t nm = __shfl_sync(0xffffffffu, (uint32_t)n_mma, 0);
+  const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
+  const int steps = __shfl_sync(0xffffffffu, nks, 0);
+  const uint32_t fresh = __shfl_sync(0xffffffffu, first_chunk ? 1u : 0u, 0);
+  if (elect_one()) {
+    uint64_t dah = smem_desc(base, lba, 128), dal = smem_desc(base + A_PLANE, lba, 128);
+    uint64_t dbh = smem_desc(base + 2 * A_PLANE, lbb, 128), dbl = smem_desc(base + 2 * A_PLANE + B_PLANE, lbb, 128);
+    const uint32_t idesc = idesc_tf32(128, (int)nm, 0, 0);
+    const uint64_t a_step = (uint64_t)((2 * lba) >> 4), b_step = (uint64_t)((2 * lbb) >> 4);
+    for (int ks = 0; ks < steps; ++ks) {
+      mma_tf32(tm, dal, dbh, idesc, !(fresh && ks == 0));
+      mma_tf32(tm, dah, dbl, idesc, true);
+      mma_tf32(tm, dah, dbh, idesc, true);
+      dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
+    }
+    mma_commit(&c.done[s]);
+  }
+  __syncwarp();
 }
-__device__ __forceinline__ void note_commit(Pipe& c, int s) {
-  c.ph = (c.ph & (256u << s)) ? (c.ph ^ (1u << s)) : (c.ph | (256u << s));
+
+// ---- epilogue transpose: a worker warp turns its TMEM block (lane = feature, 16 consecutive columns) into
+// (feature = 8 fi + lane / 4, 4 consecutive columns at 4 (lane % 4)) so that every global access of the warp touches
+// 64 contiguous bytes per feature instead of 16.  Scratch: 32 x 20 floats per warp (B planes of stage 1, idle now).
+constexpr int TP_PITCH = 20;
+__device__ __forceinline__ float* tp_scratch(const Pipe& c) {
+  return reinterpret_cast<float*>(c.stages + (size_t)STAGE_BYTES + 2 * A_PLANE) + c.warp * (32 * TP_PITCH);
+}
+__device__ __forceinline__ void tp_write(float* sc, int lane, const float* v) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(sc + lane * TP_PITCH + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+}
+__device__ __forceinline__ float4 tp_read(const float* sc, int lane, int fi) {
+  return *reinterpret_cast<const float4*>(sc + (fi * 8 + (lane >> 2)) * TP_PITCH + (lane & 3) * 4);
 }
 
 // ======================================================================================================================
 // forward / input-gradient GEMM item:  D[n][m] = sum_r A[n][r] * B[m][r]
-//   WT  : A = W[n][r] (forward)          !WT : A = W[r][n] (input gradient)
-//   B = operand g.a (feature-major [r][m] in memory, transformed), m = batch rows of this tile
-// Operand kind (AK) and epilogue (EK) are compile-time; the tile height (64 / 128 rows) is a shift.
+//   A = pre-split weights (prep op), streamed by the producer warp;  B = operand g.a (feature-major [r][m] in memory,
+//   transformed in registers), m = batch rows of this tile.  AK / EK are compile-time; the tile height is a shift.
 // ======================================================================================================================
-template <bool WT, int AK, int EK>
-__device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt_shift, const int item) {
+template <int AK, int EK, int NT>
+__device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float* wprep, const int item) {
+  constexpr int nt_shift = NT == 128 ? 7 : 6;
+  constexpr int NB = NT >> 5;                 // operand groups (4 features x 1 batch row) per thread and chunk: 2 or 4
+  constexpr int RING = 8 / NB;                // chunks in flight in registers: 4 or 2
+  constexpr int NCB = NT >> 5;                // epilogue column blocks of 16 batch rows per thread: 2 or 4
   const int tid = c.tid;
   const int M = g.M, ld = g.ld, N = g.N;
   const int R = min(g.R, g.a.rows);
-  const int Nt = 1 << nt_shift;
+  constexpr int Nt = NT;
   const int ntm = (M + Nt - 1) >> nt_shift, nmt = (N + 127) >> 7;
   const int rt = item % ntm, t2 = item / ntm, mt = t2 % nmt;
   const int pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
   const int m0 = rt << nt_shift, n0 = mt << 7;
   const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
   const int nchunks = (R + KC - 1) / KC;
-  const int ldw = g.ldw;
+
+  // ---------------------------------------------------- producer ----------------------------------------------------
+  if (c.warp == PRODUCER_WARP) {
+    const float* src = wprep + (size_t)mt * nchunks * CHUNK_FLOATS;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int s = ch & 1;
+      const uint32_t k = next_use(c, s);
+      const int nk4 = 2 * ((min(KC, R - ch * KC) + 7) >> 3);
+      wait_stage_free(c, s, k);
+      if (elect_one()) {
+        uint8_t* dst = c.stages + (size_t)s * STAGE_BYTES;
+        const uint32_t bytes = (uint32_t)nk4 * LBO_A;
+        mbar_arrive_expect_tx(&c.full[s], 2 * bytes);
+        bulk_g2s(dst, src + (size_t)ch * CHUNK_FLOATS, bytes, &c.full[s]);
+        bulk_g2s(dst + A_PLANE, src + (size_t)ch * CHUNK_FLOATS + WPLANE_FLOATS, bytes, &c.full[s]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  // ----------------------------------------------------- issuer -----------------------------------------------------
+  if (c.warp == ISSUER_WARP) {
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int s = ch & 1;
+      const uint32_t k = next_use(c, s);
+      const int nks = (min(KC, R - ch * KC) + 7) >> 3;
+      issue_chunk(c, s, k, nks, Nt, LBO_A, lbo_b, ch == 0);
+    }
+    return;
+  }
+  // ----------------------------------------------------- workers ----------------------------------------------------
   const float slope = g.slope;
   float* cs_a = c.cs;
-  float* cs_e = c.cs + (AK == OP_BN_ACT ? 3 * g.a.bn.C : (AK == OP_BN_BWD ? 5 * g.a.bn.C : 0));
   const int Ca = (AK == OP_BN_ACT || AK == OP_BN_BWD) ? g.a.bn.C : 0;
+  float* cs_e = c.cs + (AK == OP_BN_ACT ? 3 * Ca : (AK == OP_BN_BWD ? 5 * Ca : 0));
   long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
   MK_T(q0);
 
-  // ---- per-thread operand addressing (fixed for the whole item) -----------------------------------------------------
-  const float* pa[2];
-  uint32_t sa[2];
-  int ka[2];
-  bool va[2];
-  const bool wvec = WT && (((ldw | g.wcol0) & 3) == 0);
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int idx = tid + j * THREADS;
-    const int k4 = WT ? (idx & 7) : (idx >> 7);
-    const int nl = WT ? (idx >> 3) : (idx & 127);
-    ka[j] = k4 * 4;
-    va[j] = n0 + nl < N;
-    sa[j] = (uint32_t)k4 * LBO_A + (uint32_t)nl * 16u;
-    pa[j] = WT ? g.W + (size_t)(n0 + nl) * ldw + g.wcol0 + k4 * 4 : g.W + (size_t)(k4 * 4) * ldw + g.wcol0 + n0 + nl;
-  }
-  const float* pb[2];
-  const float* ph[2];
-  uint32_t sb[2];
-  int kb[2];
-  bool vb[2];
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int idx = tid + j * THREADS;
-    const int ml = idx & (Nt - 1), k4 = idx >> nt_shift;
-    const int m = m0 + ml;
-    kb[j] = k4 * 4;
-    vb[j] = (k4 < KG) && (m < M);
-    sb[j] = (uint32_t)k4 * lbo_b + (uint32_t)ml * 16u;
-    pb[j] = (AK == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + (size_t)(k4 * 4) * ld + m;
-    ph[j] = (AK == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + (size_t)(k4 * 4) * ld + m : nullptr;
-  }
-  const bool two_b = Nt > 64;      // 128-row tiles: two operand groups per thread
+  // operand addressing: thread -> batch row ml0, k-groups k40 + j * k4step (j < NB)
+  const int ml0 = tid & (Nt - 1), k40 = tid >> nt_shift;
+  constexpr int k4step = WORKERS >> nt_shift;
+  const bool row_ok = m0 + ml0 < M;
+  const float* pb = (AK == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + m0 + ml0;
+  const float* ph = (AK == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + m0 + ml0 : nullptr;
 
-  float4 ra[2];
-  float rb[2][4], rh[2][4];
-  auto load_chunk = [&](int ch) {
+  // register ring: the loads of chunk ch + RING are issued when chunk ch has been staged, so every load has RING chunk
+  // times (several MMA batches) to land - the workers never wait for L2
+  float rb[RING][NB][4], rh[(AK == OP_BN_BWD) ? RING : 1][NB][4];
+  auto load_chunk = [&](int ch, auto slot_c) {
+    constexpr int slot = decltype(slot_c)::value;
     const int r0 = ch * KC;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int r = r0 + ka[j];
-      if (va[j] && r < R) {
-        if (WT) {
-          const float* src = pa[j] + r0;
-          if (wvec && r + 3 < R) {
-            w = ldg4(src);
-          } else {
-            w.x = ldg1(src);
-            if (r + 1 < R) w.y = ldg1(src + 1);
-            if (r + 2 < R) w.z = ldg1(src + 2);
-            if (r + 3 < R) w.w = ldg1(src + 3);
-          }
-        } else {
-          const float* src = pa[j] + (size_t)r0 * ldw;
-          w.x = ldg1(src);
-          if (r + 1 < R) w.y = ldg1(src + (size_t)ldw);
-          if (r + 2 < R) w.z = ldg1(src + 2 * (size_t)ldw);
-          if (r + 3 < R) w.w = ldg1(src + 3 * (size_t)ldw);
-        }
-      }
-      ra[j] = w;
-    }
+    for (int j = 0; j < NB; ++j) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (j == 0 || two_b) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = r0 + kb[j] + i;
-          rb[j][i] = 0.f;
-          rh[j][i] = 0.f;
-          if (AK != OP_CONST && vb[j] && r < R) {
-            rb[j][i] = ldg1(pb[j] + (size_t)(r0 + i) * ld);
-            if (AK == OP_BN_BWD) rh[j][i] = ldg1(ph[j] + (size_t)(r0 + i) * ld);
-          }
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + (k40 + j * k4step) * 4 + i;
+        rb[slot][j][i] = 0.f;
+        if (AK == OP_BN_BWD) rh[(AK == OP_BN_BWD) ? slot : 0][j][i] = 0.f;
+        if (AK != OP_CONST && row_ok && r < R) {
+          rb[slot][j][i] = ldg1(pb + (size_t)r * ld);
+          if (AK == OP_BN_BWD) rh[(AK == OP_BN_BWD) ? slot : 0][j][i] = ldg1(ph + (size_t)r * ld);
         }
       }
     }
   };
-  auto store_chunk = [&](int ch, int s, int nk4) {
-    uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
+  auto store_chunk = [&](int ch, int s, int nk4, auto slot_c) {
+    constexpr int slot = decltype(slot_c)::value;
+    uint8_t* base = c.stages + (size_t)s * STAGE_BYTES + 2 * A_PLANE;
     const int r0 = ch * KC;
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if ((ka[j] >> 2) < nk4) st_split4(base, base + A_PLANE, sa[j], ra[j]);
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if ((j == 0 || two_b) && (kb[j] >> 2) < nk4) {
-        float v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = r0 + kb[j] + i;
-          v[i] = (vb[j] && r < R) ? mk_xform<AK>(rb[j][i], rh[j][i], cs_a, Ca, r, slope, g.a.cst) : 0.f;
-        }
-        st_split4(base + 2 * A_PLANE, base + 2 * A_PLANE + B_PLANE, sb[j], make_float4(v[0], v[1], v[2], v[3]));
+    for (int j = 0; j < NB; ++j) {
+      const int k4 = k40 + j * k4step;
+      if (k4 < nk4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok) v = mk_xform4<AK>(rb[slot][j], rh[(AK == OP_BN_BWD) ? slot : 0][j], cs_a, Ca, r0 + k4 * 4, R, slope, g.a.cst);
+        st_split4(base, base + B_PLANE, (uint32_t)k4 * lbo_b + (uint32_t)ml0 * 16u, v);
       }
     }
   };
 
-  load_chunk(0);     // in flight while the constants are prepared
+  // in flight while the constants are prepared
+  load_chunk(0, std::integral_constant<int, 0>{});
+  if (RING > 1 && nchunks > 1) load_chunk(1, std::integral_constant<int, 1 % RING>{});
+  if (RING > 2 && nchunks > 2) load_chunk(2, std::integral_constant<int, 2 % RING>{});
+  if (RING > 3 && nchunks > 3) load_chunk(3, std::integral_constant<int, 3 % RING>{});
 
   // ---- per-feature constants -----------------------------------------------------------------------------------------
-  mk_operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a);
+  mk_operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a, tid);
   if (EK == EP_DBN) {
     const int C = g.prev_bn.C;
-    for (int ch = tid; ch < C; ch += THREADS) {
+    for (int ch = tid; ch < C; ch += WORKERS) {
       float mean, rstd;
       mk_bn_mean_rstd(g.prev_bn, pass, ch, g.Bg, g.bn_eps, mean, rstd);
       cs_e[ch] = ldg1(g.prev_bn.gamma + ch) * rstd;
@@ -400,99 +453,123 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt
       cs_e[3 * C + ch] = rstd;
     }
   }
-  if (AK == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum);
+  if (AK == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum, tid);
 
-  // ---- epilogue addressing + the values it needs from memory, requested now ------------------------------------------
+  // ---- epilogue addressing: thread -> features n0 + 32 q + 8 fi + lane / 4 (fi = 0..3), column group lane % 4 ----------
   const int q = c.warp & 3, cgp = c.warp >> 2;
-  const int n = n0 + q * 32 + c.lane;
-  const bool nvalid = n < N;
-  const int colw = Nt >> 2;                  // columns (batch rows) per column group: 16 or 32
-  float scale = 1.0f, bias = 0.f;
+  const int fl0 = q * 32 + (c.lane >> 2), rg4 = (c.lane & 3) * 4;
+  float scale = 1.0f;
   if (g.scale) scale = ldg1(g.scale + pass);
-  if (EK == EP_LINEAR && nvalid) {
-    bias = g.bias ? ldg1(g.bias + n) : 0.f;
-    if (g.wlabel) bias += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (EK == EP_LINEAR) {
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+      const int n = n0 + fl0 + fi * 8;
+      if (n < N) {
+        bias[fi] = g.bias ? ldg1(g.bias + n) : 0.f;
+        if (g.wlabel) bias[fi] += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
+      }
+    }
   }
-  __syncthreads();
+  worker_bar();
   MK_T(q1);
   MK_ACC(0, q0, q1);
 
-  for (int ch = 0; ch < nchunks; ++ch) {
+  auto do_chunk = [&](int ch, auto slot_c) {
     const int s = ch & 1;
-    const int klen = min(KC, R - ch * KC);
-    const int nks = (klen + 7) >> 3;
+    const uint32_t k = next_use(c, s);
+    const int nks = (min(KC, R - ch * KC) + 7) >> 3;
     MK_T(q2);
-    if (ch >= NSTAGE) wait_stage(c, s);             // the MMAs that read this stage two chunks ago have completed
+    wait_stage_free(c, s, k);
     MK_T(q3);
     MK_ACC(1, q2, q3);
-    store_chunk(ch, s, 2 * nks);
+    store_chunk(ch, s, 2 * nks, slot_c);
     MK_T(q2);
     MK_ACC(2, q3, q2);
-    if (ch + 1 < nchunks) load_chunk(ch + 1);
+    if (ch + RING < nchunks) load_chunk(ch + RING, slot_c);
     fence_proxy_async_smem();
-    __syncthreads();
+    mbar_arrive(&c.full[s]);
     MK_T(q3);
     MK_ACC(3, q2, q3);
-    issue_chunk(c, s, nks, Nt, lbo_b, ch == 0);
-    note_commit(c, s);
-    MK_T(q2);
-    MK_ACC(4, q3, q2);
+  };
+  for (int ch0 = 0; ch0 < nchunks; ch0 += RING) {
+    do_chunk(ch0, std::integral_constant<int, 0>{});
+    if (RING > 1 && ch0 + 1 < nchunks) do_chunk(ch0 + 1, std::integral_constant<int, 1 % RING>{});
+    if (RING > 2 && ch0 + 2 < nchunks) do_chunk(ch0 + 2, std::integral_constant<int, 2 % RING>{});
+    if (RING > 3 && ch0 + 3 < nchunks) do_chunk(ch0 + 3, std::integral_constant<int, 3 % RING>{});
   }
 
-  // ---- epilogue: thread = (output feature = TMEM lane, 16-row column blocks).  The memory operands of the first block
-  // are requested before the MMAs are waited for.
-  float e_sc = 0.f, e_sh = 0.f, e_mean = 0.f, e_rstd = 0.f;
-  if (EK == EP_DBN && nvalid) {
+  // ---- epilogue --------------------------------------------------------------------------------------------------------
+  float e_sc[4], e_sh[4], e_mean[4], e_rstd[4];
+  if (EK == EP_DBN) {
     const int C = g.prev_bn.C;
-    e_sc = cs_e[n]; e_sh = cs_e[C + n]; e_mean = cs_e[2 * C + n]; e_rstd = cs_e[3 * C + n];
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+      const int n = min(n0 + fl0 + fi * 8, C - 1);
+      e_sc[fi] = cs_e[n]; e_sh[fi] = cs_e[C + n]; e_mean[fi] = cs_e[2 * C + n]; e_rstd[fi] = cs_e[3 * C + n];
+    }
   }
   const float keep_inv = g.keep_inv;
   const uint8_t* mask_p = (EK == EP_LINEAR || EK == EP_DACT) && g.mask ? g.mask + (long long)pass * g.smask : nullptr;
   const float* prev_p = (EK == EP_DBN || EK == EP_DACT) ? g.prev + (long long)pass * g.sprev : nullptr;
   float* Yp = g.Y + (long long)pass * g.sY;
-  float4 pv[4];
-  uchar4 mkv[4];
-  auto epi_prefetch = [&](int hb) {
-    const int col = cgp * colw + hb * 16;
+  const bool acc_y = EK == EP_STORE && g.accumulate;
+  constexpr int colw = Nt >> 1;              // columns (batch rows) per column group of two warps: 32 or 64
+  constexpr int ncb = NCB;
+  constexpr bool need_pv = EK == EP_DBN || EK == EP_DACT || EK == EP_STORE;
+  constexpr bool need_mk = EK == EP_LINEAR || EK == EP_DACT;
+  // every memory operand of the epilogue is requested before the MMAs are waited for
+  float4 pv[need_pv ? NCB : 1][4];
+  uchar4 mkv[need_mk ? NCB : 1][4];
 #pragma unroll
-    for (int gq = 0; gq < 4; ++gq) {
-      const int m = m0 + col + gq * 4;
-      pv[gq] = make_float4(0.f, 0.f, 0.f, 0.f);
-      mkv[gq] = make_uchar4(1, 1, 1, 1);
-      if (nvalid && m < M) {
+  for (int cb = 0; cb < NCB; ++cb) {
+    const int m = m0 + cgp * colw + cb * 16 + rg4;
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+      const int n = n0 + fl0 + fi * 8;
+      if (need_pv) pv[need_pv ? cb : 0][fi] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (need_mk) mkv[need_mk ? cb : 0][fi] = make_uchar4(1, 1, 1, 1);
+      if (n < N && m < M) {
         const size_t off = (size_t)n * ld + m;
-        if (prev_p) pv[gq] = ldg4(prev_p + off);
-        if (mask_p) mkv[gq] = __ldcg(reinterpret_cast<const uchar4*>(mask_p + off));
-        if (EK == EP_STORE && g.accumulate) pv[gq] = ldg4(Yp + off);
+        if (need_pv && prev_p) pv[need_pv ? cb : 0][fi] = ldg4(prev_p + off);
+        if (need_mk && mask_p) mkv[need_mk ? cb : 0][fi] = __ldcg(reinterpret_cast<const uchar4*>(mask_p + off));
+        if (EK == EP_STORE && acc_y) pv[need_pv ? cb : 0][fi] = ldg4(Yp + off);
       }
     }
-  };
-  epi_prefetch(0);
+  }
   MK_T(q2);
-  wait_stage(c, 0);
-  if (nchunks > 1) wait_stage(c, 1);
+  wait_stage_done(c, 0);
+  if (nchunks > 1) wait_stage_done(c, 1);
   tc_fence_after_sync();
   MK_T(q3);
   MK_ACC(5, q2, q3);
-  if (c.prof && c.tid == 0) { c.prof[8] += nchunks; c.prof[9] += 1; }
+  if (c.prof && c.tid == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 8, (unsigned long long)nchunks); atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 9, 1ull); }
 
-  double s1 = 0.0, s2 = 0.0, tot = 0.0, klsum = 0.0;
-  const int nhb = Nt >> 6;
-  for (int hb = 0; hb < nhb; ++hb) {
-    const int col = cgp * colw + hb * 16;
-    float v[16];
-    tmem_ld16(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
-    tmem_wait_ld();
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+  double tot = 0.0, klsum = 0.0;
+  float* tps = tp_scratch(c);
 #pragma unroll
-    for (int gq = 0; gq < 4; ++gq) {
-      const int m = m0 + col + gq * 4;
-      if (!nvalid || m >= M) continue;
-      float y[4] = {v[gq * 4], v[gq * 4 + 1], v[gq * 4 + 2], v[gq * 4 + 3]};
+  for (int cb = 0; cb < ncb; ++cb) {
+    const int col = cgp * colw + cb * 16;
+    {
+      float v[16];
+      tmem_ld16(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+      tmem_wait_ld();
+      tp_write(tps, c.lane, v);
+    }
+    __syncwarp();
+    const int m = m0 + col + rg4;
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+      const int n = n0 + fl0 + fi * 8;
+      if (n >= N || m >= M) continue;
+      const float4 yy = tp_read(tps, c.lane, fi);
+      float y[4] = {yy.x, yy.y, yy.z, yy.w};
       const bool rowv[4] = {true, m + 1 < M, m + 2 < M, m + 3 < M};
       const size_t off = (size_t)n * ld + m;
       if (EK == EP_LINEAR) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) y[i] = fmaf(y[i], scale, bias);
+        for (int i = 0; i < 4; ++i) y[i] = fmaf(y[i], scale, bias[fi]);
         if (g.kl_acc) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -501,7 +578,7 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt
         if (g.ostats) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (rowv[i]) { s1 += (double)y[i]; s2 += (double)y[i] * (double)y[i]; }
+            if (rowv[i]) { s1[fi] += (double)y[i]; s2[fi] += (double)y[i] * (double)y[i]; }
         }
         if (g.act == ACT_LRELU) {
 #pragma unroll
@@ -514,10 +591,10 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt
           for (int i = 0; i < 4; ++i) y[i] = 1.0f / (1.0f + expf(-y[i]));
         }
         if (mask_p) {
-          y[0] = mkv[gq].x ? y[0] * keep_inv : 0.f;
-          y[1] = mkv[gq].y ? y[1] * keep_inv : 0.f;
-          y[2] = mkv[gq].z ? y[2] * keep_inv : 0.f;
-          y[3] = mkv[gq].w ? y[3] * keep_inv : 0.f;
+          y[0] = mkv[need_mk ? cb : 0][fi].x ? y[0] * keep_inv : 0.f;
+          y[1] = mkv[need_mk ? cb : 0][fi].y ? y[1] * keep_inv : 0.f;
+          y[2] = mkv[need_mk ? cb : 0][fi].z ? y[2] * keep_inv : 0.f;
+          y[3] = mkv[need_mk ? cb : 0][fi].w ? y[3] * keep_inv : 0.f;
         }
         if (g.osum) {
 #pragma unroll
@@ -526,24 +603,24 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt
         }
         st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
       } else if (EK == EP_DBN) {
-        const float hh[4] = {pv[gq].x, pv[gq].y, pv[gq].z, pv[gq].w};
+        const float hh[4] = {pv[need_pv ? cb : 0][fi].x, pv[need_pv ? cb : 0][fi].y, pv[need_pv ? cb : 0][fi].z, pv[need_pv ? cb : 0][fi].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float pre = fmaf(hh[i] - e_mean, e_sc, e_sh);
+          const float pre = fmaf(hh[i] - e_mean[fi], e_sc[fi], e_sh[fi]);
           const float dy = rowv[i] ? (pre > 0.f ? y[i] : y[i] * slope) : 0.f;
           y[i] = dy;
-          s1 += (double)dy;
-          s2 += (double)(dy * ((hh[i] - e_mean) * e_rstd));
+          s1[fi] += (double)dy;
+          s2[fi] += (double)(dy * ((hh[i] - e_mean[fi]) * e_rstd[fi]));
         }
         st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
       } else if (EK == EP_DACT) {
-        const float aa[4] = {pv[gq].x, pv[gq].y, pv[gq].z, pv[gq].w};
+        const float aa[4] = {pv[need_pv ? cb : 0][fi].x, pv[need_pv ? cb : 0][fi].y, pv[need_pv ? cb : 0][fi].z, pv[need_pv ? cb : 0][fi].w};
         float keep[4] = {1.f, 1.f, 1.f, 1.f};
         if (mask_p) {
-          keep[0] = mkv[gq].x ? keep_inv : 0.f;
-          keep[1] = mkv[gq].y ? keep_inv : 0.f;
-          keep[2] = mkv[gq].z ? keep_inv : 0.f;
-          keep[3] = mkv[gq].w ? keep_inv : 0.f;
+          keep[0] = mkv[need_mk ? cb : 0][fi].x ? keep_inv : 0.f;
+          keep[1] = mkv[need_mk ? cb : 0][fi].y ? keep_inv : 0.f;
+          keep[2] = mkv[need_mk ? cb : 0][fi].z ? keep_inv : 0.f;
+          keep[3] = mkv[need_mk ? cb : 0][fi].w ? keep_inv : 0.f;
         }
         const float neg = (g.act == ACT_LRELU) ? slope : 0.f;
 #pragma unroll
@@ -554,7 +631,7 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt
         st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
       } else if (EK == EP_STORE) {
         float4 o = make_float4(y[0] * scale, y[1] * scale, y[2] * scale, y[3] * scale);
-        if (g.accumulate) { o.x += pv[gq].x; o.y += pv[gq].y; o.z += pv[gq].z; o.w += pv[gq].w; }
+        if (acc_y) { o.x += pv[need_pv ? cb : 0][fi].x; o.y += pv[need_pv ? cb : 0][fi].y; o.z += pv[need_pv ? cb : 0][fi].z; o.w += pv[need_pv ? cb : 0][fi].w; }
         st4(Yp + off, o);
       } else if (EK == EP_REPARAM_BWD) {
         const float4 mu = ldg4(g.mu + off), lv = ldg4(g.lv + off), ee4 = ldg4(g.eps + off);
@@ -570,72 +647,79 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const int nt
       }
     }
     __syncwarp();
-    if (hb + 1 < nhb) epi_prefetch(hb + 1);
   }
   tc_fence_before_sync();
   if ((EK == EP_LINEAR || EK == EP_DBN) && g.ostats) {
-    // the four column groups of a feature meet in shared memory: one atomic pair per (feature, tile)
-    const int slot = (cgp * 128 + q * 32 + c.lane) * 2;
-    c.red[slot] = s1;
-    c.red[slot + 1] = s2;
-    __syncthreads();
-    if (cgp == 0 && nvalid) {
-      const int b = (q * 32 + c.lane) * 2;
-      const double t1 = (c.red[b] + c.red[256 + b]) + (c.red[512 + b] + c.red[768 + b]);
-      const double t2s = (c.red[b + 1] + c.red[256 + b + 1]) + (c.red[512 + b + 1] + c.red[768 + b + 1]);
+    // per feature: the 4 column lanes of a warp by shuffle, the two column groups through shared memory, then one
+    // atomic pair per (feature, tile)
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+      s1[fi] += __shfl_xor_sync(0xffffffffu, s1[fi], 1);
+      s1[fi] += __shfl_xor_sync(0xffffffffu, s1[fi], 2);
+      s2[fi] += __shfl_xor_sync(0xffffffffu, s2[fi], 1);
+      s2[fi] += __shfl_xor_sync(0xffffffffu, s2[fi], 2);
+    }
+    if (cgp == 1 && (c.lane & 3) == 0) {
+#pragma unroll
+      for (int fi = 0; fi < 4; ++fi) {
+        c.red[(fl0 + fi * 8) * 2] = s1[fi];
+        c.red[(fl0 + fi * 8) * 2 + 1] = s2[fi];
+      }
+    }
+    worker_bar();
+    if (cgp == 0 && (c.lane & 3) == 0) {
       double* st = g.ostats + (long long)pass * g.sostats;
-      atomicAdd(st + n, t1);
-      atomicAdd(st + N + n, t2s);
+#pragma unroll
+      for (int fi = 0; fi < 4; ++fi) {
+        const int n = n0 + fl0 + fi * 8;
+        if (n < N) {
+          atomicAdd(st + n, s1[fi] + c.red[(fl0 + fi * 8) * 2]);
+          atomicAdd(st + N + n, s2[fi] + c.red[(fl0 + fi * 8) * 2 + 1]);
+        }
+      }
     }
   }
-  if (EK == EP_LINEAR && g.osum) {
-    // one atomic per tile (the sums of the 16 warps meet in shared memory first)
+  if (EK == EP_LINEAR && (g.osum || g.kl_acc)) {
+    // one atomic per tile (the sums of the 8 worker warps meet in shared memory first)
     tot = warp_sum_d(tot);
-    __syncthreads();
-    if (c.lane == 0) c.red[c.warp] = tot;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < THREADS / 32; ++w) t += c.red[w];
-      if (t != 0.0) atomicAdd(g.osum + pass, t);
-    }
-  }
-  if (EK == EP_LINEAR && g.kl_acc) {
     klsum = warp_sum_d(klsum);
-    __syncthreads();
-    if (c.lane == 0) c.red[c.warp] = klsum;
-    __syncthreads();
+    worker_bar();
+    if (c.lane == 0) { c.red[512 + c.warp] = tot; c.red[528 + c.warp] = klsum; }
+    worker_bar();
     if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < THREADS / 32; ++w) t += c.red[w];
-      if (t != 0.0) atomicAdd(g.kl_acc, t);
+      double t = 0.0, kk = 0.0;
+      for (int w = 0; w < WORKERS / 32; ++w) { t += c.red[512 + w]; kk += c.red[528 + w]; }
+      if (g.osum && t != 0.0) atomicAdd(g.osum + pass, t);
+      if (g.kl_acc && kk != 0.0) atomicAdd(g.kl_acc, kk);
     }
   }
-  __syncthreads();     // TMEM drained, constants and the reduction scratch free for the next item
+  worker_bar();     // TMEM drained, constants / reduction scratch / transpose scratch free for the next item
   MK_T(q2);
   MK_ACC(6, q3, q2);
 }
 
 // run-time kinds -> the instantiations the steps use (same list as dispatch_mn in gemm.cuh)
-__device__ __forceinline__ void mn_dispatch(Pipe& c, const GemmArgs& g, bool wt, int nt_shift, int items, int i0, int G) {
-#define CVG_MK_MN(W, A, E)                                                    \
-  if (wt == W && g.a.kind == A && g.ekind == E) {                             \
-    for (int it = i0; it < items; it += G) mn_item<W, A, E>(c, g, nt_shift, it); \
-    return;                                                                   \
+__device__ __forceinline__ void mn_dispatch(Pipe& c, const GemmArgs& g, int nt, const float* wprep, int items, int i0, int G) {
+#define CVG_MK_MN(A, E)                                                                          \
+  if (g.a.kind == A && g.ekind == E) {                                                           \
+    if (nt == 128) { for (int it = i0; it < items; it += G) mn_item<A, E, 128>(c, g, wprep, it); } \
+    else           { for (int it = i0; it < items; it += G) mn_item<A, E, 64>(c, g, wprep, it); }  \
+    return;                                                                                      \
   }
-  CVG_MK_MN(true, OP_PLAIN, EP_LINEAR)
-  CVG_MK_MN(true, OP_BN_ACT, EP_LINEAR)
-  CVG_MK_MN(false, OP_PLAIN, EP_DACT)
-  CVG_MK_MN(false, OP_CONST, EP_DACT)
-  CVG_MK_MN(false, OP_PLAIN, EP_STORE)
-  CVG_MK_MN(false, OP_PLAIN, EP_DBN)
-  CVG_MK_MN(false, OP_BN_BWD, EP_DBN)
-  CVG_MK_MN(false, OP_BN_BWD, EP_REPARAM_BWD)
+  CVG_MK_MN(OP_PLAIN, EP_LINEAR)
+  CVG_MK_MN(OP_BN_ACT, EP_LINEAR)
+  CVG_MK_MN(OP_PLAIN, EP_DACT)
+  CVG_MK_MN(OP_CONST, EP_DACT)
+  CVG_MK_MN(OP_PLAIN, EP_STORE)
+  CVG_MK_MN(OP_PLAIN, EP_DBN)
+  CVG_MK_MN(OP_BN_BWD, EP_DBN)
+  CVG_MK_MN(OP_BN_BWD, EP_REPARAM_BWD)
 #undef CVG_MK_MN
 }
 
 // ======================================================================================================================
 // weight-gradient GEMM item:  part[z][n][k] = sum_{m in slice} P[n][m] * Q[k][m]      (+ bias partial sum_m P[n][m])
+// Both operands are activations: the workers stage them (thread = feature x 4-row group); the producer only arrives.
 // ======================================================================================================================
 struct DwScratch { float* part; float* bpart; int nsplit; int kp; };
 
@@ -651,98 +735,120 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   const int mend = min(M, mbeg + g.rows_per_cta);
   const int npad = (K + 15) & ~15;
   const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
+  const int nchunks = mend > mbeg ? (mend - mbeg + KC - 1) / KC : 0;
+
+  if (c.warp == PRODUCER_WARP) {
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int s = ch & 1;
+      const uint32_t k = next_use(c, s);
+      wait_stage_free(c, s, k);
+      if (elect_one()) mbar_arrive(&c.full[s]);
+      __syncwarp();
+    }
+    return;
+  }
+  if (c.warp == ISSUER_WARP) {
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int s = ch & 1;
+      const uint32_t k = next_use(c, s);
+      const int nks = (min(KC, mend - (mbeg + ch * KC)) + 7) >> 3;
+      issue_chunk(c, s, k, nks, npad, LBO_AP, lbo_b, ch == 0);
+    }
+    return;
+  }
+
   const float slope = g.slope;
   float* cs_p = c.cs;
   const int Cp = (PK == OP_BN_BWD) ? g.p.bn.C : 0;
   const int Cq = (QK == OP_BN_ACT) ? g.q.bn.C : 0;
   float* cs_q = c.cs + 5 * Cp;
-  const int nchunks = mend > mbeg ? (mend - mbeg + KC - 1) / KC : 0;
   const int prows = min(N, g.p.rows), qrows = min(K, g.q.rows);
 
-  // thread -> (feature rows f0 + 64 j, row group rgp): 8 lanes cover the 32 batch rows of a chunk for one feature
+  // thread -> (feature rows f0 + 32 j, row group rgp): 8 lanes cover the 32 batch rows of a chunk for one feature
   const int rgp = tid & 7, f0 = tid >> 3;
-  const size_t step64 = (size_t)64 * ld;
+  const size_t step32 = (size_t)32 * ld;
   const float* pp0 = (PK == OP_CONST) ? nullptr : g.p.p + (long long)pass * g.p.sp + (size_t)(n0 + f0) * ld + rgp * 4;
   const float* ph0 = (PK == OP_BN_BWD) ? g.p.h + (long long)pass * g.p.sh + (size_t)(n0 + f0) * ld + rgp * 4 : nullptr;
   const float* pq0 = g.q.p + (long long)pass * g.q.sp + (size_t)f0 * ld + rgp * 4;
+  const int nq = (npad + 31) >> 5;    // Q feature groups of 32 this thread stages (K <= 256 -> at most 8)
 
-  float4 rp[2], rph[2], rq[4];
-  auto load_chunk = [&](int mb) {
-    const bool rows_ok = mb + rgp * 4 < mend;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      rph[j] = rp[j];
-      if (PK != OP_CONST && n0 + f0 + j * 64 < prows && rows_ok) {
-        rp[j] = ldg4(pp0 + j * step64 + mb);
-        if (PK == OP_BN_BWD) rph[j] = ldg4(ph0 + j * step64 + mb);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      rq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f0 + j * 64 < qrows && rows_ok) rq[j] = ldg4(pq0 + j * step64 + mb);
-    }
-  };
-  float bsum[2] = {0.f, 0.f};
-  auto store_chunk = [&](int mb, int s) {
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  // one chunk = 32 batch rows: P (128 features) then Q (npad features), each staged in sub-passes of 4 loads in flight
+  auto stage_chunk = [&](int mb, int s) {
     uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
     const int m = mb + rgp * 4;
+    const bool rows_ok = m < mend;
+    {
+      float4 rp[4], rph[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int f = n0 + f0 + j * 64;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f < prows && m < mend) {
-        v.x = mk_xform<PK>(rp[j].x, rph[j].x, cs_p, Cp, f, slope, g.p.cst);
-        v.y = (m + 1 < mend) ? mk_xform<PK>(rp[j].y, rph[j].y, cs_p, Cp, f, slope, g.p.cst) : 0.f;
-        v.z = (m + 2 < mend) ? mk_xform<PK>(rp[j].z, rph[j].z, cs_p, Cp, f, slope, g.p.cst) : 0.f;
-        v.w = (m + 3 < mend) ? mk_xform<PK>(rp[j].w, rph[j].w, cs_p, Cp, f, slope, g.p.cst) : 0.f;
-      }
-      bsum[j] += (v.x + v.y) + (v.z + v.w);
-      st_split4(base, base + A_PLANE, (uint32_t)rgp * LBO_A + (uint32_t)(f0 + j * 64) * 16u, v);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int f = f0 + j * 64;
-      if (f < npad) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < qrows && m < mend) {
-          v.x = mk_xform<QK>(rq[j].x, 0.f, cs_q, Cq, f, slope, 0.f);
-          v.y = (m + 1 < mend) ? mk_xform<QK>(rq[j].y, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
-          v.z = (m + 2 < mend) ? mk_xform<QK>(rq[j].z, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
-          v.w = (m + 3 < mend) ? mk_xform<QK>(rq[j].w, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rph[j] = rp[j];
+        if (PK != OP_CONST && n0 + f0 + j * 32 < prows && rows_ok) {
+          rp[j] = ldg4(pp0 + j * step32 + mb);
+          if (PK == OP_BN_BWD) rph[j] = ldg4(ph0 + j * step32 + mb);
         }
-        st_split4(base + 2 * A_PLANE, base + 2 * A_PLANE + B_PLANE, (uint32_t)rgp * lbo_b + (uint32_t)f * 16u, v);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = n0 + f0 + j * 32;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < prows && rows_ok) {
+          v.x = mk_xform<PK>(rp[j].x, rph[j].x, cs_p, Cp, f, slope, g.p.cst);
+          v.y = (m + 1 < mend) ? mk_xform<PK>(rp[j].y, rph[j].y, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+          v.z = (m + 2 < mend) ? mk_xform<PK>(rp[j].z, rph[j].z, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+          v.w = (m + 3 < mend) ? mk_xform<PK>(rp[j].w, rph[j].w, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+        }
+        bsum[j] += (v.x + v.y) + (v.z + v.w);
+        st_split4(base, base + A_PLANE, (uint32_t)rgp * LBO_AP + (uint32_t)(f0 + j * 32) * 16u, v);
+      }
+    }
+    for (int jq = 0; jq < nq; jq += 4) {
+      float4 rq[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        rq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jq + j < nq && f0 + (jq + j) * 32 < qrows && rows_ok) rq[j] = ldg4(pq0 + (jq + j) * step32 + mb);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = f0 + (jq + j) * 32;
+        if (jq + j < nq && f < npad) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < qrows && rows_ok) {
+            v.x = mk_xform<QK>(rq[j].x, 0.f, cs_q, Cq, f, slope, 0.f);
+            v.y = (m + 1 < mend) ? mk_xform<QK>(rq[j].y, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+            v.z = (m + 2 < mend) ? mk_xform<QK>(rq[j].z, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+            v.w = (m + 3 < mend) ? mk_xform<QK>(rq[j].w, 0.f, cs_q, Cq, f, slope, 0.f) : 0.f;
+          }
+          st_split4(base + 2 * A_PLANE, base + 2 * A_PLANE + B_PLANE, (uint32_t)rgp * lbo_b + (uint32_t)f * 16u, v);
+        }
       }
     }
   };
 
-  if (nchunks > 0) load_chunk(mbeg);
-  mk_operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p);
-  mk_operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q);
-  __syncthreads();
+  mk_operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p, tid);
+  mk_operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q, tid);
+  worker_bar();
 
   for (int ch = 0; ch < nchunks; ++ch) {
     const int s = ch & 1;
-    const int mb = mbeg + ch * KC;
-    const int nks = (min(KC, mend - mb) + 7) >> 3;
-    if (ch >= NSTAGE) wait_stage(c, s);
-    store_chunk(mb, s);
-    if (ch + 1 < nchunks) load_chunk(mb + KC);
+    const uint32_t k = next_use(c, s);
+    wait_stage_free(c, s, k);
+    stage_chunk(mbeg + ch * KC, s);
     fence_proxy_async_smem();
-    __syncthreads();
-    issue_chunk(c, s, nks, npad, lbo_b, ch == 0);
-    note_commit(c, s);
+    mbar_arrive(&c.full[s]);
   }
-  if (nchunks > 0) wait_stage(c, 0);
-  if (nchunks > 1) wait_stage(c, 1);
+  if (nchunks > 0) wait_stage_done(c, 0);
+  if (nchunks > 1) wait_stage_done(c, 1);
   tc_fence_after_sync();
 
-  // ---- epilogue: the partial tile goes to its scratch slot (row pitch kp), 16 columns per TMEM load ---------------------
+  // ---- epilogue: the partial tile goes to its scratch slot (row pitch kp): 16 columns per TMEM load, transposed in shared
+  // memory so that a warp writes 64 contiguous bytes per row
   const int q = c.warp & 3, cgp = c.warp >> 2;
-  const int n = n0 + q * 32 + c.lane;
-  float* prow = sc.part + ((size_t)z * N + n) * sc.kp;
-  for (int b = cgp; b < npad / 16; b += 4) {
+  const int fl0 = q * 32 + (c.lane >> 2), rg4 = (c.lane & 3) * 4;
+  float* tps = tp_scratch(c);
+  for (int b = cgp; b < npad / 16; b += 2) {
     float v[16];
     if (nchunks > 0) {
       tmem_ld16(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 16), v);
@@ -751,24 +857,27 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = 0.f;
     }
-    if (n < N) {
+    tp_write(tps, c.lane, v);
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) st4(prow + b * 16 + i * 4, make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]));
+    for (int fi = 0; fi < 4; ++fi) {
+      const int n = n0 + fl0 + fi * 8;
+      if (n < N) st4(sc.part + ((size_t)z * N + n) * sc.kp + b * 16 + rg4, tp_read(tps, c.lane, fi));
     }
     __syncwarp();
   }
   // bias partial: the 8 lanes that staged the 8 row groups of a feature
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int j = 0; j < 4; ++j) {
     float b = bsum[j];
     b += __shfl_xor_sync(0xffffffffu, b, 1);
     b += __shfl_xor_sync(0xffffffffu, b, 2);
     b += __shfl_xor_sync(0xffffffffu, b, 4);
-    const int f = n0 + f0 + j * 64;
+    const int f = n0 + f0 + j * 32;
     if (rgp == 0 && f < N) sc.bpart[(size_t)z * N + f] = b;
   }
   tc_fence_before_sync();
-  __syncthreads();
+  worker_bar();
 }
 
 __device__ __forceinline__ void dw_dispatch(Pipe& c, const DwArgs& g, const DwScratch& sc, int items, int i0, int G) {
@@ -783,6 +892,42 @@ __device__ __forceinline__ void dw_dispatch(Pipe& c, const DwArgs& g, const DwSc
   CVG_MK_DW(OP_BN_BWD, OP_BN_ACT)
   CVG_MK_DW(OP_BN_BWD, OP_PLAIN)
 #undef CVG_MK_DW
+}
+
+// ---- weight preparation: hi / lo planes of every 128 x 32 chunk of a GEMM's A operand, in shared-memory order ----------
+//   chunk (mt, kc) = [hi: 8 k-groups x 128 rows x 4][lo: same]; element (row, k) at (k / 4) * 512 + row * 4 + k % 4 floats
+struct PrepEntry {
+  const float* W;
+  int ldw, wcol0;
+  int wt;          // 1: A[n][r] = W[n][r] (forward)   0: A[n][r] = W[r][n] (input gradient)
+  int R, N;        // contraction length, A rows
+  long long off;   // floats into the prepped buffer
+};
+struct PrepArgs {
+  PrepEntry e[4];
+  int n;
+  float* wprep;
+};
+__device__ __forceinline__ int prep_chunks(const PrepEntry& e) { return ((e.N + 127) >> 7) * ((e.R + KC - 1) / KC); }
+
+__device__ void prep_item(const PrepArgs& a, int item) {
+  int ei = 0, ch = item;
+  while (ei < a.n && ch >= prep_chunks(a.e[ei])) { ch -= prep_chunks(a.e[ei]); ++ei; }
+  if (ei >= a.n) return;
+  const PrepEntry e = a.e[ei];
+  const int nkc = (e.R + KC - 1) / KC;
+  const int mt = ch / nkc, kc = ch % nkc;
+  float* dst = a.wprep + e.off + (size_t)ch * CHUNK_FLOATS;
+  for (int i = threadIdx.x; i < WPLANE_FLOATS; i += THREADS) {
+    const int k4 = i >> 9, row = (i >> 2) & 127, kk = i & 3;
+    const int n = mt * 128 + row, r = kc * KC + k4 * 4 + kk;
+    float w = 0.f;
+    if (n < e.N && r < e.R) w = e.wt ? ldg1(e.W + (size_t)n * e.ldw + e.wcol0 + r) : ldg1(e.W + (size_t)r * e.ldw + e.wcol0 + n);
+    float hi, lo;
+    split_tf32(w, hi, lo);
+    dst[i] = hi;
+    dst[WPLANE_FLOATS + i] = lo;
+  }
 }
 
 // sums the row-slice partials in a fixed order and adds them to the gradient buffer (deterministic)
@@ -845,10 +990,13 @@ __device__ void fill_item(const FillArgs& a, int item) {
   const uint32_t keep_thr = (uint32_t)((double)a.keep_prob * 4294967296.0);
   const uint64_t seed = a.ctl ? __ldcg(&a.ctl->seed) : a.seed;
   const uint64_t counter = a.ctl ? __ldcg(&a.ctl->counter) + a.counter_off : a.counter;
-  for (long long t = (long long)vb * THREADS + threadIdx.x; t < total; t += (long long)FILL_VB * THREADS) {
-    const int m = (int)(t % a.M);
-    const int fg = (int)((t / a.M) % ngroups);
-    const int pass = (int)(t / ((long long)a.M * ngroups));
+  // (batch row, feature group, pass) of an element; all counts fit 32 bits (rows <= max_batch, groups <= 256, passes <= 2)
+  const unsigned uM = (unsigned)a.M, uMG = uM * (unsigned)ngroups;
+  for (unsigned t = (unsigned)vb * THREADS + threadIdx.x; t < (unsigned)total; t += (unsigned)FILL_VB * THREADS) {
+    const int pass = (int)(t / uMG);
+    const unsigned rem = t - (unsigned)pass * uMG;
+    const int fg = (int)(rem / uM);
+    const int m = (int)(rem - (unsigned)fg * uM);
     float vals[4] = {0.f, 0.f, 0.f, 0.f};
     uint8_t bits[4] = {0, 0, 0, 0};
     if (j.injected) {
@@ -921,16 +1069,17 @@ __device__ void reparam_item(const ReparamArgs& a, int item) {
 }
 
 // LayerNorm forward: 64 batch rows per item; warp = (row half, feature group), lane = row
-__device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] */) {
-  const int nrb = (g.M + 63) / 64;
+__device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [8][32] */) {
+  const int nrb = (g.M + 31) / 32;
   const int pass = item / nrb, rb = item % nrb;
-  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7, hf = threadIdx.x >> 8;
-  const int m = rb * 64 + hf * 32 + lane;
-  const bool valid = m < g.M;
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7;
+  const bool worker = threadIdx.x < WORKERS;
+  const int m = rb * 32 + lane;
+  const bool valid = worker && m < g.M;
   const int fpt = (g.C + 7) / 8;
   const int c0 = w * fpt;
   const float* h = g.h + (long long)pass * g.sh + (valid ? m : 0);
-  float* rd = red + hf * 256;
+  float* rd = red;
   float v[MK_LN_F];
   float s = 0.f;
 #pragma unroll
@@ -939,7 +1088,7 @@ __device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] 
     v[i] = (i < fpt && cc < g.C && valid) ? ldg1(h + (size_t)cc * g.ld) : 0.f;
     s += v[i];
   }
-  rd[w * 32 + lane] = s;
+  if (worker) rd[w * 32 + lane] = s;
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
@@ -952,7 +1101,7 @@ __device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] 
     const int cc = c0 + i;
     if (i < fpt && cc < g.C) { const float d = v[i] - mean; qv = fmaf(d, d, qv); }
   }
-  rd[w * 32 + lane] = qv;
+  if (worker) rd[w * 32 + lane] = qv;
   __syncthreads();
   tot = 0.f;
 #pragma unroll
@@ -981,12 +1130,13 @@ __device__ void ln_fwd_item(const LnArgs& g, int item, float* red /* [2][8][32] 
 }
 
 // LayerNorm backward; the affine gradients of an item go to a scratch slot (summed in order by the last... see host)
-__device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8][32] */) {
-  const int nrb = (g.M + 63) / 64;
+__device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][8][32] */) {
+  const int nrb = (g.M + 31) / 32;
   const int pass = item / nrb, rb = item % nrb;
-  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7, hf = threadIdx.x >> 8;
-  const int m = rb * 64 + hf * 32 + lane;
-  const bool valid = m < g.M;
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 7;
+  const bool worker = threadIdx.x < WORKERS;
+  const int m = rb * 32 + lane;
+  const bool valid = worker && m < g.M;
   const int mm = valid ? m : 0;
   const int fpt = (g.C + 7) / 8;
   const int c0 = w * fpt;
@@ -994,7 +1144,7 @@ __device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8
   float* dn = g.dn + (long long)pass * g.sdn + mm;
   const float* rs = g.rs + (long long)pass * g.srs;
   const float mean = ldg1(rs + mm), rstd = ldg1(rs + g.ld + mm);
-  float* r1 = red + hf * 512;
+  float* r1 = red;
   float* r2 = r1 + 256;
   float xh[MK_LN_F], d[MK_LN_F];
   float s1 = 0.f, s2 = 0.f;
@@ -1008,8 +1158,10 @@ __device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8
     s1 += dx;
     s2 = fmaf(dx, xh[i], s2);
   }
-  r1[w * 32 + lane] = s1;
-  r2[w * 32 + lane] = s2;
+  if (worker) {
+    r1[w * 32 + lane] = s1;
+    r2[w * 32 + lane] = s2;
+  }
   __syncthreads();
   s1 = 0.f; s2 = 0.f;
 #pragma unroll
@@ -1019,7 +1171,7 @@ __device__ void ln_bwd_item(const LnBwdArgs& g, int item, float* red /* [2][2][8
 #pragma unroll
   for (int i = 0; i < MK_LN_F; ++i) {
     const int cc = c0 + i;
-    const bool on = i < fpt && cc < g.C;       // warp-uniform
+    const bool on = worker && i < fpt && cc < g.C;       // warp-uniform
     if (!on) continue;
     if (valid) dn[(size_t)cc * g.ld] = rstd * (d[i] * ldg1(g.g + cc) - s1 - xh[i] * s2);
     if (g.dg) {
@@ -1305,11 +1457,14 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   c.tid = threadIdx.x;
   c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);
   c.lane = c.tid & 31;
-  c.ph = 0u;
+  c.use0 = 0u;
+  c.use1 = 0u;
   c.prof = blockIdx.x == 0 ? P.prof : nullptr;
   if (c.tid == 0) {
-    mbar_init(&S->bar[0], 1);
-    mbar_init(&S->bar[1], 1);
+    for (int s2 = 0; s2 < NSTAGE; ++s2) {
+      mbar_init(&S->full[s2], WORKERS + 1);
+      mbar_init(&S->done[s2], 1);
+    }
     fence_mbar_init();
     S->nvl_epoch0 = P.nvl.world > 1 ? *reinterpret_cast<volatile unsigned long long*>(P.nvl.epoch) : 0ull;
   }
@@ -1318,7 +1473,8 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   c.tmem = __shfl_sync(0xffffffffu, S->tmem_slot, 0);
-  c.bar = S->bar;
+  c.full = S->full;
+  c.done = S->done;
   const unsigned long long nvl_epoch0 = S->nvl_epoch0;
   unsigned int target = 0;
   const int G = (int)gridDim.x;
@@ -1335,7 +1491,9 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
     switch (sop->kind) {
       case K_MN: {
         const GemmArgs& g = payload<GemmArgs>(sop);
-        mn_dispatch(c, g, sop->aux[0] != 0, sop->aux[1] == 128 ? 7 : 6, items, i0, G);
+        const float* wp;
+        memcpy(&wp, sop->payload + sizeof(GemmArgs), sizeof(float*));
+        mn_dispatch(c, g, sop->aux[1], wp, items, i0, G);
       } break;
       case K_DW: {
         const DwArgs& g = payload<DwArgs>(sop);
@@ -1345,6 +1503,10 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
         sc.nsplit = sop->aux[0];
         sc.kp = sop->aux[1];
         dw_dispatch(c, g, sc, items, i0, G);
+      } break;
+      case K_PREP: {
+        const PrepArgs& a = payload<PrepArgs>(sop);
+        for (int it = i0; it < items; it += G) prep_item(a, it);
       } break;
       case K_DWRED: {
         const DwRedArgs& a = payload<DwRedArgs>(sop);
@@ -1464,7 +1626,8 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   if (c.warp == 0) tmem_dealloc(c.tmem, TMEM_COLS);
 }
 
-static_assert(sizeof(GemmArgs) <= OP_BYTES - 32, "GemmArgs does not fit an op record");
+static_assert(sizeof(GemmArgs) + sizeof(float*) <= OP_BYTES - 32, "GemmArgs does not fit an op record");
+static_assert(sizeof(PrepArgs) <= OP_BYTES - 32, "PrepArgs does not fit an op record");
 static_assert(sizeof(DwArgs) + 2 * sizeof(float*) <= OP_BYTES - 32, "DwArgs does not fit an op record");
 static_assert(sizeof(FillArgs) <= OP_BYTES - 32, "FillArgs does not fit an op record");
 static_assert(sizeof(SnArgs) <= OP_BYTES - 32, "SnArgs does not fit an op record");

@@ -199,7 +199,12 @@ int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
     int Nt = 64;
     if ((long long)((g.M + 63) / 64) * nmt * zp > 3 * e.num_sms / 2) Nt = 128;
     const int items = zp * nmt * ((g.M + Nt - 1) / Nt);
-    return mk_push(e, mk::K_MN, &g, sizeof(g), items, wt ? 1 : 0, Nt);
+    const bool par = e.mk.par_next;
+    const float* wp = nullptr;
+    bool prepped_now = false;
+    CVG_TRY(mk_weight_operand(e, g, wt, &wp, &prepped_now));   // may emit a prep op into the current phase ...
+    e.mk.par_next = par && !prepped_now;                       // ... which this GEMM must then wait for
+    return mk_push(e, mk::K_MN, &g, sizeof(g), items, wt ? 1 : 0, Nt, 0, 0, &wp, sizeof(wp));
   }
   dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, zp);
   const size_t smem = gemm_mn_smem(g);
@@ -558,7 +563,7 @@ int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool 
       a.a = w.c_a2; a.sa = (long long)p.out * ld;
       a.rs = w.c_rs; a.srs = 2 * (long long)ld;
       if (e.mk.recording) {
-        CVG_TRY(mk_push(e, mk::K_LN_FWD, &a, sizeof(a), npass * ((M + 63) / 64)));
+        CVG_TRY(mk_push(e, mk::K_LN_FWD, &a, sizeof(a), npass * ((M + 31) / 32)));
       } else {
         ln_fwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
         CVG_LAUNCH_CHECK();
@@ -715,7 +720,7 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       a.dg = want_dw ? e.G(net, p1.gamma) : nullptr;
       a.db = want_dw ? e.G(net, p1.beta) : nullptr;
       if (e.mk.recording) {
-        CVG_TRY(mk_push(e, mk::K_LN_BWD, &a, sizeof(a), npass * ((M + 63) / 64)));
+        CVG_TRY(mk_push(e, mk::K_LN_BWD, &a, sizeof(a), npass * ((M + 31) / 32)));
       } else {
         ln_bwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
         CVG_LAUNCH_CHECK();
@@ -858,6 +863,7 @@ int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov) {
     int si = 0;
     for (int net = 0; net < 4; ++net)
       if (net_mask & (1 << net)) { op.t_off[si++] = e.mk.adam_inc[net]; e.mk.adam_inc[net]++; }
+    mk_weights_updated(e, net_mask);
     return mk_push(e, mk::K_ADAM, &op, sizeof(op), a.nseg * mk::ADAM_VB);
   }
   int blocks = (int)((nmax + 255) / 256);
@@ -965,6 +971,38 @@ static void fill_args(Engine& e, FillArgs& f, const StepRng& rng, int B) {
   }
 }
 
+// Program kernel: pre-split (hi / lo, operand order) copies of the weight operands a step is going to use, emitted into the
+// step's first phase so that no GEMM has to wait for its own prep op.  fwd: W[n][r]; dx: W[r][n]; first_dx: also the input
+// gradient of the first Linear (without its one-hot label column).
+static int prep_net(Engine& e, int net, bool fwd, bool dx, bool first_dx) {
+  if (!e.mk.recording) return 0;
+  const int first_k = (net == CVG_NET_GENERATOR) ? e.Z : e.F;
+  for (int l = 0; l < e.lay[net].nlin; ++l) {
+    const LinearP& p = e.lay[net].lin[l];
+    GemmArgs g;
+    g.W = e.P(net, p.w);
+    g.ldw = p.in;
+    g.wcol0 = 0;
+    const float* wp = nullptr;
+    if (fwd) {
+      g.R = (l == 0) ? first_k : p.in;
+      g.a.rows = g.R;
+      g.N = p.out;
+      e.mk.par_next = true;
+      CVG_TRY(mk_weight_operand(e, g, true, &wp));
+    }
+    if (dx && (l > 0 || first_dx)) {
+      g.R = p.out;
+      g.a.rows = g.R;
+      g.N = (l == 0) ? first_k : p.in;
+      e.mk.par_next = true;
+      CVG_TRY(mk_weight_operand(e, g, false, &wp));
+    }
+  }
+  e.mk.par_next = false;
+  return 0;
+}
+
 static int emit_ce(Engine& e, const CeArgs& c, int B, int npass, cudaStream_t st) {
   if (e.mk.recording) return mk_push(e, mk::K_CE, &c, sizeof(c), npass * ((B + mk::THREADS - 1) / mk::THREADS));
   ce_kernel<<<dim3((B + 127) / 128, npass), 128, 0, st>>>(c);
@@ -989,6 +1027,8 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
   CVG_PAR(e);
   CVG_TRY(emit_zero(e, w.sn_G, sizeof(float) * 2 * e.lay[D].n_param, st));
+  CVG_TRY(prep_net(e, CVG_NET_GENERATOR, true, false, false));
+  CVG_TRY(prep_net(e, D, true, true, false));
   FillArgs f;
   fill_args(e, f, rng, B);
   add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
@@ -1056,6 +1096,8 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   const int C = CVG_NET_CLASSIFIER;
   if (rng.set) CVG_PAR(e);
   CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
+  CVG_TRY(prep_net(e, CVG_NET_GENERATOR, true, false, false));
+  CVG_TRY(prep_net(e, C, true, true, false));
   FillArgs f;
   fill_args(e, f, rng, B);
   add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
@@ -1097,6 +1139,7 @@ int step_classifier(Engine& e, const float* x, const long long* labels, int B, c
   const float Bg = (float)B * (float)e.world;
   if (rng.set) CVG_PAR(e);
   CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
+  CVG_TRY(prep_net(e, C, true, true, false));
   FillArgs f;
   fill_args(e, f, rng, B);
   add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
@@ -1135,6 +1178,10 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   const int E = CVG_NET_ENCODER, G = CVG_NET_GENERATOR;
   if (rng.set) CVG_PAR(e);
   CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
+  CVG_TRY(prep_net(e, E, true, true, false));
+  CVG_TRY(prep_net(e, G, true, true, true));
+  CVG_TRY(prep_net(e, CVG_NET_DISCRIMINATOR, true, true, true));
+  CVG_TRY(prep_net(e, CVG_NET_CLASSIFIER, true, rng.lambda_nonzero, true));
   FillArgs f;
   fill_args(e, f, rng, B);
   // eps: slot 0 of ws.z for the stand-alone kernels (reparameterisation fused into the operand load); the program

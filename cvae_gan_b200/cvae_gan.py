@@ -41,6 +41,19 @@ def _dist_info():
     return 0, 1
 
 
+def dataset_tensors(dataset):
+    """(samples [N, F], labels [N]) of the dataset that was PASSED IN (the reference iterates `for sample, label in
+    dataset`, cvae_gan.py:239).  Fast paths: this package's own Dataset (`tensors()` method) and torch's TensorDataset
+    (`tensors` tuple); anything else is iterated."""
+    t = getattr(dataset, "tensors", None)
+    if callable(t):
+        return t()
+    if isinstance(t, (tuple, list)) and len(t) == 2:
+        return t[0], t[1]
+    xs, ys = zip(*[dataset[i] for i in range(len(dataset))])
+    return torch.stack([torch.as_tensor(v) for v in xs]), torch.stack([torch.as_tensor(v) for v in ys])
+
+
 class CVAEGAN:
     def __init__(self, config=None, datasets=None, max_rows: int = None):
         """`config` / `datasets`: modules with the reference's names (defaults: this package's mirrors;
@@ -155,13 +168,7 @@ class CVAEGAN:
     def _divide_samples(self, dataset) -> None:
         """cvae_gan.py:238-245, without the O(N^2) per-row torch.cat: one stable partition on the device.
         Key order = first occurrence in the data, rows keep their order, exactly like the reference."""
-        if hasattr(dataset, "tensors"):
-            x, y = dataset.tensors()
-        elif hasattr(self.datasets, "tr_samples") and len(self.datasets.tr_labels) == len(dataset):
-            x, y = self.datasets.tr_samples, self.datasets.tr_labels
-        else:
-            xs, ys = zip(*[dataset[i] for i in range(len(dataset))])
-            x, y = torch.stack(list(xs)), torch.stack(list(ys))
+        x, y = dataset_tensors(dataset)
         x = x.to(self.engine.device, torch.float32)
         y = y.to(self.engine.device).long()
         labels, first = [], {}

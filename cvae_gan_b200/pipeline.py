@@ -40,7 +40,7 @@ def minmax_scale_(datasets=_datasets, device: Optional[str] = None):
     x = x - x.min()
     datasets.tr_samples, datasets.te_samples = x[:n_tr].cpu(), x[n_tr:].cpu()
     datasets.feature_num = int(x.shape[1])
-    datasets.label_num = int(torch.unique(datasets.tr_labels).numel())
+    datasets.label_num = int(datasets.tr_labels.max()) + 1      # utils.set_dataset_values (utils.py:77-83): max label + 1
 
 
 def balance(gan: CVAEGAN, datasets=_datasets, verbose: bool = False):
