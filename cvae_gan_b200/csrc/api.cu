@@ -495,6 +495,12 @@ int cvg_debug_mk_cycles(CvgHandle* h, long long* out, int capacity, int* count) 
   const int n = e.mk.last_nops < capacity ? e.mk.last_nops : capacity;
   if (count) *count = n;
   if (out && n > 0) CVG_CUDA(cudaMemcpy(out, e.ws.mk_dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  if (out && capacity >= 2048 + 64 && n <= 1024) {
+    // out[1024 + i]: start clock of op i (CTA 0);  out[3072 + i] (capacity >= 4096): kind | bar_before << 8 | items << 16
+    CVG_CUDA(cudaMemcpy(out + 1024, e.ws.mk_dbg + 1024, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+    if (capacity >= 4096)
+      for (int i = 0; i < n && i < (int)e.mk.last_kinds.size(); ++i) out[3072 + i] = e.mk.last_kinds[i];
+  }
   if (out && capacity >= 2048 + 64) CVG_CUDA(cudaMemcpy(out + 2048, e.ws.mk_dbg + 2048, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -121,6 +121,7 @@ struct MkState {
   std::vector<MkSlot> slots;
   unsigned long long clock = 0;
   int last_nops = 0;
+  std::vector<int> last_kinds;     // per op of the last program: kind | bar_before << 8 | items << 16
 };
 
 struct ProfRec {

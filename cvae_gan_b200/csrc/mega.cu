@@ -265,7 +265,12 @@ int mk_flush(Engine& e, cudaStream_t st) {
   P.nops = m.nops;
   P.bar_counter = e.ws.mk_bar;
   if (e.world > 1 && e.nvl.on) P.nvl = e.nvl.dev;
-  P.dbg = (getenv("CVG_MK_DBG") && m.nops <= 2048) ? e.ws.mk_dbg : nullptr;
+  P.dbg = (getenv("CVG_MK_DBG") && m.nops <= 1024) ? e.ws.mk_dbg : nullptr;     // [0, 1024): cycles per op, [1024, 2048): start clocks
+  m.last_kinds.clear();
+  for (int i = 0; i < m.nops; ++i) {
+    const OpRec* r = reinterpret_cast<const OpRec*>(m.ops.data() + (size_t)i * sizeof(OpRec));
+    m.last_kinds.push_back(r->kind | (r->bar_before << 8) | (r->items << 16));
+  }
   P.prof = (P.dbg && getenv("CVG_MK_PROF")) ? e.ws.mk_dbg + 2048 : nullptr;
   if (P.prof) CVG_CUDA(cudaMemsetAsync(P.prof, 0, 64 * sizeof(long long), st));
   m.last_nops = m.nops;

@@ -44,6 +44,16 @@ constexpr int LBO_B_MAX = B_MAXN * 16 + 16;
 constexpr int B_PLANE = KG * LBO_B_MAX;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // hi + lo planes of both operands
 constexpr int NSTAGE = 2;
+// Shared-memory pool (2 * STAGE_BYTES).  Weight-gradient items use it as two stages {P hi, P lo, Q hi, Q lo}; forward /
+// input-gradient items as 3 weight slots (TMA), 2 operand slots (hi + lo planes of up to 128 batch rows) and a ring of
+// raw activation rows (TMA).  The epilogue's transpose scratch sits inside operand slot 1 in both maps.
+constexpr int MN_A_SLOT = 2 * KG * 128 * 16;                   // 32768
+constexpr int MN_B_OFF = 3 * MN_A_SLOT;                        // 98304
+constexpr int MN_B_PLANE = KG * (128 * 16 + 16);               // 16512
+constexpr int MN_B_SLOT = 2 * MN_B_PLANE;                      // 33024
+constexpr int MN_RAW_OFF = MN_B_OFF + 2 * MN_B_SLOT;           // 164352
+constexpr int TP_OFF = 131840;                                 // 8 warps x 32 x 20 floats
+constexpr int TP_BYTES = 8 * 32 * 20 * 4;
 constexpr int CS_FLOATS = 2560;               // per-feature constants of the operand transforms / epilogues (C <= 256)
 constexpr int RED_DOUBLES = 1024;
 constexpr int TMEM_COLS = 256;
@@ -100,15 +110,22 @@ struct Params {
   long long* prof;               // optional section counters of the GEMM items (CTA 0, development)
 };
 
+// mbarriers.  Slot ids (bit positions of Pipe::ub): A 0-2, B 3-4, RAW 5-8.
 struct Ctrl {
-  uint64_t full[NSTAGE];
-  uint64_t done[NSTAGE];
+  uint64_t a_full[3], a_free[3];       // pre-split weight chunks (TMA) / their MMAs have completed
+  uint64_t b_full[2], done[2];         // activation operand staged by the workers / its MMAs have completed
+  uint64_t raw_full[4], raw_free[4];   // raw activation rows (TMA) / the workers have consumed them
+  unsigned int seq;                    // GEMM items of this CTA whose MMAs have all completed (gates the producer: pool reuse)
   uint32_t tmem_slot;
   uint32_t pad;
   unsigned long long nvl_epoch0;
 };
 
 constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + CS_FLOATS * 4 + RED_DOUBLES * 8 + OP_BYTES + sizeof(Ctrl) + 64;
+constexpr int MN_RAW_BYTES = NSTAGE * STAGE_BYTES - MN_RAW_OFF;   // 33280
+static_assert(MN_RAW_BYTES >= 32768, "raw ring");
+static_assert(TP_OFF >= MN_B_OFF + MN_B_SLOT && TP_OFF + TP_BYTES <= MN_RAW_OFF, "transpose scratch inside operand slot 1");
+static_assert(TP_OFF >= STAGE_BYTES + 2 * A_PLANE && TP_OFF + TP_BYTES <= STAGE_BYTES + 2 * A_PLANE + B_PLANE, "transpose scratch inside Q-hi of stage 1");
 
 // Per-CTA pipeline state.  Everything here lives in registers (all users are force-inlined): with ~215 KB of shared
 // memory the L1 has ~10 KB left, so a single spilled word costs an L2 round trip.
@@ -124,10 +141,10 @@ struct Pipe {
   uint8_t* stages;
   float* cs;
   double* red;
-  uint64_t* full;       // [NSTAGE]
-  uint64_t* done;       // [NSTAGE]
+  Ctrl* S;
   uint32_t tmem;
-  uint32_t use0, use1;  // how many times stage 0 / 1 has been filled so far by this CTA (every role counts identically)
+  uint32_t ub;          // per slot id: bit i = uses so far mod 2, bit 16 + i = used at least once (every role counts identically)
+  uint32_t nitem;       // GEMM items this CTA has started
   int tid, warp, lane;
   long long* prof;
 };
@@ -275,36 +292,40 @@ __device__ __forceinline__ void st_split4(uint8_t* hi_plane, uint8_t* lo_plane, 
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
 
-// ---- stage bookkeeping: every role calls next_use() once per chunk, so the parities agree without communication --------
-__device__ __forceinline__ uint32_t next_use(Pipe& c, int s) {       // returns the 1-based use index of stage s
-  if (s == 0) return ++c.use0;
-  return ++c.use1;
+// ---- slot bookkeeping: every role that touches a slot calls use_begin() once per chunk, so the mbarrier parities agree
+// without communication.  Returns the parity on which THIS use completes; `first` = the slot has never been used.
+enum { ID_A = 0, ID_B = 3, ID_RAW = 5 };
+__device__ __forceinline__ uint32_t use_begin(Pipe& c, int id, bool& first) {
+  const uint32_t par = (c.ub >> id) & 1u;
+  first = ((c.ub >> (16 + id)) & 1u) == 0u;
+  c.ub = (c.ub ^ (1u << id)) | (1u << (16 + id));
+  return par;
 }
-// workers / producer: the MMAs of the previous use of this stage have finished reading it
-__device__ __forceinline__ void wait_stage_free(const Pipe& c, int s, uint32_t k) {
-  if (k > 1) mbar_wait(&c.done[s], (k - 2) & 1u);
+// the release ("free" / "done") barrier of the PREVIOUS use of a slot, before it is overwritten
+__device__ __forceinline__ void wait_prev_release(uint64_t* bar, uint32_t par, bool first) {
+  if (!first) mbar_wait(bar, par ^ 1u);
 }
-// workers, end of an item: the MMAs of the newest use have completed (accumulator final)
-__device__ __forceinline__ void wait_stage_done(const Pipe& c, int s) {
-  const uint32_t k = s == 0 ? c.use0 : c.use1;
-  if (k > 0) mbar_wait(&c.done[s], (k - 1) & 1u);
+// workers, end of an item: the MMAs of the newest use of operand slot s have completed (accumulator final)
+__device__ __forceinline__ void wait_last_done(const Pipe& c, int s) {
+  if ((c.ub >> (16 + ID_B + s)) & 1u) mbar_wait(&c.S->done[s], ((c.ub >> (ID_B + s)) & 1u) ^ 1u);
 }
 
-// issuer warp: MMAs of one staged chunk - nks steps of 8 contraction values, three tf32 MMAs each (small terms first)
-__device__ __forceinline__ void issue_chunk(const Pipe& c, int s, uint32_t k, int nks, int n_mma, uint32_t lbo_a, uint32_t lbo_b,
-                                            bool first_chunk) {
-  mbar_wait(&c.full[s], (k - 1) & 1u);
+// issuer warp: MMAs of one staged chunk - nks steps of 8 contraction values, three tf32 MMAs each (small terms first);
+// commits to `bar1` (and `bar2`).  Descriptor inputs are broadcast from lane 0 (uniform registers in the issue loop).
+__device__ __forceinline__ void issue_mmas(const Pipe& c, uint32_t a_addr, uint32_t a_lo_off, uint32_t lbo_a, uint32_t b_addr,
+                                           uint32_t b_lo_off, uint32_t lbo_b, int nks, int n_mma, bool first_chunk, uint64_t* bar1,
+                                           uint64_t* bar2) {
   tc_fence_after_sync();
-  const uint32_t base = __shfl_sync(0xffffffffu, smem_u32(c.stages) + (uint32_t)s * STAGE_BYTES, 0);
-  const uint32_t lbb = __shfl_sync(0xffffffffu, lbo_b, 0);
-  const uint32_t lba = __shfl_sync(0xffffffffu, lbo_a, 0);
+  const uint32_t aa = __shfl_sync(0xffffffffu, a_addr, 0), ab = __shfl_sync(0xffffffffu, b_addr, 0);
+  const uint32_t alo = __shfl_sync(0xffffffffu, a_lo_off, 0), blo = __shfl_sync(0xffffffffu, b_lo_off, 0);
+  const uint32_t lba = __shfl_sync(0xffffffffu, lbo_a, 0), lbb = __shfl_sync(0xffffffffu, lbo_b, 0);
   const uint32_t nm = __shfl_sync(0xffffffffu, (uint32_t)n_mma, 0);
   const uint32_t tm = __shfl_sync(0xffffffffu, c.tmem, 0);
   const int steps = __shfl_sync(0xffffffffu, nks, 0);
   const uint32_t fresh = __shfl_sync(0xffffffffu, first_chunk ? 1u : 0u, 0);
   if (elect_one()) {
-    uint64_t dah = smem_desc(base, lba, 128), dal = smem_desc(base + A_PLANE, lba, 128);
-    uint64_t dbh = smem_desc(base + 2 * A_PLANE, lbb, 128), dbl = smem_desc(base + 2 * A_PLANE + B_PLANE, lbb, 128);
+    uint64_t dah = smem_desc(aa, lba, 128), dal = smem_desc(aa + alo, lba, 128);
+    uint64_t dbh = smem_desc(ab, lbb, 128), dbl = smem_desc(ab + blo, lbb, 128);
     const uint32_t idesc = idesc_tf32(128, (int)nm, 0, 0);
     const uint64_t a_step = (uint64_t)((2 * lba) >> 4), b_step = (uint64_t)((2 * lbb) >> 4);
     for (int ks = 0; ks < steps; ++ks) {
@@ -313,7 +334,8 @@ __device__ __forceinline__ void issue_chunk(const Pipe& c, int s, uint32_t k, in
       mma_tf32(tm, dah, dbh, idesc, true);
       dah += a_step; dal += a_step; dbh += b_step; dbl += b_step;
     }
-    mma_commit(&c.done[s]);
+    mma_commit(bar1);
+    if (bar2) mma_commit(bar2);
   }
   __syncwarp();
 }
@@ -323,7 +345,7 @@ __device__ __forceinline__ void issue_chunk(const Pipe& c, int s, uint32_t k, in
 // 64 contiguous bytes per feature instead of 16.  Scratch: 32 x 20 floats per warp (B planes of stage 1, idle now).
 constexpr int TP_PITCH = 20;
 __device__ __forceinline__ float* tp_scratch(const Pipe& c) {
-  return reinterpret_cast<float*>(c.stages + (size_t)STAGE_BYTES + 2 * A_PLANE) + c.warp * (32 * TP_PITCH);
+  return reinterpret_cast<float*>(c.stages + TP_OFF) + c.warp * (32 * TP_PITCH);
 }
 __device__ __forceinline__ void tp_write(float* sc, int lane, const float* v) {
 #pragma unroll
@@ -342,8 +364,10 @@ template <int AK, int EK, int NT>
 __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float* wprep, const int item) {
   constexpr int nt_shift = NT == 128 ? 7 : 6;
   constexpr int NB = NT >> 5;                 // operand groups (4 features x 1 batch row) per thread and chunk: 2 or 4
-  constexpr int RING = 8 / NB;                // chunks in flight in registers: 4 or 2
   constexpr int NCB = NT >> 5;                // epilogue column blocks of 16 batch rows per thread: 2 or 4
+  constexpr int RAW_PLANES = (AK == OP_BN_BWD) ? 2 : 1;
+  constexpr int RAW_CHUNK = RAW_PLANES * KC * NT * 4;                  // bytes of raw rows per chunk: 8 / 16 / 32 KB
+  constexpr int RS = (AK == OP_CONST) ? 1 : (32768 / RAW_CHUNK > 4 ? 4 : 32768 / RAW_CHUNK);   // raw ring slots: 4 / 2 / 1
   const int tid = c.tid;
   const int M = g.M, ld = g.ld, N = g.N;
   const int R = min(g.R, g.a.rows);
@@ -352,35 +376,74 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
   const int rt = item % ntm, t2 = item / ntm, mt = t2 % nmt;
   const int pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
   const int m0 = rt << nt_shift, n0 = mt << 7;
-  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
+  constexpr uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
   const int nchunks = (R + KC - 1) / KC;
+  Ctrl* S = c.S;
 
   // ---------------------------------------------------- producer ----------------------------------------------------
+  // weights run 3 chunks ahead of the MMAs, raw activation rows RS chunks ahead of the workers
+  const uint32_t my_item = c.nitem++;
   if (c.warp == PRODUCER_WARP) {
-    const float* src = wprep + (size_t)mt * nchunks * CHUNK_FLOATS;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int s = ch & 1;
-      const uint32_t k = next_use(c, s);
-      const int nk4 = 2 * ((min(KC, R - ch * KC) + 7) >> 3);
-      wait_stage_free(c, s, k);
+    // every MMA of the previous GEMM items of this CTA has completed (a weight-gradient item uses the whole pool)
+    for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(&S->seq) < my_item; ++spin)
+      if (spin > (1u << 28)) __trap();
+    const float* wsrc = wprep + (size_t)mt * nchunks * CHUNK_FLOATS;
+    const int row_bytes = min(Nt, ld - m0) * 4;
+    const float* rsrc = (AK == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + m0;
+    const float* hsrc = (AK == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + m0 : nullptr;
+    auto load_weights = [&](int ch) {
+      const int sl = ch % 3;
+      bool first;
+      const uint32_t par = use_begin(c, ID_A + sl, first);
+      wait_prev_release(&S->a_free[sl], par, first);
       if (elect_one()) {
-        uint8_t* dst = c.stages + (size_t)s * STAGE_BYTES;
+        const int nk4 = 2 * ((min(KC, R - ch * KC) + 7) >> 3);
+        uint8_t* dst = c.stages + (size_t)sl * MN_A_SLOT;
         const uint32_t bytes = (uint32_t)nk4 * LBO_A;
-        mbar_arrive_expect_tx(&c.full[s], 2 * bytes);
-        bulk_g2s(dst, src + (size_t)ch * CHUNK_FLOATS, bytes, &c.full[s]);
-        bulk_g2s(dst + A_PLANE, src + (size_t)ch * CHUNK_FLOATS + WPLANE_FLOATS, bytes, &c.full[s]);
+        mbar_arrive_expect_tx(&S->a_full[sl], 2 * bytes);
+        bulk_g2s(dst, wsrc + (size_t)ch * CHUNK_FLOATS, bytes, &S->a_full[sl]);
+        bulk_g2s(dst + MN_A_SLOT / 2, wsrc + (size_t)ch * CHUNK_FLOATS + WPLANE_FLOATS, bytes, &S->a_full[sl]);
       }
       __syncwarp();
+    };
+    auto load_raw = [&](int ch) {
+      if (AK == OP_CONST) return;
+      const int sl = ch % RS;
+      bool first;
+      const uint32_t par = use_begin(c, ID_RAW + sl, first);
+      wait_prev_release(&S->raw_free[sl], par, first);
+      const int r0 = ch * KC;
+      const int nr = min(KC, R - r0);
+      uint8_t* dst = c.stages + MN_RAW_OFF + (size_t)sl * RAW_CHUNK;
+      if (c.lane == 0) mbar_arrive_expect_tx(&S->raw_full[sl], (uint32_t)(RAW_PLANES * nr * row_bytes));
+      __syncwarp();
+      if (c.lane < nr) {      // one feature row per lane: Nt consecutive batch rows = one contiguous run in the feature-major workspace
+        bulk_g2s(dst + (size_t)c.lane * Nt * 4, rsrc + (size_t)(r0 + c.lane) * ld, (uint32_t)row_bytes, &S->raw_full[sl]);
+        if (AK == OP_BN_BWD) bulk_g2s(dst + (size_t)(KC + c.lane) * Nt * 4, hsrc + (size_t)(r0 + c.lane) * ld, (uint32_t)row_bytes, &S->raw_full[sl]);
+      }
+      __syncwarp();
+    };
+    for (int ch = 0; ch < min(RS, nchunks); ++ch) load_raw(ch);
+    for (int ch = 0; ch < min(3, nchunks); ++ch) load_weights(ch);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      if (ch + RS < nchunks) load_raw(ch + RS);
+      if (ch + 3 < nchunks) load_weights(ch + 3);
     }
     return;
   }
   // ----------------------------------------------------- issuer -----------------------------------------------------
   if (c.warp == ISSUER_WARP) {
+    const uint32_t pool = smem_u32(c.stages);
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int s = ch & 1;
-      const uint32_t k = next_use(c, s);
+      const int sa = ch % 3, sb = ch & 1;
+      bool f1, f2;
+      const uint32_t pa = use_begin(c, ID_A + sa, f1);
+      const uint32_t pbb = use_begin(c, ID_B + sb, f2);
       const int nks = (min(KC, R - ch * KC) + 7) >> 3;
-      issue_chunk(c, s, k, nks, Nt, LBO_A, lbo_b, ch == 0);
+      mbar_wait(&S->a_full[sa], pa);
+      mbar_wait(&S->b_full[sb], pbb);
+      issue_mmas(c, pool + (uint32_t)sa * MN_A_SLOT, MN_A_SLOT / 2, LBO_A, pool + MN_B_OFF + (uint32_t)sb * MN_B_SLOT, MN_B_PLANE, lbo_b, nks,
+                 Nt, ch == 0, &S->done[sb], &S->a_free[sa]);
     }
     return;
   }
@@ -396,49 +459,6 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
   const int ml0 = tid & (Nt - 1), k40 = tid >> nt_shift;
   constexpr int k4step = WORKERS >> nt_shift;
   const bool row_ok = m0 + ml0 < M;
-  const float* pb = (AK == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + m0 + ml0;
-  const float* ph = (AK == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + m0 + ml0 : nullptr;
-
-  // register ring: the loads of chunk ch + RING are issued when chunk ch has been staged, so every load has RING chunk
-  // times (several MMA batches) to land - the workers never wait for L2
-  float rb[RING][NB][4], rh[(AK == OP_BN_BWD) ? RING : 1][NB][4];
-  auto load_chunk = [&](int ch, auto slot_c) {
-    constexpr int slot = decltype(slot_c)::value;
-    const int r0 = ch * KC;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + (k40 + j * k4step) * 4 + i;
-        rb[slot][j][i] = 0.f;
-        if (AK == OP_BN_BWD) rh[(AK == OP_BN_BWD) ? slot : 0][j][i] = 0.f;
-        if (AK != OP_CONST && row_ok && r < R) {
-          rb[slot][j][i] = ldg1(pb + (size_t)r * ld);
-          if (AK == OP_BN_BWD) rh[(AK == OP_BN_BWD) ? slot : 0][j][i] = ldg1(ph + (size_t)r * ld);
-        }
-      }
-    }
-  };
-  auto store_chunk = [&](int ch, int s, int nk4, auto slot_c) {
-    constexpr int slot = decltype(slot_c)::value;
-    uint8_t* base = c.stages + (size_t)s * STAGE_BYTES + 2 * A_PLANE;
-    const int r0 = ch * KC;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int k4 = k40 + j * k4step;
-      if (k4 < nk4) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok) v = mk_xform4<AK>(rb[slot][j], rh[(AK == OP_BN_BWD) ? slot : 0][j], cs_a, Ca, r0 + k4 * 4, R, slope, g.a.cst);
-        st_split4(base, base + B_PLANE, (uint32_t)k4 * lbo_b + (uint32_t)ml0 * 16u, v);
-      }
-    }
-  };
-
-  // in flight while the constants are prepared
-  load_chunk(0, std::integral_constant<int, 0>{});
-  if (RING > 1 && nchunks > 1) load_chunk(1, std::integral_constant<int, 1 % RING>{});
-  if (RING > 2 && nchunks > 2) load_chunk(2, std::integral_constant<int, 2 % RING>{});
-  if (RING > 3 && nchunks > 3) load_chunk(3, std::integral_constant<int, 3 % RING>{});
 
   // ---- per-feature constants -----------------------------------------------------------------------------------------
   mk_operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a, tid);
@@ -475,28 +495,48 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
   MK_T(q1);
   MK_ACC(0, q0, q1);
 
-  auto do_chunk = [&](int ch, auto slot_c) {
-    const int s = ch & 1;
-    const uint32_t k = next_use(c, s);
-    const int nks = (min(KC, R - ch * KC) + 7) >> 3;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int sb = ch & 1, sr = ch % RS;
+    const int r0 = ch * KC;
+    const int nk4 = 2 * ((min(KC, R - r0) + 7) >> 3);
+    bool first;
     MK_T(q2);
-    wait_stage_free(c, s, k);
+    const float* raw = reinterpret_cast<const float*>(c.stages + MN_RAW_OFF + (size_t)sr * RAW_CHUNK);
+    if (AK != OP_CONST) {
+      const uint32_t pr = use_begin(c, ID_RAW + sr, first);
+      mbar_wait(&S->raw_full[sr], pr);                    // the raw rows of this chunk have landed
+    }
+    const uint32_t pbb = use_begin(c, ID_B + sb, first);
+    wait_prev_release(&S->done[sb], pbb, first);          // the MMAs that read this operand slot two chunks ago are done
     MK_T(q3);
     MK_ACC(1, q2, q3);
-    store_chunk(ch, s, 2 * nks, slot_c);
+    uint8_t* base = c.stages + MN_B_OFF + (size_t)sb * MN_B_SLOT;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int k4 = k40 + j * k4step;
+      if (k4 < nk4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (AK != OP_CONST) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (r0 + k4 * 4 + i < R) {
+              a[i] = raw[(k4 * 4 + i) * Nt + ml0];
+              if (AK == OP_BN_BWD) b[i] = raw[(KC + k4 * 4 + i) * Nt + ml0];
+            }
+          }
+        }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok) v = mk_xform4<AK>(a, b, cs_a, Ca, r0 + k4 * 4, R, slope, g.a.cst);
+        st_split4(base, base + MN_B_PLANE, (uint32_t)k4 * lbo_b + (uint32_t)ml0 * 16u, v);
+      }
+    }
     MK_T(q2);
     MK_ACC(2, q3, q2);
-    if (ch + RING < nchunks) load_chunk(ch + RING, slot_c);
     fence_proxy_async_smem();
-    mbar_arrive(&c.full[s]);
+    mbar_arrive(&S->b_full[sb]);
+    if (AK != OP_CONST) mbar_arrive(&S->raw_free[sr]);
     MK_T(q3);
     MK_ACC(3, q2, q3);
-  };
-  for (int ch0 = 0; ch0 < nchunks; ch0 += RING) {
-    do_chunk(ch0, std::integral_constant<int, 0>{});
-    if (RING > 1 && ch0 + 1 < nchunks) do_chunk(ch0 + 1, std::integral_constant<int, 1 % RING>{});
-    if (RING > 2 && ch0 + 2 < nchunks) do_chunk(ch0 + 2, std::integral_constant<int, 2 % RING>{});
-    if (RING > 3 && ch0 + 3 < nchunks) do_chunk(ch0 + 3, std::integral_constant<int, 3 % RING>{});
   }
 
   // ---- epilogue --------------------------------------------------------------------------------------------------------
@@ -538,9 +578,9 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
     }
   }
   MK_T(q2);
-  wait_stage_done(c, 0);
-  if (nchunks > 1) wait_stage_done(c, 1);
+  wait_last_done(c, (nchunks - 1) & 1);          // tcgen05.commit covers every MMA issued before it
   tc_fence_after_sync();
+  if (tid == 0) *reinterpret_cast<volatile unsigned int*>(&S->seq) = my_item + 1u;
   MK_T(q3);
   MK_ACC(5, q2, q3);
   if (c.prof && c.tid == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 8, (unsigned long long)nchunks); atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 9, 1ull); }
@@ -737,22 +777,19 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
   const int nchunks = mend > mbeg ? (mend - mbeg + KC - 1) / KC : 0;
 
-  if (c.warp == PRODUCER_WARP) {
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int s = ch & 1;
-      const uint32_t k = next_use(c, s);
-      wait_stage_free(c, s, k);
-      if (elect_one()) mbar_arrive(&c.full[s]);
-      __syncwarp();
-    }
-    return;
-  }
+  Ctrl* S = c.S;
+  const uint32_t my_item = c.nitem++;
+  if (c.warp == PRODUCER_WARP) return;         // both operands are activations: nothing to stream
   if (c.warp == ISSUER_WARP) {
+    const uint32_t pool = smem_u32(c.stages);
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int s = ch & 1;
-      const uint32_t k = next_use(c, s);
+      const int sb = ch & 1;
+      bool first;
+      const uint32_t pbb = use_begin(c, ID_B + sb, first);
       const int nks = (min(KC, mend - (mbeg + ch * KC)) + 7) >> 3;
-      issue_chunk(c, s, k, nks, npad, LBO_AP, lbo_b, ch == 0);
+      mbar_wait(&S->b_full[sb], pbb);
+      const uint32_t st = pool + (uint32_t)sb * STAGE_BYTES;
+      issue_mmas(c, st, A_PLANE, LBO_AP, st + 2 * A_PLANE, B_PLANE, lbo_b, nks, npad, ch == 0, &S->done[sb], nullptr);
     }
     return;
   }
@@ -832,16 +869,17 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   worker_bar();
 
   for (int ch = 0; ch < nchunks; ++ch) {
-    const int s = ch & 1;
-    const uint32_t k = next_use(c, s);
-    wait_stage_free(c, s, k);
-    stage_chunk(mbeg + ch * KC, s);
+    const int sb = ch & 1;
+    bool first;
+    const uint32_t pbb = use_begin(c, ID_B + sb, first);
+    wait_prev_release(&S->done[sb], pbb, first);
+    stage_chunk(mbeg + ch * KC, sb);
     fence_proxy_async_smem();
-    mbar_arrive(&c.full[s]);
+    mbar_arrive(&S->b_full[sb]);
   }
-  if (nchunks > 0) wait_stage_done(c, 0);
-  if (nchunks > 1) wait_stage_done(c, 1);
+  if (nchunks > 0) wait_last_done(c, (nchunks - 1) & 1);
   tc_fence_after_sync();
+  if (tid == 0) *reinterpret_cast<volatile unsigned int*>(&S->seq) = my_item + 1u;
 
   // ---- epilogue: the partial tile goes to its scratch slot (row pitch kp): 16 columns per TMEM load, transposed in shared
   // memory so that a warp writes 64 contiguous bytes per row
@@ -1457,15 +1495,16 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   c.tid = threadIdx.x;
   c.warp = __shfl_sync(0xffffffffu, c.tid >> 5, 0);
   c.lane = c.tid & 31;
-  c.use0 = 0u;
-  c.use1 = 0u;
+  c.ub = 0u;
+  c.nitem = 0u;
+  c.S = S;
   c.prof = blockIdx.x == 0 ? P.prof : nullptr;
   if (c.tid == 0) {
-    for (int s2 = 0; s2 < NSTAGE; ++s2) {
-      mbar_init(&S->full[s2], WORKERS + 1);
-      mbar_init(&S->done[s2], 1);
-    }
+    for (int i2 = 0; i2 < 3; ++i2) { mbar_init(&S->a_full[i2], 1); mbar_init(&S->a_free[i2], 1); }
+    for (int i2 = 0; i2 < 2; ++i2) { mbar_init(&S->b_full[i2], WORKERS); mbar_init(&S->done[i2], 1); }
+    for (int i2 = 0; i2 < 4; ++i2) { mbar_init(&S->raw_full[i2], 1); mbar_init(&S->raw_free[i2], WORKERS); }
     fence_mbar_init();
+    S->seq = 0u;
     S->nvl_epoch0 = P.nvl.world > 1 ? *reinterpret_cast<volatile unsigned long long*>(P.nvl.epoch) : 0ull;
   }
   if (c.warp == 0) tmem_alloc(&S->tmem_slot, TMEM_COLS);
@@ -1473,8 +1512,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   c.tmem = __shfl_sync(0xffffffffu, S->tmem_slot, 0);
-  c.full = S->full;
-  c.done = S->done;
+
   const unsigned long long nvl_epoch0 = S->nvl_epoch0;
   unsigned int target = 0;
   const int G = (int)gridDim.x;
@@ -1485,7 +1523,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
     if (c.tid < OP_BYTES / 4) reinterpret_cast<uint32_t*>(sop)[c.tid] = reinterpret_cast<const uint32_t*>(P.ops + oi)[c.tid];
     __syncthreads();
     if (sop->bar_before) grid_barrier(P.bar_counter, target);
-    if (P.dbg && blockIdx.x == 0 && c.tid == 0) t_op = clock64();
+    if (P.dbg && blockIdx.x == 0 && c.tid == 0) { t_op = clock64(); P.dbg[1024 + oi] = t_op; }
     const int items = sop->items;
     const int i0 = (((int)blockIdx.x - sop->first) % G + G) % G;
     switch (sop->kind) {

@@ -346,9 +346,11 @@ class Engine:
     def mk_cycles(self):
         """Per-op cycle counts of the last step program (CVG_MK_DBG=1)."""
         n = C.c_int()
-        buf = (C.c_longlong * (2048 + 64))()
-        check(self.lib.cvg_debug_mk_cycles(self.h, buf, 2048 + 64, C.byref(n)))
+        buf = (C.c_longlong * 4096)()
+        check(self.lib.cvg_debug_mk_cycles(self.h, buf, 4096, C.byref(n)))
         self.mk_sections = list(buf[2048:2048 + 16])
+        self.mk_starts = list(buf[1024:1024 + n.value])
+        self.mk_ops = [(int(v) & 255, (int(v) >> 8) & 1, int(v) >> 16) for v in buf[3072:3072 + n.value]]
         return list(buf[:n.value])
 
 
