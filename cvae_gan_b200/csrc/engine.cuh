@@ -116,6 +116,7 @@ struct MkState {
   std::vector<MkPendingRed> pending_red;
   std::vector<MkPrepSlot> prep;    // per program: which weight operands have been pre-split, and where
   long long prep_off = 0;
+  bool prep_open = false;          // the newest op is a prep op that can still take entries
   const float* src_rows = nullptr;   // inside a visit program: class table the next step draws its batch from
   long long src_n = 0, src_Bg = 0, src_off = 0;
   std::vector<MkSlot> slots;

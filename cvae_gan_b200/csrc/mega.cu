@@ -72,15 +72,34 @@ int mk_weight_operand(Engine& e, const GemmArgs& g, bool wt, const float** out, 
     slot = &m.prep.back();
   }
   if (!slot->fresh) {
-    mk::PrepArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = 1;
-    a.e[0].W = slot->W; a.e[0].ldw = slot->ldw; a.e[0].wcol0 = slot->wcol0; a.e[0].wt = slot->wt;
-    a.e[0].R = slot->R; a.e[0].N = slot->N; a.e[0].off = slot->off;
-    a.wprep = e.ws.mk_wprep;
+    // append to the newest prep op of the current phase when there is room, else start a new op in this phase
     const int chunks = ((slot->N + 127) / 128) * ((slot->R + mk::KC - 1) / mk::KC);
-    if (m.nops > 0) m.par_next = true;
-    CVG_TRY(mk_push(e, mk::K_PREP, &a, sizeof(a), chunks));
+    mk::PrepEntry pe;
+    memset(&pe, 0, sizeof(pe));
+    pe.W = slot->W; pe.ldw = slot->ldw; pe.wcol0 = slot->wcol0; pe.wt = slot->wt; pe.R = slot->R; pe.N = slot->N; pe.off = slot->off;
+    OpRec* last = m.nops > 0 ? reinterpret_cast<OpRec*>(m.ops.data() + (size_t)(m.nops - 1) * sizeof(OpRec)) : nullptr;
+    bool appended = false;
+    if (last && last->kind == mk::K_PREP && m.prep_open) {
+      mk::PrepArgs a;
+      memcpy(&a, last->payload, sizeof(a));
+      if (a.n < mk::PREP_MAX) {
+        a.e[a.n++] = pe;
+        memcpy(last->payload, &a, sizeof(a));
+        last->items += chunks;
+        m.phase_items += chunks;
+        appended = true;
+      }
+    }
+    if (!appended) {
+      mk::PrepArgs a;
+      memset(&a, 0, sizeof(a));
+      a.n = 1;
+      a.e[0] = pe;
+      a.wprep = e.ws.mk_wprep;
+      if (m.nops > 0) m.par_next = true;
+      CVG_TRY(mk_push(e, mk::K_PREP, &a, sizeof(a), chunks));
+      m.prep_open = true;
+    }
     slot->fresh = true;
     if (emitted) *emitted = true;
   }
@@ -99,6 +118,7 @@ int mk_push(Engine& e, int kind, const void* payload, size_t bytes, int items, i
   if (bytes + extra_bytes > sizeof(OpRec::payload)) CVG_FAIL("mk_push: payload too large");
   const bool par = m.par_next && !m.allbar && m.nops > 0;
   m.par_next = false;
+  if (kind != mk::K_PREP) m.prep_open = false;
   if (m.max_ops >= 0 && m.nops >= m.max_ops) return 0;
   if (items <= 0) return 0;
   OpRec r;

@@ -357,238 +357,87 @@ __device__ __forceinline__ float4 tp_read(const float* sc, int lane, int fi) {
 
 // ======================================================================================================================
 // forward / input-gradient GEMM item:  D[n][m] = sum_r A[n][r] * B[m][r]
-//   A = pre-split weights (prep op), streamed by the producer warp;  B = operand g.a (feature-major [r][m] in memory,
-//   transformed in registers), m = batch rows of this tile.  AK / EK are compile-time; the tile height is a shift.
+//   A = pre-split weights (prep op), streamed by the producer warp;  B = operand g.a (feature-major [r][m] in memory):
+//   raw rows streamed by the producer warp (TMA), transformed + hi/lo split by the workers; m = batch rows of this tile.
+// Kinds are run-time switches and the loops are real loops on purpose: a step touches every code path once or twice, so
+// the instruction cache sees the code cold - compact code beats unrolled code here.
 // ======================================================================================================================
-template <int AK, int EK, int NT>
-__device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float* wprep, const int item) {
-  constexpr int nt_shift = NT == 128 ? 7 : 6;
-  constexpr int NB = NT >> 5;                 // operand groups (4 features x 1 batch row) per thread and chunk: 2 or 4
-  constexpr int NCB = NT >> 5;                // epilogue column blocks of 16 batch rows per thread: 2 or 4
-  constexpr int RAW_PLANES = (AK == OP_BN_BWD) ? 2 : 1;
-  constexpr int RAW_CHUNK = RAW_PLANES * KC * NT * 4;                  // bytes of raw rows per chunk: 8 / 16 / 32 KB
-  constexpr int RS = (AK == OP_CONST) ? 1 : (32768 / RAW_CHUNK > 4 ? 4 : 32768 / RAW_CHUNK);   // raw ring slots: 4 / 2 / 1
-  const int tid = c.tid;
-  const int M = g.M, ld = g.ld, N = g.N;
-  const int R = min(g.R, g.a.rows);
-  constexpr int Nt = NT;
-  const int ntm = (M + Nt - 1) >> nt_shift, nmt = (N + 127) >> 7;
-  const int rt = item % ntm, t2 = item / ntm, mt = t2 % nmt;
-  const int pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
-  const int m0 = rt << nt_shift, n0 = mt << 7;
-  constexpr uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
-  const int nchunks = (R + KC - 1) / KC;
-  Ctrl* S = c.S;
+struct MnGeo {
+  int M, ld, N, R, pass, m0, n0, mt, nchunks, nt_shift, ak, raw_chunk, rs;
+};
 
-  // ---------------------------------------------------- producer ----------------------------------------------------
-  // weights run 3 chunks ahead of the MMAs, raw activation rows RS chunks ahead of the workers
-  const uint32_t my_item = c.nitem++;
-  if (c.warp == PRODUCER_WARP) {
-    // every MMA of the previous GEMM items of this CTA has completed (a weight-gradient item uses the whole pool)
-    for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(&S->seq) < my_item; ++spin)
-      if (spin > (1u << 28)) __trap();
-    const float* wsrc = wprep + (size_t)mt * nchunks * CHUNK_FLOATS;
-    const int row_bytes = min(Nt, ld - m0) * 4;
-    const float* rsrc = (AK == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + m0;
-    const float* hsrc = (AK == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + m0 : nullptr;
-    auto load_weights = [&](int ch) {
-      const int sl = ch % 3;
-      bool first;
-      const uint32_t par = use_begin(c, ID_A + sl, first);
-      wait_prev_release(&S->a_free[sl], par, first);
-      if (elect_one()) {
-        const int nk4 = 2 * ((min(KC, R - ch * KC) + 7) >> 3);
-        uint8_t* dst = c.stages + (size_t)sl * MN_A_SLOT;
-        const uint32_t bytes = (uint32_t)nk4 * LBO_A;
-        mbar_arrive_expect_tx(&S->a_full[sl], 2 * bytes);
-        bulk_g2s(dst, wsrc + (size_t)ch * CHUNK_FLOATS, bytes, &S->a_full[sl]);
-        bulk_g2s(dst + MN_A_SLOT / 2, wsrc + (size_t)ch * CHUNK_FLOATS + WPLANE_FLOATS, bytes, &S->a_full[sl]);
-      }
-      __syncwarp();
-    };
-    auto load_raw = [&](int ch) {
-      if (AK == OP_CONST) return;
-      const int sl = ch % RS;
-      bool first;
-      const uint32_t par = use_begin(c, ID_RAW + sl, first);
-      wait_prev_release(&S->raw_free[sl], par, first);
-      const int r0 = ch * KC;
-      const int nr = min(KC, R - r0);
-      uint8_t* dst = c.stages + MN_RAW_OFF + (size_t)sl * RAW_CHUNK;
-      if (c.lane == 0) mbar_arrive_expect_tx(&S->raw_full[sl], (uint32_t)(RAW_PLANES * nr * row_bytes));
-      __syncwarp();
-      if (c.lane < nr) {      // one feature row per lane: Nt consecutive batch rows = one contiguous run in the feature-major workspace
-        bulk_g2s(dst + (size_t)c.lane * Nt * 4, rsrc + (size_t)(r0 + c.lane) * ld, (uint32_t)row_bytes, &S->raw_full[sl]);
-        if (AK == OP_BN_BWD) bulk_g2s(dst + (size_t)(KC + c.lane) * Nt * 4, hsrc + (size_t)(r0 + c.lane) * ld, (uint32_t)row_bytes, &S->raw_full[sl]);
-      }
-      __syncwarp();
-    };
-    for (int ch = 0; ch < min(RS, nchunks); ++ch) load_raw(ch);
-    for (int ch = 0; ch < min(3, nchunks); ++ch) load_weights(ch);
-    for (int ch = 0; ch < nchunks; ++ch) {
-      if (ch + RS < nchunks) load_raw(ch + RS);
-      if (ch + 3 < nchunks) load_weights(ch + 3);
-    }
-    return;
-  }
-  // ----------------------------------------------------- issuer -----------------------------------------------------
-  if (c.warp == ISSUER_WARP) {
-    const uint32_t pool = smem_u32(c.stages);
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int sa = ch % 3, sb = ch & 1;
-      bool f1, f2;
-      const uint32_t pa = use_begin(c, ID_A + sa, f1);
-      const uint32_t pbb = use_begin(c, ID_B + sb, f2);
-      const int nks = (min(KC, R - ch * KC) + 7) >> 3;
-      mbar_wait(&S->a_full[sa], pa);
-      mbar_wait(&S->b_full[sb], pbb);
-      issue_mmas(c, pool + (uint32_t)sa * MN_A_SLOT, MN_A_SLOT / 2, LBO_A, pool + MN_B_OFF + (uint32_t)sb * MN_B_SLOT, MN_B_PLANE, lbo_b, nks,
-                 Nt, ch == 0, &S->done[sb], &S->a_free[sa]);
-    }
-    return;
-  }
-  // ----------------------------------------------------- workers ----------------------------------------------------
-  const float slope = g.slope;
-  float* cs_a = c.cs;
-  const int Ca = (AK == OP_BN_ACT || AK == OP_BN_BWD) ? g.a.bn.C : 0;
-  float* cs_e = c.cs + (AK == OP_BN_ACT ? 3 * Ca : (AK == OP_BN_BWD ? 5 * Ca : 0));
-  long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-  MK_T(q0);
+__device__ __forceinline__ float4 mk_xform4_rt(int ak, const float* a, const float* b, const float* cs, int C, int r, int R, float slope,
+                                               float cst) {
+  if (ak == OP_BN_ACT) return mk_xform4<OP_BN_ACT>(a, b, cs, C, r, R, slope, cst);
+  if (ak == OP_BN_BWD) return mk_xform4<OP_BN_BWD>(a, b, cs, C, r, R, slope, cst);
+  if (ak == OP_CONST) return mk_xform4<OP_CONST>(a, b, cs, C, r, R, slope, cst);
+  return mk_xform4<OP_PLAIN>(a, b, cs, C, r, R, slope, cst);
+}
 
-  // operand addressing: thread -> batch row ml0, k-groups k40 + j * k4step (j < NB)
-  const int ml0 = tid & (Nt - 1), k40 = tid >> nt_shift;
-  constexpr int k4step = WORKERS >> nt_shift;
-  const bool row_ok = m0 + ml0 < M;
-
-  // ---- per-feature constants -----------------------------------------------------------------------------------------
-  mk_operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a, tid);
-  if (EK == EP_DBN) {
-    const int C = g.prev_bn.C;
-    for (int ch = tid; ch < C; ch += WORKERS) {
-      float mean, rstd;
-      mk_bn_mean_rstd(g.prev_bn, pass, ch, g.Bg, g.bn_eps, mean, rstd);
-      cs_e[ch] = ldg1(g.prev_bn.gamma + ch) * rstd;
-      cs_e[C + ch] = ldg1(g.prev_bn.beta + ch);
-      cs_e[2 * C + ch] = mean;
-      cs_e[3 * C + ch] = rstd;
-    }
-  }
-  if (AK == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum, tid);
-
-  // ---- epilogue addressing: thread -> features n0 + 32 q + 8 fi + lane / 4 (fi = 0..3), column group lane % 4 ----------
+// epilogue of one kind: thread -> features n0 + 32 q + 8 fi + lane / 4 (fi = 0..3), 4 batch rows at column 4 (lane % 4) of
+// every 16-column block.  The memory operands of block cb + 1 are requested before block cb is processed.
+template <int EK>
+__device__ __forceinline__ void mn_epilogue(Pipe& c, const GemmArgs& g, const MnGeo& geo, const float* cs_e, float scale) {
+  const int M = geo.M, ld = geo.ld, N = geo.N, pass = geo.pass, m0 = geo.m0, n0 = geo.n0;
+  const int Nt = 1 << geo.nt_shift;
   const int q = c.warp & 3, cgp = c.warp >> 2;
   const int fl0 = q * 32 + (c.lane >> 2), rg4 = (c.lane & 3) * 4;
-  float scale = 1.0f;
-  if (g.scale) scale = ldg1(g.scale + pass);
-  float bias[4] = {0.f, 0.f, 0.f, 0.f};
-  if (EK == EP_LINEAR) {
-#pragma unroll
-    for (int fi = 0; fi < 4; ++fi) {
-      const int n = n0 + fl0 + fi * 8;
-      if (n < N) {
-        bias[fi] = g.bias ? ldg1(g.bias + n) : 0.f;
-        if (g.wlabel) bias[fi] += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
-      }
-    }
-  }
-  worker_bar();
-  MK_T(q1);
-  MK_ACC(0, q0, q1);
-
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int sb = ch & 1, sr = ch % RS;
-    const int r0 = ch * KC;
-    const int nk4 = 2 * ((min(KC, R - r0) + 7) >> 3);
-    bool first;
-    MK_T(q2);
-    const float* raw = reinterpret_cast<const float*>(c.stages + MN_RAW_OFF + (size_t)sr * RAW_CHUNK);
-    if (AK != OP_CONST) {
-      const uint32_t pr = use_begin(c, ID_RAW + sr, first);
-      mbar_wait(&S->raw_full[sr], pr);                    // the raw rows of this chunk have landed
-    }
-    const uint32_t pbb = use_begin(c, ID_B + sb, first);
-    wait_prev_release(&S->done[sb], pbb, first);          // the MMAs that read this operand slot two chunks ago are done
-    MK_T(q3);
-    MK_ACC(1, q2, q3);
-    uint8_t* base = c.stages + MN_B_OFF + (size_t)sb * MN_B_SLOT;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int k4 = k40 + j * k4step;
-      if (k4 < nk4) {
-        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-        if (AK != OP_CONST) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (r0 + k4 * 4 + i < R) {
-              a[i] = raw[(k4 * 4 + i) * Nt + ml0];
-              if (AK == OP_BN_BWD) b[i] = raw[(KC + k4 * 4 + i) * Nt + ml0];
-            }
-          }
-        }
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok) v = mk_xform4<AK>(a, b, cs_a, Ca, r0 + k4 * 4, R, slope, g.a.cst);
-        st_split4(base, base + MN_B_PLANE, (uint32_t)k4 * lbo_b + (uint32_t)ml0 * 16u, v);
-      }
-    }
-    MK_T(q2);
-    MK_ACC(2, q3, q2);
-    fence_proxy_async_smem();
-    mbar_arrive(&S->b_full[sb]);
-    if (AK != OP_CONST) mbar_arrive(&S->raw_free[sr]);
-    MK_T(q3);
-    MK_ACC(3, q2, q3);
-  }
-
-  // ---- epilogue --------------------------------------------------------------------------------------------------------
-  float e_sc[4], e_sh[4], e_mean[4], e_rstd[4];
-  if (EK == EP_DBN) {
-    const int C = g.prev_bn.C;
-#pragma unroll
-    for (int fi = 0; fi < 4; ++fi) {
-      const int n = min(n0 + fl0 + fi * 8, C - 1);
-      e_sc[fi] = cs_e[n]; e_sh[fi] = cs_e[C + n]; e_mean[fi] = cs_e[2 * C + n]; e_rstd[fi] = cs_e[3 * C + n];
-    }
-  }
-  const float keep_inv = g.keep_inv;
-  const uint8_t* mask_p = (EK == EP_LINEAR || EK == EP_DACT) && g.mask ? g.mask + (long long)pass * g.smask : nullptr;
+  const int colw = Nt >> 1, ncb = Nt >> 5;
+  const float slope = g.slope, keep_inv = g.keep_inv;
+  constexpr bool need_pv = EK == EP_DBN || EK == EP_DACT || EK == EP_STORE;
+  constexpr bool need_mk = EK == EP_LINEAR || EK == EP_DACT;
+  const uint8_t* mask_p = (need_mk && g.mask) ? g.mask + (long long)pass * g.smask : nullptr;
   const float* prev_p = (EK == EP_DBN || EK == EP_DACT) ? g.prev + (long long)pass * g.sprev : nullptr;
   float* Yp = g.Y + (long long)pass * g.sY;
   const bool acc_y = EK == EP_STORE && g.accumulate;
-  constexpr int colw = Nt >> 1;              // columns (batch rows) per column group of two warps: 32 or 64
-  constexpr int ncb = NCB;
-  constexpr bool need_pv = EK == EP_DBN || EK == EP_DACT || EK == EP_STORE;
-  constexpr bool need_mk = EK == EP_LINEAR || EK == EP_DACT;
-  // every memory operand of the epilogue is requested before the MMAs are waited for
-  float4 pv[need_pv ? NCB : 1][4];
-  uchar4 mkv[need_mk ? NCB : 1][4];
+
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  float e_sc[4], e_sh[4], e_mean[4], e_rstd[4];
 #pragma unroll
-  for (int cb = 0; cb < NCB; ++cb) {
+  for (int fi = 0; fi < 4; ++fi) {
+    const int n = n0 + fl0 + fi * 8;
+    if (EK == EP_LINEAR && n < N) {
+      bias[fi] = g.bias ? ldg1(g.bias + n) : 0.f;
+      if (g.wlabel) bias[fi] += scale * ldg1(g.wlabel + (size_t)n * g.ldwl);
+    }
+    if (EK == EP_DBN) {
+      const int C = g.prev_bn.C;
+      const int nn = min(n, C - 1);
+      e_sc[fi] = cs_e[nn]; e_sh[fi] = cs_e[C + nn]; e_mean[fi] = cs_e[2 * C + nn]; e_rstd[fi] = cs_e[3 * C + nn];
+    }
+  }
+  float4 pv[4], pvn[4];
+  uchar4 mkv[4], mkn[4];
+  auto fetch = [&](int cb, float4* pvx, uchar4* mkx) {
     const int m = m0 + cgp * colw + cb * 16 + rg4;
 #pragma unroll
     for (int fi = 0; fi < 4; ++fi) {
       const int n = n0 + fl0 + fi * 8;
-      if (need_pv) pv[need_pv ? cb : 0][fi] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (need_mk) mkv[need_mk ? cb : 0][fi] = make_uchar4(1, 1, 1, 1);
+      pvx[fi] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mkx[fi] = make_uchar4(1, 1, 1, 1);
       if (n < N && m < M) {
         const size_t off = (size_t)n * ld + m;
-        if (need_pv && prev_p) pv[need_pv ? cb : 0][fi] = ldg4(prev_p + off);
-        if (need_mk && mask_p) mkv[need_mk ? cb : 0][fi] = __ldcg(reinterpret_cast<const uchar4*>(mask_p + off));
-        if (EK == EP_STORE && acc_y) pv[need_pv ? cb : 0][fi] = ldg4(Yp + off);
+        if (need_pv && prev_p) pvx[fi] = ldg4(prev_p + off);
+        if (need_mk && mask_p) mkx[fi] = __ldcg(reinterpret_cast<const uchar4*>(mask_p + off));
+        if (EK == EP_STORE && acc_y) pvx[fi] = ldg4(Yp + off);
       }
     }
-  }
-  MK_T(q2);
-  wait_last_done(c, (nchunks - 1) & 1);          // tcgen05.commit covers every MMA issued before it
+  };
+  long long e0 = 0, e1 = 0;
+  MK_T(e0);
+  fetch(0, pv, mkv);                               // the first two blocks: in flight while the last MMAs complete
+  if (ncb > 1) fetch(1, pvn, mkn);
+  MK_T(e1);
+  MK_ACC(10, e0, e1);
+  wait_last_done(c, (geo.nchunks - 1) & 1);        // tcgen05.commit covers every MMA issued before it
   tc_fence_after_sync();
-  if (tid == 0) *reinterpret_cast<volatile unsigned int*>(&S->seq) = my_item + 1u;
-  MK_T(q3);
-  MK_ACC(5, q2, q3);
-  if (c.prof && c.tid == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 8, (unsigned long long)nchunks); atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 9, 1ull); }
+  MK_T(e0);
+  MK_ACC(11, e1, e0);
 
   double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
   double tot = 0.0, klsum = 0.0;
   float* tps = tp_scratch(c);
-#pragma unroll
+#pragma unroll 1
   for (int cb = 0; cb < ncb; ++cb) {
     const int col = cgp * colw + cb * 16;
     {
@@ -598,6 +447,8 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
       tp_write(tps, c.lane, v);
     }
     __syncwarp();
+    MK_T(e1);
+    MK_ACC(12, e0, e1);
     const int m = m0 + col + rg4;
 #pragma unroll
     for (int fi = 0; fi < 4; ++fi) {
@@ -631,10 +482,10 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
           for (int i = 0; i < 4; ++i) y[i] = 1.0f / (1.0f + expf(-y[i]));
         }
         if (mask_p) {
-          y[0] = mkv[need_mk ? cb : 0][fi].x ? y[0] * keep_inv : 0.f;
-          y[1] = mkv[need_mk ? cb : 0][fi].y ? y[1] * keep_inv : 0.f;
-          y[2] = mkv[need_mk ? cb : 0][fi].z ? y[2] * keep_inv : 0.f;
-          y[3] = mkv[need_mk ? cb : 0][fi].w ? y[3] * keep_inv : 0.f;
+          y[0] = mkv[fi].x ? y[0] * keep_inv : 0.f;
+          y[1] = mkv[fi].y ? y[1] * keep_inv : 0.f;
+          y[2] = mkv[fi].z ? y[2] * keep_inv : 0.f;
+          y[3] = mkv[fi].w ? y[3] * keep_inv : 0.f;
         }
         if (g.osum) {
 #pragma unroll
@@ -643,7 +494,7 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
         }
         st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
       } else if (EK == EP_DBN) {
-        const float hh[4] = {pv[need_pv ? cb : 0][fi].x, pv[need_pv ? cb : 0][fi].y, pv[need_pv ? cb : 0][fi].z, pv[need_pv ? cb : 0][fi].w};
+        const float hh[4] = {pv[fi].x, pv[fi].y, pv[fi].z, pv[fi].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float pre = fmaf(hh[i] - e_mean[fi], e_sc[fi], e_sh[fi]);
@@ -654,13 +505,13 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
         }
         st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
       } else if (EK == EP_DACT) {
-        const float aa[4] = {pv[need_pv ? cb : 0][fi].x, pv[need_pv ? cb : 0][fi].y, pv[need_pv ? cb : 0][fi].z, pv[need_pv ? cb : 0][fi].w};
+        const float aa[4] = {pv[fi].x, pv[fi].y, pv[fi].z, pv[fi].w};
         float keep[4] = {1.f, 1.f, 1.f, 1.f};
         if (mask_p) {
-          keep[0] = mkv[need_mk ? cb : 0][fi].x ? keep_inv : 0.f;
-          keep[1] = mkv[need_mk ? cb : 0][fi].y ? keep_inv : 0.f;
-          keep[2] = mkv[need_mk ? cb : 0][fi].z ? keep_inv : 0.f;
-          keep[3] = mkv[need_mk ? cb : 0][fi].w ? keep_inv : 0.f;
+          keep[0] = mkv[fi].x ? keep_inv : 0.f;
+          keep[1] = mkv[fi].y ? keep_inv : 0.f;
+          keep[2] = mkv[fi].z ? keep_inv : 0.f;
+          keep[3] = mkv[fi].w ? keep_inv : 0.f;
         }
         const float neg = (g.act == ACT_LRELU) ? slope : 0.f;
 #pragma unroll
@@ -671,7 +522,7 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
         st4(Yp + off, make_float4(y[0], y[1], y[2], y[3]));
       } else if (EK == EP_STORE) {
         float4 o = make_float4(y[0] * scale, y[1] * scale, y[2] * scale, y[3] * scale);
-        if (acc_y) { o.x += pv[need_pv ? cb : 0][fi].x; o.y += pv[need_pv ? cb : 0][fi].y; o.z += pv[need_pv ? cb : 0][fi].z; o.w += pv[need_pv ? cb : 0][fi].w; }
+        if (acc_y) { o.x += pv[fi].x; o.y += pv[fi].y; o.z += pv[fi].z; o.w += pv[fi].w; }
         st4(Yp + off, o);
       } else if (EK == EP_REPARAM_BWD) {
         const float4 mu = ldg4(g.mu + off), lv = ldg4(g.lv + off), ee4 = ldg4(g.eps + off);
@@ -687,6 +538,11 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
       }
     }
     __syncwarp();
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) { pv[fi] = pvn[fi]; mkv[fi] = mkn[fi]; }
+    if (cb + 2 < ncb) fetch(cb + 2, pvn, mkn);     // two blocks ahead
+    MK_T(e0);
+    MK_ACC(13, e1, e0);
   }
   tc_fence_before_sync();
   if ((EK == EP_LINEAR || EK == EP_DBN) && g.ostats) {
@@ -726,42 +582,213 @@ __device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float*
     worker_bar();
     if (c.lane == 0) { c.red[512 + c.warp] = tot; c.red[528 + c.warp] = klsum; }
     worker_bar();
-    if (tid == 0) {
+    if (c.tid == 0) {
       double t = 0.0, kk = 0.0;
       for (int w = 0; w < WORKERS / 32; ++w) { t += c.red[512 + w]; kk += c.red[528 + w]; }
       if (g.osum && t != 0.0) atomicAdd(g.osum + pass, t);
       if (g.kl_acc && kk != 0.0) atomicAdd(g.kl_acc, kk);
     }
   }
-  worker_bar();     // TMEM drained, constants / reduction scratch / transpose scratch free for the next item
-  MK_T(q2);
-  MK_ACC(6, q3, q2);
+  MK_T(e1);
+  MK_ACC(14, e0, e1);
 }
 
-// run-time kinds -> the instantiations the steps use (same list as dispatch_mn in gemm.cuh)
-__device__ __forceinline__ void mn_dispatch(Pipe& c, const GemmArgs& g, int nt, const float* wprep, int items, int i0, int G) {
-#define CVG_MK_MN(A, E)                                                                          \
-  if (g.a.kind == A && g.ekind == E) {                                                           \
-    if (nt == 128) { for (int it = i0; it < items; it += G) mn_item<A, E, 128>(c, g, wprep, it); } \
-    else           { for (int it = i0; it < items; it += G) mn_item<A, E, 64>(c, g, wprep, it); }  \
-    return;                                                                                      \
+__device__ __forceinline__ void mn_item(Pipe& c, const GemmArgs& g, const float* wprep, const int nt_shift, const int item) {
+  MnGeo geo;
+  geo.M = g.M; geo.ld = g.ld; geo.N = g.N;
+  geo.R = min(g.R, g.a.rows);
+  geo.nt_shift = nt_shift;
+  geo.ak = g.a.kind;
+  const int Nt = 1 << nt_shift;
+  {
+    const int ntm = (geo.M + Nt - 1) >> nt_shift, nmt = (geo.N + 127) >> 7;
+    const int rt = item % ntm, t2 = item / ntm;
+    geo.mt = t2 % nmt;
+    geo.pass = g.only_pass >= 0 ? g.only_pass : t2 / nmt;
+    geo.m0 = rt << nt_shift;
+    geo.n0 = geo.mt << 7;
   }
-  CVG_MK_MN(OP_PLAIN, EP_LINEAR)
-  CVG_MK_MN(OP_BN_ACT, EP_LINEAR)
-  CVG_MK_MN(OP_PLAIN, EP_DACT)
-  CVG_MK_MN(OP_CONST, EP_DACT)
-  CVG_MK_MN(OP_PLAIN, EP_STORE)
-  CVG_MK_MN(OP_PLAIN, EP_DBN)
-  CVG_MK_MN(OP_BN_BWD, EP_DBN)
-  CVG_MK_MN(OP_BN_BWD, EP_REPARAM_BWD)
-#undef CVG_MK_MN
+  geo.nchunks = (geo.R + KC - 1) / KC;
+  const int raw_planes = geo.ak == OP_BN_BWD ? 2 : 1;
+  geo.raw_chunk = raw_planes * KC * Nt * 4;                                   // bytes of raw rows per chunk: 8 / 16 / 32 KB
+  geo.rs = geo.ak == OP_CONST ? 1 : min(4, 32768 / geo.raw_chunk);            // raw ring slots: 4 / 2 / 1
+  const int M = geo.M, ld = geo.ld, R = geo.R, pass = geo.pass, m0 = geo.m0, nchunks = geo.nchunks, ak = geo.ak, RS = geo.rs;
+  const uint32_t lbo_b = (uint32_t)Nt * 16u + 16u;
+  Ctrl* S = c.S;
+  const uint32_t my_item = c.nitem++;
+
+  // ---------------------------------------------------- producer ----------------------------------------------------
+  // weights run 3 chunks ahead of the MMAs, raw activation rows RS chunks ahead of the workers
+  if (c.warp == PRODUCER_WARP) {
+    // every MMA of the previous GEMM items of this CTA has completed (a weight-gradient item uses the whole pool)
+    for (uint32_t spin = 0; *reinterpret_cast<volatile unsigned int*>(&S->seq) < my_item; ++spin)
+      if (spin > (1u << 28)) __trap();
+    const float* wsrc = wprep + (size_t)geo.mt * nchunks * CHUNK_FLOATS;
+    const int row_bytes = min(Nt, ld - m0) * 4;
+    const float* rsrc = (ak == OP_CONST) ? nullptr : g.a.p + (long long)pass * g.a.sp + m0;
+    const float* hsrc = (ak == OP_BN_BWD) ? g.a.h + (long long)pass * g.a.sh + m0 : nullptr;
+    auto load_weights = [&](int ch) {
+      const int sl = ch % 3;
+      bool first;
+      const uint32_t par = use_begin(c, ID_A + sl, first);
+      wait_prev_release(&S->a_free[sl], par, first);
+      if (elect_one()) {
+        const int nk4 = 2 * ((min(KC, R - ch * KC) + 7) >> 3);
+        uint8_t* dst = c.stages + (size_t)sl * MN_A_SLOT;
+        const uint32_t bytes = (uint32_t)nk4 * LBO_A;
+        mbar_arrive_expect_tx(&S->a_full[sl], 2 * bytes);
+        bulk_g2s(dst, wsrc + (size_t)ch * CHUNK_FLOATS, bytes, &S->a_full[sl]);
+        bulk_g2s(dst + MN_A_SLOT / 2, wsrc + (size_t)ch * CHUNK_FLOATS + WPLANE_FLOATS, bytes, &S->a_full[sl]);
+      }
+      __syncwarp();
+    };
+    auto load_raw = [&](int ch) {
+      if (ak == OP_CONST) return;
+      const int sl = ch % RS;
+      bool first;
+      const uint32_t par = use_begin(c, ID_RAW + sl, first);
+      wait_prev_release(&S->raw_free[sl], par, first);
+      const int r0 = ch * KC;
+      const int nr = min(KC, R - r0);
+      uint8_t* dst = c.stages + MN_RAW_OFF + (size_t)sl * geo.raw_chunk;
+      if (c.lane == 0) mbar_arrive_expect_tx(&S->raw_full[sl], (uint32_t)(raw_planes * nr * row_bytes));
+      __syncwarp();
+      if (c.lane < nr) {      // one feature row per lane: Nt consecutive batch rows = one contiguous run in the feature-major workspace
+        bulk_g2s(dst + (size_t)c.lane * Nt * 4, rsrc + (size_t)(r0 + c.lane) * ld, (uint32_t)row_bytes, &S->raw_full[sl]);
+        if (ak == OP_BN_BWD) bulk_g2s(dst + (size_t)(KC + c.lane) * Nt * 4, hsrc + (size_t)(r0 + c.lane) * ld, (uint32_t)row_bytes, &S->raw_full[sl]);
+      }
+      __syncwarp();
+    };
+    for (int ch = 0; ch < min(RS, nchunks); ++ch) load_raw(ch);
+    for (int ch = 0; ch < min(3, nchunks); ++ch) load_weights(ch);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      if (ch + RS < nchunks) load_raw(ch + RS);
+      if (ch + 3 < nchunks) load_weights(ch + 3);
+    }
+    return;
+  }
+  // ----------------------------------------------------- issuer -----------------------------------------------------
+  if (c.warp == ISSUER_WARP) {
+    const uint32_t pool = smem_u32(c.stages);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int sa = ch % 3, sb = ch & 1;
+      bool f1, f2;
+      const uint32_t pa = use_begin(c, ID_A + sa, f1);
+      const uint32_t pbb = use_begin(c, ID_B + sb, f2);
+      const int nks = (min(KC, R - ch * KC) + 7) >> 3;
+      mbar_wait(&S->a_full[sa], pa);
+      mbar_wait(&S->b_full[sb], pbb);
+      issue_mmas(c, pool + (uint32_t)sa * MN_A_SLOT, MN_A_SLOT / 2, LBO_A, pool + MN_B_OFF + (uint32_t)sb * MN_B_SLOT, MN_B_PLANE, lbo_b, nks,
+                 Nt, ch == 0, &S->done[sb], &S->a_free[sa]);
+    }
+    return;
+  }
+  // ----------------------------------------------------- workers ----------------------------------------------------
+  const int tid = c.tid;
+  const float slope = g.slope;
+  float* cs_a = c.cs;
+  const int Ca = (ak == OP_BN_ACT || ak == OP_BN_BWD) ? g.a.bn.C : 0;
+  float* cs_e = c.cs + (ak == OP_BN_ACT ? 3 * Ca : (ak == OP_BN_BWD ? 5 * Ca : 0));
+  long long q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+  MK_T(q0);
+
+  // per-feature constants
+  if (ak == OP_BN_ACT) mk_operand_consts<OP_BN_ACT>(g.a, pass, g.Bg, g.bn_eps, cs_a, tid);
+  else if (ak == OP_BN_BWD) mk_operand_consts<OP_BN_BWD>(g.a, pass, g.Bg, g.bn_eps, cs_a, tid);
+  if (g.ekind == EP_DBN) {
+    const int C = g.prev_bn.C;
+    for (int ch = tid; ch < C; ch += WORKERS) {
+      float mean, rstd;
+      mk_bn_mean_rstd(g.prev_bn, pass, ch, g.Bg, g.bn_eps, mean, rstd);
+      cs_e[ch] = ldg1(g.prev_bn.gamma + ch) * rstd;
+      cs_e[C + ch] = ldg1(g.prev_bn.beta + ch);
+      cs_e[2 * C + ch] = mean;
+      cs_e[3 * C + ch] = rstd;
+    }
+  }
+  if (ak == OP_BN_ACT && g.a.bn.update_running && !g.a.bn.eval && item == 0) mk_bn_update_running(g.a.bn, g.npass, g.Bg, g.momentum, tid);
+  float scale = 1.0f;
+  if (g.scale) scale = ldg1(g.scale + pass);
+  worker_bar();
+  MK_T(q1);
+  MK_ACC(0, q0, q1);
+
+  // operand staging: thread -> batch row ml0, k-groups k40 + j * k4step (j < nb)
+  const int ml0 = tid & (Nt - 1), k40 = tid >> nt_shift;
+  const int k4step = WORKERS >> nt_shift, nb = Nt >> 5;
+  const bool row_ok = m0 + ml0 < M;
+#pragma unroll 1
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int sb = ch & 1, sr = ch % RS;
+    const int r0 = ch * KC;
+    const int nk4 = 2 * ((min(KC, R - r0) + 7) >> 3);
+    bool first;
+    MK_T(q2);
+    const float* raw = reinterpret_cast<const float*>(c.stages + MN_RAW_OFF + (size_t)sr * geo.raw_chunk);
+    if (ak != OP_CONST) {
+      const uint32_t pr = use_begin(c, ID_RAW + sr, first);
+      mbar_wait(&S->raw_full[sr], pr);                    // the raw rows of this chunk have landed
+    }
+    const uint32_t pbb = use_begin(c, ID_B + sb, first);
+    wait_prev_release(&S->done[sb], pbb, first);          // the MMAs that read this operand slot two chunks ago are done
+    MK_T(q3);
+    MK_ACC(1, q2, q3);
+    uint8_t* base = c.stages + MN_B_OFF + (size_t)sb * MN_B_SLOT;
+#pragma unroll 1
+    for (int j = 0; j < nb; ++j) {
+      const int k4 = k40 + j * k4step;
+      if (k4 < nk4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ak != OP_CONST) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (r0 + k4 * 4 + i < R) {
+              a[i] = raw[(k4 * 4 + i) * Nt + ml0];
+              if (ak == OP_BN_BWD) b[i] = raw[(KC + k4 * 4 + i) * Nt + ml0];
+            }
+          }
+        }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok) v = mk_xform4_rt(ak, a, b, cs_a, Ca, r0 + k4 * 4, R, slope, g.a.cst);
+        st_split4(base, base + MN_B_PLANE, (uint32_t)k4 * lbo_b + (uint32_t)ml0 * 16u, v);
+      }
+    }
+    MK_T(q2);
+    MK_ACC(2, q3, q2);
+    fence_proxy_async_smem();
+    mbar_arrive(&S->b_full[sb]);
+    if (ak != OP_CONST) mbar_arrive(&S->raw_free[sr]);
+    MK_T(q3);
+    MK_ACC(3, q2, q3);
+  }
+
+  MK_T(q2);
+  switch (g.ekind) {
+    case EP_LINEAR: mn_epilogue<EP_LINEAR>(c, g, geo, cs_e, scale); break;
+    case EP_DBN: mn_epilogue<EP_DBN>(c, g, geo, cs_e, scale); break;
+    case EP_DACT: mn_epilogue<EP_DACT>(c, g, geo, cs_e, scale); break;
+    case EP_STORE: mn_epilogue<EP_STORE>(c, g, geo, cs_e, scale); break;
+    default: mn_epilogue<EP_REPARAM_BWD>(c, g, geo, cs_e, scale); break;
+  }
+  if (tid == 0) *reinterpret_cast<volatile unsigned int*>(&S->seq) = my_item + 1u;
+  if (c.prof && c.tid == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 8, (unsigned long long)nchunks); atomicAdd(reinterpret_cast<unsigned long long*>(c.prof) + 9, 1ull); }
+  worker_bar();     // TMEM drained, constants / reduction scratch / transpose scratch free for the next item
+  MK_T(q3);
+  MK_ACC(6, q2, q3);
 }
 
 // ======================================================================================================================
 // weight-gradient GEMM item:  part[z][n][k] = sum_{m in slice} P[n][m] * Q[k][m]      (+ bias partial sum_m P[n][m])
-// Both operands are activations: the workers stage them (thread = feature x 4-row group); the producer only arrives.
+// Both operands are activations: the workers stage them (thread = feature x 4-row group); the producer idles.
 // ======================================================================================================================
 struct DwScratch { float* part; float* bpart; int nsplit; int kp; };
+
+__device__ __forceinline__ float mk_xform_rt(int kind, float a, float b, const float* cs, int C, int r, float slope, float cst) {
+  if (kind == OP_BN_ACT) return mk_xform<OP_BN_ACT>(a, b, cs, C, r, slope, cst);
+  if (kind == OP_BN_BWD) return mk_xform<OP_BN_BWD>(a, b, cs, C, r, slope, cst);
+  if (kind == OP_CONST) return cst;
+  return a;
+}
 
 template <int PK, int QK>
 __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratch& sc, const int item) {
@@ -776,7 +803,6 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   const int npad = (K + 15) & ~15;
   const uint32_t lbo_b = (uint32_t)npad * 16u + 16u;
   const int nchunks = mend > mbeg ? (mend - mbeg + KC - 1) / KC : 0;
-
   Ctrl* S = c.S;
   const uint32_t my_item = c.nitem++;
   if (c.warp == PRODUCER_WARP) return;         // both operands are activations: nothing to stream
@@ -809,43 +835,57 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   const float* pq0 = g.q.p + (long long)pass * g.q.sp + (size_t)f0 * ld + rgp * 4;
   const int nq = (npad + 31) >> 5;    // Q feature groups of 32 this thread stages (K <= 256 -> at most 8)
 
+  if (PK == OP_BN_BWD) mk_operand_consts<OP_BN_BWD>(g.p, pass, g.Bg, g.bn_eps, cs_p, tid);
+  if (QK == OP_BN_ACT) mk_operand_consts<OP_BN_ACT>(g.q, pass, g.Bg, g.bn_eps, cs_q, tid);
+  worker_bar();
+
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-  // one chunk = 32 batch rows: P (128 features) then Q (npad features), each staged in sub-passes of 4 loads in flight
-  auto stage_chunk = [&](int mb, int s) {
-    uint8_t* base = c.stages + (size_t)s * STAGE_BYTES;
+#pragma unroll 1
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int sb = ch & 1;
+    const int mb = mbeg + ch * KC;
     const int m = mb + rgp * 4;
     const bool rows_ok = m < mend;
-    {
-      float4 rp[4], rph[4];
+    float4 rp[4], rph[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        rph[j] = rp[j];
-        if (PK != OP_CONST && n0 + f0 + j * 32 < prows && rows_ok) {
-          rp[j] = ldg4(pp0 + j * step32 + mb);
-          if (PK == OP_BN_BWD) rph[j] = ldg4(ph0 + j * step32 + mb);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int f = n0 + f0 + j * 32;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < prows && rows_ok) {
-          v.x = mk_xform<PK>(rp[j].x, rph[j].x, cs_p, Cp, f, slope, g.p.cst);
-          v.y = (m + 1 < mend) ? mk_xform<PK>(rp[j].y, rph[j].y, cs_p, Cp, f, slope, g.p.cst) : 0.f;
-          v.z = (m + 2 < mend) ? mk_xform<PK>(rp[j].z, rph[j].z, cs_p, Cp, f, slope, g.p.cst) : 0.f;
-          v.w = (m + 3 < mend) ? mk_xform<PK>(rp[j].w, rph[j].w, cs_p, Cp, f, slope, g.p.cst) : 0.f;
-        }
-        bsum[j] += (v.x + v.y) + (v.z + v.w);
-        st_split4(base, base + A_PLANE, (uint32_t)rgp * LBO_AP + (uint32_t)(f0 + j * 32) * 16u, v);
+    for (int j = 0; j < 4; ++j) {
+      rp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rph[j] = rp[j];
+      if (PK != OP_CONST && n0 + f0 + j * 32 < prows && rows_ok) {
+        rp[j] = ldg4(pp0 + j * step32 + mb);
+        if (PK == OP_BN_BWD) rph[j] = ldg4(ph0 + j * step32 + mb);
       }
     }
-    for (int jq = 0; jq < nq; jq += 4) {
-      float4 rq[4];
+    float4 rq[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        rq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (jq + j < nq && f0 + (jq + j) * 32 < qrows && rows_ok) rq[j] = ldg4(pq0 + (jq + j) * step32 + mb);
+    for (int j = 0; j < 4; ++j) {
+      rq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < nq && f0 + j * 32 < qrows && rows_ok) rq[j] = ldg4(pq0 + j * step32 + mb);
+    }
+    bool first;
+    const uint32_t pbb = use_begin(c, ID_B + sb, first);
+    wait_prev_release(&S->done[sb], pbb, first);
+    uint8_t* base = c.stages + (size_t)sb * STAGE_BYTES;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int f = n0 + f0 + j * 32;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < prows && rows_ok) {
+        v.x = mk_xform<PK>(rp[j].x, rph[j].x, cs_p, Cp, f, slope, g.p.cst);
+        v.y = (m + 1 < mend) ? mk_xform<PK>(rp[j].y, rph[j].y, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+        v.z = (m + 2 < mend) ? mk_xform<PK>(rp[j].z, rph[j].z, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+        v.w = (m + 3 < mend) ? mk_xform<PK>(rp[j].w, rph[j].w, cs_p, Cp, f, slope, g.p.cst) : 0.f;
+      }
+      bsum[j] += (v.x + v.y) + (v.z + v.w);
+      st_split4(base, base + A_PLANE, (uint32_t)rgp * LBO_AP + (uint32_t)(f0 + j * 32) * 16u, v);
+    }
+#pragma unroll 1
+    for (int jq = 0; jq < nq; jq += 4) {
+      float4 rn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {        // the next sub-pass is requested before this one is transformed
+        rn[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jq + 4 + j < nq && f0 + (jq + 4 + j) * 32 < qrows && rows_ok) rn[j] = ldg4(pq0 + (jq + 4 + j) * step32 + mb);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -861,19 +901,9 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
           st_split4(base + 2 * A_PLANE, base + 2 * A_PLANE + B_PLANE, (uint32_t)rgp * lbo_b + (uint32_t)f * 16u, v);
         }
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rq[j] = rn[j];
     }
-  };
-
-  mk_operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p, tid);
-  mk_operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q, tid);
-  worker_bar();
-
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int sb = ch & 1;
-    bool first;
-    const uint32_t pbb = use_begin(c, ID_B + sb, first);
-    wait_prev_release(&S->done[sb], pbb, first);
-    stage_chunk(mbeg + ch * KC, sb);
     fence_proxy_async_smem();
     mbar_arrive(&S->b_full[sb]);
   }
@@ -886,6 +916,7 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   const int q = c.warp & 3, cgp = c.warp >> 2;
   const int fl0 = q * 32 + (c.lane >> 2), rg4 = (c.lane & 3) * 4;
   float* tps = tp_scratch(c);
+#pragma unroll 1
   for (int b = cgp; b < npad / 16; b += 2) {
     float v[16];
     if (nchunks > 0) {
@@ -918,20 +949,6 @@ __device__ __forceinline__ void dw_item(Pipe& c, const DwArgs& g, const DwScratc
   worker_bar();
 }
 
-__device__ __forceinline__ void dw_dispatch(Pipe& c, const DwArgs& g, const DwScratch& sc, int items, int i0, int G) {
-#define CVG_MK_DW(P_, Q_)                                                  \
-  if (g.p.kind == P_ && g.q.kind == Q_) {                                  \
-    for (int it = i0; it < items; it += G) dw_item<P_, Q_>(c, g, sc, it);  \
-    return;                                                                \
-  }
-  CVG_MK_DW(OP_PLAIN, OP_PLAIN)
-  CVG_MK_DW(OP_CONST, OP_PLAIN)
-  CVG_MK_DW(OP_PLAIN, OP_BN_ACT)
-  CVG_MK_DW(OP_BN_BWD, OP_BN_ACT)
-  CVG_MK_DW(OP_BN_BWD, OP_PLAIN)
-#undef CVG_MK_DW
-}
-
 // ---- weight preparation: hi / lo planes of every 128 x 32 chunk of a GEMM's A operand, in shared-memory order ----------
 //   chunk (mt, kc) = [hi: 8 k-groups x 128 rows x 4][lo: same]; element (row, k) at (k / 4) * 512 + row * 4 + k % 4 floats
 struct PrepEntry {
@@ -941,8 +958,9 @@ struct PrepEntry {
   int R, N;        // contraction length, A rows
   long long off;   // floats into the prepped buffer
 };
+constexpr int PREP_MAX = 10;
 struct PrepArgs {
-  PrepEntry e[4];
+  PrepEntry e[PREP_MAX];
   int n;
   float* wprep;
 };
@@ -1277,26 +1295,31 @@ __device__ void seed_item(const SeedArgs& g, int item) {
   }
 }
 
-// spectral norm power iteration of one critic layer (item = layer), `npass` consecutive forwards; sm: 3 * 1024 + 512 floats
+// spectral norm power iteration of one critic layer (item = layer), `npass` consecutive forwards.  W is copied to shared
+// memory once (at most 128 x 256 floats = 128 KB of the pool); the three mat-vecs of every pass then run from there.
+// sm: W at [0, rows * cols), then u, v, t (SN_MAXDIM each) and THREADS partials
 __device__ void sn_power_item(const SnArgs& g, int item, float* sm, double* red) {
-  float* su = sm;
-  float* sv = sm + SN_MAXDIM;
-  float* stt = sm + 2 * SN_MAXDIM;
-  float* part = sm + 3 * SN_MAXDIM;
   const SnLayer L = g.L[item];
+  const int n_el = L.rows * L.cols;
+  float* Ws = sm;
+  float* su = sm + ((n_el + 3) & ~3);
+  float* sv = su + SN_MAXDIM;
+  float* stt = sv + SN_MAXDIM;
+  float* part = stt + SN_MAXDIM;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = THREADS >> 5;
+  for (int i = tid; i < n_el; i += THREADS) Ws[i] = ldg1(L.W + i);
   for (int i = tid; i < L.rows; i += THREADS) su[i] = ldg1(L.u + i);
   for (int i = tid; i < L.cols; i += THREADS) sv[i] = ldg1(L.v + i);
   __syncthreads();
   int cp = 1;
   while (cp < L.cols) cp <<= 1;
-  if (cp > THREADS) cp = THREADS;
-  const int ng = THREADS / cp, kq = tid % cp, gq = tid / cp;
+  if (cp > 256) cp = 256;
+  const int ng = 256 / cp, kq = tid % cp, gq = tid / cp;     // threads >= 256 idle in the column-parallel product
   for (int p = 0; p < g.npass; ++p) {
     if (g.do_power) {
       for (int n = w; n < L.rows; n += nw) {
         float s = 0.f;
-        for (int k = lane; k < L.cols; k += 32) s = fmaf(ldg1(L.W + (size_t)n * L.cols + k), sv[k], s);
+        for (int k = lane; k < L.cols; k += 32) s = fmaf(Ws[n * L.cols + k], sv[k], s);
         s = warp_sum(s);
         if (lane == 0) stt[n] = s;
       }
@@ -1310,11 +1333,11 @@ __device__ void sn_power_item(const SnArgs& g, int item, float* sm, double* red)
       for (int k0 = 0; k0 < L.cols; k0 += cp) {
         const int k = k0 + kq;
         float s = 0.f;
-        if (k < L.cols)
-          for (int n = gq; n < L.rows; n += ng) s = fmaf(ldg1(L.W + (size_t)n * L.cols + k), su[n], s);
-        part[tid] = s;
+        if (tid < 256 && k < L.cols)
+          for (int n = gq; n < L.rows; n += ng) s = fmaf(Ws[n * L.cols + k], su[n], s);
+        if (tid < 256) part[tid] = s;
         __syncthreads();
-        if (gq == 0 && k < L.cols) {
+        if (tid < 256 && gq == 0 && k < L.cols) {
           float t = 0.f;
           for (int j = 0; j < ng; ++j) t += part[j * cp + kq];
           stt[k] = t;
@@ -1331,7 +1354,7 @@ __device__ void sn_power_item(const SnArgs& g, int item, float* sm, double* red)
     double sg = 0.0;
     for (int n = w; n < L.rows; n += nw) {
       float s = 0.f;
-      for (int k = lane; k < L.cols; k += 32) s = fmaf(ldg1(L.W + (size_t)n * L.cols + k), sv[k], s);
+      for (int k = lane; k < L.cols; k += 32) s = fmaf(Ws[n * L.cols + k], sv[k], s);
       s = warp_sum(s);
       if (lane == 0) sg += (double)s * su[n];
     }
@@ -1531,7 +1554,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
         const GemmArgs& g = payload<GemmArgs>(sop);
         const float* wp;
         memcpy(&wp, sop->payload + sizeof(GemmArgs), sizeof(float*));
-        mn_dispatch(c, g, sop->aux[1], wp, items, i0, G);
+        for (int it = i0; it < items; it += G) mn_item(c, g, wp, sop->aux[1] == 128 ? 7 : 6, it);
       } break;
       case K_DW: {
         const DwArgs& g = payload<DwArgs>(sop);
@@ -1540,7 +1563,12 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
         memcpy(&sc.bpart, sop->payload + sizeof(DwArgs) + sizeof(float*), sizeof(float*));
         sc.nsplit = sop->aux[0];
         sc.kp = sop->aux[1];
-        dw_dispatch(c, g, sc, items, i0, G);
+        const int pk = g.p.kind, qk = g.q.kind;
+        if (pk == OP_PLAIN && qk == OP_PLAIN) { for (int it = i0; it < items; it += G) dw_item<OP_PLAIN, OP_PLAIN>(c, g, sc, it); }
+        else if (pk == OP_CONST && qk == OP_PLAIN) { for (int it = i0; it < items; it += G) dw_item<OP_CONST, OP_PLAIN>(c, g, sc, it); }
+        else if (pk == OP_PLAIN && qk == OP_BN_ACT) { for (int it = i0; it < items; it += G) dw_item<OP_PLAIN, OP_BN_ACT>(c, g, sc, it); }
+        else if (pk == OP_BN_BWD && qk == OP_BN_ACT) { for (int it = i0; it < items; it += G) dw_item<OP_BN_BWD, OP_BN_ACT>(c, g, sc, it); }
+        else { for (int it = i0; it < items; it += G) dw_item<OP_BN_BWD, OP_PLAIN>(c, g, sc, it); }
       } break;
       case K_PREP: {
         const PrepArgs& a = payload<PrepArgs>(sop);

@@ -198,6 +198,7 @@ int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
     const int nmt = (g.N + 127) / 128;
     int Nt = 64;
     if ((long long)((g.M + 63) / 64) * nmt * zp > 3 * e.num_sms / 2) Nt = 128;
+    if (const char* f = getenv("CVG_MK_NT")) { if (atoi(f) == 128 && g.M > 64) Nt = 128; if (atoi(f) == 64) Nt = 64; }
     const int items = zp * nmt * ((g.M + Nt - 1) / Nt);
     const bool par = e.mk.par_next;
     const float* wp = nullptr;
@@ -1038,10 +1039,10 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_TRY(launch_fill(e, f, st));
   CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, st));
+  CVG_PAR(e);                           // the power iterations only touch the critic's weights and u / v: first phase
+  CVG_TRY(launch_sn(e, 2, true, st));   // D(real) then D(fake): two consecutive power iterations
   // G(z) under no_grad, still in train mode: batch stats, running stats updated (cvae_gan.py:113-115)
   CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
-  CVG_PAR(e);                           // the power iterations only touch the critic's weights and u / v
-  CVG_TRY(launch_sn(e, 2, true, st));   // D(real) then D(fake): two consecutive power iterations
   const long long sx = w.g_out - w.xT;  // pass 0 reads xT, pass 1 reads g_out (pass slot 0)
   CVG_TRY(fwd_critic(e, w.xT, sx, 2, label, B, w.loss + L_DREAL, st));
   const float seedv[2] = {-1.0f / Bg, 1.0f / Bg};   // d_loss = -mean D(real) + mean D(fake)
@@ -1197,6 +1198,8 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, st));
 
+  CVG_PAR(e);
+  CVG_TRY(launch_sn(e, 1, true, st));   // critic power iteration: independent of everything before D(x_fake)
   // forward: E -> (mu, logvar); G on z_enc (pass 0) and z_prior (pass 1); D and C on x_fake
   CVG_TRY(fwd_encoder(e, true, label, B, Bg_bn, local_bn, st));
   if (e.mk.recording) {
@@ -1206,8 +1209,6 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   }
   CVG_TRY(fwd_generator(e, 2, true, true, label, B, Bg_bn, local_bn, st));
   const float* x_fake = w.g_out + (size_t)e.F * ld;
-  CVG_PAR(e);
-  CVG_TRY(launch_sn(e, 1, true, st));
   CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, st));
   CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, st));
   CeArgs c;

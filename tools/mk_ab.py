@@ -129,7 +129,7 @@ def main():
         cyc = eb.mk_cycles() if os.environ.get("CVG_MK_DBG") else []
         if cyc:
             print("   op cycles (CTA 0):", cyc)
-            print("   mn sections (CTA 0) [preamble, wait, store, load+sync, issue, final wait, epilogue, -, chunks, items]:", eb.mk_sections)
+            print("   mn sections (CTA 0) [preamble, wait, store, arrive, -, -, epilogue+bar, -, chunks, items | epi: fetch0, mma wait, tmem+transpose, groups, stats]:", eb.mk_sections)
         ea.close()
         eb.close()
     print("A/B", "FAIL" if bad else "OK", bad)
