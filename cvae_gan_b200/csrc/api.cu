@@ -92,10 +92,10 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
   {
     const char* off = getenv("CVG_DISABLE_TC");
     e.use_tc = tc_supported(e) && !(off && off[0] == '1');
-    // training steps: ONE persistent tcgen05 kernel per step / label visit (mega.cuh).  CVG_TRAIN_MODE=ffma keeps the
-    // stand-alone FP32-FMA layer kernels (the A/B reference); widths the program kernel does not cover use them too.
+    // training executors: the stand-alone FP32-FMA layer kernels (default: faster at the benchmarked batch of 4096), or -
+    // CVG_TRAIN_MODE=mk / cvg_debug_set("train_mode", 1) - ONE persistent tcgen05 kernel per step / label visit (mega.cuh)
     const char* tm = getenv("CVG_TRAIN_MODE");
-    e.mk.enabled = mk_supported(e) && !(tm && !strcmp(tm, "ffma"));
+    e.mk.enabled = mk_supported(e) && tm && !strcmp(tm, "mk");
     const char* coop = getenv("CVG_MK_COOP");
     e.mk.coop = !(coop && coop[0] == '0');
     const char* ab = getenv("CVG_MK_ALLBAR");

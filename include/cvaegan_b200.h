@@ -237,8 +237,8 @@ int cvg_profile_read(CvgHandle* h, int kernel_class, int64_t* launches, double* 
 int64_t cvg_launch_count(const CvgHandle* h);
 
 /* Training executor switches (tests, A/B runs; the defaults come from the environment at cvg_create).
- *   "train_mode"  1 = step-program kernel: one persistent tcgen05 kernel per optimiser step / label visit (default),
- *                 0 = stand-alone FP32-FMA layer kernels (CVG_TRAIN_MODE=ffma)
+ *   "train_mode"  0 = stand-alone FP32-FMA layer kernels (default),
+ *                 1 = step-program kernel: one persistent tcgen05 kernel per optimiser step / label visit (CVG_TRAIN_MODE=mk)
  *   "mk_max_ops"  truncate every recorded program after this many ops (-1 = off; bisecting)
  *   "mk_allbar"   grid barrier before every op       "mk_coop"  cooperative launch on / off
  * cvg_debug_get: "train_mode", "mk_supported", "mk_last_nops" (ops of the last program incl. the finish op).

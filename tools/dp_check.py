@@ -4,7 +4,8 @@
 
 Every rank trains `VISITS` label visits on its shard (rows keyed by GLOBAL row index); rank 0 also runs the same
 visits on ONE GPU with the global batch and compares all parameters (the sums are re-associated across ranks, so
-the comparison is at 1e-4, not bit-exact).  All ranks must hold bit-identical parameters afterwards.  Also prints
+the multi-visit comparison is informational).  All ranks must hold bit-identical parameters afterwards, and ONE
+optimiser step of each kind (no update) must reproduce the single-GPU gradients / statistics / losses (tools/dp_parity.py).  Also prints
 the time per visit.  CVG_DISABLE_NVL=1 selects NCCL for the exchanges instead of the peer-memory all-reduce."""
 import os
 import sys
@@ -98,11 +99,13 @@ def main():
         print(f"max relative deviation of any tensor vs the single-GPU run on the global batch: {worst:.3e} ({worst_key})", flush=True)
         print("losses dp :", [round(x, 5) for x in loss[-1].tolist()], flush=True)
         print("losses one:", [round(x, 5) for x in loss1[-1].tolist()], flush=True)
-        # parameters whose gradient is ~0 take +-lr Adam steps of arbitrary sign, so the verdict uses what is well
-        # conditioned: bit-identical replicas and the losses of the last step against the single-GPU run
-        lo, l1 = loss[-1].tolist(), loss1[-1].tolist()
-        ok_loss = all(abs(a - b) <= 2e-3 * abs(b) + 1e-5 for a, b in zip(lo, l1))
-        print("DP_CHECK", "OK" if (flag.item() == 1 and ok_loss) else "FAIL", flush=True)
+        print("(multi-visit trajectories differ by Adam-amplified round-off on both sides; the verdict is the one-step check below)", flush=True)
+    # the verdict: one D / C / G step without update against a single-GPU run on the global batch, tensor by tensor
+    from tools.dp_parity import run_dp_parity
+    par = run_dp_parity(world, rank, dev, B_LOCAL)
+    if rank == 0:
+        print("dp_parity", par, flush=True)
+        print("DP_CHECK", "OK" if (flag.item() == 1 and par["ok"]) else "FAIL", flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
