@@ -156,6 +156,7 @@ int cvg_bind_workspace(CvgHandle* h, void* workspace, int64_t bytes, void* strea
   H_OR_FAIL(h);
   if (!workspace) CVG_FAIL("null workspace");
   CVG_TRY(carve_workspace(h->e, workspace, bytes));
+  if (mk_supported(h->e)) CVG_TRY(mk_alloc_slots(h->e));   // program buffers of the step-program executor
   // rows beyond the batch are never read un-masked, but start from a defined state
   CVG_CUDA(cudaMemsetAsync(workspace, 0, (size_t)bytes, (cudaStream_t)stream));
   return 0;

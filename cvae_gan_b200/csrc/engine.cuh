@@ -200,6 +200,7 @@ int comm_all_reduce_stats(Engine& e, double* p, int npass, int C, cudaStream_t s
 bool mk_supported(const Engine& e);
 void mk_set_kernel_attributes();
 void mk_destroy(Engine& e);
+int mk_alloc_slots(Engine& e);
 int mk_begin(Engine& e);                                   // start recording (no-op when the program kernel is off)
 int mk_flush(Engine& e, cudaStream_t st);                  // finish + upload + launch the recorded program
 int mk_push(Engine& e, int kind, const void* payload, size_t bytes, int items, int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0,

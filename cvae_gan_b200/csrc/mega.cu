@@ -202,8 +202,21 @@ static unsigned long long fnv1a(const unsigned char* p, size_t n) {
   return h;
 }
 
-constexpr int MK_SLOTS = 48;
-constexpr size_t MK_SLOT_BYTES = 512 * 1024;
+constexpr int MK_SLOTS = 32;
+constexpr size_t MK_SLOT_BYTES = 384 * 1024;
+
+// Program buffers (device + pinned host mirror): allocated when the workspace is bound, i.e. outside any stream capture
+int mk_alloc_slots(Engine& e) {
+  MkState& m = e.mk;
+  if (!m.slots.empty()) return 0;
+  m.slots.resize(MK_SLOTS);
+  for (auto& s : m.slots) {
+    CVG_CUDA(cudaMalloc(&s.dev, MK_SLOT_BYTES));          // program text, not tensor memory
+    CVG_CUDA(cudaMallocHost(&s.host, MK_SLOT_BYTES));
+    CVG_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  }
+  return 0;
+}
 
 static int mk_program_slot(Engine& e, cudaStream_t st, const void** dev_out) {
   MkState& m = e.mk;
@@ -213,13 +226,8 @@ static int mk_program_slot(Engine& e, cudaStream_t st, const void** dev_out) {
   CVG_CUDA(cudaStreamIsCapturing(st, &cap));
   const bool capturing = cap != cudaStreamCaptureStatusNone;
   if (m.slots.empty()) {
-    if (capturing) CVG_FAIL("step program: run the call once outside stream capture first (its program buffers are allocated then)");
-    m.slots.resize(MK_SLOTS);
-    for (auto& s : m.slots) {
-      CVG_CUDA(cudaMalloc(&s.dev, MK_SLOT_BYTES));          // program text, not tensor memory
-      CVG_CUDA(cudaMallocHost(&s.host, MK_SLOT_BYTES));
-      CVG_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
-    }
+    if (capturing) CVG_FAIL("step program: program buffers are not allocated (cvg_bind_workspace does it) and a stream capture is active");
+    CVG_TRY(mk_alloc_slots(e));
   }
   const unsigned long long h = fnv1a(m.ops.data(), bytes);
   ++m.clock;

@@ -185,8 +185,9 @@ class InjectedNoise:
     Keep-masks hold 0.0 / 1.0 (1 = kept); the oracle divides by (1-p) like F.dropout.
     """
 
-    def __init__(self):
+    def __init__(self, dtype=torch.float32):
         self.q: Dict[str, List[torch.Tensor]] = {}
+        self.dtype = dtype          # float64: the twin run that measures the reference's fp32 round-off (tests)
 
     def push(self, tag: str, t: torch.Tensor):
         self.q.setdefault(tag, []).append(t)
@@ -200,17 +201,17 @@ class InjectedNoise:
     def randn(self, rows, cols, tag="z"):
         t = self._pop(tag)
         assert tuple(t.shape) == (rows, cols), (tag, t.shape, rows, cols)
-        return t
+        return t.to(self.dtype)
 
     def randn_like(self, ref, tag="eps"):
         t = self._pop(tag)
         assert t.shape == ref.shape
-        return t
+        return t.to(self.dtype)
 
     def dropout_mask(self, rows, cols, p, tag=""):
         t = self._pop(tag)
         assert tuple(t.shape) == (rows, cols), (tag, t.shape, rows, cols)
-        return t.float()
+        return t.to(self.dtype)
 
     def randperm(self, n):
         return self._pop("idx")
@@ -231,8 +232,8 @@ LRELU = 0.2
 DROP_P = 0.3
 
 
-def _one_hot(label: int, rows: int, K: int) -> torch.Tensor:
-    return F.one_hot(torch.full([rows], int(label), dtype=torch.long), num_classes=K).float()
+def _one_hot(label: int, rows: int, K: int, dtype=torch.float32) -> torch.Tensor:
+    return F.one_hot(torch.full([rows], int(label), dtype=torch.long), num_classes=K).to(dtype)
 
 
 def _bn(x, sd, prefix, train: bool, dp=None):
@@ -267,7 +268,7 @@ def _bn(x, sd, prefix, train: bool, dp=None):
 def encoder_forward(sd, x, label: int, train: bool, dp=None):
     """cvae_gan_models.py:49-64: cat(x, onehot) -> [Lin, BN, LReLU]x3 -> fc_mu, fc_logvar."""
     K = sd["encoder.0.weight"].shape[1] - x.shape[1]
-    h = torch.cat([x, _one_hot(label, x.shape[0], K)], dim=1)
+    h = torch.cat([x, _one_hot(label, x.shape[0], K, x.dtype)], dim=1)
     for li in (0, 3, 6):
         h = F.linear(h, sd[f"encoder.{li}.weight"], sd[f"encoder.{li}.bias"])
         h = _bn(h, sd, f"encoder.{li + 1}", train, dp)
@@ -280,7 +281,7 @@ def encoder_forward(sd, x, label: int, train: bool, dp=None):
 def generator_forward(sd, z, label: int, train: bool, dp=None):
     """cvae_gan_models.py:136-156: cat(z, onehot) -> [Lin, BN, LReLU]x3 -> Lin -> Sigmoid."""
     K = sd["main_model.0.weight"].shape[1] - z.shape[1]
-    h = torch.cat([z, _one_hot(label, z.shape[0], K)], dim=1)
+    h = torch.cat([z, _one_hot(label, z.shape[0], K, z.dtype)], dim=1)
     for li in (0, 3, 6):
         h = F.linear(h, sd[f"main_model.{li}.weight"], sd[f"main_model.{li}.bias"])
         h = _bn(h, sd, f"main_model.{li + 1}", train, dp)
@@ -307,7 +308,7 @@ def discriminator_forward(sd, x, label: int, train: bool, noise=None, mask_tags=
     """cvae_gan_models.py:215-230: cat(x, onehot) -> SN-Lin, LReLU, Drop -> SN-Lin, LReLU, Drop
     -> SN-Lin, LReLU -> SN-Lin.  Raw critic score [B,1]."""
     K = sd["discriminator_network.0.parametrizations.weight.original"].shape[1] - x.shape[1]
-    h = torch.cat([x, _one_hot(label, x.shape[0], K)], dim=1)
+    h = torch.cat([x, _one_hot(label, x.shape[0], K, x.dtype)], dim=1)
     for i, li in enumerate((0, 3, 6)):
         p = f"discriminator_network.{li}"
         h = F.linear(h, _sn_weight(sd, p, train), sd[p + ".bias"])
@@ -455,6 +456,32 @@ class OracleCVAEGAN:
                 sd[key] = t
             self.sd[net] = sd
         return self
+
+    def twin64(self):
+        """The same model in float64 (parameters, buffers, Adam moments): running identical steps on it measures how far
+        the reference's OWN float32 arithmetic is from the exact result - the yardstick for tolerances (tests/parity.py)."""
+        import copy
+        t = copy.copy(self)
+        t.sd = {n: OrderedDict() for n in NETS}
+        for n in NETS:
+            for k, v in self.sd[n].items():
+                if v.is_floating_point():
+                    w = v.detach().double().clone()
+                    t.sd[n][k] = w.requires_grad_(True) if v.requires_grad else w
+                else:
+                    t.sd[n][k] = v.clone()
+        t.samples = OrderedDict((k, v.double()) for k, v in self.samples.items())
+        t.loss_history = {k: [] for k in self.loss_history}
+        t.training = dict(self.training)
+        t.last_losses = {}
+        t.opt = {}
+        if self.opt:
+            t.make_optimizers()
+            for n in NETS:
+                t.opt[n].t = self.opt[n].t
+                t.opt[n].m = [m.double().clone() for m in self.opt[n].m]
+                t.opt[n].v = [v.double().clone() for v in self.opt[n].v]
+        return t
 
     def init_like_reference(self, generator: Optional[torch.Generator] = None):
         """Same *distributions* as the reference constructor (utils.py:95-102 + torch defaults for

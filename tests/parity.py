@@ -95,8 +95,8 @@ def draw_noise(kind: str, B: int, Z: int, g: torch.Generator, h1=256, h2=128):
 
 
 def close(a: torch.Tensor, b: torch.Tensor, rtol=RTOL, atol_frac=ATOL_FRAC, atol_abs=0.0):
-    a = a.detach().float().cpu()
-    b = b.detach().float().cpu()
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
     scale = float(b.abs().max()) if b.numel() else 0.0
     tol = rtol * b.abs() + atol_frac * scale + atol_abs
     err = (a - b).abs()
@@ -105,12 +105,22 @@ def close(a: torch.Tensor, b: torch.Tensor, rtol=RTOL, atol_frac=ATOL_FRAC, atol
     return ok, worst, float(err.max()) if b.numel() else 0.0
 
 
-def compare_grads(eng, orc, net_names, grads, report):
+def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_factor=4.0):
+    """`grads64`: the same step on the float64 twin of the oracle.  |g32 - g64| is how far the REFERENCE's own float32
+    arithmetic is from the exact gradient; where the problem is ill-conditioned (BatchNorm backward cancels the row-constant
+    part of dy, and a pre-activation within round-off of 0 flips a LeakyReLU derivative from 1 to 0.2 - at batch 4096 a few
+    of the 10^6 activations always are) no float32 implementation can agree with another to 1e-3, so the tolerance is
+    widened by `envelope_factor` times that measured distance.  The comparison is then made against the float64 gradient."""
     for name in net_names:
         i = NETS.index(name)
-        for key, g_ref in zip(orc.param_keys(name), grads[name]):
+        for j, (key, g_ref) in enumerate(zip(orc.param_keys(name), grads[name])):
             got = eng.view(i, key, "grads")
-            ok, worst, mx = close(got, g_ref, atol_abs=1e-9)
+            if grads64 is None:
+                ok, worst, mx = close(got, g_ref, atol_abs=1e-9)
+            else:
+                g64 = grads64[name][j]
+                env = float((g_ref.double() - g64).abs().max())
+                ok, worst, mx = close(got.double().cpu(), g64, atol_abs=1e-9 + envelope_factor * env)
             report.append((f"grad {name}/{key}", ok, worst, mx, float(g_ref.abs().max())))
 
 
@@ -159,11 +169,34 @@ def assert_report(report, what=""):
         raise AssertionError(f"{what}: {len(bad)}/{len(report)} tensors outside tolerance\n{lines}")
 
 
-def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True):
-    """One optimiser step on both sides with shared noise; returns (oracle losses, engine losses)."""
+def twin_step(kind, orc64, x, label, inj64, lambda_class=0.25, update=False):
+    """The same step on the float64 twin (oracle.twin64()) with the same injected noise; returns its gradients."""
+    xd = x.double()
+    if kind == "d":
+        _, grads = orc64.step_d(xd, label, inj64, apply_update=update)
+    elif kind == "c":
+        _, grads = orc64.step_c(xd, label, inj64, apply_update=update)
+    else:
+        _, grads = orc64.step_g(xd, label, inj64, lambda_class, apply_update=update)
+    return grads
+
+
+def clone_noise(inj, dtype=torch.float64):
+    """A second InjectedNoise with the same queued tensors (FIFO queues are consumed by a step)."""
+    c = O.InjectedNoise(dtype)
+    c.q = {k: list(v) for k, v in inj.q.items()}
+    return c
+
+
+def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True, twin=None):
+    """One optimiser step on both sides with shared noise; returns (oracle losses, engine losses, oracle gradients).
+    `twin`: float64 twin of the oracle taking the same step (its gradients land in run_step.last_twin_grads)."""
     from cvae_gan_b200._lib import STEP_NO_UPDATE
     B = x.shape[0]
     inj, dev = draw_noise(kind, B, orc.cfg.z_size, g)
+    run_step.last_twin_grads = None
+    if twin is not None:
+        run_step.last_twin_grads = twin_step(kind, twin, x, label, clone_noise(inj), lambda_class, update)
     flags = 0 if update else STEP_NO_UPDATE
     xd = x.cuda()
     if kind == "d":

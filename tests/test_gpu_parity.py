@@ -24,16 +24,21 @@ def _single_thread_cpu():
 # (10, 5, 4096) is BASELINE.json configs[1] (the benchmarked shape); (10, 4, 4096) is the OTIDS class count of configs[2]
 @pytest.mark.parametrize("F_,K,B", [(10, 5, 64), (10, 4, 200), (30, 5, 128), (10, 5, 333), (10, 5, 4096), (10, 4, 4096)])
 @pytest.mark.parametrize("kind", ["d", "c", "g"])
-def test_step_losses_and_gradients(kind, F_, K, B):
+@pytest.mark.parametrize("executor", ["ffma", "program"])
+def test_step_losses_and_gradients(kind, F_, K, B, executor):
+    """Both training executors: the stand-alone FFMA layer kernels and the step-program kernel (tcgen05, mega.cuh)."""
     orc, eng, g = P.make_pair(F_, K, B, seed=5 + B)
+    eng.debug_set("train_mode", 1 if executor == "program" else 0)
     x, y = P.make_data(F_, K, [B] * K, seed=1)
     xb = x[y == (K - 1)][:B].contiguous()
     eng.zero_grads()
-    ref, got, grads = P.run_step(kind, orc, eng, xb, K - 1, g, lambda_class=0.25, update=False)
+    # batch 4096: measure the reference's own float32 round-off on the float64 twin (parity.compare_grads explains)
+    twin = orc.twin64() if B >= 4096 else None
+    ref, got, grads = P.run_step(kind, orc, eng, xb, K - 1, g, lambda_class=0.25, update=False, twin=twin)
     assert P.losses_close(ref, got), (ref, got)
     report = []
     nets = {"d": ["discriminator"], "c": ["classifier"], "g": ["encoder", "generator"]}[kind]
-    P.compare_grads(eng, orc, nets, grads, report)
+    P.compare_grads(eng, orc, nets, grads, report, grads64=P.run_step.last_twin_grads)
     # pre-BN biases: the reference gradient itself is pure round-off (see parity.PRE_BN_BIASES)
     report = [r for r in report if not any(r[0].endswith(k) for ks in P.PRE_BN_BIASES.values() for k in ks)]
     P.assert_report(report, f"step_{kind} gradients")
