@@ -532,8 +532,11 @@ def run_fit_leg(dev, epochs=6, rows_per_class=20000):
         torch.cuda.synchronize()
         dt2 = time.perf_counter() - t1
         n_q = 200_000
+        # a label this young classifier accepts at all (the reference's loop gives up after 20 empty chunks of 10)
+        accs = [float(gan.engine.generate_filter(lab, 20_000, 0.0, seed=5, capacity=1)[2].item()) for lab in range(K_)]
+        q_label = int(max(range(K_), key=lambda lab: accs[lab]))
         t2 = time.perf_counter()
-        q = gan.generate_qualified_samples(1, n_q, 0.0)
+        q = gan.generate_qualified_samples(q_label, n_q, 0.0)
         dq = time.perf_counter() - t2
         samples = OPT_STEPS * BATCH_PER_GPU * K_ * epochs
         out = {"value": samples / dt2, "unit": "samples/s", "first_fit_value": samples / dt, "epochs": epochs, "rows": rows_per_class * K_,
@@ -541,7 +544,7 @@ def run_fit_leg(dev, epochs=6, rows_per_class=20000):
                "api": "CVAEGAN().fit(TrDataset()) at batch 4096: _divide_samples + graph capture + epochs x K label visits + loss read-back",
                "generate_qualified_samples": {"requested": n_q, "returned": int(q.shape[0]) if q.dim() == 2 else 0, "seconds": dq,
                                               "rows_per_s": (int(q.shape[0]) if q.dim() == 2 else 0) / dq, "threshold": 0.0,
-                                              "api": "gan.generate_qualified_samples(1, 200000, 0.0) -> CPU tensor"}}
+                                              "label": q_label, "api": "gan.generate_qualified_samples(label, 200000, 0.0) -> CPU tensor"}}
         gan.engine.close()
         return out
     finally:
@@ -558,7 +561,7 @@ GEN_FLOP_PER_ROW = 2 * (75_648 + 43_840)
 
 K_OTIDS = 4
 OTIDS_FRACTIONS = (0.90, 0.06, 0.03, 0.01)
-FILTER_TRAIN_EPOCHS = int(os.environ.get("CVG_BENCH_FILTER_EPOCHS", "60"))
+FILTER_TRAIN_EPOCHS = int(os.environ.get("CVG_BENCH_FILTER_EPOCHS", "400"))
 
 
 def trained_otids_engine(dev, world, rank):
@@ -667,6 +670,23 @@ def run_filter_leg(eng_unused, dev, world, rank, pk, iters=3):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / k
 
+    # the NAMED configuration first: minority label, threshold 0.5 - measured even when the acceptance is ~0
+    named = None
+    if fallback:
+        nl = max(acc, key=lambda k: acc[k])
+        keep_lt = (label, thr)
+        label, thr = nl, 0.5
+        ms_n = timed(gen_filter, iters, 2)
+        acc_n = torch.tensor([float(eng.count_buf.item())], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(acc_n)
+        named = {"label": nl, "threshold": 0.5, "ms_per_pass": ms_n, "generated_rows_per_s": n * world / (ms_n * 1e-3),
+                 "accepted_rows_per_s": float(acc_n.item()) / (ms_n * 1e-3), "acceptance_rate": float(acc_n.item()) / (n * world),
+                 "note": "the classifier separates the REAL classes (accuracy 1.0, confidence ~0.99 after the training above) but the "
+                         "generator trained by the reference's algorithm at these settings does not carry the class into its samples "
+                         "(recon loss flat, KL -> 0; the CPU oracle shows the same curve, tools/diag_longrun.py), so nothing "
+                         "passes 0.5: `value` is therefore measured at the lowered threshold and flagged threshold_fallback"}
+        label, thr = keep_lt
     ms = timed(gen_filter, iters, 3)
     accepted = int(eng.count_buf.item())
     dbg = None
@@ -699,7 +719,7 @@ def run_filter_leg(eng_unused, dev, world, rank, pk, iters=3):
         "config": {"workload": "minority-class generation + classifier-confidence filter, OTIDS shape F=10 K=4 Z=128 "
                                "(BASELINE.json configs[3]): 12.5 M generated rows per GPU, threshold 0.5",
                    "model": train_info, "minority_acceptance_at_thr": {str(k): v for k, v in acc.items()},
-                   "threshold_fallback": fallback},
+                   "threshold_fallback": fallback, "named_config_measured": named},
         "e2e": {"value": accepted_all / (ms_e2e * 1e-3), "generated_rows_per_s": n * world / (ms_e2e * 1e-3),
                 "unit": "accepted rows/s", "ms_per_pass": ms_e2e, "d2h_bytes_per_pass": accepted * (F_ * 4) + 8,
                 "api": "cvg_generate_filter + count read-back + accepted rows copied to pinned host memory"},

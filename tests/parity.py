@@ -105,7 +105,7 @@ def close(a: torch.Tensor, b: torch.Tensor, rtol=RTOL, atol_frac=ATOL_FRAC, atol
     return ok, worst, float(err.max()) if b.numel() else 0.0
 
 
-def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_factor=4.0):
+def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_factor=4.0, atol_frac=ATOL_FRAC):
     """`grads64`: the same step on the float64 twin of the oracle.  |g32 - g64| is how far the REFERENCE's own float32
     arithmetic is from the exact gradient; where the problem is ill-conditioned (BatchNorm backward cancels the row-constant
     part of dy, and a pre-activation within round-off of 0 flips a LeakyReLU derivative from 1 to 0.2 - at batch 4096 a few
@@ -120,7 +120,7 @@ def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_fac
             else:
                 g64 = grads64[name][j]
                 env = float((g_ref.double() - g64).abs().max())
-                ok, worst, mx = close(got.double().cpu(), g64, atol_abs=1e-9 + envelope_factor * env)
+                ok, worst, mx = close(got.double().cpu(), g64, atol_abs=1e-9 + envelope_factor * env, atol_frac=atol_frac)
             report.append((f"grad {name}/{key}", ok, worst, mx, float(g_ref.abs().max())))
 
 
@@ -142,21 +142,32 @@ def close_mostly(a, b, rtol, atol_frac, atol_abs, outlier_frac, hard_atol):
     return ok, worst, mx
 
 
-def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=ATOL_FRAC, outlier_frac=0.0, hard_atol=0.0):
+def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=ATOL_FRAC, outlier_frac=0.0, hard_atol=0.0,
+                  twin=None, envelope_factor=3.0):
+    """`twin`: the float64 twin that took the same steps.  Its distance from the float32 oracle, per tensor, is the
+    reference's own round-off after the trajectory (Adam turns round-off-sized gradient differences into +-lr parameter steps,
+    so trajectories of ANY two float32 implementations drift apart); the tolerance is widened by `envelope_factor` times it."""
     st = orc.state()
+    st64 = twin.state() if twin is not None else None
     for name in nets:
         i = NETS.index(name)
         for key in eng.tables[i]:
             got = eng.view(i, key)
             ref = st[name][key]
+            if st64 is not None and ref.is_floating_point():
+                env = float((ref.double() - st64[name][key].double()).abs().max())
+                hard_atol_k, extra_env = hard_atol + envelope_factor * env, envelope_factor * env
+            else:
+                hard_atol_k, extra_env = hard_atol, 0.0
             # running_mean of the BN that follows such a bias tracks mean(h) = ... + bias: same looseness
             loose = key in PRE_BN_BIASES.get(name, ()) or (name in PRE_BN_BIASES and key.endswith("running_mean"))
             extra = loose_prebn_atol if loose else 0.0
             if ONE_HOT_FIRST.get(name) == key and loose_prebn_atol:
                 extra = torch.zeros(ref.shape)
                 extra[:, ref.shape[1] - orc.label_num:] = loose_prebn_atol
+            extra = extra + extra_env
             if outlier_frac > 0.0:
-                ok, worst, mx = close_mostly(got, ref, RTOL, atol_frac, extra, outlier_frac, hard_atol)
+                ok, worst, mx = close_mostly(got, ref, RTOL, atol_frac, extra, outlier_frac, hard_atol_k)
             else:
                 ok, worst, mx = close(got, ref, atol_abs=extra, atol_frac=atol_frac)
             report.append((f"state {name}/{key}", ok, worst, mx, float(ref.abs().max())))
