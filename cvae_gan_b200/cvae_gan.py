@@ -110,6 +110,15 @@ class CVAEGAN:
         """cvae_gan.py:59-236."""
         gc = self.config.gan_config
         eng = self.engine
+        # the learning rates and loss weights were handed to the engine at construction (CvgConfig); the reference re-reads them
+        # here (cvae_gan.py:75-97, 207-212) - refuse to train silently with stale values
+        want = (float(gc.g_lr), float(gc.d_lr), float(gc.c_lr), float(self.lambda_recon), float(self.lambda_kl), float(self.lambda_adv))
+        have = (eng.cfg.g_lr, eng.cfg.d_lr, eng.cfg.c_lr, eng.cfg.lambda_recon, eng.cfg.lambda_kl, eng.cfg.lambda_adv)
+        if any(abs(a - b) > 1e-12 + 1e-6 * abs(b) for a, b in zip(want, have)):
+            raise ValueError("g_lr / d_lr / c_lr / lambda_recon / lambda_kl / lambda_adv changed after CVAEGAN() was constructed: "
+                             f"configured {want}, engine holds {have}; construct a new CVAEGAN after changing them")
+        if self.world_size > 1:
+            eng.verify_replicas()
         for m in (self.encoder, self.generator, self.discriminator, self.classifier):
             m.train()
         self._divide_samples(dataset)

@@ -125,6 +125,21 @@ class Engine:
             self.nvl = bool(int(flag.item()) == 1)
             dist.barrier()
 
+    def verify_replicas(self):
+        """Data parallel: every rank must start from the same parameters / BatchNorm / spectral-norm state (only gradients
+        are all-reduced afterwards).  Compares a checksum across ranks and raises on a mismatch."""
+        import torch.distributed as dist
+        if self.world_size <= 1:
+            return
+        cs = torch.stack([t.double().sum() for t in (self.params + self.state)] +
+                         [t.double().abs().sum() for t in (self.params + self.state)])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi):
+            raise _lib.CvgError("data-parallel replicas differ before training (parameters / BatchNorm / spectral-norm state): seed every "
+                                "rank identically or broadcast rank 0's state (Engine.load_state) before fit()")
+
     # ---- named views ---------------------------------------------------------------------------------
     def view(self, net: int, key: str, which: str = "params") -> torch.Tensor:
         """View of one tensor (reference state_dict key) inside a flat buffer; `which` in

@@ -26,6 +26,7 @@ def main():
             models.CVAEGANClassifierModel(F_, K)]
     for net, m in enumerate(mods):
         eng.load_state(net, m.state_dict())
+    eng.debug_set("train_mode", 1)
     rows = torch.rand(200000, F_, device="cuda")
     eng.ctl_set(seed=1, counter=0, lambda_class=0.25)
     for _ in range(3):
