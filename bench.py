@@ -314,7 +314,9 @@ def run_ours(args):
     for label in range(K_):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            eng.visit(label, Bg, class_rows=tabs[label], loops=LOOPS, loss_out=loss)
+            # --quick only (diagnostics): CVG_BENCH_VISIT_FLAGS=2 times the visit with per-rank BatchNorm sums
+            eng.visit(label, Bg, class_rows=tabs[label], loops=LOOPS, loss_out=loss,
+                      flags=int(os.environ.get("CVG_BENCH_VISIT_FLAGS", "0")) if args.quick else 0)
         graphs[label] = g
 
     def visit_resident(label):

@@ -96,6 +96,7 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
     // CVG_TRAIN_MODE=mk / cvg_debug_set("train_mode", 1) - ONE persistent tcgen05 kernel per step / label visit (mega.cuh)
     const char* tm = getenv("CVG_TRAIN_MODE");
     e.mk.enabled = mk_supported(e) && tm && !strcmp(tm, "mk");
+    if (const char* hv = getenv("CVG_HOIST")) e.hoist = atoi(hv) != 0;   // 0: every step of a visit runs its own G(z)
     const char* coop = getenv("CVG_MK_COOP");
     e.mk.coop = !(coop && coop[0] == '0');
     const char* ab = getenv("CVG_MK_ALLBAR");
@@ -472,6 +473,8 @@ int cvg_debug_set(CvgHandle* h, const char* key, int value) {
   } else if (k == "mk_max_ops") e.mk.max_ops = value;
   else if (k == "mk_allbar") e.mk.allbar = value != 0;
   else if (k == "mk_coop") e.mk.coop = value != 0;
+  else if (k == "hoist") e.hoist = value != 0;
+  else if (k == "fuse_stats") e.nvl.fuse = value != 0;
   else CVG_FAIL("cvg_debug_set: unknown key");
   return 0;
 }

@@ -30,12 +30,21 @@ struct NvlDev {
   unsigned int* done;                   // local: CTAs of the running launch that finished
 };
 
+struct NvlPending {                     // batch sums pushed by their producer, not yet taken up by a reader
+  const double* stats;
+  int npass;
+};
+
 struct NvlState {
   bool on = false;
   void* local = nullptr;
   size_t total_bytes = 0;
   NvlDev dev{};
   bool opened[NVL_MAX_WORLD] = {};
+  NvlDev* dev_d = nullptr;              // device copy of `dev` for the kernels that fold the exchange in
+  bool fuse = true;                     // CVG_FUSE_STATS=0: BatchNorm sums go through nvl_allreduce_kernel launches
+  NvlPending pending[4];
+  int n_pending = 0;
 };
 
 __host__ __device__ inline unsigned long long nvl_slot_off(const NvlDev& d, int parity, int src) {
@@ -139,6 +148,102 @@ __global__ void __launch_bounds__(NVL_THREADS) nvl_allreduce_kernel(const NvlDev
       __threadfence();
       *reinterpret_cast<volatile unsigned long long*>(d.epoch) = ep;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same exchange folded into the GEMM kernels either side of it (BatchNorm batch sums; gemm.cuh):
+//   * the LAST CTA of the kernel that accumulated the local sums (found with the `done` counter) reads the finished
+//     sums and stores them as LL packets into slot[ep & 1][rank] of every peer, then records `ep` next to the sums
+//     and advances the epoch - no separate launch, and the packets fly while the next kernel is being launched;
+//   * every CTA of the FIRST kernel that uses those sums polls its own slots for the features it needs and adds the
+//     ranks' values in rank order (bit-identical on all ranks and to nvl_allreduce_kernel); one CTA writes the
+//     global sums back for the later readers of the same statistics.
+// The parity argument above holds unchanged: a rank's last CTA pushes ep + 1 only after all of its CTAs finished
+// polling ep.
+// ------------------------------------------------------------------------------------------------
+// Two elements at once (a feature's pair of sums): all 4 * world loads are issued before the first flag is looked at,
+// so a poll that finds its packets costs one L2 round trip whatever the world size.
+__device__ __forceinline__ void nvl_poll_f64x2(const NvlDev& d, unsigned int ep32, int par, long long e0, long long e1,
+                                               double& out0, double& out1) {
+  const unsigned char* base = d.peer[d.rank];
+  const int world = d.world;
+  const unsigned long long off0 = (unsigned long long)e0 * 16, off1 = (unsigned long long)e1 * 16;
+  unsigned int w0[NVL_MAX_WORLD][2], w1[NVL_MAX_WORLD][2];
+  const long long t0 = clock64();
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NVL_MAX_WORLD; ++q) {
+      if (q < world) {
+        const unsigned char* src = base + nvl_slot_off(d, par, q);
+        unsigned int f0, f1, f2, f3;
+        ll_load(src + off0, w0[q][0], f0);
+        ll_load(src + off0 + 8, w0[q][1], f1);
+        ll_load(src + off1, w1[q][0], f2);
+        ll_load(src + off1 + 8, w1[q][1], f3);
+        ok = ok && f0 == ep32 && f1 == ep32 && f2 == ep32 && f3 == ep32;
+      }
+    }
+    if (ok) break;
+    if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never arrived
+  }
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int q = 0; q < NVL_MAX_WORLD; ++q) {
+    if (q < world) {
+      s0 += __hiloint2double((int)w0[q][1], (int)w0[q][0]);
+      s1 += __hiloint2double((int)w1[q][1], (int)w1[q][0]);
+    }
+  }
+  out0 = s0;
+  out1 = s1;
+}
+
+// Called by EVERY thread of EVERY CTA as the last statement of a kernel that accumulated `npass` slots of 2 C doubles
+// (`stride` doubles apart) into `stats` with atomics.  stats[stride - 1] receives the exchange number for the reader.
+__device__ __forceinline__ void nvl_push_stats_tail(const NvlDev& d, double* stats, long long stride, int npass, int C,
+                                                    unsigned int total_ctas) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(d.done, 1u) == total_ctas - 1u) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const unsigned long long ep = *reinterpret_cast<volatile unsigned long long*>(d.epoch) + 1ull;
+  const unsigned int ep32 = (unsigned int)ep;
+  const int par = (int)(ep & 1ull);
+  const int n = npass * 2 * C;
+  for (int e0 = threadIdx.x; e0 < n; e0 += 4 * blockDim.x) {     // loads first: one round trip for up to 4 elements
+    double x[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k * blockDim.x;
+      if (e < n) {
+        const int ps = e / (2 * C), idx = e - ps * 2 * C;
+        x[k] = __ldcg(stats + (long long)ps * stride + idx);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k * blockDim.x;
+      if (e < n) {
+        const unsigned int lo = (unsigned int)__double2loint(x[k]), hi = (unsigned int)__double2hiint(x[k]);
+        for (int p = 0; p < d.world; ++p) {
+          unsigned char* dst = d.peer[p] + nvl_slot_off(d, par, d.rank) + (unsigned long long)e * 16;
+          ll_store(dst, lo, ep32);
+          ll_store(dst + 8, hi, ep32);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *d.done = 0u;
+    stats[stride - 1] = (double)ep;
+    __threadfence();
+    *reinterpret_cast<volatile unsigned long long*>(d.epoch) = ep;
   }
 }
 

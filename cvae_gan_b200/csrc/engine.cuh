@@ -9,6 +9,7 @@ typedef struct ncclComm* ncclComm_t;
 
 namespace cvg {
 
+constexpr int HOIST_MAX = 16;  // generator passes one hoisted forward can hold (d_loop + c_loop of a visit)
 constexpr int STAT_C = 1024;   // max features of a BatchNorm layer (stats slots are [2][STAT_C])
 
 // feature-major workspace (all float matrices are [features][ld], two pass slots where noted)
@@ -25,6 +26,11 @@ struct Workspace {
   // generator
   float *g_h[3] = {nullptr, nullptr, nullptr};   // [2][Hi][ld] pre-BN
   float* g_out = nullptr;                        // [2][F][ld]
+  // generator forward of every critic / classifier step of a visit, run once up front (train.cu hoist_generator)
+  float* hz = nullptr;                           // [HOIST_MAX][Z][ld]
+  float* hh[3] = {nullptr, nullptr, nullptr};    // [HOIST_MAX][Hi][ld] pre-BN
+  float* hout = nullptr;                         // [HOIST_MAX][F][ld]
+  double* hfst = nullptr;                        // [3 layers][HOIST_MAX][2 * STAT_C]
   float *g_dy[3] = {nullptr, nullptr, nullptr};
   float* g_dout = nullptr;                       // [2][F][ld]
   // encoder
@@ -143,6 +149,8 @@ struct Engine {
   void* ws_base = nullptr;
   int64_t ws_bytes = 0;
   int64_t launches = 0;
+  const float* hoist_x = nullptr;   // visit(): G(z) of the step being emitted, computed up front (null: the step runs G)
+  int hoist = 1;                    // CVG_HOIST=0: every step runs its own generator forward
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
   NvlState nvl;            // NVLink peer-memory all-reduce for the latency-bound exchanges (comm_nvl.cuh)
@@ -234,8 +242,16 @@ int tc_encoder_forward(Engine& e, const float* x, int label, int64_t n, float* m
 // shared launch helpers (train.cu)
 int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st);
 int launch_dw(Engine& e, const DwArgs& g, cudaStream_t st);
+// where a generator forward reads z and keeps its activations / batch sums (default: the two-pass step buffers)
+struct GenBufs {
+  const float* z;
+  float* h[3];
+  float* out;
+  double* fst[3];
+  uint64_t pad = 0;
+};
 int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int label, int M, float Bg, bool local_bn,
-                  cudaStream_t st);
+                  cudaStream_t st, const GenBufs* gb = nullptr);
 int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool train, int M, cudaStream_t st);
 int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn, cudaStream_t st);
 

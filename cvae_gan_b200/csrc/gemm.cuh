@@ -11,7 +11,9 @@
 // never written to memory; epilogues fuse bias / one-hot column / 1/sigma / activation / dropout /
 // batch-moment accumulation / KL / activation derivatives.
 #pragma once
+#include <cstddef>
 #include "common.cuh"
+#include "comm_nvl.cuh"
 
 namespace cvg {
 
@@ -38,6 +40,9 @@ struct BnRef {
   int C = 0;
   int eval = 0;
   int update_running = 0;          // CTA (0,0,0) applies the momentum update for all passes, in order
+  // data parallel, exchange folded into the kernels (comm_nvl.cuh): the sums named by `poll_which` (1 fstats, 2 bstats)
+  // are still in flight as `poll_npass` passes of LL packets; this kernel is their first reader
+  int poll = 0;                    // which | passes << 4   (the NvlDev pointer travels in GemmArgs / DwArgs ::nvl)
 };
 
 struct Operand {
@@ -97,7 +102,11 @@ struct GemmArgs {
   const float* eps = nullptr;
   float kl_coef = 0.f;
   int only_pass = -1;              // if >= 0 the grid has one pass slot mapped to this pass index
+  const NvlDev* nvl = nullptr;     // data parallel with the exchange folded in: polling (a.bn.poll) and / or ...
+  int push = 0;                    // ... the last CTA sends ostats to every peer (nvl_push_stats_tail)
 };
+// what a step-program op record carries of it (mega.cuh): everything before the folded-exchange fields
+constexpr size_t GEMM_ARGS_OP_BYTES = offsetof(GemmArgs, nvl);
 
 struct DwArgs {
   int M = 0, ld = 0, npass = 1;
@@ -115,21 +124,53 @@ struct DwArgs {
   int add_affine = 0;
   int rows_per_cta = 256;
   float bn_eps = 1e-5f, slope = 0.2f;
+  const NvlDev* nvl = nullptr;     // set when p.bn.poll / q.bn.poll is
 };
 
 // ------------------------------------------------------------------------------------------------
 // per-CTA BatchNorm constants
 // ------------------------------------------------------------------------------------------------
+// A feature's pair of batch sums, [sum (C) | second sum (C)] of `which` (1 forward, 2 backward).
+// nvl != null: this CTA takes in-flight sums from the LL packets instead of the buffer.
+__device__ __forceinline__ void bn_stat2(const BnRef& bn, int which, int pass, int c, const NvlDev* nvl, double& s1,
+                                         double& s2) {
+  const double* base = which == 1 ? bn.fstats : bn.bstats;
+  const long long stride = which == 1 ? bn.sf : bn.sb;
+  if (nvl == nullptr || (bn.poll & 15) != which) {
+    s1 = base[(long long)pass * stride + c];
+    s2 = base[(long long)pass * stride + bn.C + c];
+    return;
+  }
+  const unsigned long long ep = (unsigned long long)base[stride - 1];
+  const long long e = (long long)pass * 2 * bn.C + c;
+  nvl_poll_f64x2(*nvl, (unsigned int)ep, (int)(ep & 1ull), e, e + bn.C, s1, s2);
+}
+
+// The CTA that owns the write-back: global sums of passes [p0, p0 + np) from the packets into the buffer.
+__device__ __forceinline__ void bn_poll_writeback(const BnRef& bn, int p0, int np, const NvlDev* nvl) {
+  const int which = bn.poll & 15;
+  double* base = const_cast<double*>(which == 1 ? bn.fstats : bn.bstats);
+  const long long stride = which == 1 ? bn.sf : bn.sb;
+  for (int i = threadIdx.x; i < np * bn.C; i += blockDim.x) {
+    const int ps = p0 + i / bn.C, c = i % bn.C;
+    double s1, s2;
+    bn_stat2(bn, which, ps, c, nvl, s1, s2);
+    base[(long long)ps * stride + c] = s1;
+    base[(long long)ps * stride + bn.C + c] = s2;
+  }
+}
+
 __device__ __forceinline__ void bn_mean_rstd(const BnRef& bn, int pass, int c, float Bg, float eps, float& mean,
-                                             float& rstd, float& var_biased) {
+                                             float& rstd, float& var_biased, const NvlDev* poll = nullptr) {
   if (bn.eval) {
     mean = bn.rmean[c];
     var_biased = bn.rvar[c];
   } else {
-    const double* s = bn.fstats + (long long)pass * bn.sf;
     const double inv = 1.0 / (double)Bg;
-    double m = s[c] * inv;
-    double v = s[bn.C + c] * inv - m * m;
+    double s1, s2;
+    bn_stat2(bn, 1, pass, c, poll, s1, s2);
+    double m = s1 * inv;
+    double v = s2 * inv - m * m;
     if (v < 0.0) v = 0.0;
     mean = (float)m;
     var_biased = (float)v;
@@ -139,12 +180,13 @@ __device__ __forceinline__ void bn_mean_rstd(const BnRef& bn, int pass, int c, f
 
 // fills cs[] for an operand; all threads of the CTA participate; caller syncs afterwards
 template <int KIND>
-__device__ __forceinline__ void operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs) {
+__device__ __forceinline__ void operand_consts(const Operand& o, int pass, float Bg, float eps, float* cs,
+                                               const NvlDev* poll = nullptr) {
   if (KIND == OP_BN_ACT) {
     const int C = o.bn.C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float mean, rstd, var;
-      bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd, var);
+      bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd, var, poll);
       // y = (h - mean) * (gamma * rstd) + beta : the subtraction is exact-ish even when |mean| >> std
       cs[c] = o.bn.gamma[c] * rstd;
       cs[C + c] = o.bn.beta[c];
@@ -152,13 +194,14 @@ __device__ __forceinline__ void operand_consts(const Operand& o, int pass, float
     }
   } else if (KIND == OP_BN_BWD) {
     const int C = o.bn.C;
-    const double* bs = o.bn.bstats + (long long)pass * o.bn.sb;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float mean, rstd, var;
-      bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd, var);
+      double b1, b2;
+      bn_stat2(o.bn, 2, pass, c, poll, b1, b2);     // first: the sums that may still be in flight
+      bn_mean_rstd(o.bn, pass, c, Bg, eps, mean, rstd, var, poll);
       cs[c] = o.bn.gamma[c] * rstd;                 // c1
-      cs[C + c] = (float)(bs[c] / (double)Bg);      // c2 = dbeta / B
-      cs[2 * C + c] = (float)(bs[C + c] / (double)Bg);  // c3 = dgamma / B
+      cs[C + c] = (float)(b1 / (double)Bg);         // c2 = dbeta / B
+      cs[2 * C + c] = (float)(b2 / (double)Bg);     // c3 = dgamma / B
       cs[3 * C + c] = mean;
       cs[4 * C + c] = rstd;
     }
@@ -283,7 +326,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mn_kernel(const GemmArgs
   float* cs_e = dyn_smem + operand_const_floats(g.a);      // epilogue constants (EP_DBN: 4 * C)
 
   // ---- preamble: per-feature constants ---------------------------------------------------------
-  operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a);
+  // in-flight batch sums (data parallel): CTA (0,0,0) lands every pass in the buffer, the others read the packets
+  const NvlDev* poll_a = ((AK == OP_BN_ACT || AK == OP_BN_BWD) && g.a.bn.poll) ? g.nvl : nullptr;
+  if (poll_a && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    bn_poll_writeback(g.a.bn, 0, g.a.bn.poll >> 4, poll_a);
+    __syncthreads();
+    poll_a = nullptr;
+  }
+  operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a, poll_a);
   if (EK == EP_DBN) {
     const int C = g.prev_bn.C;
     for (int c = tid; c < C; c += GEMM_THREADS) {
@@ -550,6 +600,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mn_kernel(const GemmArgs
     klsum = warp_sum_d(klsum);
     if ((tid & 31) == 0) atomicAdd(g.kl_acc, klsum);
   }
+  if (g.push) nvl_push_stats_tail(*g.nvl, g.ostats, g.sostats, (int)gridDim.z, g.N, gridDim.x * gridDim.y * gridDim.z);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -572,8 +623,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_dw_kernel(const DwArgs g
   const int mbeg = split * g.rows_per_cta;
   const int mend = min(g.M, mbeg + g.rows_per_cta);
 
-  operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p);
-  operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q);
+  const NvlDev* poll_p = ((PK == OP_BN_ACT || PK == OP_BN_BWD) && g.p.bn.poll) ? g.nvl : nullptr;
+  const NvlDev* poll_q = ((QK == OP_BN_ACT || QK == OP_BN_BWD) && g.q.bn.poll) ? g.nvl : nullptr;
+  if ((poll_p || poll_q) && blockIdx.x == 0 && blockIdx.y == 0 && split == 0) {   // this pass's write-back CTA
+    if (poll_p) bn_poll_writeback(g.p.bn, pass, 1, poll_p);
+    if (poll_q) bn_poll_writeback(g.q.bn, pass, 1, poll_q);
+    __syncthreads();
+    poll_p = poll_q = nullptr;
+  }
+  operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p, poll_p);
+  operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q, poll_q);
   // BatchNorm affine gradients are exactly the backward batch sums (appendix A.2): dbeta = sum dy,
   // dgamma = sum dy*xhat.  One CTA per pass adds them to the gradient buffer.
   if (g.add_affine && g.dgamma && blockIdx.x == 0 && blockIdx.y == 0 && split == 0) {

@@ -255,6 +255,10 @@ static size_t carve(const Engine& e, Workspace& w, void* base) {
   w.mk_bar = c.take<unsigned int>(64);
   w.z_eps = c.take<float>((size_t)Z * ld);
   w.mk_dbg = c.take<long long>(2048 + 64);
+  w.hz = c.take<float>((size_t)HOIST_MAX * Z * ld);
+  for (int i = 0; i < 3; ++i) w.hh[i] = c.take<float>((size_t)HOIST_MAX * e.gh[i] * ld);
+  w.hout = c.take<float>((size_t)HOIST_MAX * F * ld);
+  w.hfst = c.take<double>((size_t)3 * HOIST_MAX * 2 * STAT_C);
   return c.off + 256;
 }
 

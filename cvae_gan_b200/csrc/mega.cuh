@@ -1046,7 +1046,7 @@ __device__ void fill_item(const FillArgs& a, int item) {
   const uint32_t keep_thr = (uint32_t)((double)a.keep_prob * 4294967296.0);
   const uint64_t seed = a.ctl ? __ldcg(&a.ctl->seed) : a.seed;
   const uint64_t counter = a.ctl ? __ldcg(&a.ctl->counter) + a.counter_off : a.counter;
-  // (batch row, feature group, pass) of an element; all counts fit 32 bits (rows <= max_batch, groups <= 256, passes <= 2)
+  // (batch row, feature group, pass) of an element; all counts fit 32 bits (rows <= max_batch, groups <= 256, passes <= HOIST_MAX)
   const unsigned uM = (unsigned)a.M, uMG = uM * (unsigned)ngroups;
   for (unsigned t = (unsigned)vb * THREADS + threadIdx.x; t < (unsigned)total; t += (unsigned)FILL_VB * THREADS) {
     const int pass = (int)(t / uMG);
@@ -1065,7 +1065,8 @@ __device__ void fill_item(const FillArgs& a, int item) {
         }
       }
     } else {
-      const U4 r = philox_at(seed, counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
+      const U4 r = j.cstep ? philox_at(seed, counter + (uint64_t)pass * j.cstep, (uint32_t)j.stream, 0u, a.row_base + (uint64_t)m, (uint32_t)fg)
+                           : philox_at(seed, counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
       if (j.kind == 0) {
         box_muller(r.x, r.y, vals[0], vals[1]);
         box_muller(r.z, r.w, vals[2], vals[3]);
@@ -1553,7 +1554,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
       case K_MN: {
         const GemmArgs& g = payload<GemmArgs>(sop);
         const float* wp;
-        memcpy(&wp, sop->payload + sizeof(GemmArgs), sizeof(float*));
+        memcpy(&wp, sop->payload + GEMM_ARGS_OP_BYTES, sizeof(float*));
         for (int it = i0; it < items; it += G) mn_item(c, g, wp, sop->aux[1] == 128 ? 7 : 6, it);
       } break;
       case K_DW: {
@@ -1692,7 +1693,7 @@ __global__ void __launch_bounds__(THREADS, 1) step_program_kernel(const __grid_c
   if (c.warp == 0) tmem_dealloc(c.tmem, TMEM_COLS);
 }
 
-static_assert(sizeof(GemmArgs) + sizeof(float*) <= OP_BYTES - 32, "GemmArgs does not fit an op record");
+static_assert(GEMM_ARGS_OP_BYTES + sizeof(float*) <= OP_BYTES - 32, "GemmArgs does not fit an op record");
 static_assert(sizeof(PrepArgs) <= OP_BYTES - 32, "PrepArgs does not fit an op record");
 static_assert(sizeof(DwArgs) + 2 * sizeof(float*) <= OP_BYTES - 32, "DwArgs does not fit an op record");
 static_assert(sizeof(FillArgs) <= OP_BYTES - 32, "FillArgs does not fit an op record");

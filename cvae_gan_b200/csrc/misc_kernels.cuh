@@ -482,6 +482,7 @@ struct FillJob {
   const void* injected;  // row-major [npass][M][nfeat] or null
   int kind;              // 0 normal float, 1 keep-mask uint8
   int nfeat, npass, stream;
+  int cstep;             // != 0: pass i is the single pass of the step `i * cstep` counter values ahead (hoisted draws)
 };
 struct FillArgs {
   FillJob job[6];
@@ -516,7 +517,8 @@ __global__ void fill_noise_kernel(const FillArgs a) {
         }
       }
     } else {
-      const U4 r = philox_at(seed, counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
+      const U4 r = j.cstep ? philox_at(seed, counter + (uint64_t)pass * j.cstep, (uint32_t)j.stream, 0u, a.row_base + (uint64_t)m, (uint32_t)fg)
+                           : philox_at(seed, counter, (uint32_t)j.stream, (uint32_t)pass, a.row_base + (uint64_t)m, (uint32_t)fg);
       if (j.kind == 0) {
         box_muller(r.x, r.y, vals[0], vals[1]);
         box_muller(r.z, r.w, vals[2], vals[3]);

@@ -109,6 +109,9 @@ int nvl_attach(Engine& e, const void* handles) {
     e.nvl.dev.peer[p] = (unsigned char*)ptr;
     e.nvl.opened[p] = true;
   }
+  CVG_CUDA(cudaMalloc(&e.nvl.dev_d, sizeof(NvlDev)));
+  CVG_CUDA(cudaMemcpy(e.nvl.dev_d, &e.nvl.dev, sizeof(NvlDev), cudaMemcpyHostToDevice));
+  if (const char* f = getenv("CVG_FUSE_STATS")) e.nvl.fuse = atoi(f) != 0;
   e.nvl.on = true;
   return 0;
 }
@@ -117,6 +120,8 @@ void nvl_destroy(Engine& e) {
   for (int p = 0; p < NVL_MAX_WORLD; ++p)
     if (e.nvl.opened[p]) { cudaIpcCloseMemHandle(e.nvl.dev.peer[p]); e.nvl.opened[p] = false; }
   if (e.nvl.local) cudaFree(e.nvl.local);
+  if (e.nvl.dev_d) cudaFree(e.nvl.dev_d);
+  e.nvl.dev_d = nullptr;
   e.nvl.local = nullptr;
   e.nvl.on = false;
 }
@@ -132,6 +137,7 @@ static int nvl_all_reduce(Engine& e, T* p, int64_t seg_len, int64_t seg_stride, 
     if ((unsigned long long)n * sizeof(T) * 2 > e.nvl.dev.slot_bytes) CVG_FAIL("step program: exchange larger than the NVLink staging slot");
     return mk_push(e, sizeof(T) == 8 ? mk::K_NVL_F64 : mk::K_NVL_F32, &a, sizeof(a), mk::NVL_VB);
   }
+  if (e.nvl.n_pending) CVG_FAIL("internal: a folded BatchNorm exchange has no reader before the next exchange");
   int grid = (int)((n + NVL_THREADS - 1) / NVL_THREADS);     // one element per thread where possible
   if (grid < 1) grid = 1;
   if (grid > NVL_MAX_CTAS) grid = NVL_MAX_CTAS;
@@ -191,7 +197,25 @@ static void prof_end(Engine& e, cudaStream_t st) {
   cudaEventRecord(e.prof_recs.back().b, st);
 }
 
-int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
+// first reader of batch sums a producer pushed over NVLink (launch_mn_stats below): it polls the packets
+static bool take_pending(Engine& e, Operand& o) {
+  if (!e.nvl.n_pending || (o.kind != OP_BN_ACT && o.kind != OP_BN_BWD)) return false;
+  for (int i = 0; i < e.nvl.n_pending; ++i) {
+    const NvlPending pd = e.nvl.pending[i];
+    int which = 0;
+    if (pd.stats == o.bn.fstats) which = 1;
+    if (o.kind == OP_BN_BWD && pd.stats == o.bn.bstats) which = 2;
+    if (!which) continue;
+    o.bn.poll = which | (pd.npass << 4);
+    e.nvl.pending[i] = e.nvl.pending[--e.nvl.n_pending];
+    return true;
+  }
+  return false;
+}
+
+int launch_mn(Engine& e, bool wt, const GemmArgs& g_in, cudaStream_t st) {
+  GemmArgs g = g_in;
+  if (!e.mk.recording && take_pending(e, g.a)) g.nvl = e.nvl.dev_d;
   const int zp = g.only_pass >= 0 ? 1 : g.npass;
   if (e.mk.recording) {
     // 64-row tiles while they still fit one wave and a half of CTAs, 128-row tiles (full-rate MMAs) for larger batches
@@ -205,7 +229,7 @@ int launch_mn(Engine& e, bool wt, const GemmArgs& g, cudaStream_t st) {
     bool prepped_now = false;
     CVG_TRY(mk_weight_operand(e, g, wt, &wp, &prepped_now));   // may emit a prep op into the current phase ...
     e.mk.par_next = par && !prepped_now;                       // ... which this GEMM must then wait for
-    return mk_push(e, mk::K_MN, &g, sizeof(g), items, wt ? 1 : 0, Nt, 0, 0, &wp, sizeof(wp));
+    return mk_push(e, mk::K_MN, &g, GEMM_ARGS_OP_BYTES, items, wt ? 1 : 0, Nt, 0, 0, &wp, sizeof(wp));
   }
   dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN, zp);
   const size_t smem = gemm_mn_smem(g);
@@ -232,6 +256,8 @@ int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
   rows = ((rows + DW_MC - 1) / DW_MC) * DW_MC;
   nsplit = (g.M + rows - 1) / rows;
   g.rows_per_cta = rows;
+  if (take_pending(e, g.p)) g.nvl = e.nvl.dev_d;
+  if (take_pending(e, g.q)) g.nvl = e.nvl.dev_d;
   dim3 grid(kt, nt, g.npass * nsplit);
   prof_begin(e, 2, 2.0 * g.M * (double)g.N * g.K * g.npass, st);
   const cudaError_t err = dispatch_dw(g, nsplit, grid, gemm_dw_smem(g), st);
@@ -297,6 +323,21 @@ static int sync_stats(Engine& e, double* p, int npass, int C, bool local_bn, cud
   return comm_all_reduce_stats(e, p, npass, C, st);
 }
 
+// Data parallel BatchNorm sums without a launch of their own (comm_nvl.cuh): the producing GEMM pushes them from its
+// last CTA (g.push), the first GEMM that reads them polls (BnRef::poll, set by take_pending at its launch).
+static bool fold_stats(const Engine& e, bool local_bn) {
+  return e.world > 1 && !local_bn && e.nvl.on && e.nvl.fuse && e.nvl.dev_d && !e.mk.recording;
+}
+static int launch_mn_stats(Engine& e, bool wt, GemmArgs& g, int npass_sync, bool local_bn, cudaStream_t st) {
+  const bool fold = fold_stats(e, local_bn) && g.only_pass <= 0;
+  if (fold) { g.push = 1; g.nvl = e.nvl.dev_d; }
+  CVG_TRY(launch_mn(e, wt, g, st));
+  if (!fold) return sync_stats(e, g.ostats, npass_sync, g.N, local_bn, st);
+  if (e.nvl.n_pending >= 4) CVG_FAIL("internal: too many folded exchanges in flight");
+  e.nvl.pending[e.nvl.n_pending++] = NvlPending{g.ostats, g.only_pass >= 0 ? 1 : g.npass};
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // noise + inputs
 // ------------------------------------------------------------------------------------------------
@@ -324,6 +365,7 @@ static void add_job(FillArgs& a, void* out, const void* inj, int kind, int nfeat
   j.nfeat = nfeat;
   j.npass = npass;
   j.stream = stream;
+  j.cstep = 0;
 }
 
 static int emit_zero(Engine& e, void* p, size_t bytes, cudaStream_t st) {
@@ -360,10 +402,17 @@ static int stage_x(Engine& e, const float* x_real, int M, cudaStream_t st) {
 // forward passes
 // ------------------------------------------------------------------------------------------------
 int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int label, int M, float Bg, bool local_bn,
-                  cudaStream_t st) {
+                  cudaStream_t st, const GenBufs* gb) {
   const int net = CVG_NET_GENERATOR;
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
+  GenBufs b;
+  if (gb) {
+    b = *gb;
+  } else {
+    b.z = w.z; b.out = w.g_out;
+    for (int l = 0; l < 3; ++l) { b.h[l] = w.g_h[l]; b.fst[l] = fst_of(e, net, l); }
+  }
   for (int l = 0; l < 4; ++l) {
     const LinearP& p = lin(e, net, l);
     GemmArgs g = base_args(e, M, Bg, npass);
@@ -372,7 +421,7 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
     if (l == 0) {
       g.a.kind = (reparam_pass0 && !e.mk.recording) ? OP_REPARAM : OP_PLAIN;
       g.a.rows = e.Z;
-      g.a.p = w.z;
+      g.a.p = b.z;
       g.a.sp = (long long)e.Z * ld;
       g.a.mu = w.e_ml;
       g.a.lv = w.e_ml + (size_t)e.Z * ld;
@@ -383,27 +432,31 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
     } else {
       g.a.kind = OP_BN_ACT;
       g.a.rows = p.in;
-      g.a.p = w.g_h[l - 1];
+      g.a.p = b.h[l - 1];
       g.a.sp = (long long)p.in * ld;
       g.a.bn = bn_ref(e, net, l - 1, !train, true);
+      g.a.bn.fstats = b.fst[l - 1];
     }
     g.W = e.P(net, p.w);
     g.ldw = p.in;
     g.bias = e.P(net, p.b);
     if (l < 3) {
-      g.Y = w.g_h[l];
+      g.Y = b.h[l];
       g.sY = (long long)p.out * ld;
       if (train) {
-        g.ostats = fst_of(e, net, l);
+        g.ostats = b.fst[l];
         g.sostats = 2 * STAT_C;
       }
     } else {
       g.act = ACT_SIGMOID;
-      g.Y = w.g_out;
+      g.Y = b.out;
       g.sY = (long long)e.F * ld;
     }
-    CVG_TRY(launch_mn(e, true, g, st));
-    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 2, p.out, local_bn, st));
+    if (l < 3 && train) {
+      CVG_TRY(launch_mn_stats(e, true, g, npass > 2 ? npass : 2, local_bn, st));
+    } else {
+      CVG_TRY(launch_mn(e, true, g, st));
+    }
   }
   return 0;
 }
@@ -444,8 +497,11 @@ int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn
         g.kl_split = e.Z;
       }
     }
-    CVG_TRY(launch_mn(e, true, g, st));
-    if (l < 3 && train) CVG_TRY(sync_stats(e, fst_of(e, net, l), 1, p.out, local_bn, st));
+    if (l < 3 && train) {
+      CVG_TRY(launch_mn_stats(e, true, g, 1, local_bn, st));
+    } else {
+      CVG_TRY(launch_mn(e, true, g, st));
+    }
   }
   return 0;
 }
@@ -778,8 +834,7 @@ static int bwd_bn_net(Engine& e, const BnNetBwd& b, int M, float Bg_bn, float kl
       g.sY = (long long)pp.out * ld;
       g.ostats = bst_of(e, net, l - 1);
       g.sostats = 2 * STAT_C;
-      CVG_TRY(launch_mn(e, false, g, st));
-      CVG_TRY(sync_stats(e, bst_of(e, net, l - 1), b.npass, pp.out, local_bn, st));
+      CVG_TRY(launch_mn_stats(e, false, g, b.npass, local_bn, st));
     } else if (b.want_first_dx) {
       GemmArgs g = base_args(e, M, Bg_bn, b.npass);
       g.only_pass = 0;
@@ -946,6 +1001,7 @@ struct ProgramScope {
 };
 
 static int begin_step(Engine& e, const StepRng& rng, bool with_lambda, cudaStream_t st) {
+  e.nvl.n_pending = 0;
   e.mk.scratch_off = 0;      // the previous step's weight-gradient slices were reduced before its last barrier
   if (!rng.set) return 0;
   if (e.mk.recording) {
@@ -1032,7 +1088,7 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_TRY(prep_net(e, D, true, true, false));
   FillArgs f;
   fill_args(e, f, rng, B);
-  add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
+  if (!e.hoist_x) add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
   add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 2, RS_DMASK1);
   add_job(f, w.d_m2, nz ? nz->d_mask2 : nullptr, 1, e.dh[1], 2, RS_DMASK2);
   CVG_PAR(e);
@@ -1042,8 +1098,8 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_PAR(e);                           // the power iterations only touch the critic's weights and u / v: first phase
   CVG_TRY(launch_sn(e, 2, true, st));   // D(real) then D(fake): two consecutive power iterations
   // G(z) under no_grad, still in train mode: batch stats, running stats updated (cvae_gan.py:113-115)
-  CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
-  const long long sx = w.g_out - w.xT;  // pass 0 reads xT, pass 1 reads g_out (pass slot 0)
+  if (!e.hoist_x) CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  const long long sx = (e.hoist_x ? e.hoist_x : w.g_out) - w.xT;  // pass 0 reads xT, pass 1 reads G(z)
   CVG_TRY(fwd_critic(e, w.xT, sx, 2, label, B, w.loss + L_DREAL, st));
   const float seedv[2] = {-1.0f / Bg, 1.0f / Bg};   // d_loss = -mean D(real) + mean D(fake)
   CVG_TRY(bwd_critic(e, w.xT, sx, 2, label, B, seedv, true, false, st));
@@ -1101,15 +1157,15 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_TRY(prep_net(e, C, true, true, false));
   FillArgs f;
   fill_args(e, f, rng, B);
-  add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
+  if (!e.hoist_x) add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
   add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 2, RS_CMASK1);
   add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 2, RS_CMASK2);
   CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
   CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, st));
-  CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
-  const long long sx = w.g_out - w.xT;
+  if (!e.hoist_x) CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  const long long sx = (e.hoist_x ? e.hoist_x : w.g_out) - w.xT;
   CVG_TRY(fwd_classifier(e, w.xT, sx, 2, true, B, st));
   CeArgs c;
   c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 2; c.label = label;
@@ -1275,6 +1331,35 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
 // counter, Adam step counts, lambda_class) is read from the device control block, so the sequence can be
 // captured into a CUDA graph once per (label, lambda_class != 0) and replayed.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// The generator's parameters do not change during the critic and classifier steps of a visit (cvae_gan.py:104-157 only
+// step D's and C's optimisers), so G(z) of all d_loop + c_loop of them is one forward with one pass per step, run before
+// the first step: 4 launches and 3 BatchNorm exchanges instead of 4 and 3 per step.  Each pass has its own batch sums and
+// its z comes from the step's own Philox counter (two values per step: draw, noise), so the values are the ones the
+// steps would have computed; the running statistics take the passes' updates in step order (appendix A.2).
+// ------------------------------------------------------------------------------------------------
+static int hoist_generator(Engine& e, int nh, int label, int B, int flags, cudaStream_t st) {
+  const Workspace& w = e.ws;
+  const bool local_bn = flags & CVG_STEP_LOCAL_BN;
+  const float Bg_bn = local_bn ? (float)B : (float)B * (float)e.world;
+  StepRng rng;
+  rng.set = false;
+  rng.off = 1;
+  if (e.mk.recording) e.mk.par_next = false;
+  CVG_TRY(emit_zero(e, w.hfst, sizeof(double) * 3 * HOIST_MAX * 2 * STAT_C, st));
+  CVG_TRY(prep_net(e, CVG_NET_GENERATOR, true, false, false));
+  FillArgs f;
+  fill_args(e, f, rng, B);
+  add_job(f, w.hz, nullptr, 0, e.Z, nh, RS_Z);
+  f.job[0].cstep = 2;
+  CVG_PAR(e);
+  CVG_TRY(launch_fill(e, f, st));
+  GenBufs b;
+  b.z = w.hz; b.out = w.hout;
+  for (int l = 0; l < 3; ++l) { b.h[l] = w.hh[l]; b.fst[l] = w.hfst + (size_t)l * HOIST_MAX * 2 * STAT_C; }
+  return fwd_generator(e, nh, true, false, label, B, Bg_bn, local_bn, st, &b);
+}
+
 int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows, int64_t n_rows, const float* x_batches,
           int d_loop, int c_loop, int g_loop, int flags, float* loss_out, cudaStream_t st) {
   CVG_TRY(check_step(e, B));
@@ -1282,10 +1367,13 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
   if (B_global != (int64_t)B * e.world) CVG_FAIL("cvg_visit: B_global must be B_local * world_size");
   // step-program kernel: the whole visit is ONE program = one launch (batch draws included)
   ProgramScope prog(e);
+  const int nh = e.hoist ? (d_loop + c_loop < HOIST_MAX ? d_loop + c_loop : HOIST_MAX) : 0;
+  if (nh > 0) CVG_TRY(hoist_generator(e, nh, label, B, flags, st));
   int i = 0;
   for (int kind = 0; kind < 3; ++kind) {
     const int reps = kind == 0 ? d_loop : (kind == 1 ? c_loop : g_loop);
     for (int r = 0; r < reps; ++r, ++i) {
+      e.hoist_x = (kind < 2 && i < nh) ? e.ws.hout + (size_t)i * e.F * e.ws.ld : nullptr;
       const float* x = nullptr;
       if (x_batches) {
         x = x_batches + (size_t)i * B * e.F;
@@ -1308,6 +1396,7 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       else if (kind == 1) CVG_TRY(step_c(e, x, label, B, nullptr, rng, sf, lo, st));
       else CVG_TRY(step_g(e, x, label, B, nullptr, rng, sf, lo, st));
       e.mk.src_rows = nullptr;
+      e.hoist_x = nullptr;
       if (e.mk.recording) {
         e.mk.dcounter += 2;                                    // applied once by the program's finish op
       } else {
