@@ -107,12 +107,29 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
     delete h;
     return 1;
   }
+  {
+    SideStreams& ms = h->e.ms;
+    const char* off = getenv("CVG_STREAMS");
+    ms.on = !(off && off[0] == '0');
+    bool ok = true;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&ms.s[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreateWithFlags(&ms.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      cvg::set_error("creating the side streams failed");
+      cvg_destroy(h);
+      return 1;
+    }
+  }
   *out = h;
   return 0;
 }
 
 void cvg_destroy(CvgHandle* h) {
   if (!h) return;
+  for (int i = 0; i < 2; ++i)
+    if (h->e.ms.s[i]) cudaStreamDestroy(h->e.ms.s[i]);
+  for (int i = 0; i < 8; ++i)
+    if (h->e.ms.ev[i]) cudaEventDestroy(h->e.ms.ev[i]);
   nvl_destroy(h->e);
   comm_destroy(h->e);
   mk_destroy(h->e);
@@ -474,6 +491,7 @@ int cvg_debug_set(CvgHandle* h, const char* key, int value) {
   else if (k == "mk_allbar") e.mk.allbar = value != 0;
   else if (k == "mk_coop") e.mk.coop = value != 0;
   else if (k == "hoist") e.hoist = value != 0;
+  else if (k == "streams") e.ms.on = value != 0;
   else if (k == "fuse_stats") e.nvl.fuse = value != 0;
   else CVG_FAIL("cvg_debug_set: unknown key");
   return 0;

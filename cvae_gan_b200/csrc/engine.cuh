@@ -137,6 +137,18 @@ struct ProfRec {
   double flops;
 };
 
+// Two extra streams beside the caller's: the stand-alone layer kernels are latency bound at the benchmarked sizes, so
+// independent ones (weight gradients beside the input-gradient chain, the critic's power iteration and the batch staging
+// beside the noise fill, C beside D in the E/G step) run concurrently.  Fork / join with events, so the work stays
+// capturable in the caller's CUDA graph and ordered with the caller's stream.
+struct SideStreams {
+  bool on = false;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t ev[8] = {};
+  unsigned next = 0;
+  bool dirty[2] = {false, false};
+};
+
 struct Engine {
   bool prof = false;
   std::vector<ProfRec> prof_recs;
@@ -150,6 +162,7 @@ struct Engine {
   int64_t ws_bytes = 0;
   int64_t launches = 0;
   const float* hoist_x = nullptr;   // visit(): G(z) of the step being emitted, computed up front (null: the step runs G)
+  SideStreams ms;
   int hoist = 1;                    // CVG_HOIST=0: every step runs its own generator forward
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;

@@ -341,6 +341,26 @@ static int launch_mn_stats(Engine& e, bool wt, GemmArgs& g, int npass_sync, bool
 // ------------------------------------------------------------------------------------------------
 // noise + inputs
 // ------------------------------------------------------------------------------------------------
+// side stream `i`, ordered after everything enqueued on `st` so far (SideStreams, engine.cuh)
+static cudaStream_t fork_to(Engine& e, int i, cudaStream_t st) {
+  if (!e.ms.on || e.mk.recording) return st;
+  cudaEvent_t ev = e.ms.ev[e.ms.next++ & 7];
+  cudaEventRecord(ev, st);
+  cudaStreamWaitEvent(e.ms.s[i], ev, 0);
+  e.ms.dirty[i] = true;
+  return e.ms.s[i];
+}
+// `st` continues after everything enqueued on the side streams
+static void join_sides(Engine& e, cudaStream_t st, int only = -1) {
+  for (int i = 0; i < 2; ++i) {
+    if (!e.ms.dirty[i] || (only >= 0 && only != i)) continue;
+    cudaEvent_t ev = e.ms.ev[e.ms.next++ & 7];
+    cudaEventRecord(ev, e.ms.s[i]);
+    cudaStreamWaitEvent(st, ev, 0);
+    e.ms.dirty[i] = false;
+  }
+}
+
 static int launch_fill(Engine& e, FillArgs& a, cudaStream_t st) {
   if (a.njobs == 0) return 0;
   if (e.mk.recording) return mk_push(e, mk::K_FILL, &a, sizeof(a), a.njobs * mk::FILL_VB);
@@ -654,6 +674,7 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
     if (want_dw) {
       // OP_CONST carries one value: run the two passes of layer 4 as separate launches
       const int reps = (l == 3 && npass > 1) ? npass : 1;
+      const cudaStream_t sw = fork_to(e, 0, st);      // beside the input-gradient chain: both only read dY of layer l
       for (int r = 0; r < reps; ++r) {
         if (r > 0) CVG_PAR(e);
         DwArgs d = base_dw(e, M, (float)M, reps > 1 ? 1 : npass);
@@ -670,7 +691,7 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
         d.ldw = p.in;
         d.db = (l == 3) ? nullptr : e.G(net, p.b);   // score-bias gradient is added analytically (sn_grad_kernel)
         d.label_col = (l == 0) ? e.F + label : -1;
-        CVG_TRY(launch_dw(e, d, st));
+        CVG_TRY(launch_dw(e, d, sw));
       }
     }
     if (l == 0 && !want_dx) break;
@@ -713,8 +734,9 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
 }
 
 // classifier backward from ws.c_dlogit.
+// dx_after: a stream whose enqueued work writes ws.dx first (the critic's backward, when this one runs beside it).
 static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass, int M, bool want_dw, bool want_dx,
-                          bool dx_accumulate, cudaStream_t st) {
+                          bool dx_accumulate, cudaStream_t st, cudaStream_t dx_after = nullptr) {
   const int net = CVG_NET_CLASSIFIER;
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
@@ -741,9 +763,14 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       d.sdW = 0;
       d.ldw = p.in;
       d.db = e.G(net, p.b);
-      CVG_TRY(launch_dw(e, d, st));
+      CVG_TRY(launch_dw(e, d, fork_to(e, 0, st)));
     }
     if (l == 0 && !want_dx) break;
+    if (l == 0 && dx_after && dx_after != st) {
+      cudaEvent_t ev = e.ms.ev[e.ms.next++ & 7];
+      cudaEventRecord(ev, dx_after);
+      cudaStreamWaitEvent(st, ev, 0);
+    }
     GemmArgs g = base_args(e, M, (float)M, npass);
     g.R = p.out;
     g.N = p.in;
@@ -879,7 +906,7 @@ static int bwd_bn_net(Engine& e, const BnNetBwd& b, int M, float Bg_bn, float kl
       // gradient all-reduce (sum).  With local BatchNorm every rank adds its own.
       d.add_affine = (e.world <= 1 || local_bn || e.rank == 0) ? 1 : 0;
     }
-    CVG_TRY(launch_dw(e, d, st));
+    CVG_TRY(launch_dw(e, d, fork_to(e, 0, st)));
   }
   return 0;
 }
@@ -938,6 +965,7 @@ static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, floa
   for (int net = 0; net < 4; ++net)
     if (net_mask & (1 << net)) { first = net; break; }
   float* tail = e.buf[first].grads + e.lay[first].n_param;
+  join_sides(e, st);
   if (e.mk.recording) {
     const bool had_red = !e.mk.pending_red.empty();
     CVG_TRY(mk_emit_dwred(e));                 // deterministic sums of the weight-gradient row slices
@@ -1094,15 +1122,17 @@ int step_d(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
   CVG_PAR(e);
-  CVG_TRY(stage_x(e, x_real, B, st));
+  CVG_TRY(stage_x(e, x_real, B, fork_to(e, 1, st)));
   CVG_PAR(e);                           // the power iterations only touch the critic's weights and u / v: first phase
-  CVG_TRY(launch_sn(e, 2, true, st));   // D(real) then D(fake): two consecutive power iterations
+  CVG_TRY(launch_sn(e, 2, true, fork_to(e, 0, st)));   // D(real) then D(fake): two consecutive power iterations
   // G(z) under no_grad, still in train mode: batch stats, running stats updated (cvae_gan.py:113-115)
   if (!e.hoist_x) CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  join_sides(e, st);
   const long long sx = (e.hoist_x ? e.hoist_x : w.g_out) - w.xT;  // pass 0 reads xT, pass 1 reads G(z)
   CVG_TRY(fwd_critic(e, w.xT, sx, 2, label, B, w.loss + L_DREAL, st));
   const float seedv[2] = {-1.0f / Bg, 1.0f / Bg};   // d_loss = -mean D(real) + mean D(fake)
   CVG_TRY(bwd_critic(e, w.xT, sx, 2, label, B, seedv, true, false, st));
+  join_sides(e, st);
   {
     SnGradArgs a;
     int off = 0;
@@ -1163,8 +1193,9 @@ int step_c(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
   CVG_PAR(e);
-  CVG_TRY(stage_x(e, x_real, B, st));
+  CVG_TRY(stage_x(e, x_real, B, fork_to(e, 1, st)));
   if (!e.hoist_x) CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  join_sides(e, st);
   const long long sx = (e.hoist_x ? e.hoist_x : w.g_out) - w.xT;
   CVG_TRY(fwd_classifier(e, w.xT, sx, 2, true, B, st));
   CeArgs c;
@@ -1252,11 +1283,12 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
   CVG_PAR(e);
-  CVG_TRY(stage_x(e, x_real, B, st));
+  CVG_TRY(stage_x(e, x_real, B, fork_to(e, 1, st)));
 
   CVG_PAR(e);
-  CVG_TRY(launch_sn(e, 1, true, st));   // critic power iteration: independent of everything before D(x_fake)
+  CVG_TRY(launch_sn(e, 1, true, fork_to(e, 0, st)));   // critic power iteration: independent of everything before D(x_fake)
   // forward: E -> (mu, logvar); G on z_enc (pass 0) and z_prior (pass 1); D and C on x_fake
+  join_sides(e, st, 1);
   CVG_TRY(fwd_encoder(e, true, label, B, Bg_bn, local_bn, st));
   if (e.mk.recording) {
     mk::ReparamArgs ra;
@@ -1265,8 +1297,11 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   }
   CVG_TRY(fwd_generator(e, 2, true, true, label, B, Bg_bn, local_bn, st));
   const float* x_fake = w.g_out + (size_t)e.F * ld;
+  join_sides(e, st);
+  // the classifier branch (forward, loss, backward to x_fake) runs beside the critic's; they meet at ws.dx
+  const cudaStream_t sc = rng.lambda_nonzero ? fork_to(e, 1, st) : st;
   CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, st));
-  CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, st));
+  CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, sc));
   CeArgs c;
   c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
   c.logits = w.c_logit; c.sl = (long long)e.K * ld;
@@ -1274,12 +1309,13 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
   c.ctl = w.ctl;
   c.loss = w.loss + L_CE0;
-  CVG_TRY(emit_ce(e, c, B, 1, st));
+  CVG_TRY(emit_ce(e, c, B, 1, sc));
 
   // backward to x_fake: adv = -mean D(x_fake) (cvae_gan.py:189), then the classification term
   const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
   CVG_TRY(bwd_critic(e, x_fake, 0, 1, label, B, seedv, false, true, st));
-  if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, st));
+  if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, sc, st));
+  join_sides(e, st);
 
   // generator output gradients: recon MSE on pass 0, dx on pass 1, through the sigmoid
   SeedArgs s;
@@ -1381,8 +1417,8 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
         e.mk.src_rows = class_rows; e.mk.src_n = n_rows; e.mk.src_Bg = B_global; e.mk.src_off = (long long)e.rank * B;
         x = class_rows;
       } else {
-        sample_rows_kernel<<<(B + 127) / 128, 128, 0, st>>>(class_rows, n_rows, B_global, (long long)e.rank * B, B, e.F,
-                                                           0, 0, e.ws.ctl, 0, e.ws.x_stage, nullptr);
+        sample_rows_kernel<<<(B + 127) / 128, 128, 0, fork_to(e, 1, st)>>>(class_rows, n_rows, B_global, (long long)e.rank * B,
+                                                                            B, e.F, 0, 0, e.ws.ctl, 0, e.ws.x_stage, nullptr);
         CVG_LAUNCH_CHECK();
         x = e.ws.x_stage;
       }
