@@ -163,6 +163,7 @@ struct Engine {
   int64_t launches = 0;
   const float* hoist_x = nullptr;   // visit(): G(z) of the step being emitted, computed up front (null: the step runs G)
   SideStreams ms;
+  unsigned long long step_dcounter = 0;   // visit(): Philox counter values the step being emitted uses (advanced at its end)
   int hoist = 1;                    // CVG_HOIST=0: every step runs its own generator forward
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0;
@@ -207,7 +208,7 @@ void set_all_kernel_attributes();
 struct AdamOverride {
   float lr, beta1, beta2, eps;
 };
-int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov = nullptr);
+int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov = nullptr, bool steps_advanced = false);
 int step_classifier(Engine& e, const float* x, const long long* labels, int B, const CvgNoise* noise, const StepRng& rng,
                     const AdamOverride& ov, int flags, float* loss_out, cudaStream_t st);
 int nvl_local_handle(Engine& e, void* out64);

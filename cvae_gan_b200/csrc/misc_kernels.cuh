@@ -420,6 +420,7 @@ struct AdamArgs {
   int nseg;
   float b1, b2, eps;
   int clear_grad;
+  int t_add = 1;               // 0: the step counters were already advanced (loss_tail_kernel)
 };
 
 __global__ void adam_kernel(const AdamArgs a) {
@@ -427,7 +428,7 @@ __global__ void adam_kernel(const AdamArgs a) {
   // bias corrections in double like torch's Python scalars: step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t)
   __shared__ float sh[2];
   if (threadIdx.x == 0) {
-    const double t = (double)(*s.t_prev + 1);
+    const double t = (double)(*s.t_prev + a.t_add);
     sh[0] = (float)((double)s.lr / (1.0 - pow((double)a.b1, t)));
     sh[1] = (float)sqrt(1.0 - pow((double)a.b2, t));
   }
@@ -452,6 +453,35 @@ __global__ void adam_kernel(const AdamArgs a) {
 // parallel all-reduce sums them with the gradients) -> loss_out after the reduction.
 __global__ void pack_loss_kernel(const double* acc, float* tail) {
   if (threadIdx.x < L_COUNT) tail[threadIdx.x] = (float)acc[threadIdx.x];
+}
+// End of a step in one launch: pack; on one GPU (unpack != 0) also the unpack below; and the control block's bookkeeping -
+// the Philox counter moves on by `dcounter`, Adam's state['step'] of the networks in `adam_mask` by one (the Adam launch
+// that follows runs with t_add = 0).
+__global__ void loss_tail_kernel(const double* acc, float* tail, float* out, int kind, float Bg, float F, int unpack,
+                                 StepCtl* c, unsigned long long dcounter, int adam_mask) {
+  __shared__ float t[L_COUNT];
+  if (threadIdx.x < L_COUNT) t[threadIdx.x] = (float)acc[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < L_COUNT && !unpack) tail[threadIdx.x] = t[threadIdx.x];
+  if (threadIdx.x == 0) {
+    if (unpack && out) {
+      if (kind == 0) {
+        const float r = t[L_DREAL] / Bg, f = t[L_DFAKE] / Bg;
+        out[0] = -r + f; out[1] = r; out[2] = f; out[3] = 0.f;
+      } else if (kind == 1) {
+        const float r = t[L_CE0] / Bg, f = t[L_CE1] / Bg;
+        out[0] = r + f; out[1] = r; out[2] = f; out[3] = 0.f;
+      } else {
+        out[0] = t[L_RECON] / (Bg * F);
+        out[1] = t[L_KL] / Bg;
+        out[2] = -t[L_DFAKE] / Bg;
+        out[3] = t[L_CE0] / Bg;
+      }
+    }
+    c->counter += dcounter;
+    for (int n = 0; n < 4; ++n)
+      if (adam_mask & (1 << n)) c->adam_t[n] += 1;
+  }
 }
 // kind 0: step_d, 1: step_c, 2: step_g
 __global__ void unpack_loss_kernel(const float* tail, float* out, int kind, float Bg, float F, int clear, float* tail_w) {

@@ -920,7 +920,7 @@ static float net_lr(const Engine& e, int net) {
   return e.cfg.g_lr;
 }
 
-int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov) {
+int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov, bool steps_advanced) {
   AdamArgs a;
   a.nseg = 0;
   a.b1 = ov ? ov->beta1 : e.cfg.adam_beta1;
@@ -951,10 +951,13 @@ int run_adam(Engine& e, int net_mask, cudaStream_t st, const AdamOverride* ov) {
   }
   int blocks = (int)((nmax + 255) / 256);
   if (blocks > 2 * e.num_sms) blocks = 2 * e.num_sms;
+  a.t_add = steps_advanced ? 0 : 1;
   adam_kernel<<<dim3(blocks, a.nseg), 256, 0, st>>>(a);
   CVG_LAUNCH_CHECK();
-  ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 0ull, net_mask);   // state['step'] += 1
-  CVG_LAUNCH_CHECK();
+  if (!steps_advanced) {
+    ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 0ull, net_mask);   // state['step'] += 1
+    CVG_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -989,16 +992,23 @@ static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, floa
     }
     return 0;
   }
-  pack_loss_kernel<<<1, 32, 0, st>>>(e.ws.loss, tail);
+  // one launch: loss sums -> gradient tail (or, on one GPU, straight to loss_out), Philox counter and Adam step counters
+  const bool update = !(flags & CVG_STEP_NO_UPDATE);
+  const bool one = e.world <= 1;
+  loss_tail_kernel<<<1, 32, 0, st>>>(e.ws.loss, tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, one ? 1 : 0,
+                                     e.ws.ctl, e.step_dcounter, update ? net_mask : 0);
   CVG_LAUNCH_CHECK();
-  for (int net = 0; net < 4; ++net)
-    if (net_mask & (1 << net))
-      CVG_TRY(comm_all_reduce_f32(e, e.buf[net].grads, e.lay[net].n_param + (net == first ? CVG_GRAD_TAIL : 0), st));
-  if (loss_out) {
-    unpack_loss_kernel<<<1, 32, 0, st>>>(tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, 1, tail);
-    CVG_LAUNCH_CHECK();
+  e.step_dcounter = 0;
+  if (!one) {
+    for (int net = 0; net < 4; ++net)
+      if (net_mask & (1 << net))
+        CVG_TRY(comm_all_reduce_f32(e, e.buf[net].grads, e.lay[net].n_param + (net == first ? CVG_GRAD_TAIL : 0), st));
+    if (loss_out) {
+      unpack_loss_kernel<<<1, 32, 0, st>>>(tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, 1, tail);
+      CVG_LAUNCH_CHECK();
+    }
   }
-  if (!(flags & CVG_STEP_NO_UPDATE)) CVG_TRY(run_adam(e, net_mask, st, ov));
+  if (update) CVG_TRY(run_adam(e, net_mask, st, ov, true));
   return 0;
 }
 
@@ -1032,6 +1042,7 @@ static int begin_step(Engine& e, const StepRng& rng, bool with_lambda, cudaStrea
   e.nvl.n_pending = 0;
   e.mk.scratch_off = 0;      // the previous step's weight-gradient slices were reduced before its last barrier
   if (!rng.set) return 0;
+  e.step_dcounter = 0;       // a step called on its own sets the Philox counter itself
   if (e.mk.recording) {
     // the ops of this program take the Philox key / counter from their own arguments (fill_args); the control block is
     // still brought up to date for ops that read lambda_class from it and for later calls
@@ -1428,6 +1439,7 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       rng.lambda_nonzero = !(flags & CVG_VISIT_LAMBDA_ZERO);
       float* lo = loss_out ? loss_out + 4 * i : nullptr;
       const int sf = flags & (CVG_STEP_LOCAL_BN | CVG_STEP_NO_UPDATE);
+      if (!e.mk.recording) e.step_dcounter = 2;      // two counter values per step (draw + noise), advanced by the step's tail
       if (kind == 0) CVG_TRY(step_d(e, x, label, B, nullptr, rng, sf, lo, st));
       else if (kind == 1) CVG_TRY(step_c(e, x, label, B, nullptr, rng, sf, lo, st));
       else CVG_TRY(step_g(e, x, label, B, nullptr, rng, sf, lo, st));
@@ -1435,9 +1447,6 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       e.hoist_x = nullptr;
       if (e.mk.recording) {
         e.mk.dcounter += 2;                                    // applied once by the program's finish op
-      } else {
-        ctl_bump_kernel<<<1, 32, 0, st>>>(e.ws.ctl, 2ull, 0);    // two counter values per step: draw + noise
-        CVG_LAUNCH_CHECK();
       }
     }
   }
