@@ -113,7 +113,8 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
     ms.on = !(off && off[0] == '0');
     bool ok = true;
     for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&ms.s[i], cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreateWithFlags(&ms.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < SIDE_EVENTS && ok; ++i) ok = cudaEventCreateWithFlags(&ms.ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&ms.layer[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
       cvg::set_error("creating the side streams failed");
       cvg_destroy(h);
@@ -128,8 +129,10 @@ void cvg_destroy(CvgHandle* h) {
   if (!h) return;
   for (int i = 0; i < 2; ++i)
     if (h->e.ms.s[i]) cudaStreamDestroy(h->e.ms.s[i]);
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < SIDE_EVENTS; ++i)
     if (h->e.ms.ev[i]) cudaEventDestroy(h->e.ms.ev[i]);
+  for (int i = 0; i < 4; ++i)
+    if (h->e.ms.layer[i]) cudaEventDestroy(h->e.ms.layer[i]);
   nvl_destroy(h->e);
   comm_destroy(h->e);
   mk_destroy(h->e);

@@ -31,8 +31,8 @@ struct NvlDev {
 };
 
 struct NvlPending {                     // batch sums pushed by their producer, not yet taken up by a reader
-  const double* stats;
-  int npass;
+  const double* stats;                  // slot of the first pushed pass
+  int npass, pass0, channel;
 };
 
 struct NvlState {
@@ -41,9 +41,13 @@ struct NvlState {
   size_t total_bytes = 0;
   NvlDev dev{};
   bool opened[NVL_MAX_WORLD] = {};
-  NvlDev* dev_d = nullptr;              // device copy of `dev` for the kernels that fold the exchange in
+  // Channel 1: a second staging area with its own exchange numbering inside the same allocation, for the GEMM chain that
+  // runs on a side stream beside the caller's (exchange numbers are per stream order, so two streams need two channels).
+  NvlDev dev1{};
+  NvlDev* dev_d[2] = {nullptr, nullptr};   // device copies for the kernels that fold the exchange in
   bool fuse = true;                     // CVG_FUSE_STATS=0: BatchNorm sums go through nvl_allreduce_kernel launches
-  NvlPending pending[4];
+  bool via_lead = false;                // folded exchange: one CTA per pass polls for the launch (gemm.cuh bn_publish)
+  NvlPending pending[8];
   int n_pending = 0;
 };
 
@@ -76,68 +80,103 @@ __device__ __forceinline__ void ll_load(const unsigned char* p, unsigned int& wo
   asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(word), "=r"(ep) : "l"(p) : "memory");
 }
 
-// The vector is `nseg` segments of `seg_len` elements, `seg_stride` apart (BatchNorm moments live in per-pass slots of
-// 2 * STAT_C doubles of which only the first 2 C entries are used); a contiguous vector is one segment.
+// One exchange, the part every participating thread runs: elements first, first + step, ... of a vector of `nseg`
+// segments of `seg_len` elements, `seg_stride` apart (BatchNorm moments live in per-pass slots of 2 * STAT_C doubles of
+// which only the first 2 C entries are used; a contiguous vector is one segment).  U elements are in flight per thread:
+// their loads (push: the local values; poll: all `world` packets of each) are issued before the first one is used, so a
+// round of the loop costs one memory round trip whatever the world size.
 template <typename T>
-__global__ void __launch_bounds__(NVL_THREADS) nvl_allreduce_kernel(const NvlDev d, T* __restrict__ data, long long seg_len,
-                                                                    long long seg_stride, int nseg) {
+__device__ __forceinline__ void nvl_exchange(const NvlDev& d, T* __restrict__ data, long long seg_len, long long seg_stride,
+                                             int nseg, unsigned long long ep, long long first, long long step) {
   constexpr int W = sizeof(T) / 4;
-  __shared__ unsigned long long ep_s;
-  const int tid = threadIdx.x;
-  if (tid == 0) ep_s = *reinterpret_cast<volatile unsigned long long*>(d.epoch) + 1ull;
-  __syncthreads();
-  const unsigned long long ep = ep_s;
+  constexpr int U = 4 / W;                      // 4 floats or 2 doubles
   const unsigned int ep32 = (unsigned int)ep;
   const int par = (int)(ep & 1ull);
+  const int world = d.world;
   const long long n = seg_len * nseg;
-  const long long stride = (long long)gridDim.x * NVL_THREADS;
   // 1. my elements -> slot[par][rank] of every peer (self included), packed (no segment gaps)
-  for (long long e = (long long)blockIdx.x * NVL_THREADS + tid; e < n; e += stride) {
-    const long long sg = e / seg_len, off = e - sg * seg_len;
-    const T x = data[sg * seg_stride + off];
-    unsigned int w[W];
-    memcpy(w, &x, sizeof(T));
-    for (int p = 0; p < d.world; ++p) {
-      unsigned char* dst = d.peer[p] + nvl_slot_off(d, par, d.rank) + (unsigned long long)e * (W * 8);
+  for (long long e0 = first; e0 < n; e0 += U * step) {
+    T x[U];
 #pragma unroll
-      for (int k = 0; k < W; ++k) ll_store(dst + k * 8, w[k], ep32);
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * step;
+      if (e < n) {
+        const long long sg = e / seg_len, off = e - sg * seg_len;
+        x[u] = __ldcg(data + sg * seg_stride + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * step;
+      if (e < n) {
+        unsigned int w[W];
+        memcpy(w, &x[u], sizeof(T));
+        for (int p = 0; p < world; ++p) {
+          unsigned char* dst = d.peer[p] + nvl_slot_off(d, par, d.rank) + (unsigned long long)e * (W * 8);
+#pragma unroll
+          for (int k = 0; k < W; ++k) ll_store(dst + k * 8, w[k], ep32);
+        }
+      }
     }
   }
   // 2. poll the packets of every source and sum IN RANK ORDER (identical on every rank)
   const unsigned char* base = d.peer[d.rank];
   const long long t0 = clock64();
-  for (long long e = (long long)blockIdx.x * NVL_THREADS + tid; e < n; e += stride) {
-    unsigned int w[NVL_MAX_WORLD][W];
-    unsigned int pending = (1u << d.world) - 1u;
-    while (pending) {
+  for (long long e0 = first; e0 < n; e0 += U * step) {
+    unsigned int w[U][NVL_MAX_WORLD][W];
+    for (;;) {
+      bool ok = true;
 #pragma unroll
-      for (int q = 0; q < NVL_MAX_WORLD; ++q) {
-        if (q < d.world && ((pending >> q) & 1u)) {
-          const unsigned char* src = base + nvl_slot_off(d, par, q) + (unsigned long long)e * (W * 8);
-          bool ok = true;
+      for (int u = 0; u < U; ++u) {
+        const long long e = e0 + u * step;
+        if (e < n) {
 #pragma unroll
-          for (int k = 0; k < W; ++k) {
-            unsigned int f;
-            ll_load(src + k * 8, w[q][k], f);
-            ok &= (f == ep32);
+          for (int q = 0; q < NVL_MAX_WORLD; ++q) {
+            if (q < world) {
+              const unsigned char* src = base + nvl_slot_off(d, par, q) + (unsigned long long)e * (W * 8);
+#pragma unroll
+              for (int k = 0; k < W; ++k) {
+                unsigned int f;
+                ll_load(src + k * 8, w[u][q][k], f);
+                ok = ok && (f == ep32);
+              }
+            }
           }
-          if (ok) pending &= ~(1u << q);
         }
       }
-      if (pending && clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never arrived
+      if (ok) break;
+      if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer never arrived
     }
-    T s = 0;
 #pragma unroll
-    for (int q = 0; q < NVL_MAX_WORLD; ++q) {
-      if (q < d.world) {
-        T x;
-        memcpy(&x, w[q], sizeof(T));
-        s += x;
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * step;
+      if (e < n) {
+        T s = 0;
+#pragma unroll
+        for (int q = 0; q < NVL_MAX_WORLD; ++q) {
+          if (q < world) {
+            T x;
+            memcpy(&x, w[u][q], sizeof(T));
+            s += x;
+          }
+        }
+        const long long sg = e / seg_len, off = e - sg * seg_len;
+        data[sg * seg_stride + off] = s;
       }
     }
-    const long long sg = e / seg_len, off = e - sg * seg_len;
-    data[sg * seg_stride + off] = s;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NVL_THREADS) nvl_allreduce_kernel(const NvlDev d, T* __restrict__ data, long long seg_len,
+                                                                    long long seg_stride, int nseg) {
+  __shared__ unsigned long long ep_s;
+  const int tid = threadIdx.x;
+  if (tid == 0) ep_s = *reinterpret_cast<volatile unsigned long long*>(d.epoch) + 1ull;
+  __syncthreads();
+  const unsigned long long ep = ep_s;
+  nvl_exchange<T>(d, data, seg_len, seg_stride, nseg, ep, (long long)blockIdx.x * NVL_THREADS + tid,
+                  (long long)gridDim.x * NVL_THREADS);
   // 3. the last CTA of the launch completes the exchange
   __syncthreads();
   if (tid == 0) {
@@ -202,6 +241,7 @@ __device__ __forceinline__ void nvl_poll_f64x2(const NvlDev& d, unsigned int ep3
 
 // Called by EVERY thread of EVERY CTA as the last statement of a kernel that accumulated `npass` slots of 2 C doubles
 // (`stride` doubles apart) into `stats` with atomics.  stats[stride - 1] receives the exchange number for the reader.
+// `stats` = slot of the first pass of the launch.
 __device__ __forceinline__ void nvl_push_stats_tail(const NvlDev& d, double* stats, long long stride, int npass, int C,
                                                     unsigned int total_ctas) {
   __shared__ unsigned int s_last;

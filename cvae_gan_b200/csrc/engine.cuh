@@ -141,10 +141,12 @@ struct ProfRec {
 // independent ones (weight gradients beside the input-gradient chain, the critic's power iteration and the batch staging
 // beside the noise fill, C beside D in the E/G step) run concurrently.  Fork / join with events, so the work stays
 // capturable in the caller's CUDA graph and ordered with the caller's stream.
+constexpr int SIDE_EVENTS = 32;   // fork / join events, used round-robin (far more than are ever pending at once)
 struct SideStreams {
   bool on = false;
   cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[SIDE_EVENTS] = {};
+  cudaEvent_t layer[4] = {};        // E/G step: layer l of the generator's z_prior pass is done (the z_enc pass waits for it)
   unsigned next = 0;
   bool dirty[2] = {false, false};
 };
@@ -264,8 +266,16 @@ struct GenBufs {
   double* fst[3];
   uint64_t pad = 0;
 };
+// one pass of a two-pass generator forward run as a chain of its own (E/G step): which pass, the exchange channel of its
+// stream, and the per-layer events it records (rec) or waits for before each layer after the first (wait)
+struct GenSplit {
+  int only_pass = -1;
+  int channel = 0;
+  cudaEvent_t* rec = nullptr;
+  cudaEvent_t* wait = nullptr;
+};
 int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int label, int M, float Bg, bool local_bn,
-                  cudaStream_t st, const GenBufs* gb = nullptr);
+                  cudaStream_t st, const GenBufs* gb = nullptr, const GenSplit* split = nullptr);
 int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool train, int M, cudaStream_t st);
 int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn, cudaStream_t st);
 

@@ -42,7 +42,7 @@ struct BnRef {
   int update_running = 0;          // CTA (0,0,0) applies the momentum update for all passes, in order
   // data parallel, exchange folded into the kernels (comm_nvl.cuh): the sums named by `poll_which` (1 fstats, 2 bstats)
   // are still in flight as `poll_npass` passes of LL packets; this kernel is their first reader
-  int poll = 0;                    // which | passes << 4   (the NvlDev pointer travels in GemmArgs / DwArgs ::nvl)
+  int poll = 0;                    // which | passes << 4 | first pass << 12 | via_lead << 20  (NvlDev pointer: GemmArgs / DwArgs ::nvl)
 };
 
 struct Operand {
@@ -137,12 +137,13 @@ __device__ __forceinline__ void bn_stat2(const BnRef& bn, int which, int pass, i
   const double* base = which == 1 ? bn.fstats : bn.bstats;
   const long long stride = which == 1 ? bn.sf : bn.sb;
   if (nvl == nullptr || (bn.poll & 15) != which) {
-    s1 = base[(long long)pass * stride + c];
-    s2 = base[(long long)pass * stride + bn.C + c];
+    s1 = __ldcg(base + (long long)pass * stride + c);        // L2: another CTA of this launch may have just written them
+    s2 = __ldcg(base + (long long)pass * stride + bn.C + c);
     return;
   }
-  const unsigned long long ep = (unsigned long long)base[stride - 1];
-  const long long e = (long long)pass * 2 * bn.C + c;
+  const int p0 = (bn.poll >> 12) & 255;           // the pushed group's first pass: its slot holds the exchange number
+  const unsigned long long ep = (unsigned long long)base[(long long)p0 * stride + stride - 1];
+  const long long e = (long long)(pass - p0) * 2 * bn.C + c;
   nvl_poll_f64x2(*nvl, (unsigned int)ep, (int)(ep & 1ull), e, e + bn.C, s1, s2);
 }
 
@@ -158,6 +159,35 @@ __device__ __forceinline__ void bn_poll_writeback(const BnRef& bn, int p0, int n
     base[(long long)ps * stride + c] = s1;
     base[(long long)ps * stride + bn.C + c] = s2;
   }
+}
+
+// With many ranks every CTA polling world x 2 C packets itself costs more L2 bandwidth than the exchange is worth
+// (8 ranks, 512 CTAs, C = 256: 33 MB per launch).  via_lead: only the write-back CTA polls; it then publishes the exchange
+// number next to the sums (slot[stride - 2]) and the other CTAs of that pass wait for it and read the 4 KB of global sums.
+// A waiting CTA always has a higher linear index than its write-back CTA, which therefore was dispatched before it.
+__device__ __forceinline__ void bn_publish(const BnRef& bn, int p0, int np) {
+  const int which = bn.poll & 15;
+  double* base = const_cast<double*>(which == 1 ? bn.fstats : bn.bstats);
+  const long long stride = which == 1 ? bn.sf : bn.sb;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double ep = base[(long long)((bn.poll >> 12) & 255) * stride + stride - 1];
+    for (int p = p0; p < p0 + np; ++p) *reinterpret_cast<volatile double*>(base + (long long)p * stride + stride - 2) = ep;
+  }
+}
+__device__ __forceinline__ void bn_wait_published(const BnRef& bn, int pass) {
+  const int which = bn.poll & 15;
+  const double* base = which == 1 ? bn.fstats : bn.bstats;
+  const long long stride = which == 1 ? bn.sf : bn.sb;
+  if (threadIdx.x == 0) {
+    const double ep = base[(long long)((bn.poll >> 12) & 255) * stride + stride - 1];
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile double*>(base + (long long)pass * stride + stride - 2) != ep)
+      if (clock64() - t0 > 120000000000ll) __trap();
+    __threadfence();
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ void bn_mean_rstd(const BnRef& bn, int pass, int c, float Bg, float eps, float& mean,
@@ -329,8 +359,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mn_kernel(const GemmArgs
   // in-flight batch sums (data parallel): CTA (0,0,0) lands every pass in the buffer, the others read the packets
   const NvlDev* poll_a = ((AK == OP_BN_ACT || AK == OP_BN_BWD) && g.a.bn.poll) ? g.nvl : nullptr;
   if (poll_a && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    bn_poll_writeback(g.a.bn, 0, g.a.bn.poll >> 4, poll_a);
+    bn_poll_writeback(g.a.bn, (g.a.bn.poll >> 12) & 255, (g.a.bn.poll >> 4) & 255, poll_a);
+    if (g.a.bn.poll >> 20) bn_publish(g.a.bn, (g.a.bn.poll >> 12) & 255, (g.a.bn.poll >> 4) & 255);
     __syncthreads();
+    poll_a = nullptr;
+  } else if (poll_a && (g.a.bn.poll >> 20)) {
+    bn_wait_published(g.a.bn, pass);
     poll_a = nullptr;
   }
   operand_consts<AK>(g.a, pass, g.Bg, g.bn_eps, cs_a, poll_a);
@@ -600,7 +634,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mn_kernel(const GemmArgs
     klsum = warp_sum_d(klsum);
     if ((tid & 31) == 0) atomicAdd(g.kl_acc, klsum);
   }
-  if (g.push) nvl_push_stats_tail(*g.nvl, g.ostats, g.sostats, (int)gridDim.z, g.N, gridDim.x * gridDim.y * gridDim.z);
+  if (g.push)
+    nvl_push_stats_tail(*g.nvl, g.ostats + (long long)(g.only_pass > 0 ? g.only_pass : 0) * g.sostats, g.sostats, (int)gridDim.z, g.N,
+                        gridDim.x * gridDim.y * gridDim.z);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -626,10 +662,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_dw_kernel(const DwArgs g
   const NvlDev* poll_p = ((PK == OP_BN_ACT || PK == OP_BN_BWD) && g.p.bn.poll) ? g.nvl : nullptr;
   const NvlDev* poll_q = ((QK == OP_BN_ACT || QK == OP_BN_BWD) && g.q.bn.poll) ? g.nvl : nullptr;
   if ((poll_p || poll_q) && blockIdx.x == 0 && blockIdx.y == 0 && split == 0) {   // this pass's write-back CTA
-    if (poll_p) bn_poll_writeback(g.p.bn, pass, 1, poll_p);
-    if (poll_q) bn_poll_writeback(g.q.bn, pass, 1, poll_q);
+    if (poll_p) { bn_poll_writeback(g.p.bn, pass, 1, poll_p); if (g.p.bn.poll >> 20) bn_publish(g.p.bn, pass, 1); }
+    if (poll_q) { bn_poll_writeback(g.q.bn, pass, 1, poll_q); if (g.q.bn.poll >> 20) bn_publish(g.q.bn, pass, 1); }
     __syncthreads();
     poll_p = poll_q = nullptr;
+  } else {
+    if (poll_p && (g.p.bn.poll >> 20)) { bn_wait_published(g.p.bn, pass); poll_p = nullptr; }
+    if (poll_q && (g.q.bn.poll >> 20)) { bn_wait_published(g.q.bn, pass); poll_q = nullptr; }
   }
   operand_consts<PK>(g.p, pass, g.Bg, g.bn_eps, cs_p, poll_p);
   operand_consts<QK>(g.q, pass, g.Bg, g.bn_eps, cs_q, poll_q);

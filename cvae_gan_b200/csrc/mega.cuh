@@ -1449,57 +1449,8 @@ __device__ void zero_item(const ZeroArgs& a, int item) {
 // one exchange of the LL all-reduce of comm_nvl.cuh; ep = exchange number on every rank
 template <typename T>
 __device__ void nvl_item(const NvlDev& d, const NvlArgs& a, unsigned long long ep, int item) {
-  constexpr int W = sizeof(T) / 4;
-  T* data = reinterpret_cast<T*>(a.data);
-  const unsigned int ep32 = (unsigned int)ep;
-  const int par = (int)(ep & 1ull);
-  const long long n = a.seg_len * a.nseg;
-  const long long stride = (long long)NVL_VB * THREADS;
-  for (long long e = (long long)item * THREADS + threadIdx.x; e < n; e += stride) {
-    const long long sg = e / a.seg_len, off = e - sg * a.seg_len;
-    const T x = __ldcg(data + sg * a.seg_stride + off);
-    unsigned int w[W];
-    memcpy(w, &x, sizeof(T));
-    for (int p = 0; p < d.world; ++p) {
-      unsigned char* dst = d.peer[p] + nvl_slot_off(d, par, d.rank) + (unsigned long long)e * (W * 8);
-#pragma unroll
-      for (int k = 0; k < W; ++k) ll_store(dst + k * 8, w[k], ep32);
-    }
-  }
-  const unsigned char* base = d.peer[d.rank];
-  const long long t0 = clock64();
-  for (long long e = (long long)item * THREADS + threadIdx.x; e < n; e += stride) {
-    unsigned int w[NVL_MAX_WORLD][W];
-    unsigned int pending = (1u << d.world) - 1u;
-    while (pending) {
-#pragma unroll
-      for (int q = 0; q < NVL_MAX_WORLD; ++q) {
-        if (q < d.world && ((pending >> q) & 1u)) {
-          const unsigned char* src = base + nvl_slot_off(d, par, q) + (unsigned long long)e * (W * 8);
-          bool ok = true;
-#pragma unroll
-          for (int k = 0; k < W; ++k) {
-            unsigned int f;
-            ll_load(src + k * 8, w[q][k], f);
-            ok &= (f == ep32);
-          }
-          if (ok) pending &= ~(1u << q);
-        }
-      }
-      if (pending && clock64() - t0 > 120000000000ll) __trap();
-    }
-    T s = 0;
-#pragma unroll
-    for (int q = 0; q < NVL_MAX_WORLD; ++q) {
-      if (q < d.world) {
-        T x;
-        memcpy(&x, w[q], sizeof(T));
-        s += x;
-      }
-    }
-    const long long sg = e / a.seg_len, off = e - sg * a.seg_len;
-    data[sg * a.seg_stride + off] = s;
-  }
+  nvl_exchange<T>(d, reinterpret_cast<T*>(a.data), a.seg_len, a.seg_stride, a.nseg, ep, (long long)item * THREADS + threadIdx.x,
+                  (long long)NVL_VB * THREADS);
 }
 
 // ======================================================================================================================

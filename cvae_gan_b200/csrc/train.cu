@@ -78,9 +78,9 @@ int nvl_local_handle(Engine& e, void* out64) {
     if (b > slot) slot = b;
   }
   slot = 2 * ((slot + 255) & ~(size_t)255);      // LL packets: 8 bytes on the wire per 4-byte word
-  const size_t total = nvl_total_bytes(e.world, slot);
-  CVG_CUDA(cudaMalloc(&e.nvl.local, total));     // communication staging only (never tensor memory)
-  CVG_CUDA(cudaMemset(e.nvl.local, 0, total));
+  const size_t total = (nvl_total_bytes(e.world, slot) + 255) & ~(size_t)255;      // one channel; two are allocated
+  CVG_CUDA(cudaMalloc(&e.nvl.local, 2 * total));     // communication staging only (never tensor memory)
+  CVG_CUDA(cudaMemset(e.nvl.local, 0, 2 * total));
   CVG_CUDA(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   CVG_CUDA(cudaIpcGetMemHandle(&h, e.nvl.local));
@@ -95,6 +95,11 @@ int nvl_local_handle(Engine& e, void* out64) {
   unsigned char* tail = (unsigned char*)e.nvl.local + 2 * (size_t)e.world * slot + 2 * (size_t)e.world * NVL_MAX_CTAS * sizeof(unsigned int);
   d.epoch = (unsigned long long*)tail;
   d.done = (unsigned int*)(tail + 64);
+  NvlDev& d1 = e.nvl.dev1;
+  d1 = d;
+  d1.peer[e.rank] = d.peer[e.rank] + total;
+  d1.epoch = (unsigned long long*)(tail + total);
+  d1.done = (unsigned int*)(tail + total + 64);
   return 0;
 }
 
@@ -107,11 +112,16 @@ int nvl_attach(Engine& e, const void* handles) {
     void* ptr = nullptr;
     CVG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     e.nvl.dev.peer[p] = (unsigned char*)ptr;
+    e.nvl.dev1.peer[p] = (unsigned char*)ptr + e.nvl.total_bytes;
     e.nvl.opened[p] = true;
   }
-  CVG_CUDA(cudaMalloc(&e.nvl.dev_d, sizeof(NvlDev)));
-  CVG_CUDA(cudaMemcpy(e.nvl.dev_d, &e.nvl.dev, sizeof(NvlDev), cudaMemcpyHostToDevice));
+  CVG_CUDA(cudaMalloc(&e.nvl.dev_d[0], 2 * sizeof(NvlDev)));
+  e.nvl.dev_d[1] = e.nvl.dev_d[0] + 1;
+  CVG_CUDA(cudaMemcpy(e.nvl.dev_d[0], &e.nvl.dev, sizeof(NvlDev), cudaMemcpyHostToDevice));
+  CVG_CUDA(cudaMemcpy(e.nvl.dev_d[1], &e.nvl.dev1, sizeof(NvlDev), cudaMemcpyHostToDevice));
   if (const char* f = getenv("CVG_FUSE_STATS")) e.nvl.fuse = atoi(f) != 0;
+  e.nvl.via_lead = e.world >= 4;
+  if (const char* f = getenv("CVG_POLL_LEAD")) e.nvl.via_lead = atoi(f) != 0;
   e.nvl.on = true;
   return 0;
 }
@@ -120,8 +130,8 @@ void nvl_destroy(Engine& e) {
   for (int p = 0; p < NVL_MAX_WORLD; ++p)
     if (e.nvl.opened[p]) { cudaIpcCloseMemHandle(e.nvl.dev.peer[p]); e.nvl.opened[p] = false; }
   if (e.nvl.local) cudaFree(e.nvl.local);
-  if (e.nvl.dev_d) cudaFree(e.nvl.dev_d);
-  e.nvl.dev_d = nullptr;
+  if (e.nvl.dev_d[0]) cudaFree(e.nvl.dev_d[0]);
+  e.nvl.dev_d[0] = e.nvl.dev_d[1] = nullptr;
   e.nvl.local = nullptr;
   e.nvl.on = false;
 }
@@ -198,24 +208,25 @@ static void prof_end(Engine& e, cudaStream_t st) {
 }
 
 // first reader of batch sums a producer pushed over NVLink (launch_mn_stats below): it polls the packets
-static bool take_pending(Engine& e, Operand& o) {
-  if (!e.nvl.n_pending || (o.kind != OP_BN_ACT && o.kind != OP_BN_BWD)) return false;
+static const NvlDev* take_pending(Engine& e, Operand& o) {
+  if (!e.nvl.n_pending || (o.kind != OP_BN_ACT && o.kind != OP_BN_BWD)) return nullptr;
   for (int i = 0; i < e.nvl.n_pending; ++i) {
     const NvlPending pd = e.nvl.pending[i];
     int which = 0;
-    if (pd.stats == o.bn.fstats) which = 1;
-    if (o.kind == OP_BN_BWD && pd.stats == o.bn.bstats) which = 2;
+    if (pd.stats == o.bn.fstats + (long long)pd.pass0 * o.bn.sf) which = 1;
+    if (o.kind == OP_BN_BWD && pd.stats == o.bn.bstats + (long long)pd.pass0 * o.bn.sb) which = 2;
     if (!which) continue;
-    o.bn.poll = which | (pd.npass << 4);
+    o.bn.poll = which | (pd.npass << 4) | (pd.pass0 << 12) | (e.nvl.via_lead ? 1 << 20 : 0);
     e.nvl.pending[i] = e.nvl.pending[--e.nvl.n_pending];
-    return true;
+    return e.nvl.dev_d[pd.channel];
   }
-  return false;
+  return nullptr;
 }
 
 int launch_mn(Engine& e, bool wt, const GemmArgs& g_in, cudaStream_t st) {
   GemmArgs g = g_in;
-  if (!e.mk.recording && take_pending(e, g.a)) g.nvl = e.nvl.dev_d;
+  if (!e.mk.recording)
+    if (const NvlDev* ch = take_pending(e, g.a)) g.nvl = ch;
   const int zp = g.only_pass >= 0 ? 1 : g.npass;
   if (e.mk.recording) {
     // 64-row tiles while they still fit one wave and a half of CTAs, 128-row tiles (full-rate MMAs) for larger batches
@@ -256,8 +267,8 @@ int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
   rows = ((rows + DW_MC - 1) / DW_MC) * DW_MC;
   nsplit = (g.M + rows - 1) / rows;
   g.rows_per_cta = rows;
-  if (take_pending(e, g.p)) g.nvl = e.nvl.dev_d;
-  if (take_pending(e, g.q)) g.nvl = e.nvl.dev_d;
+  if (const NvlDev* ch = take_pending(e, g.p)) g.nvl = ch;
+  if (const NvlDev* ch = take_pending(e, g.q)) g.nvl = ch;
   dim3 grid(kt, nt, g.npass * nsplit);
   prof_begin(e, 2, 2.0 * g.M * (double)g.N * g.K * g.npass, st);
   const cudaError_t err = dispatch_dw(g, nsplit, grid, gemm_dw_smem(g), st);
@@ -326,15 +337,18 @@ static int sync_stats(Engine& e, double* p, int npass, int C, bool local_bn, cud
 // Data parallel BatchNorm sums without a launch of their own (comm_nvl.cuh): the producing GEMM pushes them from its
 // last CTA (g.push), the first GEMM that reads them polls (BnRef::poll, set by take_pending at its launch).
 static bool fold_stats(const Engine& e, bool local_bn) {
-  return e.world > 1 && !local_bn && e.nvl.on && e.nvl.fuse && e.nvl.dev_d && !e.mk.recording;
+  return e.world > 1 && !local_bn && e.nvl.on && e.nvl.fuse && e.nvl.dev_d[0] && !e.mk.recording;
 }
-static int launch_mn_stats(Engine& e, bool wt, GemmArgs& g, int npass_sync, bool local_bn, cudaStream_t st) {
-  const bool fold = fold_stats(e, local_bn) && g.only_pass <= 0;
-  if (fold) { g.push = 1; g.nvl = e.nvl.dev_d; }
+// channel: 0 on the caller's stream, 1 on the side stream that runs a second GEMM chain beside it
+static int launch_mn_stats(Engine& e, bool wt, GemmArgs& g, int npass_sync, bool local_bn, cudaStream_t st, int channel = 0) {
+  const bool fold = fold_stats(e, local_bn);
+  if (!fold && channel != 0 && e.world > 1 && !local_bn) CVG_FAIL("internal: an exchange launch on a side stream");
+  if (fold) { g.push = 1; g.nvl = e.nvl.dev_d[channel]; }
   CVG_TRY(launch_mn(e, wt, g, st));
   if (!fold) return sync_stats(e, g.ostats, npass_sync, g.N, local_bn, st);
-  if (e.nvl.n_pending >= 4) CVG_FAIL("internal: too many folded exchanges in flight");
-  e.nvl.pending[e.nvl.n_pending++] = NvlPending{g.ostats, g.only_pass >= 0 ? 1 : g.npass};
+  if (e.nvl.n_pending >= 8) CVG_FAIL("internal: too many folded exchanges in flight");
+  const int p0 = g.only_pass > 0 ? g.only_pass : 0;
+  e.nvl.pending[e.nvl.n_pending++] = NvlPending{g.ostats + (long long)p0 * g.sostats, g.only_pass >= 0 ? 1 : g.npass, p0, channel};
   return 0;
 }
 
@@ -344,17 +358,24 @@ static int launch_mn_stats(Engine& e, bool wt, GemmArgs& g, int npass_sync, bool
 // side stream `i`, ordered after everything enqueued on `st` so far (SideStreams, engine.cuh)
 static cudaStream_t fork_to(Engine& e, int i, cudaStream_t st) {
   if (!e.ms.on || e.mk.recording) return st;
-  cudaEvent_t ev = e.ms.ev[e.ms.next++ & 7];
+  cudaEvent_t ev = e.ms.ev[e.ms.next++ % SIDE_EVENTS];
   cudaEventRecord(ev, st);
   cudaStreamWaitEvent(e.ms.s[i], ev, 0);
   e.ms.dirty[i] = true;
   return e.ms.s[i];
 }
+// `waiter` continues after everything enqueued on `signaller` so far
+static void wait_for(Engine& e, cudaStream_t waiter, cudaStream_t signaller) {
+  if (waiter == signaller) return;
+  cudaEvent_t ev = e.ms.ev[e.ms.next++ % SIDE_EVENTS];
+  cudaEventRecord(ev, signaller);
+  cudaStreamWaitEvent(waiter, ev, 0);
+}
 // `st` continues after everything enqueued on the side streams
 static void join_sides(Engine& e, cudaStream_t st, int only = -1) {
   for (int i = 0; i < 2; ++i) {
     if (!e.ms.dirty[i] || (only >= 0 && only != i)) continue;
-    cudaEvent_t ev = e.ms.ev[e.ms.next++ & 7];
+    cudaEvent_t ev = e.ms.ev[e.ms.next++ % SIDE_EVENTS];
     cudaEventRecord(ev, e.ms.s[i]);
     cudaStreamWaitEvent(st, ev, 0);
     e.ms.dirty[i] = false;
@@ -422,7 +443,7 @@ static int stage_x(Engine& e, const float* x_real, int M, cudaStream_t st) {
 // forward passes
 // ------------------------------------------------------------------------------------------------
 int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int label, int M, float Bg, bool local_bn,
-                  cudaStream_t st, const GenBufs* gb) {
+                  cudaStream_t st, const GenBufs* gb, const GenSplit* split) {
   const int net = CVG_NET_GENERATOR;
   const Workspace& w = e.ws;
   const size_t ld = w.ld;
@@ -472,11 +493,19 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
       g.Y = b.out;
       g.sY = (long long)e.F * ld;
     }
+    if (split) {
+      // The z_enc pass applies the running-statistics update of BOTH passes, in the reference's order (z_enc, then
+      // z_prior): it waits until the z_prior chain's reader of the same sums is done (their global values are in place).
+      g.only_pass = split->only_pass;
+      if (l > 0) g.a.bn.update_running = (split->only_pass == 0 && train) ? 1 : 0;
+      if (l > 0 && split->wait) cudaStreamWaitEvent(st, split->wait[l], 0);
+    }
     if (l < 3 && train) {
-      CVG_TRY(launch_mn_stats(e, true, g, npass > 2 ? npass : 2, local_bn, st));
+      CVG_TRY(launch_mn_stats(e, true, g, npass > 2 ? npass : 2, local_bn, st, split ? split->channel : 0));
     } else {
       CVG_TRY(launch_mn(e, true, g, st));
     }
+    if (split && split->rec) cudaEventRecord(split->rec[l], st);
   }
   return 0;
 }
@@ -766,10 +795,8 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       CVG_TRY(launch_dw(e, d, fork_to(e, 0, st)));
     }
     if (l == 0 && !want_dx) break;
-    if (l == 0 && dx_after && dx_after != st) {
-      cudaEvent_t ev = e.ms.ev[e.ms.next++ & 7];
-      cudaEventRecord(ev, dx_after);
-      cudaStreamWaitEvent(st, ev, 0);
+    if (l == 0 && dx_after) {
+      wait_for(e, st, dx_after);
     }
     GemmArgs g = base_args(e, M, (float)M, npass);
     g.R = p.out;
@@ -1293,6 +1320,45 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
   CVG_PAR(e);
   CVG_TRY(launch_fill(e, f, st));
+  const float* x_fake = w.g_out + (size_t)e.F * ld;
+  CeArgs c;
+  c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
+  c.logits = w.c_logit; c.sl = (long long)e.K * ld;
+  c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
+  c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
+  c.ctl = w.ctl;
+  c.loss = w.loss + L_CE0;
+  // backward to x_fake: adv = -mean D(x_fake) (cvae_gan.py:189), then the classification term
+  const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
+  // Three chains side by side (stand-alone kernels, side streams on; data parallel: with the folded exchange, one channel
+  // per chain): x_fake = G(z_prior) does not depend on the encoder, and the critic / classifier terms only on x_fake.
+  //   caller's stream : E(x), G(z_enc)
+  //   side 1          : batch staging, G(z_prior), then D(x_fake) forward and backward to x_fake
+  //   side 0          : power iteration, then C(x_fake) forward, loss and backward to x_fake (after D's: both add to ws.dx)
+  const bool three = !e.mk.recording && e.ms.on && (e.world <= 1 || local_bn || fold_stats(e, local_bn));
+  if (three) {
+    const cudaStream_t sA = fork_to(e, 0, st), sB = fork_to(e, 1, st);
+    CVG_TRY(launch_sn(e, 1, true, sA));
+    CVG_TRY(stage_x(e, x_real, B, sB));
+    wait_for(e, st, sB);                                            // the encoder reads the staged batch
+    GenSplit prior;
+    prior.only_pass = 1; prior.channel = 1; prior.rec = e.ms.layer;
+    CVG_TRY(fwd_generator(e, 2, true, false, label, B, Bg_bn, local_bn, sB, nullptr, &prior));
+    wait_for(e, sB, sA);                                            // sigma of the critic's layers (all side 0 holds so far)
+    if (rng.lambda_nonzero) {
+      wait_for(e, sA, sB);                                          // x_fake
+      CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, sA));
+      CVG_TRY(emit_ce(e, c, B, 1, sA));
+    }
+    CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, sB));
+    CVG_TRY(bwd_critic(e, x_fake, 0, 1, label, B, seedv, false, true, sB));
+    if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, sA, sB));
+    CVG_TRY(fwd_encoder(e, true, label, B, Bg_bn, local_bn, st));
+    GenSplit enc;
+    enc.only_pass = 0; enc.channel = 0; enc.wait = e.ms.layer;
+    CVG_TRY(fwd_generator(e, 2, true, true, label, B, Bg_bn, local_bn, st, nullptr, &enc));
+    join_sides(e, st);
+  } else {
   CVG_PAR(e);
   CVG_TRY(stage_x(e, x_real, B, fork_to(e, 1, st)));
 
@@ -1307,26 +1373,16 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
     CVG_TRY(mk_push(e, mk::K_REPARAM, &ra, sizeof(ra), (int)(((long long)e.Z * ld + mk::THREADS - 1) / mk::THREADS)));
   }
   CVG_TRY(fwd_generator(e, 2, true, true, label, B, Bg_bn, local_bn, st));
-  const float* x_fake = w.g_out + (size_t)e.F * ld;
   join_sides(e, st);
   // the classifier branch (forward, loss, backward to x_fake) runs beside the critic's; they meet at ws.dx
   const cudaStream_t sc = rng.lambda_nonzero ? fork_to(e, 1, st) : st;
   CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, st));
   CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, sc));
-  CeArgs c;
-  c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
-  c.logits = w.c_logit; c.sl = (long long)e.K * ld;
-  c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
-  c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
-  c.ctl = w.ctl;
-  c.loss = w.loss + L_CE0;
   CVG_TRY(emit_ce(e, c, B, 1, sc));
-
-  // backward to x_fake: adv = -mean D(x_fake) (cvae_gan.py:189), then the classification term
-  const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
   CVG_TRY(bwd_critic(e, x_fake, 0, 1, label, B, seedv, false, true, st));
   if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, sc, st));
   join_sides(e, st);
+  }
 
   // generator output gradients: recon MSE on pass 0, dx on pass 1, through the sigmoid
   SeedArgs s;
