@@ -43,8 +43,9 @@ struct NvlState {
   bool opened[NVL_MAX_WORLD] = {};
   // Channel 1: a second staging area with its own exchange numbering inside the same allocation, for the GEMM chain that
   // runs on a side stream beside the caller's (exchange numbers are per stream order, so two streams need two channels).
-  NvlDev dev1{};
-  NvlDev* dev_d[2] = {nullptr, nullptr};   // device copies for the kernels that fold the exchange in
+  // Channel 2: the gradient reduction + Adam of a step, which a label visit runs on side stream 0 beside the next step's head.
+  NvlDev dev1{}, dev2{};
+  NvlDev* dev_d[2] = {nullptr, nullptr};   // device copies (channels 0, 1) for the kernels that fold the exchange in
   bool fuse = true;                     // CVG_FUSE_STATS=0: BatchNorm sums go through nvl_allreduce_kernel launches
   bool via_lead = false;                // folded exchange: one CTA per pass polls for the launch (gemm.cuh bn_publish)
   NvlPending pending[8];

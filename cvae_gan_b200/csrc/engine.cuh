@@ -165,6 +165,7 @@ struct Engine {
   int64_t launches = 0;
   const float* hoist_x = nullptr;   // visit(): G(z) of the step being emitted, computed up front (null: the step runs G)
   SideStreams ms;
+  bool in_visit = false;            // steps emitted by visit(): their gradient reduction + Adam may run beside the next step
   unsigned long long step_dcounter = 0;   // visit(): Philox counter values the step being emitted uses (advanced at its end)
   int hoist = 1;                    // CVG_HOIST=0: every step runs its own generator forward
   ncclComm_t comm = nullptr;
@@ -216,7 +217,7 @@ int step_classifier(Engine& e, const float* x, const long long* labels, int B, c
 int nvl_local_handle(Engine& e, void* out64);
 int nvl_attach(Engine& e, const void* handles);
 void nvl_destroy(Engine& e);
-int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st);
+int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st, int channel = 0);
 int comm_all_reduce_f64(Engine& e, double* p, int64_t n, cudaStream_t st);
 int comm_all_reduce_stats(Engine& e, double* p, int npass, int C, cudaStream_t st);
 

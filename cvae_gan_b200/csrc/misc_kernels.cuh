@@ -280,6 +280,7 @@ struct SnArgs {
   float* sigma;      // [npass][4]
   float* inv_sigma;  // [4][npass]   (per layer contiguous over passes: GemmArgs.scale[pass])
   float* u_snap; float* v_snap; long long ssnap;   // [npass][ssnap]
+  int w_smem_floats = 0;   // dynamic shared memory (floats) for a copy of W: the 3 mat-vecs per pass then read it from there
 };
 
 constexpr int SN_THREADS = 1024;
@@ -288,8 +289,18 @@ __global__ void __launch_bounds__(SN_THREADS) sn_power_kernel(const SnArgs g) {
   __shared__ float su[SN_MAXDIM], sv[SN_MAXDIM], st[SN_MAXDIM];
   __shared__ float part[SN_THREADS];
   __shared__ double red[32];
-  const SnLayer L = g.L[blockIdx.x];
+  extern __shared__ __align__(16) float sn_w[];
+  SnLayer L = g.L[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  if (L.rows * L.cols <= g.w_smem_floats) {        // one pass over W in L2 instead of 3 * npass
+    const int n_el = L.rows * L.cols;
+    if ((n_el & 3) == 0 && ((size_t)L.W & 15) == 0) {
+      for (int i = tid * 4; i < n_el; i += blockDim.x * 4) st4(sn_w + i, ld4(L.W + i));
+    } else {
+      for (int i = tid; i < n_el; i += blockDim.x) sn_w[i] = L.W[i];
+    }
+    L.W = sn_w;
+  }
   for (int i = tid; i < L.rows; i += blockDim.x) su[i] = L.u[i];
   for (int i = tid; i < L.cols; i += blockDim.x) sv[i] = L.v[i];
   __syncthreads();

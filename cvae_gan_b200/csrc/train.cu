@@ -79,8 +79,8 @@ int nvl_local_handle(Engine& e, void* out64) {
   }
   slot = 2 * ((slot + 255) & ~(size_t)255);      // LL packets: 8 bytes on the wire per 4-byte word
   const size_t total = (nvl_total_bytes(e.world, slot) + 255) & ~(size_t)255;      // one channel; two are allocated
-  CVG_CUDA(cudaMalloc(&e.nvl.local, 2 * total));     // communication staging only (never tensor memory)
-  CVG_CUDA(cudaMemset(e.nvl.local, 0, 2 * total));
+  CVG_CUDA(cudaMalloc(&e.nvl.local, 3 * total));     // communication staging only (never tensor memory)
+  CVG_CUDA(cudaMemset(e.nvl.local, 0, 3 * total));
   CVG_CUDA(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   CVG_CUDA(cudaIpcGetMemHandle(&h, e.nvl.local));
@@ -100,6 +100,11 @@ int nvl_local_handle(Engine& e, void* out64) {
   d1.peer[e.rank] = d.peer[e.rank] + total;
   d1.epoch = (unsigned long long*)(tail + total);
   d1.done = (unsigned int*)(tail + total + 64);
+  NvlDev& d2 = e.nvl.dev2;
+  d2 = d;
+  d2.peer[e.rank] = d.peer[e.rank] + 2 * total;
+  d2.epoch = (unsigned long long*)(tail + 2 * total);
+  d2.done = (unsigned int*)(tail + 2 * total + 64);
   return 0;
 }
 
@@ -113,6 +118,7 @@ int nvl_attach(Engine& e, const void* handles) {
     CVG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     e.nvl.dev.peer[p] = (unsigned char*)ptr;
     e.nvl.dev1.peer[p] = (unsigned char*)ptr + e.nvl.total_bytes;
+    e.nvl.dev2.peer[p] = (unsigned char*)ptr + 2 * e.nvl.total_bytes;
     e.nvl.opened[p] = true;
   }
   CVG_CUDA(cudaMalloc(&e.nvl.dev_d[0], 2 * sizeof(NvlDev)));
@@ -120,7 +126,9 @@ int nvl_attach(Engine& e, const void* handles) {
   CVG_CUDA(cudaMemcpy(e.nvl.dev_d[0], &e.nvl.dev, sizeof(NvlDev), cudaMemcpyHostToDevice));
   CVG_CUDA(cudaMemcpy(e.nvl.dev_d[1], &e.nvl.dev1, sizeof(NvlDev), cudaMemcpyHostToDevice));
   if (const char* f = getenv("CVG_FUSE_STATS")) e.nvl.fuse = atoi(f) != 0;
-  e.nvl.via_lead = e.world >= 4;
+  // one-CTA polling (gemm.cuh bn_publish): measured slower than every CTA polling even at 8 ranks (4.51 vs 4.45 ms per
+  // visit), so it stays an option
+  e.nvl.via_lead = false;
   if (const char* f = getenv("CVG_POLL_LEAD")) e.nvl.via_lead = atoi(f) != 0;
   e.nvl.on = true;
   return 0;
@@ -138,7 +146,7 @@ void nvl_destroy(Engine& e) {
 
 // `nseg` segments of `seg_len` elements, `seg_stride` apart
 template <typename T>
-static int nvl_all_reduce(Engine& e, T* p, int64_t seg_len, int64_t seg_stride, int nseg, cudaStream_t st) {
+static int nvl_all_reduce(Engine& e, T* p, int64_t seg_len, int64_t seg_stride, int nseg, cudaStream_t st, int channel = 0) {
   const long long n = seg_len * nseg;
   if (e.mk.recording) {
     mk::NvlArgs a;
@@ -147,11 +155,12 @@ static int nvl_all_reduce(Engine& e, T* p, int64_t seg_len, int64_t seg_stride, 
     if ((unsigned long long)n * sizeof(T) * 2 > e.nvl.dev.slot_bytes) CVG_FAIL("step program: exchange larger than the NVLink staging slot");
     return mk_push(e, sizeof(T) == 8 ? mk::K_NVL_F64 : mk::K_NVL_F32, &a, sizeof(a), mk::NVL_VB);
   }
-  if (e.nvl.n_pending) CVG_FAIL("internal: a folded BatchNorm exchange has no reader before the next exchange");
+  if (e.nvl.n_pending && channel == 0) CVG_FAIL("internal: a folded BatchNorm exchange has no reader before the next exchange");
   int grid = (int)((n + NVL_THREADS - 1) / NVL_THREADS);     // one element per thread where possible
   if (grid < 1) grid = 1;
   if (grid > NVL_MAX_CTAS) grid = NVL_MAX_CTAS;
-  nvl_allreduce_kernel<T><<<grid, NVL_THREADS, 0, st>>>(e.nvl.dev, p, seg_len, seg_stride, nseg);
+  nvl_allreduce_kernel<T><<<grid, NVL_THREADS, 0, st>>>(channel == 2 ? e.nvl.dev2 : (channel == 1 ? e.nvl.dev1 : e.nvl.dev), p, seg_len,
+                                                        seg_stride, nseg);
   CVG_CUDA(cudaGetLastError());
   e.launches++;
   return 0;
@@ -164,9 +173,10 @@ int comm_all_reduce_stats(Engine& e, double* p, int npass, int C, cudaStream_t s
   return comm_all_reduce_f64(e, p, (int64_t)npass * 2 * STAT_C, st);
 }
 
-int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st) {
+int comm_all_reduce_f32(Engine& e, float* p, int64_t n, cudaStream_t st, int channel) {
   if (e.world <= 1) return 0;
-  if (e.nvl.on && 2 * (size_t)n * sizeof(float) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<float>(e, p, n, n, 1, st);
+  if (e.nvl.on && 2 * (size_t)n * sizeof(float) <= e.nvl.dev.slot_bytes) return nvl_all_reduce<float>(e, p, n, n, 1, st, channel);
+  if (channel != 0) CVG_FAIL("internal: NCCL reduction requested on a side stream");
   if (!e.comm) CVG_FAIL("world_size > 1 but cvg_comm_init was not called");
   int r = g_nccl.AllReduce(p, p, (size_t)n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, e.comm, st);
   if (r != 0) CVG_FAIL("ncclAllReduce(f32) failed");
@@ -555,6 +565,7 @@ int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn
   return 0;
 }
 
+constexpr int SN_W_SMEM_MAX = 160 * 1024;   // widest critic layer kept in shared memory by the power iteration (128 x 256 floats)
 static int launch_sn(Engine& e, int npass, bool do_power, cudaStream_t st) {
   const int net = CVG_NET_DISCRIMINATOR;
   SnArgs a;
@@ -578,7 +589,10 @@ static int launch_sn(Engine& e, int npass, bool do_power, cudaStream_t st) {
   a.v_snap = e.ws.sn_v;
   a.ssnap = e.ws.sn_snap;
   if (e.mk.recording) return mk_push(e, mk::K_SN_POWER, &a, sizeof(a), 4);
-  sn_power_kernel<<<4, SN_THREADS, 0, st>>>(a);
+  int wmax = 0;
+  for (int l = 0; l < 4; ++l) wmax = a.L[l].rows * a.L[l].cols > wmax ? a.L[l].rows * a.L[l].cols : wmax;
+  a.w_smem_floats = wmax * 4 <= SN_W_SMEM_MAX ? wmax : 0;
+  sn_power_kernel<<<4, SN_THREADS, (size_t)a.w_smem_floats * sizeof(float), st>>>(a);
   CVG_LAUNCH_CHECK();
   return 0;
 }
@@ -1026,16 +1040,24 @@ static int finish_step(Engine& e, int net_mask, int kind, int M, int flags, floa
                                      e.ws.ctl, e.step_dcounter, update ? net_mask : 0);
   CVG_LAUNCH_CHECK();
   e.step_dcounter = 0;
+  // Inside a label visit the rest - gradient reduction (own exchange channel), loss read-out, Adam - runs on side stream 0
+  // beside the next step's head (noise fill, batch draw and staging).  Whatever needs the updated network is ordered after
+  // it: the power iteration is queued on the same stream, every step joins the side streams before its first GEMM on D or
+  // C, the E/G step and the hoisted generator forward join before they start.
+  bool beside = e.in_visit && e.ms.on && (one || e.nvl.on);
+  for (int net = 0; net < 4 && beside && !one; ++net)
+    if ((net_mask & (1 << net)) && 2 * (size_t)(e.lay[net].n_param + CVG_GRAD_TAIL) * sizeof(float) > e.nvl.dev.slot_bytes) beside = false;
+  const cudaStream_t sx = beside ? fork_to(e, 0, st) : st;
   if (!one) {
     for (int net = 0; net < 4; ++net)
       if (net_mask & (1 << net))
-        CVG_TRY(comm_all_reduce_f32(e, e.buf[net].grads, e.lay[net].n_param + (net == first ? CVG_GRAD_TAIL : 0), st));
+        CVG_TRY(comm_all_reduce_f32(e, e.buf[net].grads, e.lay[net].n_param + (net == first ? CVG_GRAD_TAIL : 0), sx, beside ? 2 : 0));
     if (loss_out) {
-      unpack_loss_kernel<<<1, 32, 0, st>>>(tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, 1, tail);
+      unpack_loss_kernel<<<1, 32, 0, sx>>>(tail, loss_out, kind, (float)M * (float)e.world, (float)e.F, 1, tail);
       CVG_LAUNCH_CHECK();
     }
   }
-  if (update) CVG_TRY(run_adam(e, net_mask, st, ov, true));
+  if (update) CVG_TRY(run_adam(e, net_mask, sx, ov, true));
   return 0;
 }
 
@@ -1336,6 +1358,7 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   //   side 1          : batch staging, G(z_prior), then D(x_fake) forward and backward to x_fake
   //   side 0          : power iteration, then C(x_fake) forward, loss and backward to x_fake (after D's: both add to ws.dx)
   const bool three = !e.mk.recording && e.ms.on && (e.world <= 1 || local_bn || fold_stats(e, local_bn));
+  join_sides(e, st);      // the previous step's Adam (visit: side stream 0) beside the fill just launched
   if (three) {
     const cudaStream_t sA = fork_to(e, 0, st), sB = fork_to(e, 1, st);
     CVG_TRY(launch_sn(e, 1, true, sA));
@@ -1449,6 +1472,7 @@ static int hoist_generator(Engine& e, int nh, int label, int B, int flags, cudaS
   rng.set = false;
   rng.off = 1;
   if (e.mk.recording) e.mk.par_next = false;
+  join_sides(e, st);
   CVG_TRY(emit_zero(e, w.hfst, sizeof(double) * 3 * HOIST_MAX * 2 * STAT_C, st));
   CVG_TRY(prep_net(e, CVG_NET_GENERATOR, true, false, false));
   FillArgs f;
@@ -1470,6 +1494,7 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
   if (B_global != (int64_t)B * e.world) CVG_FAIL("cvg_visit: B_global must be B_local * world_size");
   // step-program kernel: the whole visit is ONE program = one launch (batch draws included)
   ProgramScope prog(e);
+  struct InVisit { Engine& e; explicit InVisit(Engine& en) : e(en) { e.in_visit = true; } ~InVisit() { e.in_visit = false; } } in_visit(e);
   const int nh = e.hoist ? (d_loop + c_loop < HOIST_MAX ? d_loop + c_loop : HOIST_MAX) : 0;
   if (nh > 0) CVG_TRY(hoist_generator(e, nh, label, B, flags, st));
   int i = 0;
@@ -1506,11 +1531,13 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       }
     }
   }
+  join_sides(e, st);       // the caller's stream continues after everything the visit enqueued
   return prog.finish(st);
 }
 
 void set_all_kernel_attributes() {
   mk_set_kernel_attributes();
+  cudaFuncSetAttribute(sn_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_W_SMEM_MAX);
   // cudaFuncSetAttribute is done once, eagerly, so that nothing but launches happens during graph capture
 #define CVG_MN_ATTR(W, A, E) cudaFuncSetAttribute(gemm_mn_kernel<W, A, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   CVG_MN_ATTR(true, OP_PLAIN, EP_LINEAR) CVG_MN_ATTR(true, OP_BN_ACT, EP_LINEAR) CVG_MN_ATTR(true, OP_REPARAM, EP_LINEAR)
