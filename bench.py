@@ -298,6 +298,8 @@ def run_ours(args):
     seed = 1234
     loss = torch.zeros(OPT_STEPS, 4, device=dev)
     LOOPS = (D_LOOP, C_LOOP, G_LOOP)
+    if args.quick and os.environ.get("CVG_BENCH_LOOPS"):      # diagnostics: time one kind of step, e.g. "5,0,0"
+        LOOPS = tuple(int(v) for v in os.environ["CVG_BENCH_LOOPS"].split(","))
     eng.ctl_set(seed=seed, counter=0, lambda_class=0.25)
 
     def visit_eager(label):

@@ -9,6 +9,7 @@ from . import config, datasets, models  # noqa: F401
 from ._lib import CvgError  # noqa: F401
 from .classifier import Classifier  # noqa: F401
 from .cvae_gan import CVAEGAN, lambda_class_at  # noqa: F401
+from .cgan import CGAN  # noqa: F401
 from .engine import Engine, patience_scan  # noqa: F401
 
-__all__ = ["CVAEGAN", "Classifier", "Engine", "CvgError", "config", "datasets", "models", "patience_scan", "lambda_class_at"]
+__all__ = ["CVAEGAN", "CGAN", "Classifier", "Engine", "CvgError", "config", "datasets", "models", "patience_scan", "lambda_class_at"]

@@ -21,3 +21,10 @@ cvae_gan_config = {
     'lambda_class': 0.5,
     'confidence_threshold': 0.5,
 }
+
+# sibling trainer CGAN (/root/reference/src/config/gan_config.py:40-44, read by src/cgan.py:41-42,165-171,262)
+cgan_config = {
+    'lambda_adv': 1.0,
+    'lambda_class': 0.5,
+    'confidence_threshold': 0.5,
+}

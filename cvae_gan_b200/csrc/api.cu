@@ -247,7 +247,7 @@ int cvg_step_c(CvgHandle* h, const float* x_real, int label, int B, const CvgNoi
 int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoise* noise, uint64_t seed,
                uint64_t counter, float lambda_class_now, int flags, float* loss_out, void* stream) {
   H_OR_FAIL(h);
-  if (!x_real) CVG_FAIL("null x_real");
+  if (!x_real && !(flags & CVG_STEP_PRIOR_ONLY)) CVG_FAIL("null x_real");
   if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
   StepRng rng;
   rng.seed = seed; rng.counter = counter;

@@ -232,6 +232,7 @@ struct SeedArgs {
   float* dpre; long long sdpre;        // [2][F][ld]
   float coef_recon;
   double* recon_acc;
+  int prior_only = 0;                  // CGAN generator step: one pass, and it is the x_fake (dx) one
 };
 
 __global__ void g_seed_kernel(const SeedArgs g) {
@@ -245,7 +246,7 @@ __global__ void g_seed_kernel(const SeedArgs g) {
     if (m < g.M) {
       const float o = g.out[(long long)pass * g.sout + off];
       float dout;
-      if (pass == 0) {
+      if (pass == 0 && !g.prior_only) {
         const float diff = o - g.x[off];
         sq = (double)diff * (double)diff;
         dout = g.coef_recon * 2.0f * diff;
@@ -256,7 +257,7 @@ __global__ void g_seed_kernel(const SeedArgs g) {
     }
     g.dpre[(long long)pass * g.sdpre + off] = d;
   }
-  if (pass == 0) {
+  if (pass == 0 && !g.prior_only) {
     sq = warp_sum_d(sq);
     if ((threadIdx.x & 31) == 0 && sq != 0.0) atomicAdd(g.recon_acc, sq);
   }

@@ -1313,8 +1313,80 @@ int step_classifier(Engine& e, const float* x, const long long* labels, int B, c
 // ------------------------------------------------------------------------------------------------
 // step E+G (cvae_gan.py:160-216)
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Sibling trainer CGAN, generator step (/root/reference/src/cgan.py:138-178): x_fake = G(z_prior, onehot)
+// only - no encoder, no reconstruction / KL terms, no real batch -, total = lambda_adv * (-mean D(x_fake)) +
+// lambda_class_now * CE(C(x_fake), label), Adam on the generator alone.  The critic and classifier steps of CGAN are
+// step_d / step_c (cgan.py:84-136 is cvae_gan.py:104-157 statement for statement).  Stand-alone kernels only.
+// ------------------------------------------------------------------------------------------------
+static int step_g_prior(Engine& e, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags, float* loss_out,
+                        cudaStream_t st) {
+  CVG_TRY(check_step(e, B));
+  if (e.mk.recording || mk_usable(e)) CVG_FAIL("the CGAN generator step runs on the stand-alone executor only (unset CVG_TRAIN_MODE)");
+  CVG_TRY(begin_step(e, rng, true, st));
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const bool local_bn = flags & CVG_STEP_LOCAL_BN;
+  const float Bg = (float)B * (float)e.world;
+  const float Bg_bn = local_bn ? (float)B : Bg;
+  const int G = CVG_NET_GENERATOR;
+  CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
+  FillArgs f;
+  fill_args(e, f, rng, B);
+  add_job(f, w.z, nz ? nz->z : nullptr, 0, e.Z, 1, RS_Z);
+  add_job(f, w.d_m1, nz ? nz->d_mask1 : nullptr, 1, e.dh[0], 1, RS_DMASK1);
+  add_job(f, w.d_m2, nz ? nz->d_mask2 : nullptr, 1, e.dh[1], 1, RS_DMASK2);
+  add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
+  add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
+  CVG_TRY(launch_fill(e, f, st));
+  join_sides(e, st);                                     // the previous step's Adam (visit: side stream 0)
+  CVG_TRY(launch_sn(e, 1, true, fork_to(e, 0, st)));
+  CVG_TRY(fwd_generator(e, 1, true, false, label, B, Bg_bn, local_bn, st));
+  join_sides(e, st);
+  const float* x_fake = w.g_out;
+  const cudaStream_t sc = fork_to(e, 1, st);
+  CVG_TRY(fwd_critic(e, x_fake, 0, 1, label, B, w.loss + L_DFAKE, st));
+  {                                                      // the class loss is reported even while its weight is 0 (cgan.py:162,181)
+    CVG_TRY(fwd_classifier(e, x_fake, 0, 1, true, B, sc));
+    CeArgs c;
+    c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
+    c.logits = w.c_logit; c.sl = (long long)e.K * ld;
+    c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
+    c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
+    c.ctl = w.ctl;
+    c.loss = w.loss + L_CE0;
+    CVG_TRY(emit_ce(e, c, B, 1, sc));
+  }
+  const float seedv[2] = {-e.cfg.lambda_adv / Bg, 0.f};
+  CVG_TRY(bwd_critic(e, x_fake, 0, 1, label, B, seedv, false, true, st));
+  if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_fake, 0, 1, B, false, true, true, sc, st));
+  join_sides(e, st);
+  SeedArgs s;
+  s.M = B; s.ld = w.ld; s.F = e.F;
+  s.out = w.g_out; s.sout = (long long)e.F * ld;
+  s.x = w.xT; s.dx = w.dx;
+  s.dpre = w.g_dout; s.sdpre = (long long)e.F * ld;
+  s.coef_recon = 0.f;
+  s.recon_acc = w.loss + L_RECON;
+  s.prior_only = 1;
+  g_seed_kernel<<<dim3((unsigned)((e.F * ld + 255) / 256), 1), 256, 0, st>>>(s);
+  CVG_LAUNCH_CHECK();
+  BnNetBwd gb;
+  gb.net = G; gb.npass = 1;
+  gb.h = w.g_h; gb.dy = w.g_dy;
+  gb.top_dy = w.g_dout; gb.s_top = (long long)e.F * ld;
+  gb.first_in.kind = OP_PLAIN; gb.first_in.rows = e.Z;
+  gb.first_in.p = w.z; gb.first_in.sp = (long long)e.Z * ld;
+  gb.first_K = e.Z;
+  gb.label_col = e.Z + label;
+  gb.want_first_dx = false;
+  CVG_TRY(bwd_bn_net(e, gb, B, Bg_bn, 0.f, local_bn, st));
+  return finish_step(e, 1 << G, 2, B, flags, loss_out, st);
+}
+
 int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
            float* loss_out, cudaStream_t st) {
+  if (flags & CVG_STEP_PRIOR_ONLY) return step_g_prior(e, label, B, nz, rng, flags, loss_out, st);
   CVG_TRY(check_step(e, B));
   ProgramScope prog(e);
   CVG_TRY(begin_step(e, rng, true, st));
@@ -1503,7 +1575,10 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
     for (int r = 0; r < reps; ++r, ++i) {
       e.hoist_x = (kind < 2 && i < nh) ? e.ws.hout + (size_t)i * e.F * e.ws.ld : nullptr;
       const float* x = nullptr;
-      if (x_batches) {
+      const bool no_batch = kind == 2 && (flags & CVG_STEP_PRIOR_ONLY);     // the CGAN generator step draws no real rows
+      if (no_batch) {
+        x = nullptr;
+      } else if (x_batches) {
         x = x_batches + (size_t)i * B * e.F;
       } else if (e.mk.recording) {
         e.mk.src_rows = class_rows; e.mk.src_n = n_rows; e.mk.src_Bg = B_global; e.mk.src_off = (long long)e.rank * B;
@@ -1519,7 +1594,7 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       rng.off = 1;                                   // sampling used counter + 0
       rng.lambda_nonzero = !(flags & CVG_VISIT_LAMBDA_ZERO);
       float* lo = loss_out ? loss_out + 4 * i : nullptr;
-      const int sf = flags & (CVG_STEP_LOCAL_BN | CVG_STEP_NO_UPDATE);
+      const int sf = flags & (CVG_STEP_LOCAL_BN | CVG_STEP_NO_UPDATE | CVG_STEP_PRIOR_ONLY);
       if (!e.mk.recording) e.step_dcounter = 2;      // two counter values per step (draw + noise), advanced by the step's tail
       if (kind == 0) CVG_TRY(step_d(e, x, label, B, nullptr, rng, sf, lo, st));
       else if (kind == 1) CVG_TRY(step_c(e, x, label, B, nullptr, rng, sf, lo, st));

@@ -55,6 +55,15 @@ def dataset_tensors(dataset):
 
 
 class CVAEGAN:
+    # what the sibling trainers (cgan.py) change: the config dict, the loss_history rows taken from a step's loss_out
+    # {recon, kl, adv, class}, the visit flags, and how many generator forwards a generator step runs
+    _CONFIG_KEY = 'cvae_gan_config'
+    _HISTORY = (('recon_loss', 0), ('kl_loss', 1), ('adv_loss', 2), ('class_loss', 3))
+    _VISIT_FLAGS = 0
+    _G_FORWARDS_PER_G_STEP = 2
+    _USES_ENCODER = True
+    _NAME = "CVAE-GAN"
+
     def __init__(self, config=None, datasets=None, max_rows: int = None):
         """`config` / `datasets`: modules with the reference's names (defaults: this package's mirrors;
         pass the reference's own `src.config`, `src.datasets` to run inside its scripts)."""
@@ -66,24 +75,28 @@ class CVAEGAN:
         self.rank, self.world_size = _dist_info()
 
         # same construction (and CPU-generator draw) order as cvae_gan.py:19-39
-        self.encoder = models.CVAEGANEncoderModel(self.feature_num, self.label_num, gc.z_size)
+        encoder = models.CVAEGANEncoderModel(self.feature_num, self.label_num, gc.z_size)
+        if self._USES_ENCODER:
+            self.encoder = encoder
+        self._encoder_module = encoder      # the engine owns four networks; CGAN never runs (or exposes) this one
         self.generator = models.CVAEGANGeneratorModel(gc.z_size, self.label_num, self.feature_num)
         self.discriminator = models.CVAEGANDiscriminatorModel(self.feature_num, self.label_num)
         self.classifier = models.CVAEGANClassifierModel(self.feature_num, self.label_num)
 
         self.samples = dict()
-        cc = gc.cvae_gan_config
-        self.lambda_recon = cc['lambda_recon']
-        self.lambda_kl = cc['lambda_kl']
+        cc = getattr(gc, self._CONFIG_KEY)
+        if 'lambda_recon' in cc:
+            self.lambda_recon = cc['lambda_recon']
+            self.lambda_kl = cc['lambda_kl']
         self.lambda_adv = cc['lambda_adv']
         self.lambda_class = cc['lambda_class']
-        self.loss_history = {'recon_loss': [], 'kl_loss': [], 'adv_loss': [], 'class_loss': []}
+        self.loss_history = {k: [] for k, _ in self._HISTORY}
 
         rows = max_rows or max(int(gc.batch_size) // self.world_size, 1 << 14)
         self.engine = Engine(self.feature_num, self.label_num, gc.z_size, rows,
-                             lambda_recon=self.lambda_recon, lambda_kl=self.lambda_kl, lambda_adv=self.lambda_adv,
+                             lambda_recon=cc.get('lambda_recon', 0.0), lambda_kl=cc.get('lambda_kl', 0.0), lambda_adv=self.lambda_adv,
                              g_lr=gc.g_lr, d_lr=gc.d_lr, c_lr=gc.c_lr, world_size=self.world_size, rank=self.rank)
-        for net, mod in ((NET_ENCODER, self.encoder), (NET_GENERATOR, self.generator),
+        for net, mod in ((NET_ENCODER, encoder), (NET_GENERATOR, self.generator),
                          (NET_DISCRIMINATOR, self.discriminator), (NET_CLASSIFIER, self.classifier)):
             mod.attach(self.engine, net)
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
@@ -93,12 +106,16 @@ class CVAEGAN:
         self.use_cuda_graphs = True   # False: same kernels launched eagerly (debugging aid; identical numerics)
 
     # ------------------------------------------------------------------------------------------------
+    def _networks(self):
+        nets = (self.generator, self.discriminator, self.classifier)
+        return ((self.encoder,) + nets) if self._USES_ENCODER else nets
+
     def _next(self) -> int:
         self._counter += 1
         return self._counter
 
     def _sync_bn_counters(self):
-        for net, mod in ((NET_ENCODER, self.encoder), (NET_GENERATOR, self.generator)):
+        for net, mod in ((NET_ENCODER, self._encoder_module), (NET_GENERATOR, self.generator)):
             k = self._bn_calls[net]
             if k:
                 for m in mod.modules():
@@ -112,14 +129,15 @@ class CVAEGAN:
         eng = self.engine
         # the learning rates and loss weights were handed to the engine at construction (CvgConfig); the reference re-reads them
         # here (cvae_gan.py:75-97, 207-212) - refuse to train silently with stale values
-        want = (float(gc.g_lr), float(gc.d_lr), float(gc.c_lr), float(self.lambda_recon), float(self.lambda_kl), float(self.lambda_adv))
+        want = (float(gc.g_lr), float(gc.d_lr), float(gc.c_lr), float(getattr(self, "lambda_recon", 0.0)),
+                float(getattr(self, "lambda_kl", 0.0)), float(self.lambda_adv))
         have = (eng.cfg.g_lr, eng.cfg.d_lr, eng.cfg.c_lr, eng.cfg.lambda_recon, eng.cfg.lambda_kl, eng.cfg.lambda_adv)
         if any(abs(a - b) > 1e-12 + 1e-6 * abs(b) for a, b in zip(want, have)):
             raise ValueError("g_lr / d_lr / c_lr / lambda_recon / lambda_kl / lambda_adv changed after CVAEGAN() was constructed: "
                              f"configured {want}, engine holds {have}; construct a new CVAEGAN after changing them")
         if self.world_size > 1:
             eng.verify_replicas()
-        for m in (self.encoder, self.generator, self.discriminator, self.classifier):
+        for m in self._networks():
             m.train()
         self._divide_samples(dataset)
         # fresh optimisers every fit(), like cvae_gan.py:75-97
@@ -128,7 +146,7 @@ class CVAEGAN:
             eng.adam_v[net].zero_()
             eng.grads[net].zero_()
             eng.set_adam_step(net, 0)
-        lam = gc.cvae_gan_config['lambda_class']
+        lam = getattr(gc, self._CONFIG_KEY)['lambda_class']
         loops = (int(gc.d_loop_num), int(gc.c_loop_num), int(gc.g_loop_num))
         n_steps = sum(loops)
         batch = int(gc.batch_size)
@@ -139,7 +157,7 @@ class CVAEGAN:
         for e in range(gc.epochs):
             lam_e = lambda_class_at(e, lam)
             eng.ctl_set(lambda_class=lam_e)
-            flags = VISIT_LAMBDA_ZERO if lam_e == 0.0 else 0
+            flags = (VISIT_LAMBDA_ZERO if lam_e == 0.0 else 0) | self._VISIT_FLAGS
             for target_label in self.samples.keys():
                 key = (target_label, flags, batch, loops)
                 if self.use_cuda_graphs:
@@ -157,21 +175,20 @@ class CVAEGAN:
                     eng.visit(target_label, batch, class_rows=self.samples[target_label], loops=loops, flags=flags,
                               loss_out=losses)
                 self._counter += 2 * n_steps
-                self._bn_calls[NET_GENERATOR] += loops[0] + loops[1] + 2 * loops[2]
-                self._bn_calls[NET_ENCODER] += loops[2]
+                self._bn_calls[NET_GENERATOR] += loops[0] + loops[1] + self._G_FORWARDS_PER_G_STEP * loops[2]
+                if self._USES_ENCODER:
+                    self._bn_calls[NET_ENCODER] += loops[2]
             # one read-back per epoch: the last label's last generator step (cvae_gan.py:219-222)
-            recon, kl, adv, cls = losses[n_steps - 1].tolist()
-            self.loss_history['recon_loss'].append(recon)
-            self.loss_history['kl_loss'].append(kl)
-            self.loss_history['adv_loss'].append(adv)
-            self.loss_history['class_loss'].append(cls)
+            row = losses[n_steps - 1].tolist()
+            for key, col in self._HISTORY:
+                self.loss_history[key].append(row[col])
             if e % 50 == 0:
-                print(f"CVAE-GAN训练轮次: {e}/{gc.epochs}, 重构损失: {recon:.4f}, KL损失: {kl:.4f}, "
-                      f"对抗损失: {adv:.4f}, 分类损失: {cls:.4f}")
+                names = {'recon_loss': '重构损失', 'kl_loss': 'KL损失', 'adv_loss': '对抗损失', 'class_loss': '分类损失'}
+                print(f"{self._NAME}训练轮次: {e}/{gc.epochs}, " + ", ".join(f"{names[k]}: {row[c]:.4f}" for k, c in self._HISTORY))
         torch.cuda.synchronize(eng.device)
         graphs.clear()
         self._sync_bn_counters()
-        for m in (self.encoder, self.generator, self.discriminator, self.classifier):
+        for m in self._networks():
             m.eval()
 
     def _divide_samples(self, dataset) -> None:
@@ -244,7 +261,7 @@ class CVAEGAN:
         in large fused batches and the chunk/patience bookkeeping is replayed on the keep mask
         (cvg_patience_scan): the result is the same prefix of accepted rows of the stream."""
         if confidence_threshold is None:
-            confidence_threshold = self.config.gan_config.cvae_gan_config['confidence_threshold']
+            confidence_threshold = getattr(self.config.gan_config, self._CONFIG_KEY)['confidence_threshold']
         eng = self.engine
         num = int(num)
         if self.generator.training:

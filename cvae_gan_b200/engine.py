@@ -234,6 +234,15 @@ class Engine:
                                   float(lambda_class), flags, _ptr(out), _stream()))
         return out
 
+    def step_g_prior(self, batch: int, label: int, lambda_class: float, noise=None, seed=0, counter=0, flags=0, loss_out=None):
+        """The sibling trainer CGAN's generator step (src/cgan.py:138-178): no real batch, generator update only."""
+        from ._lib import STEP_PRIOR_ONLY
+        keep = []
+        out = self.loss_buf if loss_out is None else loss_out
+        check(self.lib.cvg_step_g(self.h, None, int(label), int(batch), self._noise(noise, keep), seed, counter,
+                                  float(lambda_class), flags | STEP_PRIOR_ONLY, _ptr(out), _stream()))
+        return out
+
     def ctl_set(self, seed=None, counter=None, lambda_class=None):
         """Write the device control block (Philox key/counter and/or this epoch's lambda_class)."""
         set_rng = seed is not None

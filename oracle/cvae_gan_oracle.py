@@ -659,6 +659,56 @@ class OracleCVAEGAN:
         self.last_losses.update(losses)
         return losses, grads
 
+    # ---- sibling trainer CGAN: cgan.py:138-178, the generator step without the VAE branch ------------
+    def step_g_prior(self, label: int, B: int, noise, lambda_class_now: float, apply_update=True):
+        """CGAN generator step: x_fake = G(z_prior, onehot) only; total = lambda_adv * (-mean D(x_fake)) + lambda_now * CE;
+        Adam on the generator alone (cgan.py:159-178).  No real batch is drawn in this step."""
+        c = self.cfg
+        tgt = torch.full([B], int(label), dtype=torch.long)
+        z_prior = noise.randn(B, c.z_size, tag="z")
+        x_fake = generator_forward(self.sd["generator"], z_prior, label, self.training["generator"], self.dp)
+        d_fake = discriminator_forward(self.sd["discriminator"], x_fake, label, self.training["discriminator"], noise)
+        adv = -self._mean(d_fake)
+        cls = self._ce(classifier_forward(self.sd["classifier"], x_fake, self.training["classifier"], noise), tgt)
+        total = c.lambda_adv * adv + lambda_class_now * cls
+        grads = self._backward(total, ["generator"], apply_update)
+        losses = {"adv_loss": self._global_scalar(adv), "class_loss": self._global_scalar(cls)}
+        self.last_losses.update(losses)
+        return losses, grads
+
+    def fit_cgan(self, x: torch.Tensor, y: torch.Tensor, noise=None, step_hook=None):
+        """CGAN.fit (cgan.py:51-196): the critic and classifier steps are the CVAE-GAN's (cgan.py:84-136 is
+        cvae_gan.py:104-157 statement for statement); the generator step is `step_g_prior`; loss_history keeps adv / class."""
+        noise = noise or TorchNoise()
+        c = self.cfg
+        self.loss_history = {"adv_loss": [], "class_loss": []}
+        for n in ("generator", "discriminator", "classifier"):
+            self.training[n] = True
+        self.divide_samples(x, y)
+        self.make_optimizers()
+        for e in range(c.epoch_offset, c.epoch_offset + c.epochs):
+            losses = None
+            for label in self.samples.keys():
+                for _ in range(c.d_loop_num):
+                    xr = self.get_target_samples(label, c.batch_size, noise)
+                    out = self.step_d(xr, label, noise)
+                    if step_hook:
+                        step_hook("d", e, label, out)
+                for _ in range(c.c_loop_num):
+                    xr = self.get_target_samples(label, c.batch_size, noise)
+                    out = self.step_c(xr, label, noise)
+                    if step_hook:
+                        step_hook("c", e, label, out)
+                for _ in range(c.g_loop_num):
+                    losses, g = self.step_g_prior(label, c.batch_size, noise, lambda_class_schedule(e, c.lambda_class))
+                    if step_hook:
+                        step_hook("g", e, label, (losses, g))
+            for k in self.loss_history:
+                self.loss_history[k].append(losses[k])
+        for n in ("generator", "discriminator", "classifier"):
+            self.training[n] = False
+        return self
+
     # ---- fit (cvae_gan.py:59-236) --------------------------------------------------------------
     def fit(self, x: torch.Tensor, y: torch.Tensor, noise=None, step_hook=None):
         noise = noise or TorchNoise()

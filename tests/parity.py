@@ -70,6 +70,8 @@ def draw_noise(kind: str, B: int, Z: int, g: torch.Generator, h1=256, h2=128):
     z = torch.randn(B, Z, generator=g)
     inj.push("z", z)
     dev["z"] = z.cuda()
+    if kind == "p":
+        kind = "gp"
     if kind == "g":
         eps = torch.randn(B, Z, generator=g)
         inj.push("eps", eps)
@@ -187,6 +189,8 @@ def twin_step(kind, orc64, x, label, inj64, lambda_class=0.25, update=False):
         _, grads = orc64.step_d(xd, label, inj64, apply_update=update)
     elif kind == "c":
         _, grads = orc64.step_c(xd, label, inj64, apply_update=update)
+    elif kind == "p":
+        _, grads = orc64.step_g_prior(label, x.shape[0], inj64, lambda_class, apply_update=update)
     else:
         _, grads = orc64.step_g(xd, label, inj64, lambda_class, apply_update=update)
     return grads
@@ -220,6 +224,11 @@ def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True, twin=N
         out = eng.step_c(xd, label, noise=dev, flags=flags).tolist()
         ref = [float(loss)]
         got = [out[0]]
+    elif kind == "p":          # sibling trainer CGAN's generator step (cgan.py:138-178): no real batch (x only gives B)
+        losses, grads = orc.step_g_prior(label, B, inj, lambda_class, apply_update=update)
+        out = eng.step_g_prior(B, label, lambda_class, noise=dev, flags=flags).tolist()
+        ref = [0.0, 0.0, losses["adv_loss"], losses["class_loss"]]
+        got = out
     else:
         losses, grads = orc.step_g(x, label, inj, lambda_class, apply_update=update)
         out = eng.step_g(xd, label, lambda_class, noise=dev, flags=flags).tolist()

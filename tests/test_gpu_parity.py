@@ -56,6 +56,52 @@ def test_step_losses_and_gradients(kind, F_, K, B, executor):
 
 
 # ---------------------------------------------------------------------------------------------------
+# the sibling trainer CGAN's generator step (src/cgan.py:138-178; its D and C steps are the ones above)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("F_,K,B", [(10, 5, 64), (10, 4, 333), (10, 5, 4096)])
+@pytest.mark.parametrize("lam", [0.0, 0.25])
+def test_cgan_generator_step_losses_and_gradients(F_, K, B, lam):
+    orc, eng, g = P.make_pair(F_, K, B, seed=9 + B)
+    x = torch.zeros(B, F_)
+    eng.zero_grads()
+    enc0 = eng.params[0].clone()
+    twin = orc.twin64() if B >= 4096 else None
+    ref, got, grads = P.run_step("p", orc, eng, x, K - 2, g, lambda_class=lam, update=False, twin=twin)
+    assert P.losses_close(ref, got), (ref, got)          # {0, 0, adv, class}: the class loss is reported even at weight 0
+    report = []
+    P.compare_grads(eng, orc, ["generator"], grads, report, grads64=P.run_step.last_twin_grads)
+    report = [r for r in report if not any(r[0].endswith(k) for ks in P.PRE_BN_BIASES.values() for k in ks)]
+    P.assert_report(report, "CGAN generator step gradients")
+    assert float(eng.grads[0].abs().max()) == 0.0 and torch.equal(eng.params[0], enc0)      # no encoder in CGAN
+    rep2 = []
+    P.compare_state(eng, orc, rep2, loose_prebn_atol=1e-3)
+    P.assert_report(rep2, "CGAN generator step state")
+    eng.close()
+
+
+def test_cgan_two_label_visits_trajectory():
+    """CGAN.fit's step sequence (5 D + 5 C + 3 generator steps per label visit) with Adam updates."""
+    F_, K, B = 10, 5, 256
+    orc, eng, g = P.make_pair(F_, K, B, seed=27)
+    x, y = P.make_data(F_, K, [400, 256, 100, 300, 300], seed=2)
+    orc.divide_samples(x, y)
+    twin = orc.twin64()
+    for label in (1, 4):
+        for kind, reps in (("d", 5), ("c", 5), ("p", 3)):
+            for _ in range(reps):
+                idx = torch.randperm(len(orc.samples[label]), generator=g)[:B]
+                xb = orc.samples[label][idx].contiguous()
+                ref, got, _ = P.run_step(kind, orc, eng, xb, label, g, lambda_class=0.25, update=True, twin=twin)
+                assert P.losses_close(ref, got, rtol=2e-3, atol=5e-4), (kind, ref, got)
+    report = []
+    P.compare_state(eng, orc, report, loose_prebn_atol=6 * 2e-4 * 1.5, atol_frac=2e-3, outlier_frac=2e-3, hard_atol=10 * 2e-4,
+                    twin=twin)
+    P.assert_report(report, "parameters after two CGAN label visits")
+    assert eng.get_adam_step(1) == 6 and eng.get_adam_step(0) == 0 and eng.get_adam_step(2) == 10
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
 # trajectory: two label visits (5 D + 5 C + 3 G steps each) with Adam updates, lambda_class != 0
 # ---------------------------------------------------------------------------------------------------
 def test_two_label_visits_trajectory():

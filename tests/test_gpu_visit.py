@@ -67,6 +67,68 @@ def test_visit_eager_equals_graph_equals_steps():
         assert torch.allclose(other[1], outs[0][1], rtol=1e-3, atol=4 * 2e-4 * 1.5)
 
 
+def test_cgan_visit_equals_steps_and_fit():
+    """CVG_STEP_PRIOR_ONLY visits (CGAN): graph replay == per-step calls; `CGAN().fit` end to end."""
+    from cvae_gan_b200._lib import STEP_PRIOR_ONLY
+    g = torch.Generator().manual_seed(0)
+    rows = torch.rand(5000, F_, generator=g).cuda()
+    loops = (2, 2, 2)
+    outs = []
+    for mode in ("graph", "steps"):
+        eng = _engine()
+        eng.ctl_set(seed=78, counter=20, lambda_class=0.25)
+        loss = torch.zeros(sum(loops), 4, device="cuda")
+        if mode == "graph":
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                eng.visit(1, B, class_rows=rows, loops=loops, loss_out=loss, flags=STEP_PRIOR_ONLY)
+            gr.replay()
+            gr.replay()
+        else:
+            c = 20
+            for _ in range(2):
+                i = 0
+                for kind, reps in zip("dcg", loops):
+                    for _ in range(reps):
+                        if kind == "g":
+                            eng.step_g_prior(B, 1, 0.25, seed=78, counter=c + 1, loss_out=loss[i])
+                        else:
+                            x = eng.sample_rows(rows, B, seed=78, counter=c)
+                            (eng.step_d if kind == "d" else eng.step_c)(x, 1, seed=78, counter=c + 1, loss_out=loss[i])
+                        c += 2
+                        i += 1
+        torch.cuda.synchronize()
+        outs.append((loss.clone(), _flat(eng), [eng.get_adam_step(n) for n in range(4)]))
+        eng.close()
+    assert outs[0][2] == outs[1][2] == [0, 4, 4, 4]
+    assert torch.allclose(outs[1][0], outs[0][0], rtol=2e-3, atol=2e-4)
+    assert torch.allclose(outs[1][1], outs[0][1], rtol=1e-3, atol=4 * 2e-4 * 1.5)
+    assert float(outs[0][0][4:, :2].abs().max()) == 0.0          # no reconstruction / KL terms
+
+    import cvae_gan_b200 as cg
+    from tests.parity import make_data
+    x, y = make_data(F_, K, [300, 260, 64, 40, 300], seed=6)
+    perm = torch.randperm(len(y), generator=torch.Generator().manual_seed(2))
+    cg.datasets.tr_samples, cg.datasets.tr_labels = x[perm], y[perm]
+    cg.datasets.feature_num, cg.datasets.label_num = F_, K
+    cg.config.gan_config.batch_size, cg.config.gan_config.epochs = 64, 3
+    torch.manual_seed(0)
+    gan = cg.CGAN()
+    assert not hasattr(gan, "encoder") and not hasattr(gan, "lambda_recon") and sorted(gan.loss_history) == ["adv_loss", "class_loss"]
+    enc0 = gan.engine.params[0].clone()
+    gan.fit(cg.datasets.TrDataset())
+    assert [len(v) for v in gan.loss_history.values()] == [3, 3]
+    assert all(abs(v) < 1e3 and v == v for vs in gan.loss_history.values() for v in vs)
+    assert torch.equal(gan.engine.params[0], enc0)                                                  # no encoder in CGAN
+    assert int(gan.generator.state_dict()["main_model.1.num_batches_tracked"]) == 3 * K * (5 + 5 + 3)
+    assert not gan.generator.training and not gan.classifier.training
+    s = gan.generate_samples(2, 50)
+    assert s.shape == (50, F_) and s.device.type == "cpu" and float(s.min()) >= 0.0 and float(s.max()) <= 1.0
+    q = gan.generate_qualified_samples(0, 20, confidence_threshold=0.0)
+    assert q.numel() == 0 or q.shape[1] == F_
+    assert sorted(gan.state_dict()) == ["classifier", "discriminator", "generator"]
+
+
 def test_cvaegan_fit_generate_and_filter():
     import cvae_gan_b200 as cg
     from tests.parity import make_data

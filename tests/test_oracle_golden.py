@@ -159,3 +159,67 @@ def test_classifier_fit_and_test_match_reference(golden_dir):
     m, cm = CO.macro_metrics(yte, CO.predict(sd, xte), K)
     assert np.array_equal(cm.numpy().astype(np.int64), gz["confusion"])
     assert np.allclose([m["Precision"], m["Recall"], m["F1"]], gz["metrics"], atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# sibling trainer CGAN (src/cgan.py) - fixtures made by oracle/make_golden_cgan.py from the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+NETS3 = ("generator", "discriminator", "classifier")
+
+
+def _replay_cgan(golden_dir, epoch_offset):
+    torch.set_num_threads(1)
+    npz = _load(golden_dir, "ref_cgan_a.npz")
+    F_, K, B, fit_seed, gen_seed, _ = [int(v) for v in npz["meta"]]
+    st = _states(npz, "init")
+    st["encoder"] = _states(_load(golden_dir, "ref_fit_a.npz"), "init")["encoder"]      # CGAN has no encoder: never touched
+    cfg = O.OracleConfig(batch_size=B, epochs=2, epoch_offset=epoch_offset)
+    orc = O.OracleCVAEGAN(F_, K, cfg).load_state(st)
+    enc0 = {k: v.detach().clone() for k, v in orc.sd["encoder"].items()}
+    torch.manual_seed(fit_seed)
+    orc.fit_cgan(torch.from_numpy(npz["x"]), torch.from_numpy(npz["y"]))
+    for k, v in orc.sd["encoder"].items():
+        assert torch.equal(v.detach(), enc0[k]), k
+    return npz, orc, gen_seed
+
+
+def test_cgan_fit_epoch0_1_and_generation_match_reference(golden_dir):
+    npz, orc, gen_seed = _replay_cgan(golden_dir, 0)
+    assert list(orc.samples.keys()) == npz["sample_keys"].tolist()
+    assert sorted(orc.loss_history) == ["adv_loss", "class_loss"]
+    for k in orc.loss_history:
+        np.testing.assert_allclose(orc.loss_history[k], npz["loss/" + k], rtol=2e-6, atol=1e-7)
+    fin = _states(npz, "final")
+    st = orc.state()
+    for net in NETS3:
+        for key, ref in fin[net].items():
+            got = st[net][key]
+            if ref.dtype == torch.int64:
+                assert torch.equal(got, ref), (net, key)
+            else:
+                torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-7, msg=f"{net}/{key}")
+    torch.manual_seed(gen_seed)
+    s = orc.generate_samples(1, 37)
+    torch.testing.assert_close(s, torch.from_numpy(npz["gen/samples_l1_n37"]), rtol=1e-5, atol=1e-6)
+    for thr in (0.2, 0.5):
+        for lab in (0, 3):
+            q = orc.generate_qualified_samples(lab, 25, thr)
+            ref = torch.from_numpy(npz[f"gen/qualified_l{lab}_thr{thr}"])
+            q = q.reshape(-1, 10) if q.numel() else torch.zeros(0, 10)
+            assert q.shape == ref.shape, (thr, lab, q.shape, ref.shape)
+            torch.testing.assert_close(q, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_cgan_fit_epoch350_lambda_class_matches_reference(golden_dir):
+    b = _load(golden_dir, "ref_cgan_b.npz")
+    _, orc, _ = _replay_cgan(golden_dir, 350)
+    for k in orc.loss_history:
+        np.testing.assert_allclose(orc.loss_history[k], b["loss/" + k], rtol=2e-6, atol=1e-7)
+    st = orc.state()
+    for net in NETS3:
+        for key, t in st[net].items():
+            f = t.double().ravel().numpy()
+            d = b[f"digest/{net}/{key}"]
+            np.testing.assert_allclose([f.sum(), (f * f).sum()], d[:2], rtol=1e-5, atol=1e-6, err_msg=f"{net}/{key}")
+            n = min(8, f.size)
+            np.testing.assert_allclose(f[:n], d[2:2 + n], rtol=2e-5, atol=2e-7)
