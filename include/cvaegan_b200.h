@@ -244,6 +244,9 @@ int64_t cvg_launch_count(const CvgHandle* h);
  *                 1 = step-program kernel: one persistent tcgen05 kernel per optimiser step / label visit (CVG_TRAIN_MODE=mk)
  *   "mk_max_ops"  truncate every recorded program after this many ops (-1 = off; bisecting)
  *   "mk_allbar"   grid barrier before every op       "mk_coop"  cooperative launch on / off
+ *   "hoist"       1 (default; CVG_HOIST): a label visit runs the generator forward of all its critic / classifier steps once, up front
+ *   "streams"     1 (default; CVG_STREAMS): independent kernels of a step run on two event-joined side streams
+ *   "fuse_stats"  1 (default; CVG_FUSE_STATS): data parallel BatchNorm sums are pushed / polled inside the GEMM kernels
  * cvg_debug_get: "train_mode", "mk_supported", "mk_last_nops" (ops of the last program incl. the finish op).
  * cvg_debug_mk_cycles: per-op cycle counts of the last program as seen by CTA 0 (needs CVG_MK_DBG=1). */
 int cvg_debug_set(CvgHandle* h, const char* key, int value);

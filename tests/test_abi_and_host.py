@@ -163,3 +163,24 @@ def test_pipeline_minmax_and_pickle_format(tmp_path):
         assert a.shape == (50, 6) and b.shape == (50,) and c.shape == (20, 6) and d.shape == (20,)
     finally:
         ds.tr_samples, ds.tr_labels, ds.te_samples, ds.te_labels, ds.feature_num, ds.label_num = saved
+
+
+def test_flag_values_match_the_header():
+    """The Python constants are the header's enum values (include/cvaegan_b200.h)."""
+    import re
+    from cvae_gan_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cvaegan_b200.h")).read()
+    vals = {k: int(v) for k, v in re.findall(r"(CVG_(?:STEP|VISIT)_[A-Z_]+)\s*=\s*(\d+)", hdr)}
+    assert vals == {"CVG_STEP_NO_UPDATE": _lib.STEP_NO_UPDATE, "CVG_STEP_LOCAL_BN": _lib.STEP_LOCAL_BN,
+                    "CVG_VISIT_LAMBDA_ZERO": _lib.VISIT_LAMBDA_ZERO, "CVG_STEP_PRIOR_ONLY": _lib.STEP_PRIOR_ONLY}
+
+
+def test_cgan_host_class_mirrors_the_reference_surface():
+    """src/cgan.py:10-309: attribute and method names a caller of the reference's CGAN uses (no GPU: class level only)."""
+    import cvae_gan_b200 as cg
+    for name in ("fit", "_divide_samples", "_get_target_samples", "plot_loss_history", "generate_samples", "generate_qualified_samples"):
+        assert callable(getattr(cg.CGAN, name)), name
+    assert cg.config.gan_config.cgan_config == {"lambda_adv": 1.0, "lambda_class": 0.5, "confidence_threshold": 0.5}
+    from cvae_gan_b200 import cgan, models
+    assert cgan.CGANGeneratorModel is models.CVAEGANGeneratorModel      # same layers and state_dict keys (cgan_models.py)
+    assert cg.CGAN._HISTORY == (("adv_loss", 2), ("class_loss", 3)) and not cg.CGAN._USES_ENCODER
