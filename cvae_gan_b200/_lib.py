@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcvaegan_b200.so")
 
 NET_ENCODER, NET_GENERATOR, NET_DISCRIMINATOR, NET_CLASSIFIER = 0, 1, 2, 3
 NET_NAMES = ("encoder", "generator", "discriminator", "classifier")
-STEP_NO_UPDATE, STEP_LOCAL_BN, VISIT_LAMBDA_ZERO, STEP_PRIOR_ONLY = 1, 2, 4, 8
+STEP_NO_UPDATE, STEP_LOCAL_BN, VISIT_LAMBDA_ZERO, STEP_PRIOR_ONLY, STEP_CVAE = 1, 2, 4, 8, 16
 GRAD_TAIL = 16
 
 

@@ -31,6 +31,7 @@ class CGAN(CVAEGAN):
     _G_FORWARDS_PER_G_STEP = 1
     _USES_ENCODER = False
     _NAME = "CGAN"
+    _BUILD_ORDER = ("generator", "discriminator", "classifier")      # cgan.py:20-34
 
     def plot_loss_history(self):
         """cgan.py:216-262 (needs matplotlib, which is not part of the hot path)."""

@@ -28,3 +28,11 @@ cgan_config = {
     'lambda_class': 0.5,
     'confidence_threshold': 0.5,
 }
+
+# sibling trainer CVAE (/root/reference/src/config/gan_config.py:51-56, read by src/cvae.py:40-42,145-151,274)
+cvae_config = {
+    'lambda_recon': 1.0,
+    'lambda_kl': 0.01,
+    'lambda_class': 0.1,
+    'confidence_threshold': 0.5,
+}

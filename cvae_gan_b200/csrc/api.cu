@@ -248,6 +248,7 @@ int cvg_step_g(CvgHandle* h, const float* x_real, int label, int B, const CvgNoi
                uint64_t counter, float lambda_class_now, int flags, float* loss_out, void* stream) {
   H_OR_FAIL(h);
   if (!x_real && !(flags & CVG_STEP_PRIOR_ONLY)) CVG_FAIL("null x_real");
+  if ((flags & CVG_STEP_PRIOR_ONLY) && (flags & CVG_STEP_CVAE)) CVG_FAIL("CVG_STEP_PRIOR_ONLY and CVG_STEP_CVAE are mutually exclusive");
   if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
   StepRng rng;
   rng.seed = seed; rng.counter = counter;
@@ -271,6 +272,8 @@ int cvg_visit(CvgHandle* h, int label, int B_local, int64_t B_global, const floa
   H_OR_FAIL(h);
   if (label < 0 || label >= h->e.K) CVG_FAIL("label out of range");
   if (d_loop < 0 || c_loop < 0 || g_loop < 0) CVG_FAIL("cvg_visit: negative loop count");
+  if ((flags & CVG_STEP_PRIOR_ONLY) && (flags & CVG_STEP_CVAE)) CVG_FAIL("CVG_STEP_PRIOR_ONLY and CVG_STEP_CVAE are mutually exclusive");
+  if ((flags & CVG_STEP_CVAE) && d_loop != 0) CVG_FAIL("cvg_visit: a CVAE visit has no critic steps (d_loop must be 0, cvae.py:86-166)");
   return visit(h->e, label, B_local, B_global, class_rows, n_rows, x_batches, d_loop, c_loop, g_loop, flags, loss_out,
                (cudaStream_t)stream);
 }

@@ -223,6 +223,8 @@ __global__ void ce_kernel(const CeArgs g) {
 //   pass 0 (x_recon): dout = lambda_recon * 2 (o - x) / (Bg F)     and  recon += (o - x)^2
 //   pass 1 (x_fake) : dout = dx (accumulated input gradient of critic + classifier)
 //   dpre = dout * o * (1 - o)
+// add_dx (sibling trainer CVAE, cvae.py:141-157): ONE pass, the classifier reads x_recon itself, so its input gradient
+// joins the reconstruction term: dout = lambda_recon * 2 (o - x) / (Bg F) + dx
 // ------------------------------------------------------------------------------------------------
 struct SeedArgs {
   int M, ld, F;
@@ -233,6 +235,7 @@ struct SeedArgs {
   float coef_recon;
   double* recon_acc;
   int prior_only = 0;                  // CGAN generator step: one pass, and it is the x_fake (dx) one
+  int add_dx = 0;                      // CVAE generator step: pass 0 also receives dx (classification term on x_recon)
 };
 
 __global__ void g_seed_kernel(const SeedArgs g) {
@@ -250,6 +253,7 @@ __global__ void g_seed_kernel(const SeedArgs g) {
         const float diff = o - g.x[off];
         sq = (double)diff * (double)diff;
         dout = g.coef_recon * 2.0f * diff;
+        if (g.add_dx) dout += g.dx[off];
       } else {
         dout = g.dx[off];
       }

@@ -1384,9 +1384,87 @@ static int step_g_prior(Engine& e, int label, int B, const CvgNoise* nz, const S
   return finish_step(e, 1 << G, 2, B, flags, loss_out, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sibling trainer CVAE, encoder / generator step (/root/reference/src/cvae.py:117-166): mu, logvar = E(x);
+// z_enc = mu + eps * std; x_recon = G(z_enc, onehot) - ONE generator pass, no critic, no z_prior -;
+// total = lambda_recon * MSE(x_recon, x) + lambda_kl * KL + lambda_class_now * CE(C(x_recon), label): the classifier reads
+// the RECONSTRUCTION, so its input gradient joins the reconstruction term at the generator's output (SeedArgs.add_dx).
+// Adam on encoder and generator.  The classifier step of CVAE is step_c (cvae.py:89-115 is cvae_gan.py:131-157 statement for
+// statement); there is no critic step.  Stand-alone kernels only, one stream.
+// ------------------------------------------------------------------------------------------------
+static int step_g_cvae(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
+                       float* loss_out, cudaStream_t st) {
+  CVG_TRY(check_step(e, B));
+  if (e.mk.recording || mk_usable(e)) CVG_FAIL("the CVAE encoder/generator step runs on the stand-alone executor only (unset CVG_TRAIN_MODE)");
+  CVG_TRY(begin_step(e, rng, true, st));
+  const Workspace& w = e.ws;
+  const size_t ld = w.ld;
+  const bool local_bn = flags & CVG_STEP_LOCAL_BN;
+  const float Bg = (float)B * (float)e.world;
+  const float Bg_bn = local_bn ? (float)B : Bg;
+  const int E = CVG_NET_ENCODER, G = CVG_NET_GENERATOR;
+  CVG_TRY(emit_zero(e, w.acc, w.acc_bytes, st));
+  FillArgs f;
+  fill_args(e, f, rng, B);
+  add_job(f, w.z, nz ? nz->eps : nullptr, 0, e.Z, 1, RS_EPS);     // eps in slot 0: reparameterisation fused into G's first operand load
+  add_job(f, w.c_m1, nz ? nz->c_mask1 : nullptr, 1, e.ch[0], 1, RS_CMASK1);
+  add_job(f, w.c_m2, nz ? nz->c_mask2 : nullptr, 1, e.ch[1], 1, RS_CMASK2);
+  CVG_TRY(launch_fill(e, f, st));
+  join_sides(e, st);                                     // the previous step's Adam (visit: side stream 0)
+  CVG_TRY(stage_x(e, x_real, B, st));
+  CVG_TRY(fwd_encoder(e, true, label, B, Bg_bn, local_bn, st));
+  CVG_TRY(fwd_generator(e, 1, true, true, label, B, Bg_bn, local_bn, st));
+  const float* x_recon = w.g_out;
+  {                                                      // the class loss is reported even while its weight is 0 (cvae.py:141-142,162)
+    CVG_TRY(fwd_classifier(e, x_recon, 0, 1, true, B, st));
+    CeArgs c;
+    c.M = B; c.ld = w.ld; c.K = e.K; c.npass = 1; c.label = label;
+    c.logits = w.c_logit; c.sl = (long long)e.K * ld;
+    c.dlogits = w.c_dlogit; c.sd = (long long)e.K * ld;
+    c.coef = 1.0f / Bg;       // times ctl->lambda_class, read on the device
+    c.ctl = w.ctl;
+    c.loss = w.loss + L_CE0;
+    CVG_TRY(emit_ce(e, c, B, 1, st));
+  }
+  if (rng.lambda_nonzero) CVG_TRY(bwd_classifier(e, x_recon, 0, 1, B, false, true, false, st));   // -> ws.dx
+  SeedArgs s;
+  s.M = B; s.ld = w.ld; s.F = e.F;
+  s.out = w.g_out; s.sout = (long long)e.F * ld;
+  s.x = w.xT; s.dx = w.dx;
+  s.dpre = w.g_dout; s.sdpre = (long long)e.F * ld;
+  s.coef_recon = e.cfg.lambda_recon / (Bg * (float)e.F);
+  s.recon_acc = w.loss + L_RECON;
+  s.add_dx = rng.lambda_nonzero ? 1 : 0;
+  g_seed_kernel<<<dim3((unsigned)((e.F * ld + 255) / 256), 1), 256, 0, st>>>(s);
+  CVG_LAUNCH_CHECK();
+  BnNetBwd gb;
+  gb.net = G; gb.npass = 1;
+  gb.h = w.g_h; gb.dy = w.g_dy;
+  gb.top_dy = w.g_dout; gb.s_top = (long long)e.F * ld;
+  gb.first_in.kind = OP_REPARAM; gb.first_in.rows = e.Z;
+  gb.first_in.p = w.z; gb.first_in.sp = (long long)e.Z * ld;
+  gb.first_in.mu = w.e_ml; gb.first_in.lv = w.e_ml + (size_t)e.Z * ld; gb.first_in.eps = w.z;
+  gb.first_in.reparam_pass = 0;
+  gb.first_K = e.Z;
+  gb.label_col = e.Z + label;
+  gb.want_first_dx = true;
+  CVG_TRY(bwd_bn_net(e, gb, B, Bg_bn, e.cfg.lambda_kl / Bg, local_bn, st));
+  BnNetBwd eb;
+  eb.net = E; eb.npass = 1;
+  eb.h = w.e_h; eb.dy = w.e_dy;
+  eb.top_dy = w.e_dml; eb.s_top = 0;
+  eb.first_in.kind = OP_PLAIN; eb.first_in.rows = e.F; eb.first_in.p = w.xT;
+  eb.first_K = e.F;
+  eb.label_col = e.F + label;
+  eb.want_first_dx = false;
+  CVG_TRY(bwd_bn_net(e, eb, B, Bg_bn, 0.f, local_bn, st));
+  return finish_step(e, (1 << E) | (1 << G), 2, B, flags, loss_out, st);
+}
+
 int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz, const StepRng& rng, int flags,
            float* loss_out, cudaStream_t st) {
   if (flags & CVG_STEP_PRIOR_ONLY) return step_g_prior(e, label, B, nz, rng, flags, loss_out, st);
+  if (flags & CVG_STEP_CVAE) return step_g_cvae(e, x_real, label, B, nz, rng, flags, loss_out, st);
   CVG_TRY(check_step(e, B));
   ProgramScope prog(e);
   CVG_TRY(begin_step(e, rng, true, st));
@@ -1594,7 +1672,7 @@ int visit(Engine& e, int label, int B, int64_t B_global, const float* class_rows
       rng.off = 1;                                   // sampling used counter + 0
       rng.lambda_nonzero = !(flags & CVG_VISIT_LAMBDA_ZERO);
       float* lo = loss_out ? loss_out + 4 * i : nullptr;
-      const int sf = flags & (CVG_STEP_LOCAL_BN | CVG_STEP_NO_UPDATE | CVG_STEP_PRIOR_ONLY);
+      const int sf = flags & (CVG_STEP_LOCAL_BN | CVG_STEP_NO_UPDATE | CVG_STEP_PRIOR_ONLY | CVG_STEP_CVAE);
       if (!e.mk.recording) e.step_dcounter = 2;      // two counter values per step (draw + noise), advanced by the step's tail
       if (kind == 0) CVG_TRY(step_d(e, x, label, B, nullptr, rng, sf, lo, st));
       else if (kind == 1) CVG_TRY(step_c(e, x, label, B, nullptr, rng, sf, lo, st));

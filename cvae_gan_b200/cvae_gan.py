@@ -62,7 +62,31 @@ class CVAEGAN:
     _VISIT_FLAGS = 0
     _G_FORWARDS_PER_G_STEP = 2
     _USES_ENCODER = True
+    _USES_CRITIC = True
     _NAME = "CVAE-GAN"
+    # the networks the reference class constructs, in ITS order (= order of the CPU-generator draws of their initialisation:
+    # cvae_gan.py:19-39); the engine always owns all four, the rest are built afterwards without touching the RNG stream
+    _BUILD_ORDER = ("encoder", "generator", "discriminator", "classifier")
+
+    @classmethod
+    def _build_networks(cls, feature_num: int, label_num: int, z_size: int):
+        """{name: module} for all four engine networks; same-seed construction gives the reference class's starting
+        parameters for the networks it has (tests/test_abi_and_host.py)."""
+        ctor = {"encoder": lambda: models.CVAEGANEncoderModel(feature_num, label_num, z_size),
+                "generator": lambda: models.CVAEGANGeneratorModel(z_size, label_num, feature_num),
+                "discriminator": lambda: models.CVAEGANDiscriminatorModel(feature_num, label_num),
+                "classifier": lambda: models.CVAEGANClassifierModel(feature_num, label_num)}
+        nets = {n: ctor[n]() for n in cls._BUILD_ORDER}
+        rest = [n for n in ctor if n not in nets]
+        if rest:
+            with torch.random.fork_rng(devices=[]):
+                for n in rest:
+                    nets[n] = ctor[n]()
+        return nets
+
+    def _loops(self, gc):
+        """(critic, classifier, encoder/generator) steps per label visit (cvae_gan.py:104,131,160)."""
+        return (int(gc.d_loop_num), int(gc.c_loop_num), int(gc.g_loop_num))
 
     def __init__(self, config=None, datasets=None, max_rows: int = None):
         """`config` / `datasets`: modules with the reference's names (defaults: this package's mirrors;
@@ -74,30 +98,35 @@ class CVAEGAN:
         self.label_num = self.datasets.label_num
         self.rank, self.world_size = _dist_info()
 
-        # same construction (and CPU-generator draw) order as cvae_gan.py:19-39
-        encoder = models.CVAEGANEncoderModel(self.feature_num, self.label_num, gc.z_size)
+        # same construction (and CPU-generator draw) order as the reference class (cvae_gan.py:19-39)
+        nets = self._build_networks(self.feature_num, self.label_num, gc.z_size)
+        encoder, critic = nets["encoder"], nets["discriminator"]
         if self._USES_ENCODER:
             self.encoder = encoder
-        self._encoder_module = encoder      # the engine owns four networks; CGAN never runs (or exposes) this one
-        self.generator = models.CVAEGANGeneratorModel(gc.z_size, self.label_num, self.feature_num)
-        self.discriminator = models.CVAEGANDiscriminatorModel(self.feature_num, self.label_num)
-        self.classifier = models.CVAEGANClassifierModel(self.feature_num, self.label_num)
+        self._encoder_module = encoder      # the engine owns four networks; CGAN never runs (or exposes) this one,
+        if self._USES_CRITIC:
+            self.discriminator = critic
+        self._critic_module = critic        # and CVAE never runs (or exposes) the critic
+        self.generator = nets["generator"]
+        self.classifier = nets["classifier"]
 
         self.samples = dict()
         cc = getattr(gc, self._CONFIG_KEY)
         if 'lambda_recon' in cc:
             self.lambda_recon = cc['lambda_recon']
             self.lambda_kl = cc['lambda_kl']
-        self.lambda_adv = cc['lambda_adv']
+        if 'lambda_adv' in cc:
+            self.lambda_adv = cc['lambda_adv']
         self.lambda_class = cc['lambda_class']
         self.loss_history = {k: [] for k, _ in self._HISTORY}
 
         rows = max_rows or max(int(gc.batch_size) // self.world_size, 1 << 14)
         self.engine = Engine(self.feature_num, self.label_num, gc.z_size, rows,
-                             lambda_recon=cc.get('lambda_recon', 0.0), lambda_kl=cc.get('lambda_kl', 0.0), lambda_adv=self.lambda_adv,
+                             lambda_recon=cc.get('lambda_recon', 0.0), lambda_kl=cc.get('lambda_kl', 0.0),
+                             lambda_adv=cc.get('lambda_adv', 0.0),
                              g_lr=gc.g_lr, d_lr=gc.d_lr, c_lr=gc.c_lr, world_size=self.world_size, rank=self.rank)
         for net, mod in ((NET_ENCODER, encoder), (NET_GENERATOR, self.generator),
-                         (NET_DISCRIMINATOR, self.discriminator), (NET_CLASSIFIER, self.classifier)):
+                         (NET_DISCRIMINATOR, critic), (NET_CLASSIFIER, self.classifier)):
             mod.attach(self.engine, net)
         self._seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
         self._counter = 0          # one Philox counter value per optimiser step / sampling call
@@ -107,7 +136,7 @@ class CVAEGAN:
 
     # ------------------------------------------------------------------------------------------------
     def _networks(self):
-        nets = (self.generator, self.discriminator, self.classifier)
+        nets = (self.generator,) + ((self.discriminator,) if self._USES_CRITIC else ()) + (self.classifier,)
         return ((self.encoder,) + nets) if self._USES_ENCODER else nets
 
     def _next(self) -> int:
@@ -130,7 +159,7 @@ class CVAEGAN:
         # the learning rates and loss weights were handed to the engine at construction (CvgConfig); the reference re-reads them
         # here (cvae_gan.py:75-97, 207-212) - refuse to train silently with stale values
         want = (float(gc.g_lr), float(gc.d_lr), float(gc.c_lr), float(getattr(self, "lambda_recon", 0.0)),
-                float(getattr(self, "lambda_kl", 0.0)), float(self.lambda_adv))
+                float(getattr(self, "lambda_kl", 0.0)), float(getattr(self, "lambda_adv", 0.0)))
         have = (eng.cfg.g_lr, eng.cfg.d_lr, eng.cfg.c_lr, eng.cfg.lambda_recon, eng.cfg.lambda_kl, eng.cfg.lambda_adv)
         if any(abs(a - b) > 1e-12 + 1e-6 * abs(b) for a, b in zip(want, have)):
             raise ValueError("g_lr / d_lr / c_lr / lambda_recon / lambda_kl / lambda_adv changed after CVAEGAN() was constructed: "
@@ -147,7 +176,7 @@ class CVAEGAN:
             eng.grads[net].zero_()
             eng.set_adam_step(net, 0)
         lam = getattr(gc, self._CONFIG_KEY)['lambda_class']
-        loops = (int(gc.d_loop_num), int(gc.c_loop_num), int(gc.g_loop_num))
+        loops = self._loops(gc)
         n_steps = sum(loops)
         batch = int(gc.batch_size)
         losses = torch.zeros(n_steps, 4, dtype=torch.float32, device=eng.device)

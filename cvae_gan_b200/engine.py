@@ -243,6 +243,13 @@ class Engine:
                                   float(lambda_class), flags | STEP_PRIOR_ONLY, _ptr(out), _stream()))
         return out
 
+    def step_g_cvae(self, x_real, label: int, lambda_class: float, noise=None, seed=0, counter=0, flags=0, loss_out=None):
+        """The sibling trainer CVAE's encoder/generator step (src/cvae.py:117-166): x_recon = G(E(x)) only, the classification
+        term on x_recon, no critic; loss_out = {recon, kl, 0, class}."""
+        from ._lib import STEP_CVAE
+        return self.step_g(x_real, label, lambda_class, noise=noise, seed=seed, counter=counter, flags=flags | STEP_CVAE,
+                           loss_out=loss_out)
+
     def ctl_set(self, seed=None, counter=None, lambda_class=None):
         """Write the device control block (Philox key/counter and/or this epoch's lambda_class)."""
         set_rng = seed is not None

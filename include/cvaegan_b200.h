@@ -38,9 +38,14 @@ enum {
   CVG_STEP_NO_UPDATE = 1,  /* compute losses + gradients, skip Adam (gradients stay in the grad buffers) */
   CVG_STEP_LOCAL_BN  = 2,  /* data parallel only: per-rank BatchNorm statistics (DEVIATES from the reference) */
   CVG_VISIT_LAMBDA_ZERO = 4, /* cvg_visit: the caller guarantees lambda_class == 0 (epochs < 200): skip the classifier backward */
-  CVG_STEP_PRIOR_ONLY = 8   /* cvg_step_g / cvg_visit: the sibling trainer CGAN's generator step (/root/reference/src/cgan.py:138-178):
+  CVG_STEP_PRIOR_ONLY = 8,  /* cvg_step_g / cvg_visit: the sibling trainer CGAN's generator step (/root/reference/src/cgan.py:138-178):
                              * x_fake = G(z_prior) only, no encoder / reconstruction / KL, Adam on the generator alone; x_real is
                              * not read (may be null) and a visit draws no batch for these steps; loss_out = {0, 0, adv, class} */
+  CVG_STEP_CVAE = 16        /* cvg_step_g / cvg_visit: the sibling trainer CVAE's encoder/generator step (/root/reference/src/cvae.py:117-166):
+                             * x_recon = G(E(x)) only, no critic and no z_prior pass; the classification term is taken on x_recon;
+                             * Adam on encoder + generator; loss_out = {recon, kl, 0, class}.  A CVAE label visit is
+                             * cvg_visit(d_loop = 0, c_loop, g_loop, flags | CVG_STEP_CVAE) (cvae.py:86-166).  Mutually exclusive
+                             * with CVG_STEP_PRIOR_ONLY. */
 };
 
 /* Mirrors /root/reference/src/config/gan_config.py:1-21 plus the torch defaults the models rely on. */

@@ -709,6 +709,81 @@ class OracleCVAEGAN:
             self.training[n] = False
         return self
 
+    # ---- sibling trainer CVAE: cvae.py:117-166, the encoder/generator step without critic and prior pass -----
+    def step_g_cvae(self, x_real, label: int, noise, lambda_class_now: float, apply_update=True):
+        """CVAE encoder/generator step: mu, logvar = E(x); z_enc = mu + eps * std; x_recon = G(z_enc, onehot);
+        total = lambda_recon * MSE + lambda_kl * KL + lambda_now * CE(C(x_recon), label) - the classifier reads the
+        RECONSTRUCTION (cvae.py:141-142) -; Adam on encoder and generator (cvae.py:153-166)."""
+        c = self.cfg
+        B = x_real.shape[0]
+        tgt = torch.full([B], int(label), dtype=torch.long)
+        mu, log_var = encoder_forward(self.sd["encoder"], x_real, label, self.training["encoder"], self.dp)
+        std = torch.exp(0.5 * log_var)
+        eps = noise.randn_like(std, tag="eps")
+        z_enc = mu + eps * std
+        x_recon = generator_forward(self.sd["generator"], z_enc, label, self.training["generator"], self.dp)
+        if self.dp is None:
+            recon = F.mse_loss(x_recon, x_real)
+            kl = -0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp()) / mu.size(0)
+        else:
+            Bg = B * self.dp.world
+            recon = ((x_recon - x_real) ** 2).sum() / (Bg * x_real.shape[1])
+            kl = -0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp()) / Bg
+        cls = self._ce(classifier_forward(self.sd["classifier"], x_recon, self.training["classifier"], noise), tgt)
+        total = c.lambda_recon * recon + c.lambda_kl * kl + lambda_class_now * cls
+        grads = self._backward(total, ["encoder", "generator"], apply_update)
+        losses = {k: self._global_scalar(v) for k, v in (("recon_loss", recon), ("kl_loss", kl), ("class_loss", cls))}
+        self.last_losses.update(losses)
+        return losses, grads
+
+    def fit_cvae(self, x: torch.Tensor, y: torch.Tensor, noise=None, step_hook=None):
+        """CVAE.fit (cvae.py:51-179): per label c_loop classifier steps (cvae.py:89-115 is cvae_gan.py:131-157 statement for
+        statement) then g_loop `step_g_cvae` steps; no critic; loss_history keeps recon / kl / class."""
+        noise = noise or TorchNoise()
+        c = self.cfg
+        self.loss_history = {"recon_loss": [], "kl_loss": [], "class_loss": []}
+        for n in ("encoder", "generator", "classifier"):
+            self.training[n] = True
+        self.divide_samples(x, y)
+        self.make_optimizers()
+        for e in range(c.epoch_offset, c.epoch_offset + c.epochs):
+            losses = None
+            for label in self.samples.keys():
+                for _ in range(c.c_loop_num):
+                    xr = self.get_target_samples(label, c.batch_size, noise)
+                    out = self.step_c(xr, label, noise)
+                    if step_hook:
+                        step_hook("c", e, label, out)
+                for _ in range(c.g_loop_num):
+                    xr = self.get_target_samples(label, c.batch_size, noise)
+                    losses, g = self.step_g_cvae(xr, label, noise, lambda_class_schedule(e, c.lambda_class))
+                    if step_hook:
+                        step_hook("g", e, label, (losses, g))
+            for k in self.loss_history:
+                self.loss_history[k].append(losses[k])
+        for n in ("encoder", "generator", "classifier"):
+            self.training[n] = False
+        return self
+
+    @torch.no_grad()
+    def reconstruct_samples_cvae(self, x: torch.Tensor, labels: torch.Tensor, noise=None) -> torch.Tensor:
+        """CVAE.reconstruct_samples (cvae.py:300-319): E and G in eval mode (running statistics, so rows are independent and
+        may be grouped by label), ONE randn_like draw for the whole batch, and both networks left in TRAIN mode afterwards."""
+        noise = noise or TorchNoise()
+        labels = labels.long()
+        mu = torch.empty(x.shape[0], self.cfg.z_size, dtype=x.dtype)
+        lv = torch.empty_like(mu)
+        groups = [(int(lab), (labels == lab).nonzero().flatten()) for lab in torch.unique(labels)]
+        for lab, sel in groups:
+            mu[sel], lv[sel] = encoder_forward(self.sd["encoder"], x[sel], lab, False, None)
+        std = torch.exp(0.5 * lv)
+        z = mu + noise.randn_like(std, tag="eps") * std
+        out = torch.empty(x.shape[0], self.feature_num, dtype=x.dtype)
+        for lab, sel in groups:
+            out[sel] = generator_forward(self.sd["generator"], z[sel], lab, False, None)
+        self.training["encoder"] = self.training["generator"] = True
+        return out
+
     # ---- fit (cvae_gan.py:59-236) --------------------------------------------------------------
     def fit(self, x: torch.Tensor, y: torch.Tensor, noise=None, step_hook=None):
         noise = noise or TorchNoise()

@@ -67,12 +67,13 @@ def draw_noise(kind: str, B: int, Z: int, g: torch.Generator, h1=256, h2=128):
     """CPU noise for one step; returns (oracle InjectedNoise, engine noise dict of CUDA tensors)."""
     inj = O.InjectedNoise()
     dev: Dict[str, torch.Tensor] = {}
-    z = torch.randn(B, Z, generator=g)
-    inj.push("z", z)
-    dev["z"] = z.cuda()
+    if kind != "v":            # the CVAE encoder/generator step draws no prior sample (cvae.py:117-166)
+        z = torch.randn(B, Z, generator=g)
+        inj.push("z", z)
+        dev["z"] = z.cuda()
     if kind == "p":
         kind = "gp"
-    if kind == "g":
+    if kind in ("g", "v"):
         eps = torch.randn(B, Z, generator=g)
         inj.push("eps", eps)
         dev["eps"] = eps.cuda()
@@ -90,6 +91,8 @@ def draw_noise(kind: str, B: int, Z: int, g: torch.Generator, h1=256, h2=128):
         masks("d", 2)
     elif kind == "c":
         masks("c", 2)
+    elif kind == "v":
+        masks("c", 1)
     else:
         masks("d", 1)
         masks("c", 1)
@@ -191,6 +194,8 @@ def twin_step(kind, orc64, x, label, inj64, lambda_class=0.25, update=False):
         _, grads = orc64.step_c(xd, label, inj64, apply_update=update)
     elif kind == "p":
         _, grads = orc64.step_g_prior(label, x.shape[0], inj64, lambda_class, apply_update=update)
+    elif kind == "v":
+        _, grads = orc64.step_g_cvae(xd, label, inj64, lambda_class, apply_update=update)
     else:
         _, grads = orc64.step_g(xd, label, inj64, lambda_class, apply_update=update)
     return grads
@@ -228,6 +233,11 @@ def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True, twin=N
         losses, grads = orc.step_g_prior(label, B, inj, lambda_class, apply_update=update)
         out = eng.step_g_prior(B, label, lambda_class, noise=dev, flags=flags).tolist()
         ref = [0.0, 0.0, losses["adv_loss"], losses["class_loss"]]
+        got = out
+    elif kind == "v":          # sibling trainer CVAE's encoder/generator step (cvae.py:117-166)
+        losses, grads = orc.step_g_cvae(x, label, inj, lambda_class, apply_update=update)
+        out = eng.step_g_cvae(xd, label, lambda_class, noise=dev, flags=flags).tolist()
+        ref = [losses["recon_loss"], losses["kl_loss"], 0.0, losses["class_loss"]]
         got = out
     else:
         losses, grads = orc.step_g(x, label, inj, lambda_class, apply_update=update)

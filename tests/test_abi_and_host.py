@@ -172,7 +172,8 @@ def test_flag_values_match_the_header():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cvaegan_b200.h")).read()
     vals = {k: int(v) for k, v in re.findall(r"(CVG_(?:STEP|VISIT)_[A-Z_]+)\s*=\s*(\d+)", hdr)}
     assert vals == {"CVG_STEP_NO_UPDATE": _lib.STEP_NO_UPDATE, "CVG_STEP_LOCAL_BN": _lib.STEP_LOCAL_BN,
-                    "CVG_VISIT_LAMBDA_ZERO": _lib.VISIT_LAMBDA_ZERO, "CVG_STEP_PRIOR_ONLY": _lib.STEP_PRIOR_ONLY}
+                    "CVG_VISIT_LAMBDA_ZERO": _lib.VISIT_LAMBDA_ZERO, "CVG_STEP_PRIOR_ONLY": _lib.STEP_PRIOR_ONLY,
+                    "CVG_STEP_CVAE": _lib.STEP_CVAE}
 
 
 def test_cgan_host_class_mirrors_the_reference_surface():
@@ -184,3 +185,50 @@ def test_cgan_host_class_mirrors_the_reference_surface():
     from cvae_gan_b200 import cgan, models
     assert cgan.CGANGeneratorModel is models.CVAEGANGeneratorModel      # same layers and state_dict keys (cgan_models.py)
     assert cg.CGAN._HISTORY == (("adv_loss", 2), ("class_loss", 3)) and not cg.CGAN._USES_ENCODER
+
+
+def test_cvae_host_class_mirrors_the_reference_surface():
+    """src/cvae.py:11-319: attribute and method names a caller of the reference's CVAE uses (no GPU: class level only)."""
+    import cvae_gan_b200 as cg
+    for name in ("fit", "_divide_samples", "_get_target_samples", "plot_loss_history", "generate_samples",
+                 "generate_qualified_samples", "reconstruct_samples"):
+        assert callable(getattr(cg.CVAE, name)), name
+    assert cg.config.gan_config.cvae_config == {"lambda_recon": 1.0, "lambda_kl": 0.01, "lambda_class": 0.1,
+                                                "confidence_threshold": 0.5}
+    from cvae_gan_b200 import cvae, models
+    assert cvae.CVAEEncoderModel is models.CVAEGANEncoderModel          # same layers and state_dict keys (cvae_models.py)
+    assert cg.CVAE._HISTORY == (("recon_loss", 0), ("kl_loss", 1), ("class_loss", 3)) and not cg.CVAE._USES_CRITIC
+
+    class _GC:
+        d_loop_num, c_loop_num, g_loop_num = 5, 4, 3
+    assert cg.CVAE._loops(None, _GC) == (0, 4, 3) and cg.CVAEGAN._loops(None, _GC) == (5, 4, 3)    # cvae.py:86-117: no critic steps
+
+
+@pytest.mark.parametrize("cls_name,fixture,nets", [("CVAEGAN", "ref_fit_a.npz", ("encoder", "generator", "discriminator", "classifier")),
+                                                   ("CGAN", "ref_cgan_a.npz", ("generator", "discriminator", "classifier")),
+                                                   ("CVAE", "ref_cvae_a.npz", ("encoder", "generator", "classifier"))])
+def test_host_classes_build_networks_in_the_reference_order(golden_dir, cls_name, fixture, nets):
+    """Same seed -> the starting parameters of the reference class: each trainer constructs its networks in its own order
+    (cvae_gan.py:19-39, cgan.py:20-34, cvae.py:19-34), which fixes the CPU-generator draws; the networks a sibling does not
+    have are built afterwards without touching the stream.  Fixtures: state_dicts right after `set_random_state(); <class>()`."""
+    import random
+    import cvae_gan_b200 as cg
+    npz = np.load(os.path.join(golden_dir, fixture))
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)
+    built = getattr(cg, cls_name)._build_networks(10, 5, 128)
+    after = torch.rand(1)
+    assert sorted(built) == ["classifier", "discriminator", "encoder", "generator"]
+    for name in nets:
+        sd = built[name].state_dict()
+        ref_keys = [k.split("/", 2)[2] for k in npz.files if k.startswith(f"init/{name}/")]
+        assert list(sd.keys()) == ref_keys
+        for k, v in sd.items():
+            assert torch.equal(v, torch.from_numpy(npz[f"init/{name}/{k}"])), (cls_name, name, k)
+    # the extra networks did not advance the generator: the next draw is the one the reference would make
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)
+    from cvae_gan_b200 import models
+    ctor = {"encoder": lambda: models.CVAEGANEncoderModel(10, 5, 128), "generator": lambda: models.CVAEGANGeneratorModel(128, 5, 10),
+            "discriminator": lambda: models.CVAEGANDiscriminatorModel(10, 5), "classifier": lambda: models.CVAEGANClassifierModel(10, 5)}
+    for name in getattr(cg, cls_name)._BUILD_ORDER:
+        ctor[name]()
+    assert torch.equal(after, torch.rand(1))

@@ -223,3 +223,71 @@ def test_cgan_fit_epoch350_lambda_class_matches_reference(golden_dir):
             np.testing.assert_allclose([f.sum(), (f * f).sum()], d[:2], rtol=1e-5, atol=1e-6, err_msg=f"{net}/{key}")
             n = min(8, f.size)
             np.testing.assert_allclose(f[:n], d[2:2 + n], rtol=2e-5, atol=2e-7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# sibling trainer CVAE (src/cvae.py) - fixtures made by oracle/make_golden_cvae.py from the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+NETS_CVAE = ("encoder", "generator", "classifier")
+
+
+def _replay_cvae(golden_dir, epoch_offset):
+    torch.set_num_threads(1)
+    npz = _load(golden_dir, "ref_cvae_a.npz")
+    F_, K, B, fit_seed, gen_seed, _ = [int(v) for v in npz["meta"]]
+    st = _states(npz, "init")
+    st["discriminator"] = _states(_load(golden_dir, "ref_fit_a.npz"), "init")["discriminator"]   # CVAE has no critic: never touched
+    # cvae_config (gan_config.py:51-56): lambda_recon 1.0, lambda_kl 0.01, lambda_class 0.1
+    cfg = O.OracleConfig(batch_size=B, epochs=2, epoch_offset=epoch_offset, lambda_recon=1.0, lambda_kl=0.01, lambda_class=0.1)
+    orc = O.OracleCVAEGAN(F_, K, cfg).load_state(st)
+    d0 = {k: v.detach().clone() for k, v in orc.sd["discriminator"].items()}
+    torch.manual_seed(fit_seed)
+    orc.fit_cvae(torch.from_numpy(npz["x"]), torch.from_numpy(npz["y"]))
+    for k, v in orc.sd["discriminator"].items():
+        assert torch.equal(v.detach(), d0[k]), k
+    return npz, orc, gen_seed
+
+
+def test_cvae_fit_epoch0_1_generation_and_reconstruction_match_reference(golden_dir):
+    npz, orc, gen_seed = _replay_cvae(golden_dir, 0)
+    assert list(orc.samples.keys()) == npz["sample_keys"].tolist()
+    assert sorted(orc.loss_history) == ["class_loss", "kl_loss", "recon_loss"]
+    for k in orc.loss_history:
+        np.testing.assert_allclose(orc.loss_history[k], npz["loss/" + k], rtol=2e-6, atol=1e-7)
+    fin = _states(npz, "final")
+    st = orc.state()
+    for net in NETS_CVAE:
+        for key, ref in fin[net].items():
+            got = st[net][key]
+            if ref.dtype == torch.int64:
+                assert torch.equal(got, ref), (net, key)
+            else:
+                torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-7, msg=f"{net}/{key}")
+    torch.manual_seed(gen_seed)
+    s = orc.generate_samples(1, 37)
+    torch.testing.assert_close(s, torch.from_numpy(npz["gen/samples_l1_n37"]), rtol=1e-5, atol=1e-6)
+    for thr in (0.2, 0.5):
+        for lab in (0, 3):
+            q = orc.generate_qualified_samples(lab, 25, thr)
+            ref = torch.from_numpy(npz[f"gen/qualified_l{lab}_thr{thr}"])
+            q = q.reshape(-1, 10) if q.numel() else torch.zeros(0, 10)
+            assert q.shape == ref.shape, (thr, lab, q.shape, ref.shape)
+            torch.testing.assert_close(q, ref, rtol=1e-5, atol=1e-6)
+    rec = orc.reconstruct_samples_cvae(torch.from_numpy(npz["rec/x"]), torch.from_numpy(npz["rec/y"]))
+    torch.testing.assert_close(rec, torch.from_numpy(npz["rec/out"]), rtol=1e-5, atol=1e-6)
+    assert npz["rec/modes_after"].tolist() == [orc.training["encoder"], orc.training["generator"], orc.training["classifier"]]
+
+
+def test_cvae_fit_epoch350_lambda_class_matches_reference(golden_dir):
+    b = _load(golden_dir, "ref_cvae_b.npz")
+    _, orc, _ = _replay_cvae(golden_dir, 350)
+    for k in orc.loss_history:
+        np.testing.assert_allclose(orc.loss_history[k], b["loss/" + k], rtol=2e-6, atol=1e-7)
+    st = orc.state()
+    for net in NETS_CVAE:
+        for key, t in st[net].items():
+            f = t.double().ravel().numpy()
+            d = b[f"digest/{net}/{key}"]
+            np.testing.assert_allclose([f.sum(), (f * f).sum()], d[:2], rtol=1e-5, atol=1e-6, err_msg=f"{net}/{key}")
+            n = min(8, f.size)
+            np.testing.assert_allclose(f[:n], d[2:2 + n], rtol=2e-5, atol=2e-7)
