@@ -101,7 +101,7 @@ class Classifier:
                                                            zero_division=0)
 
     def binary_test(self, dataset):
-        """classifier.py:108-150: every class > 0 collapses to 1, macro averages."""
+        """classifier.py:108-150: every class > 0 collapses to 1, macro averages, per-class report of the two classes."""
         from sklearn import metrics
         x_all, y_all = self._tensors(dataset)
         predicted = (self.predict(x_all).cpu() > 0).long()
@@ -110,7 +110,80 @@ class Classifier:
         self.metrics['Precision'] = metrics.precision_score(y_true=real, y_pred=predicted, average='macro', zero_division=0)
         self.metrics['Recall'] = metrics.recall_score(y_true=real, y_pred=predicted, average='macro', zero_division=0)
         self.metrics['F1'] = metrics.f1_score(y_true=real, y_pred=predicted, average='macro', zero_division=0)
+        self.class_metrics = metrics.classification_report(y_true=real, y_pred=predicted, output_dict=True, zero_division=0)
 
-    def print_metrics(self, precision: int = 4):
-        for k, v in self.metrics.items():
-            print(f'{k}: {v:.{precision}f}')
+    def print_metrics(self, decimals: int = 4, print_class_metrics: bool = True):
+        """classifier.py:152-200: the overall metrics as a rounded dict, then (optionally) the per-class rows of
+        `class_metrics`, the macro / weighted averages and the accuracy."""
+        print("整体评估指标:")
+        print({k: round(v, decimals) for k, v in self.metrics.items()})
+        if not print_class_metrics or self.class_metrics is None:
+            return
+
+        def rows(entry):
+            for title, field in (("Precision", "precision"), ("Recall", "recall"), ("F1-Score", "f1-score")):
+                print(f"  {title}: {round(entry[field], decimals)}")
+            print(f"  Support: {entry['support']}")
+
+        print("\n每个类别的评估指标:")
+        for key, entry in self.class_metrics.items():
+            if key in ('accuracy', 'macro avg', 'weighted avg') or not str(key).lstrip('-').isdigit():
+                continue
+            print(f"\n类别 {int(key)}:")
+            rows(entry)
+        for title, key in (("宏观平均", 'macro avg'), ("加权平均", 'weighted avg')):
+            print(f"\n{title}:")
+            if key in self.class_metrics:
+                rows(self.class_metrics[key])
+        if 'accuracy' in self.class_metrics:
+            print(f"\nAccuracy: {round(self.class_metrics['accuracy'], decimals)}")
+
+    # ---- classifier.py:202-303 ---------------------------------------------------------------------------------
+    @staticmethod
+    def roc_from_scores(scores: np.ndarray, labels: np.ndarray, label_num: int, is_binary: bool = False):
+        """The numbers behind `plot_roc_curve`: the reference scores with the network's raw outputs (it calls them `prob`).
+        Multi-class (more than 2 outputs and not `is_binary`): one-vs-rest, {class: (fpr, tpr, auc)}.  Otherwise the positive
+        class is column 1 and every label > 0 counts as positive: {'binary': (fpr, tpr, auc)}."""
+        from sklearn import metrics
+        if not is_binary and scores.shape[1] > 2:
+            from sklearn.preprocessing import label_binarize
+            y_bin = label_binarize(labels, classes=list(range(label_num)))
+            return {i: (*metrics.roc_curve(y_bin[:, i], scores[:, i])[:2], metrics.roc_auc_score(y_bin[:, i], scores[:, i]))
+                    for i in range(y_bin.shape[1])}
+        y_score = scores[:, 1] if scores.shape[1] > 1 else scores.reshape(-1)
+        y_test = np.where(labels > 0, 1, 0)
+        return {'binary': (*metrics.roc_curve(y_test, y_score)[:2], metrics.roc_auc_score(y_test, y_score))}
+
+    def plot_roc_curve(self, dataset, is_binary: bool = False):
+        """classifier.py:202-303 (needs matplotlib, which is not part of the hot path): scores from the CUDA classifier forward,
+        curves from `roc_from_scores`, saved as `<name>_roc_curve_{binary|multiclass}.jpg` under `path_config.gan_outs`."""
+        import matplotlib.pyplot as plt
+        eng = self._engine()
+        self.model.eval()
+        x_all, y_all = self._tensors(dataset)
+        scores = eng.classifier_forward(x_all.to(eng.device, torch.float32).contiguous()).cpu().numpy()
+        curves = self.roc_from_scores(scores, y_all.cpu().numpy(), datasets.label_num, is_binary)
+        plt.figure(figsize=(10, 8))
+        colors = ['aqua', 'darkorange', 'cornflowerblue', 'green', 'red', 'purple']
+        for n, (key, (fpr, tpr, auc)) in enumerate(curves.items()):
+            if key == 'binary':
+                plt.plot(fpr, tpr, color='darkorange', lw=2, label='ROC curve (area = %0.2f)' % auc)
+            elif n < len(colors):
+                plt.plot(fpr, tpr, color=colors[n], lw=2, label='ROC curve of class {0} (area = {1:0.2f})'.format(key, auc))
+        plt.plot([0, 1], [0, 1], color='navy', lw=2, linestyle='--')
+        plt.xlim([0.0, 1.0])
+        plt.ylim([0.0, 1.05])
+        plt.xlabel('False Positive Rate')
+        plt.ylabel('True Positive Rate')
+        plt.title(f'{self.name} Receiver Operating Characteristic (ROC) Curve')
+        plt.legend(loc="lower right")
+        plt.grid(True, alpha=0.3)
+        out_dir = getattr(getattr(config, "path_config", None), "gan_outs", None)
+        if out_dir is None:
+            import pathlib
+            out_dir = pathlib.Path(".")
+        path = out_dir / f"{self.name.replace('_classifier', '')}_roc_curve_{'binary' if is_binary else 'multiclass'}.jpg"
+        plt.savefig(path)
+        plt.close()
+        print(f"ROC曲线已保存至: {path}")
+        return curves
