@@ -15,6 +15,7 @@ NET_ENCODER, NET_GENERATOR, NET_DISCRIMINATOR, NET_CLASSIFIER = 0, 1, 2, 3
 NET_NAMES = ("encoder", "generator", "discriminator", "classifier")
 STEP_NO_UPDATE, STEP_LOCAL_BN, VISIT_LAMBDA_ZERO, STEP_PRIOR_ONLY, STEP_CVAE = 1, 2, 4, 8, 16
 GRAD_TAIL = 16
+ABI_VERSION = 2      # CVG_ABI_VERSION of include/cvaegan_b200.h this binding was written against
 
 
 class CvgError(RuntimeError):
@@ -30,6 +31,7 @@ class CvgConfig(C.Structure):
         ("adam_beta1", C.c_float), ("adam_beta2", C.c_float), ("adam_eps", C.c_float),
         ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("ln_eps", C.c_float), ("sn_eps", C.c_float),
         ("lrelu_slope", C.c_float), ("dropout_p", C.c_float),
+        ("hidden", C.c_int32 * 3),     # (0, 0, 0): the reference's widths; else the widened model's three hidden widths
     ]
 
 
@@ -49,6 +51,7 @@ _P, _I, _I64, _U64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 SIGNATURES = {
     "cvg_last_error": (C.c_char_p, []),
     "cvg_abi_version": (_I, []),
+    "cvg_config_bytes": (_I, []),
     "cvg_create": (_I, [C.POINTER(CvgConfig), C.POINTER(_P)]),
     "cvg_destroy": (None, [_P]),
     "cvg_net_sizes": (_I, [_P, _I, C.POINTER(_I64), C.POINTER(_I64)]),
@@ -105,8 +108,10 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.cvg_abi_version() != 1:
+    if lib.cvg_abi_version() != ABI_VERSION:
         raise CvgError("libcvaegan_b200.so ABI version mismatch")
+    if lib.cvg_config_bytes() != C.sizeof(CvgConfig):
+        raise CvgError(f"CvgConfig layout mismatch: library {lib.cvg_config_bytes()} bytes, binding {C.sizeof(CvgConfig)}")
     _lib = lib
     return lib
 

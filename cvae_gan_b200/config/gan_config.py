@@ -5,6 +5,11 @@ batch_size: int = 128      # GLOBAL batch; a data-parallel rank processes batch_
 
 z_size: int = 128
 
+# NOT in the reference (its layer widths are hard-coded formulas, cvae_gan_models.py:16-18,85-87,173-175,257-259): None keeps
+# them; (h1, h2, h3) builds the widened model of BASELINE.json configs[4] - e.g. (1024, 512, 256) - with these three hidden
+# widths in all four networks (multiples of 64, <= 1024, h2 <= 512)
+hidden = None
+
 g_lr: float = 2e-4
 g_loop_num: int = 3
 

@@ -60,6 +60,7 @@ extern "C" {
 
 const char* cvg_last_error(void) { return cvg::last_error(); }
 int cvg_abi_version(void) { return CVG_ABI_VERSION; }
+int cvg_config_bytes(void) { return (int)sizeof(CvgConfig); }
 
 int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
   if (!cfg || !out) CVG_FAIL("cvg_create: null argument");

@@ -30,7 +30,11 @@ struct Builder {
   }
 };
 
-static void hidden(int tin, bool fixed3, int* h) {
+static void hidden(const CvgConfig& cfg, int tin, bool fixed3, int* h) {
+  if (cfg.hidden[0] > 0) {            // widened model (BASELINE.json configs[4]): the same three widths for every network
+    for (int i = 0; i < 3; ++i) h[i] = cfg.hidden[i];
+    return;
+  }
   // cvae_gan_models.py:16-18, 85-87, 173-175, 257-259
   h[0] = tin > 256 ? tin : 256;
   h[1] = tin / 2 > 128 ? tin / 2 : 128;
@@ -39,16 +43,20 @@ static void hidden(int tin, bool fixed3, int* h) {
 
 int build_layouts(Engine& e) {
   const int F = e.F, K = e.K, Z = e.Z;
-  hidden(F + K, false, e.eh);
-  hidden(Z + K, false, e.gh);
-  hidden(F + K, true, e.dh);
-  hidden(F, true, e.ch);
+  const int* hv = e.cfg.hidden;
+  if (hv[0] != 0 || hv[1] != 0 || hv[2] != 0)
+    for (int i = 0; i < 3; ++i)
+      if (hv[i] < 64 || hv[i] % 64 != 0) CVG_FAIL("CvgConfig.hidden: all zero, or three multiples of 64");
+  hidden(e.cfg, F + K, false, e.eh);
+  hidden(e.cfg, Z + K, false, e.gh);
+  hidden(e.cfg, F + K, true, e.dh);
+  hidden(e.cfg, F, true, e.ch);
   for (int i = 0; i < 3; ++i)
     if (e.eh[i] > STAT_C || e.gh[i] > STAT_C || e.dh[i] > SN_MAXDIM || e.ch[i] > STAT_C)
       CVG_FAIL("layer wider than supported (1024)");
   if (Z % 4 != 0) CVG_FAIL("z_size must be a multiple of 4");
   if (K > FILTER_MAXK) CVG_FAIL("label_num > 32 is not supported");
-  if (e.ch[1] > 8 * LN_MAXF) CVG_FAIL("classifier LayerNorm wider than 256 is not supported");
+  if (e.ch[1] > 8 * LN_MAXF_WIDE) CVG_FAIL("classifier LayerNorm wider than 512 is not supported");
 
   {  // encoder (cvae_gan_models.py:20-35)
     NetLayout& L = e.lay[CVG_NET_ENCODER];

@@ -62,8 +62,10 @@ struct LnArgs {
 // CTA = 256 threads = 32 batch rows (lane) x 8 feature groups (warp); each thread keeps C/8 features of its
 // row in registers, row moments are combined through shared memory (two-pass variance like torch).
 constexpr int LN_ROWS = 32;
-constexpr int LN_MAXF = 32;   // features per thread (C <= 256)
+constexpr int LN_MAXF = 32;        // features per thread (C <= 256: every width the reference's formulas give up to F = 512)
+constexpr int LN_MAXF_WIDE = 64;   // second instantiation for the widened model (C <= 512, CvgConfig.hidden)
 
+template <int MAXF>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs g) {
   __shared__ float red[8][LN_ROWS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -73,10 +75,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs g) {
   const int fpt = (g.C + 7) / 8;            // features per thread
   const int c0 = w * fpt;
   const float* h = g.h + (long long)pass * g.sh + (valid ? m : 0);
-  float v[LN_MAXF];
+  float v[MAXF];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MAXF; ++i) {
     const int c = c0 + i;
     v[i] = (i < fpt && c < g.C && valid) ? h[(size_t)c * g.ld] : 0.f;
     s += v[i];
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs g) {
   __syncthreads();
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MAXF; ++i) {
     const int c = c0 + i;
     if (i < fpt && c < g.C) { const float d = v[i] - mean; q = fmaf(d, d, q); }
   }
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs g) {
   float* a = g.a + (long long)pass * g.sa + m;
   const uint8_t* mk = g.mask ? g.mask + (long long)pass * g.smask + m : nullptr;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MAXF; ++i) {
     const int c = c0 + i;
     if (i < fpt && c < g.C) {
       float n = (v[i] - mean) * rstd * g.g[c] + g.b[c];
@@ -131,6 +133,7 @@ struct LnBwdArgs {
   float* dg; float* db;                // null -> skipped
 };
 
+template <int MAXF>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs g) {
   __shared__ float red1[8][LN_ROWS], red2[8][LN_ROWS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -144,10 +147,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs g) {
   float* dn = g.dn + (long long)pass * g.sdn + mm;
   const float* rs = g.rs + (long long)pass * g.srs;
   const float mean = rs[mm], rstd = rs[g.ld + mm];
-  float xh[LN_MAXF], d[LN_MAXF];
+  float xh[MAXF], d[MAXF];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MAXF; ++i) {
     const int c = c0 + i;
     const bool on = i < fpt && c < g.C && valid;
     xh[i] = on ? (h[(size_t)c * g.ld] - mean) * rstd : 0.f;
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs g) {
   s1 /= (float)g.C;
   s2 /= (float)g.C;
 #pragma unroll
-  for (int i = 0; i < LN_MAXF; ++i) {
+  for (int i = 0; i < MAXF; ++i) {
     const int c = c0 + i;
     const bool on = i < fpt && c < g.C;       // warp-uniform
     if (!on) continue;
@@ -178,6 +181,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs g) {
       }
     }
   }
+}
+
+inline void launch_ln_fwd(const LnArgs& a, cudaStream_t st) {
+  const dim3 grid((a.M + LN_ROWS - 1) / LN_ROWS, a.npass);
+  if (a.C <= 8 * LN_MAXF) ln_fwd_kernel<LN_MAXF><<<grid, 256, 0, st>>>(a);
+  else ln_fwd_kernel<LN_MAXF_WIDE><<<grid, 256, 0, st>>>(a);
+}
+inline void launch_ln_bwd(const LnBwdArgs& a, cudaStream_t st) {
+  const dim3 grid((a.M + LN_ROWS - 1) / LN_ROWS, a.npass);
+  if (a.C <= 8 * LN_MAXF) ln_bwd_kernel<LN_MAXF><<<grid, 256, 0, st>>>(a);
+  else ln_bwd_kernel<LN_MAXF_WIDE><<<grid, 256, 0, st>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -685,7 +685,7 @@ int fwd_classifier(Engine& e, const float* xin, long long sxin, int npass, bool 
       if (e.mk.recording) {
         CVG_TRY(mk_push(e, mk::K_LN_FWD, &a, sizeof(a), npass * ((M + 31) / 32)));
       } else {
-        ln_fwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
+        launch_ln_fwd(a, st);
         CVG_LAUNCH_CHECK();
       }
     }
@@ -847,7 +847,7 @@ static int bwd_classifier(Engine& e, const float* xin, long long sxin, int npass
       if (e.mk.recording) {
         CVG_TRY(mk_push(e, mk::K_LN_BWD, &a, sizeof(a), npass * ((M + 31) / 32)));
       } else {
-        ln_bwd_kernel<<<dim3((M + LN_ROWS - 1) / LN_ROWS, npass), 256, 0, st>>>(a);
+        launch_ln_bwd(a, st);
         CVG_LAUNCH_CHECK();
       }
     }

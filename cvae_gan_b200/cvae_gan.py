@@ -69,13 +69,13 @@ class CVAEGAN:
     _BUILD_ORDER = ("encoder", "generator", "discriminator", "classifier")
 
     @classmethod
-    def _build_networks(cls, feature_num: int, label_num: int, z_size: int):
+    def _build_networks(cls, feature_num: int, label_num: int, z_size: int, hidden=None):
         """{name: module} for all four engine networks; same-seed construction gives the reference class's starting
-        parameters for the networks it has (tests/test_abi_and_host.py)."""
-        ctor = {"encoder": lambda: models.CVAEGANEncoderModel(feature_num, label_num, z_size),
-                "generator": lambda: models.CVAEGANGeneratorModel(z_size, label_num, feature_num),
-                "discriminator": lambda: models.CVAEGANDiscriminatorModel(feature_num, label_num),
-                "classifier": lambda: models.CVAEGANClassifierModel(feature_num, label_num)}
+        parameters for the networks it has (tests/test_abi_and_host.py).  `hidden`: see `gan_config.hidden`."""
+        ctor = {"encoder": lambda: models.CVAEGANEncoderModel(feature_num, label_num, z_size, hidden=hidden),
+                "generator": lambda: models.CVAEGANGeneratorModel(z_size, label_num, feature_num, hidden=hidden),
+                "discriminator": lambda: models.CVAEGANDiscriminatorModel(feature_num, label_num, hidden=hidden),
+                "classifier": lambda: models.CVAEGANClassifierModel(feature_num, label_num, hidden=hidden)}
         nets = {n: ctor[n]() for n in cls._BUILD_ORDER}
         rest = [n for n in ctor if n not in nets]
         if rest:
@@ -99,7 +99,8 @@ class CVAEGAN:
         self.rank, self.world_size = _dist_info()
 
         # same construction (and CPU-generator draw) order as the reference class (cvae_gan.py:19-39)
-        nets = self._build_networks(self.feature_num, self.label_num, gc.z_size)
+        hidden = getattr(gc, "hidden", None)        # None: the reference's widths; (h1, h2, h3): the widened model (configs[4])
+        nets = self._build_networks(self.feature_num, self.label_num, gc.z_size, hidden)
         encoder, critic = nets["encoder"], nets["discriminator"]
         if self._USES_ENCODER:
             self.encoder = encoder
@@ -124,7 +125,7 @@ class CVAEGAN:
         self.engine = Engine(self.feature_num, self.label_num, gc.z_size, rows,
                              lambda_recon=cc.get('lambda_recon', 0.0), lambda_kl=cc.get('lambda_kl', 0.0),
                              lambda_adv=cc.get('lambda_adv', 0.0),
-                             g_lr=gc.g_lr, d_lr=gc.d_lr, c_lr=gc.c_lr, world_size=self.world_size, rank=self.rank)
+                             g_lr=gc.g_lr, d_lr=gc.d_lr, c_lr=gc.c_lr, world_size=self.world_size, rank=self.rank, hidden=hidden)
         for net, mod in ((NET_ENCODER, encoder), (NET_GENERATOR, self.generator),
                          (NET_DISCRIMINATOR, critic), (NET_CLASSIFIER, self.classifier)):
             mod.attach(self.engine, net)

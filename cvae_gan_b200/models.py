@@ -35,7 +35,11 @@ def init_weights(layer: nn.Module):
         nn.init.constant_(layer.bias, 0)
 
 
-def _widths(total_in: int, fixed_last: bool):
+def _widths(total_in: int, fixed_last: bool, hidden=None):
+    """cvae_gan_models.py:16-18,85-87,173-175,257-259.  `hidden` (not expressible in the reference, whose widths are hard-coded):
+    the widened model of BASELINE.json configs[4], the same three widths for every network."""
+    if hidden:
+        return tuple(int(v) for v in hidden)
     return max(256, total_in), max(128, total_in // 2), (64 if fixed_last else max(64, total_in // 4))
 
 
@@ -73,11 +77,11 @@ class _Attached(nn.Module):
 
 
 class CVAEGANEncoderModel(_Attached):
-    def __init__(self, input_dim: int, num_classes: int, latent_dim: int = 128):
+    def __init__(self, input_dim: int, num_classes: int, latent_dim: int = 128, hidden=None):
         super().__init__()
         self.input_dim, self.num_classes, self.latent_dim = input_dim, num_classes, latent_dim
         tin = input_dim + num_classes
-        h = _widths(tin, False)
+        h = _widths(tin, False, hidden)
         self.encoder = _bn_stack([tin, *h])
         self.fc_mu = nn.Linear(h[2], latent_dim)
         self.fc_logvar = nn.Linear(h[2], latent_dim)
@@ -109,11 +113,11 @@ class CVAEGANEncoderModel(_Attached):
 
 
 class CVAEGANGeneratorModel(_Attached):
-    def __init__(self, latent_dim: int, num_classes: int, output_dim: int):
+    def __init__(self, latent_dim: int, num_classes: int, output_dim: int, hidden=None):
         super().__init__()
         self.latent_dim, self.num_classes, self.output_dim = latent_dim, num_classes, output_dim
         tin = latent_dim + num_classes
-        h = _widths(tin, False)
+        h = _widths(tin, False, hidden)
         self.main_model = _bn_stack([tin, *h])
         self.hidden_status: torch.Tensor = None
         self.last_layer = nn.Sequential(nn.Linear(h[2], output_dim), nn.Sigmoid())
@@ -161,11 +165,11 @@ class CVAEGANGeneratorModel(_Attached):
 
 
 class CVAEGANDiscriminatorModel(_Attached):
-    def __init__(self, in_features: int, num_classes: int):
+    def __init__(self, in_features: int, num_classes: int, hidden=None):
         super().__init__()
         self.in_features, self.num_classes = in_features, num_classes
         tin = in_features + num_classes
-        h = _widths(tin, True)
+        h = _widths(tin, True, hidden)
         sn = lambda i, o: spectral_norm(nn.Linear(i, o))  # noqa: E731
         self.discriminator_network = nn.Sequential(
             sn(tin, h[0]), nn.LeakyReLU(NEG_SLOPE), nn.Dropout(DROP_P),
@@ -218,10 +222,10 @@ class CVAEGANDiscriminatorModel(_Attached):
 
 
 class CVAEGANClassifierModel(_Attached):
-    def __init__(self, in_features: int, num_classes: int):
+    def __init__(self, in_features: int, num_classes: int, hidden=None):
         super().__init__()
         self.in_features, self.num_classes = in_features, num_classes
-        h = _widths(in_features, True)
+        h = _widths(in_features, True, hidden)
         self.classifier_network = nn.Sequential(
             nn.Linear(in_features, h[0]), nn.ReLU(), nn.Dropout(DROP_P),
             nn.Linear(h[0], h[1]), nn.LayerNorm(h[1]), nn.ReLU(), nn.Dropout(DROP_P),

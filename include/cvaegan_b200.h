@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CVG_ABI_VERSION 1
+#define CVG_ABI_VERSION 2
 
 /* network ids (cvae_gan.py:19-39) */
 enum { CVG_NET_ENCODER = 0, CVG_NET_GENERATOR = 1, CVG_NET_DISCRIMINATOR = 2, CVG_NET_CLASSIFIER = 3, CVG_NUM_NETS = 4 };
@@ -61,6 +61,10 @@ typedef struct CvgConfig {
   float adam_beta1, adam_beta2, adam_eps;    /* 0.5, 0.999, 1e-8 (cvae_gan.py:75-97) */
   float bn_momentum, bn_eps, ln_eps, sn_eps; /* 0.1, 1e-5, 1e-5, 1e-12 */
   float lrelu_slope, dropout_p;              /* 0.2, 0.3 */
+  int32_t hidden[3];     /* {0,0,0}: the reference's widths (cvae_gan_models.py:16-18,85-87,173-175,257-259: max(256,in) /
+                          * max(128,in/2) / max(64,in/4) | 64).  Otherwise the three hidden widths of ALL four networks - the
+                          * widened model of BASELINE.json configs[4] (1024,512,256), which the reference's hard-coded widths
+                          * cannot express; each a multiple of 64, <= 1024 (classifier LayerNorm width hidden[1] <= 512). */
 } CvgConfig;
 
 typedef struct CvgHandle CvgHandle;
@@ -92,6 +96,7 @@ typedef struct CvgNoise {
 
 const char* cvg_last_error(void);
 int cvg_abi_version(void);
+int cvg_config_bytes(void);   /* sizeof(CvgConfig) as this library was compiled: a binding checks its struct against it */
 
 /* cvae_gan.py:12-56 (CVAEGAN.__init__): sizes the four networks.  Fails unless the current CUDA device is sm_100. */
 int cvg_create(const CvgConfig* cfg, CvgHandle** out);

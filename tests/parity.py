@@ -56,7 +56,7 @@ def make_pair(F: int, K: int, B: int, seed=0, Z=128, **cfg_kw):
                     t.mul_(1.0 + 0.2 * torch.rand(t.shape, generator=g))
     orc.make_optimizers()
     eng = Engine(F, K, Z, max_batch=max(B, 64), lambda_recon=cfg.lambda_recon, lambda_kl=cfg.lambda_kl,
-                 lambda_adv=cfg.lambda_adv, g_lr=cfg.g_lr, d_lr=cfg.d_lr, c_lr=cfg.c_lr)
+                 lambda_adv=cfg.lambda_adv, g_lr=cfg.g_lr, d_lr=cfg.d_lr, c_lr=cfg.c_lr, hidden=cfg.hidden)
     st = orc.state()
     for i, net in enumerate(NETS):
         eng.load_state(i, st[net])
@@ -110,12 +110,17 @@ def close(a: torch.Tensor, b: torch.Tensor, rtol=RTOL, atol_frac=ATOL_FRAC, atol
     return ok, worst, float(err.max()) if b.numel() else 0.0
 
 
-def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_factor=4.0, atol_frac=ATOL_FRAC):
+def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_factor=4.0, atol_frac=ATOL_FRAC,
+                  outlier_frac=0.0, hard_frac=0.0):
     """`grads64`: the same step on the float64 twin of the oracle.  |g32 - g64| is how far the REFERENCE's own float32
     arithmetic is from the exact gradient; where the problem is ill-conditioned (BatchNorm backward cancels the row-constant
     part of dy, and a pre-activation within round-off of 0 flips a LeakyReLU derivative from 1 to 0.2 - at batch 4096 a few
     of the 10^6 activations always are) no float32 implementation can agree with another to 1e-3, so the tolerance is
-    widened by `envelope_factor` times that measured distance.  The comparison is then made against the float64 gradient."""
+    widened by `envelope_factor` times that measured distance.  The comparison is then made against the float64 gradient.
+    `outlier_frac` / `hard_frac` (with grads64): the flip can also happen on THIS side only - one activation, i.e. one entry of
+    the following BatchNorm's bias gradient and part of one row of the Linear's weight gradient (tools/diag_wide_flip.py,
+    profiles/r2_diag_wide_flip.log) - so up to that fraction of a tensor's entries may miss the tolerance as long as every entry
+    stays within `hard_frac` of the tensor's scale."""
     for name in net_names:
         i = NETS.index(name)
         for j, (key, g_ref) in enumerate(zip(orc.param_keys(name), grads[name])):
@@ -125,7 +130,11 @@ def compare_grads(eng, orc, net_names, grads, report, grads64=None, envelope_fac
             else:
                 g64 = grads64[name][j]
                 env = float((g_ref.double() - g64).abs().max())
-                ok, worst, mx = close(got.double().cpu(), g64, atol_abs=1e-9 + envelope_factor * env, atol_frac=atol_frac)
+                if outlier_frac > 0.0:
+                    ok, worst, mx = close_mostly(got, g64, RTOL, atol_frac, 1e-9 + envelope_factor * env, outlier_frac,
+                                                 hard_frac * float(g64.abs().max()) + envelope_factor * env)
+                else:
+                    ok, worst, mx = close(got.double().cpu(), g64, atol_abs=1e-9 + envelope_factor * env, atol_frac=atol_frac)
             report.append((f"grad {name}/{key}", ok, worst, mx, float(g_ref.abs().max())))
 
 
@@ -213,7 +222,8 @@ def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True, twin=N
     `twin`: float64 twin of the oracle taking the same step (its gradients land in run_step.last_twin_grads)."""
     from cvae_gan_b200._lib import STEP_NO_UPDATE
     B = x.shape[0]
-    inj, dev = draw_noise(kind, B, orc.cfg.z_size, g)
+    h1, h2 = (orc.cfg.hidden or (256, 128, 64))[:2]     # dropout-mask widths (every reference shape tested here gives 256 / 128)
+    inj, dev = draw_noise(kind, B, orc.cfg.z_size, g, h1=h1, h2=h2)
     run_step.last_twin_grads = None
     if twin is not None:
         run_step.last_twin_grads = twin_step(kind, twin, x, label, clone_noise(inj), lambda_class, update)

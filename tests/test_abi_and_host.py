@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cvg_abi_version() == 1
+    assert lib.cvg_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_create_fails_loudly_without_sm100(lib):

@@ -291,3 +291,32 @@ def test_cvae_fit_epoch350_lambda_class_matches_reference(golden_dir):
             np.testing.assert_allclose([f.sum(), (f * f).sum()], d[:2], rtol=1e-5, atol=1e-6, err_msg=f"{net}/{key}")
             n = min(8, f.size)
             np.testing.assert_allclose(f[:n], d[2:2 + n], rtol=2e-5, atol=2e-7)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the width-configurable restatement, checked at the reference's own widths
+# ---------------------------------------------------------------------------------------------------
+def test_configurable_widths_reproduce_the_reference_at_its_own_widths(golden_dir):
+    """`OracleConfig.hidden` (the widened model of BASELINE.json configs[4] is not expressible in the reference): with the
+    widths the reference's formulas give for F = 10, K = 5, Z = 128 - (256, 128, 64) in all four networks - the tensor tables
+    are the reference's and a 2-epoch fit replays the unmodified reference's losses and final parameters."""
+    torch.set_num_threads(1)
+    for net in NETS:
+        assert O.tensor_table(net, 10, 5, 128, hidden=(256, 128, 64)) == O.tensor_table(net, 10, 5, 128)
+        wide = dict((k, s) for k, s, _ in O.tensor_table(net, 10, 5, 128, hidden=(1024, 512, 256)))
+        assert all(len(s) < 2 or max(s) <= 1024 for s in wide.values())
+    assert dict((k, s) for k, s, _ in O.tensor_table("classifier", 10, 5, 128, hidden=(1024, 512, 256)))["classifier_network.7.weight"] == (256, 512)
+    npz = _load(golden_dir, "ref_fit_a.npz")
+    F_, K, B, fit_seed, _, _ = [int(v) for v in npz["meta"]]
+    cfg = O.OracleConfig(batch_size=B, epochs=2, hidden=(256, 128, 64))
+    orc = O.OracleCVAEGAN(F_, K, cfg).load_state(_states(npz, "init"))
+    torch.manual_seed(fit_seed)
+    orc.fit(torch.from_numpy(npz["x"]), torch.from_numpy(npz["y"]))
+    for k in orc.loss_history:
+        np.testing.assert_allclose(orc.loss_history[k], npz["loss/" + k], rtol=2e-6, atol=1e-7)
+    fin = _states(npz, "final")
+    st = orc.state()
+    for net in NETS:
+        for key, ref in fin[net].items():
+            if ref.dtype != torch.int64:
+                torch.testing.assert_close(st[net][key], ref, rtol=2e-5, atol=2e-7, msg=f"{net}/{key}")
