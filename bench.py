@@ -36,6 +36,30 @@ D_LOOP, C_LOOP, G_LOOP = 5, 5, 3    # gan_config.py:7,10,13
 OPT_STEPS = D_LOOP + C_LOOP + G_LOOP
 # minimal algorithmic work per train sample, F=10 K=5 (SURVEY.md 8d / BASELINE.md section 3)
 FLOP_PER_SAMPLE = 873_945
+WIDE_HIDDEN = (1024, 512, 256)      # BASELINE.json configs[4] / SURVEY 8(d) C5: the widened model (fp32 here; no bf16 path)
+
+
+def flop_per_train_sample(F, K, Z, hidden=None):
+    """SURVEY.md 8(d) accounting (minimal algorithmic work, MACs per batch row) for any layer widths: forward MACs of every
+    pass, backward = weight gradient + input gradient per layer, minus the input gradients nobody needs (first layers of the
+    trained networks; the critic's / classifier's weight gradients in the encoder/generator step).  2 FLOP per MAC, 13
+    optimiser steps of one row each per label visit.  flop_per_train_sample(10, 5, 128) = 873 945 (the SURVEY figure)."""
+    def widths(tin, fixed3):
+        return tuple(hidden) if hidden else (max(256, tin), max(128, tin // 2), 64 if fixed3 else max(64, tin // 4))
+
+    def macs(dims):
+        return sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    eh, gh, dh, ch = widths(F + K, False), widths(Z + K, False), widths(F + K, True), widths(F, True)
+    mE = macs((F + K, *eh)) + eh[2] * 2 * Z
+    mG = macs((Z + K, *gh, F))
+    mD = macs((F + K, *dh, 1))
+    mC = macs((F, *ch, K))
+    d_step = mG + 2 * mD + 2 * (2 * mD - (F + K) * dh[0])
+    c_step = mG + 2 * mC + 2 * (2 * mC - F * ch[0])
+    g_bwd = mD + mC + (4 * mG - (Z + K) * gh[0] - K * gh[0]) + (2 * mE - (F + K) * eh[0])
+    g_step = mE + 2 * mG + mD + mC + g_bwd
+    return 2.0 * (D_LOOP * d_step + C_LOOP * c_step + G_LOOP * g_step) / OPT_STEPS
+
 
 
 def ncu_traffic():
@@ -451,6 +475,15 @@ def run_ours(args):
         finally:
             eng.debug_set("train_mode", 0)
 
+    # ---- BASELINE.json configs[4], single GPU, fp32: the widened model (hidden 1024 / 512 / 256 in all four
+    # networks, CvgConfig.hidden) through the same label visits.  Informative leg: never lose the bench line over it. ----
+    train_wide = None
+    if world == 1 and not args.no_wide:
+        try:
+            train_wide = run_wide_leg(dev, tabs, timed, pk, max(5, min(args.steps, 20)))
+        except Exception as ex:
+            train_wide = {"error": str(ex)[:300]}
+
     # ---- the drop-in surface itself: CVAEGAN.fit(TrDataset()) + generate_qualified_samples (N = 1 only) ----
     e2e_fit = None
     if world == 1 and not args.no_fit:
@@ -487,6 +520,8 @@ def run_ours(args):
             line["train_program"] = train_program
         if e2e_fit:
             line["e2e_fit"] = e2e_fit
+        if train_wide:
+            line["train_wide"] = train_wide
         if dp_par:
             line["dp_parity"] = dp_par
         if cpu:
@@ -500,6 +535,52 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     _finish(eng, world)
 
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the widened model of BASELINE.json configs[4] on one GPU (fp32; the reference cannot express these widths)
+# ---------------------------------------------------------------------------------------------------------
+def run_wide_leg(dev, tabs, timed, pk, steps):
+    import torch
+    from cvae_gan_b200 import models
+    from cvae_gan_b200.engine import Engine
+    B = BATCH_PER_GPU
+    eng = Engine(F_, K_, Z_, max_batch=B, hidden=WIDE_HIDDEN)
+    try:
+        torch.manual_seed(0)
+        mods = [models.CVAEGANEncoderModel(F_, K_, Z_, hidden=WIDE_HIDDEN), models.CVAEGANGeneratorModel(Z_, K_, F_, hidden=WIDE_HIDDEN),
+                models.CVAEGANDiscriminatorModel(F_, K_, hidden=WIDE_HIDDEN), models.CVAEGANClassifierModel(F_, K_, hidden=WIDE_HIDDEN)]
+        for net, m in enumerate(mods):
+            eng.load_state(net, m.state_dict())
+        n_param = sum(int(p.numel()) for m in mods for p in m.parameters())
+        loss = torch.zeros(OPT_STEPS, 4, device=dev)
+        eng.ctl_set(seed=4321, counter=0, lambda_class=0.25)
+        l0 = eng.launch_count()
+        eng.visit(0, B, class_rows=tabs[0], loops=(D_LOOP, C_LOOP, G_LOOP), loss_out=loss)
+        launches = eng.launch_count() - l0
+        torch.cuda.synchronize()
+        graphs = {}
+        for label in range(K_):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng.visit(label, B, class_rows=tabs[label], loops=(D_LOOP, C_LOOP, G_LOOP), loss_out=loss)
+            graphs[label] = g
+        ms = timed(lambda lab: graphs[lab].replay(), steps, 3)
+        fin = loss.tolist()
+        value = OPT_STEPS * B * steps / (ms * 1e-3)
+        flop = flop_per_train_sample(F_, K_, Z_, WIDE_HIDDEN)
+        tf = value * flop / 1e12
+        simt = 148 * 128 * 2 * 1.965e9 / 1e12
+        del graphs
+        return {"workload": f"widened CVAE-GAN, hidden {WIDE_HIDDEN} in all four networks, F={F_} K={K_} Z={Z_}, fp32 (NOT the bf16 "
+                            f"variant BASELINE.json configs[4] names: no bf16 path is built), batch {B}, 1 GPU; same label visits",
+                "value": value, "unit": "samples/s", "ms_per_step": ms / steps, "steps": steps, "parameters": n_param,
+                "gpu_launches_per_step": launches, "flop_per_sample": flop, "whole_step_tflops": tf,
+                "frac_of_fp32_simt_nominal": tf / simt, "frac_of_bf16_sustained": tf / pk["bf16_tflops_sustained"],
+                "executor": "stand-alone fp32 FFMA layer kernels (the tcgen05 executors cover widths <= 256)",
+                "losses_finite": all(all(v == v and abs(v) < 1e6 for v in row) for row in fin)}
+    finally:
+        eng.close()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -771,6 +852,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-filter", action="store_true", help="skip the generation + filter leg")
     ap.add_argument("--no-fit", action="store_true", help="skip the CVAEGAN.fit drop-in leg")
+    ap.add_argument("--no-wide", action="store_true", help="skip the widened-model leg (BASELINE.json configs[4], fp32, 1 GPU)")
     ap.add_argument("--only-filter", action="store_true", help="dev aid: run only the generation + filter leg")
     ap.add_argument("--quick", action="store_true", help="profiling aid (ncu): resident loop only, no e2e/cpu legs; NOT a bench number")
     args = ap.parse_args()

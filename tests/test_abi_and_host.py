@@ -232,3 +232,15 @@ def test_host_classes_build_networks_in_the_reference_order(golden_dir, cls_name
     for name in getattr(cg, cls_name)._BUILD_ORDER:
         ctor[name]()
     assert torch.equal(after, torch.rand(1))
+
+
+def test_bench_flop_accounting_reproduces_the_survey_figures():
+    """bench.flop_per_train_sample generalises SURVEY.md 8(d)'s minimal-work accounting to any layer widths (needed for the
+    widened model); at the reference's widths it must give the SURVEY figures: 873 945 (F=10, K=5), 871 463 (OTIDS K=4),
+    925 145 (F=30, K=5)."""
+    import bench
+    assert round(bench.flop_per_train_sample(10, 5, 128)) == 873_945 == bench.FLOP_PER_SAMPLE
+    assert round(bench.flop_per_train_sample(10, 4, 128)) == 871_463
+    assert round(bench.flop_per_train_sample(30, 5, 128)) == 925_145
+    assert bench.flop_per_train_sample(10, 5, 128, (256, 128, 64)) == bench.flop_per_train_sample(10, 5, 128)
+    assert bench.flop_per_train_sample(10, 5, 128, bench.WIDE_HIDDEN) > 10 * bench.FLOP_PER_SAMPLE
