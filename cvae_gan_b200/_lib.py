@@ -32,6 +32,7 @@ class CvgConfig(C.Structure):
         ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("ln_eps", C.c_float), ("sn_eps", C.c_float),
         ("lrelu_slope", C.c_float), ("dropout_p", C.c_float),
         ("hidden", C.c_int32 * 3),     # (0, 0, 0): the reference's widths; else the widened model's three hidden widths
+        ("unconditional", C.c_int32),  # 1: E / G / D without the one-hot label columns (sibling trainer VAE-GAN)
     ]
 
 

@@ -41,3 +41,11 @@ cvae_config = {
     'lambda_class': 0.1,
     'confidence_threshold': 0.5,
 }
+
+# sibling trainer VAE-GAN (/root/reference/src/config/gan_config.py:33-38, read by src/vae_gan.py:29-31,131-135)
+vae_gan_config = {
+    'lambda_recon': 1.0,
+    'lambda_kl': 0.01,
+    'lambda_adv': 0.1,
+    'confidence_threshold': 0.5,
+}

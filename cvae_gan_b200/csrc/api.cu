@@ -80,6 +80,7 @@ int cvg_create(const CvgConfig* cfg, CvgHandle** out) {
   e.cfg = *cfg;
   e.F = cfg->feature_num;
   e.K = cfg->label_num;
+  e.Kc = cfg->unconditional ? 0 : cfg->label_num;
   e.Z = cfg->z_size;
   e.world = cfg->world_size;
   e.rank = cfg->rank;

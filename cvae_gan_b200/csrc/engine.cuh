@@ -156,6 +156,7 @@ struct Engine {
   std::vector<ProfRec> prof_recs;
   CvgConfig cfg{};
   int F = 0, K = 0, Z = 0;
+  int Kc = 0;                      // one-hot label columns beside the input of E, G and D: K, or 0 (CvgConfig.unconditional)
   int eh[3]{}, gh[3]{}, dh[3]{}, ch[3]{};
   NetLayout lay[4];
   NetBuffers buf[4];

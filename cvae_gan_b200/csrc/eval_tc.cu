@@ -572,6 +572,7 @@ static int tc_mode(const Engine& e) {
 // Which networks the tensor-core chain supports: every hidden width a multiple of 64 and <= 256.
 bool tc_supported(const Engine& e) {
   auto ok = [](const int* h) { return h[0] <= 256 && h[1] <= 256 && h[2] <= 256 && h[0] % 64 == 0 && h[1] % 64 == 0 && h[2] % 64 == 0; };
+  if (e.Kc != e.K) return false;      // unconditional networks (VAE-GAN sibling): the chains fold a label column into the bias
   return ok(e.eh) && ok(e.gh) && ok(e.dh) && ok(e.ch) && e.F <= TC_MAXF && e.Z % 8 == 0 && e.Z <= TC128_MAXK && 2 * e.Z <= 256 &&
          e.K <= FILTER_MAXK && e.ch[1] % 2 == 0;
 }

@@ -42,7 +42,8 @@ static void hidden(const CvgConfig& cfg, int tin, bool fixed3, int* h) {
 }
 
 int build_layouts(Engine& e) {
-  const int F = e.F, K = e.K, Z = e.Z;
+  const int F = e.F, Z = e.Z;
+  const int K = e.Kc;                  // label columns of E / G / D (0: unconditional networks); the classifier has e.K outputs
   const int* hv = e.cfg.hidden;
   if (hv[0] != 0 || hv[1] != 0 || hv[2] != 0)
     for (int i = 0; i < 3; ++i)
@@ -55,7 +56,7 @@ int build_layouts(Engine& e) {
     if (e.eh[i] > STAT_C || e.gh[i] > STAT_C || e.dh[i] > SN_MAXDIM || e.ch[i] > STAT_C)
       CVG_FAIL("layer wider than supported (1024)");
   if (Z % 4 != 0) CVG_FAIL("z_size must be a multiple of 4");
-  if (K > FILTER_MAXK) CVG_FAIL("label_num > 32 is not supported");
+  if (e.K > FILTER_MAXK) CVG_FAIL("label_num > 32 is not supported");
   if (e.ch[1] > 8 * LN_MAXF_WIDE) CVG_FAIL("classifier LayerNorm wider than 512 is not supported");
 
   {  // encoder (cvae_gan_models.py:20-35)
@@ -135,7 +136,7 @@ int build_layouts(Engine& e) {
   {  // classifier (cvae_gan_models.py:261-276)
     NetLayout& L = e.lay[CVG_NET_CLASSIFIER];
     Builder b(L);
-    int dims[5] = {F, e.ch[0], e.ch[1], e.ch[2], K};
+    int dims[5] = {F, e.ch[0], e.ch[1], e.ch[2], e.K};
     const int li[4] = {0, 3, 7, 9};
     for (int i = 0; i < 4; ++i) {
       LinearP& p = L.lin[i];

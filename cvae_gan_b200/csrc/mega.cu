@@ -12,6 +12,7 @@ using mk::OpRec;
 
 bool mk_supported(const Engine& e) {
   auto ok = [](const int* h) { return h[0] <= mk::MAX_C && h[1] <= mk::MAX_C && h[2] <= mk::MAX_C; };
+  if (e.Kc != e.K) return false;      // unconditional networks: stand-alone executor only
   return ok(e.eh) && ok(e.gh) && ok(e.dh) && ok(e.ch) && e.F + e.K <= mk::B_MAXN && e.Z <= mk::B_MAXN && 2 * e.Z <= SN_MAXDIM &&
          e.ch[1] <= 8 * mk::MK_LN_F;
 }

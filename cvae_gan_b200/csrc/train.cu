@@ -292,6 +292,13 @@ int launch_dw(Engine& e, const DwArgs& g0, cudaStream_t st) {
 
 static const LinearP& lin(const Engine& e, int net, int l) { return e.lay[net].lin[l]; }
 
+// One-hot concat of the first Linear of E / G / D == adding weight column (input width + label) to the bias (appendix A.1);
+// unconditional networks (CvgConfig.unconditional, the VAE-GAN sibling) have no such columns.
+static const float* label_column(const Engine& e, int net, const LinearP& p, int in_width, int label) {
+  return e.Kc > 0 ? e.P(net, p.w) + in_width + label : nullptr;
+}
+static int label_col_index(const Engine& e, int in_width, int label) { return e.Kc > 0 ? in_width + label : -1; }
+
 static double* fst_of(const Engine& e, int net, int l) {
   return net == CVG_NET_GENERATOR ? e.ws.g_fst + (size_t)l * 2 * 2 * STAT_C : e.ws.e_fst + (size_t)l * 2 * STAT_C;
 }
@@ -478,7 +485,7 @@ int fwd_generator(Engine& e, int npass, bool train, bool reparam_pass0, int labe
       g.a.lv = w.e_ml + (size_t)e.Z * ld;
       g.a.eps = w.z;
       g.a.reparam_pass = reparam_pass0 ? 0 : -1;
-      g.wlabel = e.P(net, p.w) + e.Z + label;   // one-hot concat == adding column Z+label (appendix A.1)
+      g.wlabel = label_column(e, net, p, e.Z, label);   // one-hot concat == adding column Z+label (appendix A.1)
       g.ldwl = p.in;
     } else {
       g.a.kind = OP_BN_ACT;
@@ -532,7 +539,7 @@ int fwd_encoder(Engine& e, bool train, int label, int M, float Bg, bool local_bn
       g.a.kind = OP_PLAIN;
       g.a.rows = e.F;
       g.a.p = w.xT;
-      g.wlabel = e.P(net, p.w) + e.F + label;
+      g.wlabel = label_column(e, net, p, e.F, label);
       g.ldwl = p.in;
     } else {
       g.a.kind = OP_BN_ACT;
@@ -614,7 +621,7 @@ static int fwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
     if (l == 0) {
       g.a.p = xin;
       g.a.sp = sxin;
-      g.wlabel = e.P(net, p.w) + e.F + label;
+      g.wlabel = label_column(e, net, p, e.F, label);
       g.ldwl = p.in;
     } else {
       g.a.p = w.d_a[l - 1];
@@ -733,7 +740,7 @@ static int bwd_critic(Engine& e, const float* xin, long long sxin, int npass, in
         d.sdW = sG;
         d.ldw = p.in;
         d.db = (l == 3) ? nullptr : e.G(net, p.b);   // score-bias gradient is added analytically (sn_grad_kernel)
-        d.label_col = (l == 0) ? e.F + label : -1;
+        d.label_col = (l == 0) ? label_col_index(e, e.F, label) : -1;
         CVG_TRY(launch_dw(e, d, sw));
       }
     }
@@ -1378,7 +1385,7 @@ static int step_g_prior(Engine& e, int label, int B, const CvgNoise* nz, const S
   gb.first_in.kind = OP_PLAIN; gb.first_in.rows = e.Z;
   gb.first_in.p = w.z; gb.first_in.sp = (long long)e.Z * ld;
   gb.first_K = e.Z;
-  gb.label_col = e.Z + label;
+  gb.label_col = label_col_index(e, e.Z, label);
   gb.want_first_dx = false;
   CVG_TRY(bwd_bn_net(e, gb, B, Bg_bn, 0.f, local_bn, st));
   return finish_step(e, 1 << G, 2, B, flags, loss_out, st);
@@ -1446,7 +1453,7 @@ static int step_g_cvae(Engine& e, const float* x_real, int label, int B, const C
   gb.first_in.mu = w.e_ml; gb.first_in.lv = w.e_ml + (size_t)e.Z * ld; gb.first_in.eps = w.z;
   gb.first_in.reparam_pass = 0;
   gb.first_K = e.Z;
-  gb.label_col = e.Z + label;
+  gb.label_col = label_col_index(e, e.Z, label);
   gb.want_first_dx = true;
   CVG_TRY(bwd_bn_net(e, gb, B, Bg_bn, e.cfg.lambda_kl / Bg, local_bn, st));
   BnNetBwd eb;
@@ -1455,7 +1462,7 @@ static int step_g_cvae(Engine& e, const float* x_real, int label, int B, const C
   eb.top_dy = w.e_dml; eb.s_top = 0;
   eb.first_in.kind = OP_PLAIN; eb.first_in.rows = e.F; eb.first_in.p = w.xT;
   eb.first_K = e.F;
-  eb.label_col = e.F + label;
+  eb.label_col = label_col_index(e, e.F, label);
   eb.want_first_dx = false;
   CVG_TRY(bwd_bn_net(e, eb, B, Bg_bn, 0.f, local_bn, st));
   return finish_step(e, (1 << E) | (1 << G), 2, B, flags, loss_out, st);
@@ -1582,7 +1589,7 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   gb.first_in.mu = w.e_ml; gb.first_in.lv = w.e_ml + (size_t)e.Z * ld; gb.first_in.eps = w.z;
   gb.first_in.reparam_pass = 0;
   gb.first_K = e.Z;
-  gb.label_col = e.Z + label;
+  gb.label_col = label_col_index(e, e.Z, label);
   gb.want_first_dx = true;
   (void)g0;
   CVG_TRY(bwd_bn_net(e, gb, B, Bg_bn, e.cfg.lambda_kl / Bg, local_bn, st));
@@ -1593,7 +1600,7 @@ int step_g(Engine& e, const float* x_real, int label, int B, const CvgNoise* nz,
   eb.top_dy = w.e_dml; eb.s_top = 0;
   eb.first_in.kind = OP_PLAIN; eb.first_in.rows = e.F; eb.first_in.p = w.xT;
   eb.first_K = e.F;
-  eb.label_col = e.F + label;
+  eb.label_col = label_col_index(e, e.F, label);
   eb.want_first_dx = false;
   CVG_TRY(bwd_bn_net(e, eb, B, Bg_bn, 0.f, local_bn, st));
 

@@ -28,9 +28,12 @@ class Engine:
 
     def __init__(self, feature_num: int, label_num: int, z_size: int = 128, max_batch: int = 4096, *,
                  lambda_recon=1.0, lambda_kl=0.1, lambda_adv=1.0, g_lr=2e-4, d_lr=2e-4, c_lr=1e-4,
-                 betas=(0.5, 0.999), adam_eps=1e-8, world_size: int = 1, rank: int = 0, device=None, hidden=None):
+                 betas=(0.5, 0.999), adam_eps=1e-8, world_size: int = 1, rank: int = 0, device=None, hidden=None,
+                 unconditional: bool = False):
         """`hidden`: None = the reference's layer widths; (h1, h2, h3) = the widened model (BASELINE.json configs[4]), the
-        same three hidden widths for all four networks (multiples of 64, <= 1024; h2 <= 512)."""
+        same three hidden widths for all four networks (multiples of 64, <= 1024; h2 <= 512).
+        `unconditional`: encoder, generator and critic without the one-hot label columns (the sibling trainer VAE-GAN's
+        networks, vae_gan_models.py); `label` arguments are then ignored."""
         if not torch.cuda.is_available():
             raise _lib.CvgError("cvae_gan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -42,7 +45,8 @@ class Engine:
         cfg = CvgConfig(self.F, self.K, self.Z, self.max_batch, self.world_size, self.rank,
                         lambda_recon, lambda_kl, lambda_adv, g_lr, d_lr, c_lr, betas[0], betas[1], adam_eps,
                         0.1, 1e-5, 1e-5, 1e-12, 0.2, 0.3,
-                        (C.c_int32 * 3)(*([int(v) for v in hidden] if hidden else [0, 0, 0])))
+                        (C.c_int32 * 3)(*([int(v) for v in hidden] if hidden else [0, 0, 0])), 1 if unconditional else 0)
+        self.unconditional = bool(unconditional)
         self.hidden = tuple(int(v) for v in hidden) if hidden else None
         self.cfg = cfg
         h = C.c_void_p()

@@ -249,3 +249,61 @@ class CVAEGANClassifierModel(_Attached):
             if hasattr(first, 'weight'):
                 return torch.mean(torch.abs(first.weight.data), dim=0)
         return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sibling trainer VAE-GAN (/root/reference/src/models/vae_gan_models.py:8-154): the same three stacks WITHOUT the label
+# columns - first Linear over input_dim (E, D) / latent_dim (G) - and forwards that take no condition.  Same attribute and
+# state_dict key names, same construction order of the layers (so the same seed gives the reference's starting parameters).
+# ---------------------------------------------------------------------------------------------------------------------
+class VAEGANEncoderModel(CVAEGANEncoderModel):
+    def __init__(self, input_dim: int, latent_dim: int = 128, hidden=None):
+        super().__init__(input_dim, 0, latent_dim, hidden=hidden)
+
+    def forward(self, x: torch.Tensor) -> tuple:
+        if x.dim() != 2:
+            raise ValueError(f"输入数据应为2D张量，实际: {x.shape}")
+        if x.size(1) != self.input_dim:
+            raise ValueError(f"输入特征维度不匹配，期望: {self.input_dim}，实际: {x.size(1)}")
+        hid = self.encoder(x)
+        return self.fc_mu(hid), self.fc_logvar(hid)
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        return self.reparameterize(*self.forward(x))
+
+
+class VAEGANGeneratorModel(CVAEGANGeneratorModel):
+    def __init__(self, latent_dim: int, output_dim: int, hidden=None):
+        super().__init__(latent_dim, 0, output_dim, hidden=hidden)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        if z.dim() != 2:
+            raise ValueError(f"潜在向量应为2D张量，实际: {z.shape}")
+        if z.size(1) != self.latent_dim:
+            raise ValueError(f"潜在维度不匹配，期望: {self.latent_dim}，实际: {z.size(1)}")
+        hid = self.main_model(z)
+        self.hidden_status = hid
+        return self.last_layer(hid).view(-1, self.output_dim)
+
+    def reconstruct(self, x: torch.Tensor, encoder: nn.Module) -> torch.Tensor:
+        with torch.no_grad():
+            return self.forward(encoder.encode(x))
+
+
+class VAEGANDiscriminatorModel(CVAEGANDiscriminatorModel):
+    def __init__(self, in_features: int, hidden=None):
+        super().__init__(in_features, 0, hidden=hidden)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() > 2:
+            x = x.view(x.size(0), -1)
+        feats = self.discriminator_network[:-1](x)
+        self.hidden_status = feats
+        return self.discriminator_network[-1](feats)
+
+    def get_feature_importance(self, x: torch.Tensor):
+        with torch.no_grad():
+            first = self.discriminator_network[0]
+            if hasattr(first, 'weight'):
+                return torch.mean(torch.abs(first.weight.data), dim=0)
+        return None

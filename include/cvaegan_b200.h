@@ -65,6 +65,10 @@ typedef struct CvgConfig {
                           * max(128,in/2) / max(64,in/4) | 64).  Otherwise the three hidden widths of ALL four networks - the
                           * widened model of BASELINE.json configs[4] (1024,512,256), which the reference's hard-coded widths
                           * cannot express; each a multiple of 64, <= 1024 (classifier LayerNorm width hidden[1] <= 512). */
+  int32_t unconditional; /* 0: encoder, generator and critic take the one-hot label beside their input (cvae_gan_models.py:47-58,
+                          * 136-150, 215-233).  1: the sibling trainer VAE-GAN's networks (/root/reference/src/models/
+                          * vae_gan_models.py:8-154): the same layers WITHOUT the label columns - first Linear of E and D over F
+                          * inputs, of G over z_size; `label` arguments of the calls are then ignored (pass 0). */
 } CvgConfig;
 
 typedef struct CvgHandle CvgHandle;

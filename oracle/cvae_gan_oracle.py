@@ -61,6 +61,7 @@ class OracleConfig:
         self.confidence_threshold = 0.5
         self.epoch_offset = 0  # first value of `e` (the reference always starts at 0)
         self.hidden = None     # (h1, h2, h3): widened restatement (BASELINE.json configs[4]); None = the reference's widths
+        self.unconditional = False   # True: E / G / D without label columns (sibling trainer VAE-GAN, src/vae_gan.py)
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)
@@ -93,11 +94,12 @@ def hidden_sizes(total_in: int, fixed3: bool, hidden=None):
     return h1, h2, h3
 
 
-def tensor_table(net: str, F_: int, K: int, Z: int, hidden=None):
+def tensor_table(net: str, F_: int, K: int, Z: int, hidden=None, unconditional=False):
     """(key, shape, kind) in reference `state_dict()` order; kind in {param, buffer}."""
     t = []
+    Kc = 0 if unconditional else K      # label columns of E / G / D (the VAE-GAN sibling's networks have none)
     if net == "encoder":
-        tin = F_ + K
+        tin = F_ + Kc
         h = hidden_sizes(tin, False, hidden)
         dims = [tin, *h]
         for i, li in enumerate((0, 3, 6)):
@@ -113,7 +115,7 @@ def tensor_table(net: str, F_: int, K: int, Z: int, hidden=None):
         t.append(("fc_logvar.weight", (Z, h[2]), "param"))
         t.append(("fc_logvar.bias", (Z,), "param"))
     elif net == "generator":
-        tin = Z + K
+        tin = Z + Kc
         h = hidden_sizes(tin, False, hidden)
         dims = [tin, *h]
         for i, li in enumerate((0, 3, 6)):
@@ -127,7 +129,7 @@ def tensor_table(net: str, F_: int, K: int, Z: int, hidden=None):
         t.append(("last_layer.0.weight", (F_, h[2]), "param"))
         t.append(("last_layer.0.bias", (F_,), "param"))
     elif net == "discriminator":
-        tin = F_ + K
+        tin = F_ + Kc
         h = hidden_sizes(tin, True, hidden)
         dims = [tin, *h, 1]
         for i, li in enumerate((0, 3, 6, 8)):
@@ -242,6 +244,14 @@ def _one_hot(label: int, rows: int, K: int, dtype=torch.float32) -> torch.Tensor
     return F.one_hot(torch.full([rows], int(label), dtype=torch.long), num_classes=K).to(dtype)
 
 
+def _cat_label(x, label, K: int):
+    """cat(x, onehot(label)) - or x itself for the unconditional networks of the VAE-GAN sibling (vae_gan_models.py:37,95,144),
+    whose first Linear has no label columns (K == 0)."""
+    if K == 0:
+        return x
+    return torch.cat([x, _one_hot(label, x.shape[0], K, x.dtype)], dim=1)
+
+
 def _bn(x, sd, prefix, train: bool, dp=None):
     """BatchNorm1d, SURVEY appendix A.2.  In train mode updates running stats in `sd` (also under
     no_grad, cvae_gan.py:113-115).  `dp` optionally all-reduces the batch moments (data parallel)."""
@@ -274,7 +284,7 @@ def _bn(x, sd, prefix, train: bool, dp=None):
 def encoder_forward(sd, x, label: int, train: bool, dp=None):
     """cvae_gan_models.py:49-64: cat(x, onehot) -> [Lin, BN, LReLU]x3 -> fc_mu, fc_logvar."""
     K = sd["encoder.0.weight"].shape[1] - x.shape[1]
-    h = torch.cat([x, _one_hot(label, x.shape[0], K, x.dtype)], dim=1)
+    h = _cat_label(x, label, K)
     for li in (0, 3, 6):
         h = F.linear(h, sd[f"encoder.{li}.weight"], sd[f"encoder.{li}.bias"])
         h = _bn(h, sd, f"encoder.{li + 1}", train, dp)
@@ -287,7 +297,7 @@ def encoder_forward(sd, x, label: int, train: bool, dp=None):
 def generator_forward(sd, z, label: int, train: bool, dp=None):
     """cvae_gan_models.py:136-156: cat(z, onehot) -> [Lin, BN, LReLU]x3 -> Lin -> Sigmoid."""
     K = sd["main_model.0.weight"].shape[1] - z.shape[1]
-    h = torch.cat([z, _one_hot(label, z.shape[0], K, z.dtype)], dim=1)
+    h = _cat_label(z, label, K)
     for li in (0, 3, 6):
         h = F.linear(h, sd[f"main_model.{li}.weight"], sd[f"main_model.{li}.bias"])
         h = _bn(h, sd, f"main_model.{li + 1}", train, dp)
@@ -314,7 +324,7 @@ def discriminator_forward(sd, x, label: int, train: bool, noise=None, mask_tags=
     """cvae_gan_models.py:215-230: cat(x, onehot) -> SN-Lin, LReLU, Drop -> SN-Lin, LReLU, Drop
     -> SN-Lin, LReLU -> SN-Lin.  Raw critic score [B,1]."""
     K = sd["discriminator_network.0.parametrizations.weight.original"].shape[1] - x.shape[1]
-    h = torch.cat([x, _one_hot(label, x.shape[0], K, x.dtype)], dim=1)
+    h = _cat_label(x, label, K)
     for i, li in enumerate((0, 3, 6)):
         p = f"discriminator_network.{li}"
         h = F.linear(h, _sn_weight(sd, p, train), sd[p + ".bias"])
@@ -448,7 +458,7 @@ class OracleCVAEGAN:
     # ---- state ------------------------------------------------------------------------------
     def load_state(self, states: Dict[str, Dict[str, torch.Tensor]]):
         for net in NETS:
-            tab = tensor_table(net, self.feature_num, self.label_num, self.cfg.z_size, self.cfg.hidden)
+            tab = tensor_table(net, self.feature_num, self.label_num, self.cfg.z_size, self.cfg.hidden, self.cfg.unconditional)
             sd = OrderedDict()
             for key, shape, kind in tab:
                 t = torch.as_tensor(states[net][key]).clone()
@@ -496,7 +506,7 @@ class OracleCVAEGAN:
         states = {}
         for net in NETS:
             sd = {}
-            for key, shape, kind in tensor_table(net, self.feature_num, self.label_num, self.cfg.z_size, self.cfg.hidden):
+            for key, shape, kind in tensor_table(net, self.feature_num, self.label_num, self.cfg.z_size, self.cfg.hidden, self.cfg.unconditional):
                 if kind == "buffer_i64":
                     sd[key] = torch.zeros((), dtype=torch.long)
                 elif key.endswith("running_mean"):
@@ -770,6 +780,82 @@ class OracleCVAEGAN:
         for n in ("encoder", "generator", "classifier"):
             self.training[n] = False
         return self
+
+    # ---- sibling trainer VAE-GAN: vae_gan.py:76-141 - unconditional networks, no classifier, no label visits ----
+    def step_g_vaegan(self, x_real, noise, apply_update=True):
+        """VAE-GAN encoder/generator step (vae_gan.py:103-141): mu, logvar = E(x); z_enc (randn_like) ; z_prior (randn);
+        x_recon = G(z_enc); x_fake = G(z_prior); total = lambda_recon * MSE + lambda_kl * KL + lambda_adv * (-mean D(x_fake));
+        Adam on encoder and generator.  The critic step is `step_d(x, None, ...)` (vae_gan.py:77-101 is cvae_gan.py:104-128
+        without the label arguments)."""
+        c = self.cfg
+        B = x_real.shape[0]
+        mu, log_var = encoder_forward(self.sd["encoder"], x_real, None, self.training["encoder"], self.dp)
+        std = torch.exp(0.5 * log_var)
+        eps = noise.randn_like(std, tag="eps")
+        z_enc = mu + eps * std
+        z_prior = noise.randn(B, c.z_size, tag="z")
+        x_recon = generator_forward(self.sd["generator"], z_enc, None, self.training["generator"], self.dp)
+        x_fake = generator_forward(self.sd["generator"], z_prior, None, self.training["generator"], self.dp)
+        if self.dp is None:
+            recon = F.mse_loss(x_recon, x_real)
+            kl = -0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp()) / mu.size(0)
+        else:
+            Bg = B * self.dp.world
+            recon = ((x_recon - x_real) ** 2).sum() / (Bg * x_real.shape[1])
+            kl = -0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp()) / Bg
+        d_fake = discriminator_forward(self.sd["discriminator"], x_fake, None, self.training["discriminator"], noise)
+        adv = -self._mean(d_fake)
+        total = c.lambda_recon * recon + c.lambda_kl * kl + c.lambda_adv * adv
+        grads = self._backward(total, ["encoder", "generator"], apply_update)
+        losses = {k: self._global_scalar(v) for k, v in (("recon_loss", recon), ("kl_loss", kl), ("adv_loss", adv))}
+        self.last_losses.update(losses)
+        return losses, grads
+
+    def get_random_samples(self, num: int, noise) -> torch.Tensor:
+        """vae_gan.py:166-178: `_get_target_samples` over ALL rows (no labels)."""
+        avail = self.samples
+        if len(avail) < num:
+            return avail[noise.randint(len(avail), num)]
+        if len(avail) == num:
+            return avail
+        return avail[noise.randperm(len(avail))[:num]]
+
+    def fit_vaegan(self, x: torch.Tensor, noise=None, step_hook=None):
+        """VAEGAN.fit (vae_gan.py:42-157): per EPOCH d_loop critic steps and g_loop encoder/generator steps on batches drawn
+        from all rows; loss_history keeps recon / kl / adv of the epoch's last step."""
+        assert self.cfg.unconditional
+        noise = noise or TorchNoise()
+        c = self.cfg
+        self.loss_history = {"recon_loss": [], "kl_loss": [], "adv_loss": []}
+        for n in ("encoder", "generator", "discriminator"):
+            self.training[n] = True
+        self.samples = x
+        self.make_optimizers()
+        for e in range(c.epoch_offset, c.epoch_offset + c.epochs):
+            losses = None
+            for _ in range(c.d_loop_num):
+                out = self.step_d(self.get_random_samples(c.batch_size, noise), None, noise)
+                if step_hook:
+                    step_hook("d", e, None, out)
+            for _ in range(c.g_loop_num):
+                losses, g = self.step_g_vaegan(self.get_random_samples(c.batch_size, noise), noise)
+                if step_hook:
+                    step_hook("g", e, None, (losses, g))
+            for k in self.loss_history:
+                self.loss_history[k].append(losses[k])
+        for n in ("encoder", "generator", "discriminator"):
+            self.training[n] = False
+        return self
+
+    @torch.no_grad()
+    def reconstruct_samples_vaegan(self, x: torch.Tensor, noise=None) -> torch.Tensor:
+        """VAEGAN.reconstruct_samples (vae_gan.py:244-261): eval-mode E and G, one randn_like, both left in TRAIN mode."""
+        noise = noise or TorchNoise()
+        mu, lv = encoder_forward(self.sd["encoder"], x, None, False, None)
+        std = torch.exp(0.5 * lv)
+        out = generator_forward(self.sd["generator"], mu + noise.randn_like(std, tag="eps") * std, None, False, None)
+        self.training["encoder"] = self.training["generator"] = True
+        return out
 
     @torch.no_grad()
     def reconstruct_samples_cvae(self, x: torch.Tensor, labels: torch.Tensor, noise=None) -> torch.Tensor:

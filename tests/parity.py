@@ -56,7 +56,8 @@ def make_pair(F: int, K: int, B: int, seed=0, Z=128, **cfg_kw):
                     t.mul_(1.0 + 0.2 * torch.rand(t.shape, generator=g))
     orc.make_optimizers()
     eng = Engine(F, K, Z, max_batch=max(B, 64), lambda_recon=cfg.lambda_recon, lambda_kl=cfg.lambda_kl,
-                 lambda_adv=cfg.lambda_adv, g_lr=cfg.g_lr, d_lr=cfg.d_lr, c_lr=cfg.c_lr, hidden=cfg.hidden)
+                 lambda_adv=cfg.lambda_adv, g_lr=cfg.g_lr, d_lr=cfg.d_lr, c_lr=cfg.c_lr, hidden=cfg.hidden,
+                 unconditional=cfg.unconditional)
     st = orc.state()
     for i, net in enumerate(NETS):
         eng.load_state(i, st[net])
@@ -73,7 +74,7 @@ def draw_noise(kind: str, B: int, Z: int, g: torch.Generator, h1=256, h2=128):
         dev["z"] = z.cuda()
     if kind == "p":
         kind = "gp"
-    if kind in ("g", "v"):
+    if kind in ("g", "v", "u"):
         eps = torch.randn(B, Z, generator=g)
         inj.push("eps", eps)
         dev["eps"] = eps.cuda()
@@ -93,6 +94,8 @@ def draw_noise(kind: str, B: int, Z: int, g: torch.Generator, h1=256, h2=128):
         masks("c", 2)
     elif kind == "v":
         masks("c", 1)
+    elif kind == "u":          # VAE-GAN encoder/generator step: no classifier (vae_gan.py:103-141)
+        masks("d", 1)
     else:
         masks("d", 1)
         masks("c", 1)
@@ -176,7 +179,7 @@ def compare_state(eng, orc, report, loose_prebn_atol=0.0, nets=NETS, atol_frac=A
             # running_mean of the BN that follows such a bias tracks mean(h) = ... + bias: same looseness
             loose = key in PRE_BN_BIASES.get(name, ()) or (name in PRE_BN_BIASES and key.endswith("running_mean"))
             extra = loose_prebn_atol if loose else 0.0
-            if ONE_HOT_FIRST.get(name) == key and loose_prebn_atol:
+            if ONE_HOT_FIRST.get(name) == key and loose_prebn_atol and not orc.cfg.unconditional:
                 extra = torch.zeros(ref.shape)
                 extra[:, ref.shape[1] - orc.label_num:] = loose_prebn_atol
             extra = extra + extra_env
@@ -205,6 +208,8 @@ def twin_step(kind, orc64, x, label, inj64, lambda_class=0.25, update=False):
         _, grads = orc64.step_g_prior(label, x.shape[0], inj64, lambda_class, apply_update=update)
     elif kind == "v":
         _, grads = orc64.step_g_cvae(xd, label, inj64, lambda_class, apply_update=update)
+    elif kind == "u":
+        _, grads = orc64.step_g_vaegan(xd, inj64, apply_update=update)
     else:
         _, grads = orc64.step_g(xd, label, inj64, lambda_class, apply_update=update)
     return grads
@@ -229,9 +234,10 @@ def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True, twin=N
         run_step.last_twin_grads = twin_step(kind, twin, x, label, clone_noise(inj), lambda_class, update)
     flags = 0 if update else STEP_NO_UPDATE
     xd = x.cuda()
+    elabel = 0 if label is None else label      # unconditional networks (VAE-GAN): the engine ignores the label
     if kind == "d":
         loss, grads = orc.step_d(x, label, inj, apply_update=update)
-        out = eng.step_d(xd, label, noise=dev, flags=flags).tolist()
+        out = eng.step_d(xd, elabel, noise=dev, flags=flags).tolist()
         ref = [float(loss)]
         got = [out[0]]
     elif kind == "c":
@@ -244,6 +250,11 @@ def run_step(kind, orc, eng, x, label, g, lambda_class=0.25, update=True, twin=N
         out = eng.step_g_prior(B, label, lambda_class, noise=dev, flags=flags).tolist()
         ref = [0.0, 0.0, losses["adv_loss"], losses["class_loss"]]
         got = out
+    elif kind == "u":          # sibling trainer VAE-GAN's encoder/generator step (vae_gan.py:103-141): unconditional, no classifier
+        losses, grads = orc.step_g_vaegan(x, inj, apply_update=update)
+        out = eng.step_g(xd, 0, 0.0, noise=dev, flags=flags).tolist()
+        ref = [losses["recon_loss"], losses["kl_loss"], losses["adv_loss"]]
+        got = out[:3]
     elif kind == "v":          # sibling trainer CVAE's encoder/generator step (cvae.py:117-166)
         losses, grads = orc.step_g_cvae(x, label, inj, lambda_class, apply_update=update)
         out = eng.step_g_cvae(xd, label, lambda_class, noise=dev, flags=flags).tolist()

@@ -244,3 +244,34 @@ def test_bench_flop_accounting_reproduces_the_survey_figures():
     assert round(bench.flop_per_train_sample(30, 5, 128)) == 925_145
     assert bench.flop_per_train_sample(10, 5, 128, (256, 128, 64)) == bench.flop_per_train_sample(10, 5, 128)
     assert bench.flop_per_train_sample(10, 5, 128, bench.WIDE_HIDDEN) > 10 * bench.FLOP_PER_SAMPLE
+
+
+def test_vaegan_host_class_and_model_mirrors():
+    """src/vae_gan.py:10-261 and src/models/vae_gan_models.py: the surface a caller of the reference's VAEGAN uses, and the
+    unconditional mirrors (same keys as the CVAE-GAN's stacks, first Linear without label columns, forwards without condition)."""
+    import cvae_gan_b200 as cg
+    from cvae_gan_b200 import models
+    for name in ("fit", "_store_samples", "_get_random_samples", "plot_loss_history", "generate_samples", "reconstruct_samples"):
+        assert callable(getattr(cg.VAEGAN, name)), name
+    assert cg.config.gan_config.vae_gan_config == {"lambda_recon": 1.0, "lambda_kl": 0.01, "lambda_adv": 0.1,
+                                                   "confidence_threshold": 0.5}
+    torch.manual_seed(2)
+    E, G, D = models.VAEGANEncoderModel(10, 128), models.VAEGANGeneratorModel(128, 10), models.VAEGANDiscriminatorModel(10)
+    assert E.state_dict()["encoder.0.weight"].shape == (256, 10) and G.state_dict()["main_model.0.weight"].shape == (256, 128)
+    assert D.state_dict()["discriminator_network.0.parametrizations.weight.original"].shape == (256, 10)
+    assert [k for k, _, _ in O.tensor_table("encoder", 10, 5, 128, unconditional=True)] == list(E.state_dict().keys())
+    assert [tuple(s) for _, s, _ in O.tensor_table("discriminator", 10, 5, 128, unconditional=True)] == \
+           [tuple(v.shape) for v in D.state_dict().values()]
+    for m in (E, G, D):
+        m.eval()
+    x = torch.rand(6, 10)
+    mu, lv = E(x)
+    assert mu.shape == lv.shape == (6, 128) and G(mu).shape == (6, 10) and D(x).shape == (6, 1)
+    with pytest.raises(ValueError):
+        E(torch.zeros(4, 11))
+    with pytest.raises(ValueError):
+        G(torch.zeros(4, 127))
+    # same arithmetic as the oracle's unconditional forwards on the same state
+    sd = {k: v.detach() for k, v in E.state_dict().items()}
+    mu_o, lv_o = O.encoder_forward(sd, x, None, False, None)
+    assert torch.allclose(mu, mu_o, atol=1e-6) and torch.allclose(lv, lv_o, atol=1e-6)

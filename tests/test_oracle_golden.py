@@ -320,3 +320,41 @@ def test_configurable_widths_reproduce_the_reference_at_its_own_widths(golden_di
         for key, ref in fin[net].items():
             if ref.dtype != torch.int64:
                 torch.testing.assert_close(st[net][key], ref, rtol=2e-5, atol=2e-7, msg=f"{net}/{key}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# sibling trainer VAE-GAN (src/vae_gan.py, unconditional networks) - fixture made by oracle/make_golden_vaegan.py
+# ---------------------------------------------------------------------------------------------------
+def test_vaegan_fit_generation_and_reconstruction_match_reference(golden_dir):
+    torch.set_num_threads(1)
+    npz = _load(golden_dir, "ref_vaegan.npz")
+    F_, K, B, fit_seed, gen_seed, epochs = [int(v) for v in npz["meta"]]
+    st = _states(npz, "init")
+    st["classifier"] = _states(_load(golden_dir, "ref_fit_a.npz"), "init")["classifier"]     # VAE-GAN has no classifier: never touched
+    # vae_gan_config (gan_config.py:33-38): lambda_recon 1.0, lambda_kl 0.01, lambda_adv 0.1
+    cfg = O.OracleConfig(batch_size=B, epochs=epochs, lambda_recon=1.0, lambda_kl=0.01, lambda_adv=0.1, unconditional=True)
+    orc = O.OracleCVAEGAN(F_, K, cfg).load_state(st)
+    assert orc.sd["encoder"]["encoder.0.weight"].shape == (256, F_) and orc.sd["generator"]["main_model.0.weight"].shape == (256, 128)
+    c0 = {k: v.detach().clone() for k, v in orc.sd["classifier"].items()}
+    torch.manual_seed(fit_seed)
+    orc.fit_vaegan(torch.from_numpy(npz["x"]))
+    assert len(orc.samples) == int(npz["n_samples"][0])
+    for k in orc.loss_history:
+        np.testing.assert_allclose(orc.loss_history[k], npz["loss/" + k], rtol=2e-6, atol=1e-7)
+    fin = _states(npz, "final")
+    stt = orc.state()
+    for net in ("encoder", "generator", "discriminator"):
+        for key, ref in fin[net].items():
+            got = stt[net][key]
+            if ref.dtype == torch.int64:
+                assert torch.equal(got, ref), (net, key)
+            else:
+                torch.testing.assert_close(got, ref, rtol=2e-5, atol=2e-7, msg=f"{net}/{key}")
+    for k, v in orc.sd["classifier"].items():
+        assert torch.equal(v.detach(), c0[k]), k
+    torch.manual_seed(gen_seed)
+    s = orc.generate_samples(None, 41)
+    torch.testing.assert_close(s, torch.from_numpy(npz["gen/samples_n41"]), rtol=1e-5, atol=1e-6)
+    rec = orc.reconstruct_samples_vaegan(torch.from_numpy(npz["rec/x"]))
+    torch.testing.assert_close(rec, torch.from_numpy(npz["rec/out"]), rtol=1e-5, atol=1e-6)
+    assert npz["rec/modes_after"].tolist() == [orc.training["encoder"], orc.training["generator"], orc.training["discriminator"]]
