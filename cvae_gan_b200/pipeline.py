@@ -1,4 +1,5 @@
-"""The reference's driver around the hot path (/root/reference/scripts/train_cvae_gan.py): min-max scaling of the
+"""The reference's driver around the hot path (/root/reference/scripts/train_cvae_gan.py; scripts/train_cgan.py and
+scripts/train_cvae.py are the same driver around the sibling trainers - `run(trainer=CGAN | CVAE)`): min-max scaling of the
 concatenated train+test features (:19-43), `CVAEGAN.fit` (:47-51), the class-balancing loop that tops every class up to
 the majority count with `generate_qualified_samples` (:60-95), the pickle hand-off `(tr_x, tr_y, te_x, te_y)` as numpy
 arrays (:131-140) and the downstream `Classifier` fine-tune + multi-class / binary test (:143-175).
@@ -72,19 +73,24 @@ def dump_dataset(path: str, datasets=_datasets):
                      datasets.te_labels.numpy()), f)
 
 
-def run(datasets=_datasets, config=_config, pickle_path: Optional[str] = None, verbose: bool = False):
-    """The whole script; returns (gan, clf, report)."""
+def run(datasets=_datasets, config=_config, pickle_path: Optional[str] = None, verbose: bool = False, trainer=None,
+        name: Optional[str] = None):
+    """The whole script; returns (gan, clf, report).  `trainer`: the host class to train - `CVAEGAN` (default), or a sibling
+    with the same surface, `CGAN` / `CVAE`: the reference's scripts/train_cgan.py and scripts/train_cvae.py are this same driver
+    around `src.CGAN()` / `src.CVAE()`; `name`: the `Classifier(name)` tag ('CVAE_GAN', 'CGAN', 'CVAE')."""
+    trainer = trainer or CVAEGAN
+    name = name or {"CVAEGAN": "CVAE_GAN"}.get(trainer.__name__, trainer.__name__)
     set_random_state(config)
     minmax_scale_(datasets)
     set_random_state(config)
-    gan = CVAEGAN(config=config, datasets=datasets)
+    gan = trainer(config=config, datasets=datasets)
     gan.fit(datasets.TrDataset())
     before = {i: len(gan.samples[i]) for i in gan.samples.keys()}
     stats = balance(gan, datasets, verbose)
     if pickle_path:
         dump_dataset(pickle_path, datasets)
     set_random_state(config)
-    clf = Classifier('CVAE_GAN')
+    clf = Classifier(name)
     clf.model = gan.classifier                      # train_cvae_gan.py:145
     clf.fit(datasets.TrDataset())
     clf.test(datasets.TeDataset())

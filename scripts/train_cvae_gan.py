@@ -26,15 +26,21 @@ def load_csv(path):
     return torch.tensor(data.fillna(0).values, dtype=torch.float32)
 
 
-def main():
+TRAINERS = {"cvae_gan": "CVAEGAN", "cgan": "CGAN", "cvae": "CVAE"}
+
+
+def main(default_trainer="cvae_gan"):
     ap = argparse.ArgumentParser()
     for a in ("--x-train", "--y-train", "--x-test", "--y-test"):
         ap.add_argument(a)
     ap.add_argument("--synthetic", action="store_true")
     ap.add_argument("--epochs", type=int, default=None)
     ap.add_argument("--clf-epochs", type=int, default=None)
-    ap.add_argument("--out", default="data_cvae_gan.pkl")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--trainer", default=default_trainer, choices=sorted(TRAINERS),
+                    help="cvae_gan (scripts/train_cvae_gan.py), cgan (scripts/train_cgan.py) or cvae (scripts/train_cvae.py) of the reference")
     args = ap.parse_args()
+    args.out = args.out or f"data_{args.trainer}.pkl"
     ds = pkg.datasets
     if args.synthetic:
         from sklearn.datasets import make_blobs
@@ -51,7 +57,7 @@ def main():
         pkg.config.gan_config.epochs = args.epochs
     if args.clf_epochs is not None:
         pkg.config.classifier_config.epochs = args.clf_epochs
-    gan, clf, rep = pipeline.run(ds, pkg.config, pickle_path=args.out, verbose=True)
+    gan, clf, rep = pipeline.run(ds, pkg.config, pickle_path=args.out, verbose=True, trainer=getattr(pkg, TRAINERS[args.trainer]))
     print("class counts before:", rep["class_counts_before"])
     print("generation:", rep["generation"])
     print("augmented train rows:", rep["train_rows"])

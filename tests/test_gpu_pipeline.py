@@ -14,7 +14,10 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def test_pipeline_end_to_end(tmp_path):
+@pytest.mark.parametrize("trainer", ["CVAEGAN", "CGAN", "CVAE"])
+def test_pipeline_end_to_end(tmp_path, trainer):
+    """`trainer`: scripts/train_cvae_gan.py, scripts/train_cgan.py and scripts/train_cvae.py of the reference are the same driver
+    around the three trainer classes."""
     import cvae_gan_b200 as pkg
     from cvae_gan_b200 import pipeline
     from sklearn.datasets import make_blobs
@@ -24,15 +27,17 @@ def test_pipeline_end_to_end(tmp_path):
     ds, cfg = pkg.datasets, pkg.config
     ds.tr_samples, ds.tr_labels, ds.te_samples, ds.te_labels = x[:1000], y[:1000], x[1000:], y[1000:]
     gc, cc = cfg.gan_config, cfg.classifier_config
-    old = (gc.epochs, gc.batch_size, cc.epochs, dict(gc.cvae_gan_config))
+    key = getattr(pkg, trainer)._CONFIG_KEY
+    old = (gc.epochs, gc.batch_size, cc.epochs, dict(getattr(gc, key)))
     gc.epochs, gc.batch_size, cc.epochs = 6, 64, 8
-    gc.cvae_gan_config['confidence_threshold'] = 0.0     # a 6-epoch classifier is not confident; keep argmax filtering
+    getattr(gc, key)['confidence_threshold'] = 0.0       # a 6-epoch classifier is not confident; keep argmax filtering
     out = str(tmp_path / "data.pkl")
     try:
-        gan, clf, rep = pipeline.run(ds, cfg, pickle_path=out)
+        gan, clf, rep = pipeline.run(ds, cfg, pickle_path=out, trainer=getattr(pkg, trainer))
     finally:
         gc.epochs, gc.batch_size, cc.epochs = old[0], old[1], old[2]
-        gc.cvae_gan_config.update(old[3])
+        getattr(gc, key).update(old[3])
+    assert type(gan).__name__ == trainer and clf.name == {"CVAEGAN": "CVAE_GAN"}.get(trainer, trainer) + "_classifier"
     # scaling: everything in [0, 1]
     assert float(ds.tr_samples.min()) >= 0.0 and float(ds.tr_samples.max()) <= 1.0 + 1e-6
     # balancing never exceeds the target and appends matching labels
