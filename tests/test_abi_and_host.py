@@ -275,3 +275,35 @@ def test_vaegan_host_class_and_model_mirrors():
     sd = {k: v.detach() for k, v in E.state_dict().items()}
     mu_o, lv_o = O.encoder_forward(sd, x, None, False, None)
     assert torch.allclose(mu, mu_o, atol=1e-6) and torch.allclose(lv, lv_o, atol=1e-6)
+
+
+def test_dataset_tensors_honours_the_dataset_that_is_passed_in():
+    """cvae_gan.py:238-245 iterates `for sample, label in dataset`: whatever dataset is PASSED is what gets partitioned - this
+    package's own Dataset (fast path), torch's TensorDataset (its `.tensors` is a tuple, not a method), a same-length subset or
+    permutation of the global training set (no length heuristics), or any indexable dataset."""
+    from torch.utils.data import Subset, TensorDataset
+    import cvae_gan_b200 as cg
+    from cvae_gan_b200.cvae_gan import dataset_tensors
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.rand(40, 6, generator=g), torch.randint(0, 3, (40,), generator=g)
+    saved = (cg.datasets.tr_samples, cg.datasets.tr_labels)
+    try:
+        cg.datasets.tr_samples, cg.datasets.tr_labels = x, y
+        a, b = dataset_tensors(cg.datasets.TrDataset())
+        assert torch.equal(a, x) and torch.equal(b, y)
+        perm = torch.randperm(40, generator=g)
+        a, b = dataset_tensors(TensorDataset(x[perm], y[perm]))              # same length as the globals, different rows
+        assert torch.equal(a, x[perm]) and torch.equal(b, y[perm])
+        a, b = dataset_tensors(Subset(TensorDataset(x, y), list(range(0, 40, 3))))
+        assert torch.equal(a, x[::3]) and torch.equal(b, y[::3])
+
+        class Plain:
+            def __len__(self):
+                return 5
+
+            def __getitem__(self, i):
+                return x[i + 10], int(y[i + 10])
+        a, b = dataset_tensors(Plain())
+        assert torch.equal(a, x[10:15]) and b.tolist() == y[10:15].tolist()
+    finally:
+        cg.datasets.tr_samples, cg.datasets.tr_labels = saved
