@@ -14,6 +14,15 @@ scratch copy of /root/reference) and stores its inputs/outputs in `tests/golden/
 `tests/test_oracle_golden.py` replays them through this file (same torch CPU generator, same
 draw order) and requires agreement to float32 round-off.  The reference
 ships no golden vectors of its own, so running it is the only pin.
+The sibling trainers restated here are pinned the same way, each by its own generating script:
+    /root/reference/src/cgan.py     step_g_prior / fit_cgan          oracle/make_golden_cgan.py   -> ref_cgan_{a,b}.npz
+    /root/reference/src/cvae.py     step_g_cvae / fit_cvae / reconstruct_samples_cvae
+                                                                     oracle/make_golden_cvae.py   -> ref_cvae_{a,b}.npz
+    /root/reference/src/vae_gan.py  step_g_vaegan / fit_vaegan / reconstruct_samples_vaegan (unconditional forwards)
+                                                                     oracle/make_golden_vaegan.py -> ref_vaegan.npz
+`OracleConfig.hidden` (layer widths the reference hard-codes; BASELINE.json configs[4]) is NOT expressible in the reference: it
+is pinned only at the reference's own widths (the golden fit replayed with hidden = (256, 128, 64)); at other widths the
+restatement is the same code path with different shapes and has no reference output to be compared with.
 
 Third-party arithmetic: everything the reference computes is a `torch` op (un-pinned by the
 reference; this image has torch 2.11.0+cu128).  Spectral-norm semantics follow the installed
