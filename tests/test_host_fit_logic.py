@@ -1,0 +1,207 @@
+"""Host logic of the four trainer classes on CPU (no GPU, no CUDA library calls): the engine is replaced by a recording stand-in
+with the Engine's Python surface, so what is checked is exactly what the host classes decide - which label visits they issue in
+which order, with which loop counts and flags (lambda_class schedule, sibling step flags), how the Philox counter and the
+BatchNorm call counters advance, which loss columns reach `loss_history`, train / eval mode hand-over, and the refusal to train
+with stale hyper-parameters.  Reference: src/cvae_gan.py:59-236, src/cgan.py:51-196, src/cvae.py:51-179, src/vae_gan.py:42-157.
+The arithmetic behind `visit` is covered by the `-m gpu` parity tests."""
+from collections import OrderedDict
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import cvae_gan_oracle as O
+
+
+class FakeEngine:
+    """Records the calls a host class makes; parameters live in flat CPU buffers with the real tensor tables' keys / shapes."""
+    created = []
+
+    def __init__(self, feature_num, label_num, z_size=128, max_batch=4096, *, lambda_recon=1.0, lambda_kl=0.1, lambda_adv=1.0,
+                 g_lr=2e-4, d_lr=2e-4, c_lr=1e-4, world_size=1, rank=0, hidden=None, unconditional=False, **_):
+        self.F, self.K, self.Z, self.max_batch = feature_num, label_num, z_size, max_batch
+        self.world_size, self.rank, self.hidden, self.unconditional = world_size, rank, hidden, unconditional
+        self.device = torch.device("cpu")
+        self.cfg = SimpleNamespace(lambda_recon=lambda_recon, lambda_kl=lambda_kl, lambda_adv=lambda_adv, g_lr=g_lr, d_lr=d_lr, c_lr=c_lr)
+        self.tables, self.params, self.state, self.grads, self.adam_m, self.adam_v = [], [], [], [], [], []
+        for net in O.NETS:
+            tab, po, so = OrderedDict(), 0, 0
+            for key, shape, kind in O.tensor_table(net, feature_num, label_num, z_size, hidden, unconditional):
+                if kind == "buffer_i64":
+                    continue
+                n = 1
+                for s in shape:
+                    n *= s
+                if kind == "param":
+                    tab[key] = (0, tuple(shape), po)
+                    po += n
+                else:
+                    tab[key] = (1, tuple(shape), so)
+                    so += n
+            self.tables.append(tab)
+            self.params.append(torch.zeros(po))
+            self.grads.append(torch.ones(po))
+            self.adam_m.append(torch.ones(po))
+            self.adam_v.append(torch.ones(po))
+            self.state.append(torch.zeros(max(so, 1)))
+        self.adam_steps = [7, 7, 7, 7]
+        self.calls = []
+        FakeEngine.created.append(self)
+
+    def view(self, net, key, which="params"):
+        kind, shape, off = self.tables[net][key]
+        n = 1
+        for s in shape:
+            n *= s
+        buf = self.state[net] if kind == 1 else getattr(self, which)[net]
+        return buf[off:off + n].view(shape)
+
+    def load_state(self, net, sd):
+        for key in self.tables[net]:
+            self.view(net, key).copy_(sd[key].float().reshape(self.tables[net][key][1]))
+
+    def set_adam_step(self, net, t):
+        self.adam_steps[net] = t
+
+    def ctl_set(self, seed=None, counter=None, lambda_class=None):
+        self.calls.append(("ctl_set", seed, counter, lambda_class))
+
+    def verify_replicas(self):
+        self.calls.append(("verify_replicas",))
+
+    def visit(self, label, batch_global, class_rows=None, x_batches=None, loops=(5, 5, 3), flags=0, loss_out=None):
+        n = sum(loops)
+        k = sum(1 for c in self.calls if c[0] == "visit")
+        self.calls.append(("visit", label, batch_global, tuple(class_rows.shape), tuple(loops), flags))
+        # the last step's row is what the host reads back: {recon, kl, adv, class} tagged with the visit number
+        loss_out[n - 1] = torch.tensor([k + 0.1, k + 0.2, k + 0.3, k + 0.4])
+        return loss_out
+
+
+@pytest.fixture
+def host(monkeypatch):
+    import cvae_gan_b200 as cg
+    from cvae_gan_b200 import cvae_gan, vae_gan
+    FakeEngine.created.clear()
+    monkeypatch.setattr(cvae_gan, "Engine", FakeEngine)
+    monkeypatch.setattr(vae_gan, "Engine", FakeEngine)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    gc = cg.config.gan_config
+    saved = (gc.epochs, gc.batch_size, gc.d_loop_num, gc.c_loop_num, gc.g_loop_num, gc.g_lr, cg.datasets.tr_samples,
+             cg.datasets.tr_labels, cg.datasets.feature_num, cg.datasets.label_num)
+    g = torch.Generator().manual_seed(1)
+    y = torch.tensor([2, 2, 0, 1, 0, 2, 1, 1, 0, 2] * 4)                 # first occurrence order: 2, 0, 1
+    cg.datasets.tr_samples, cg.datasets.tr_labels = torch.rand(40, 6, generator=g), y
+    cg.datasets.feature_num, cg.datasets.label_num = 6, 3
+    gc.batch_size, gc.d_loop_num, gc.c_loop_num, gc.g_loop_num = 16, 5, 4, 3
+    yield cg
+    (gc.epochs, gc.batch_size, gc.d_loop_num, gc.c_loop_num, gc.g_loop_num, gc.g_lr, cg.datasets.tr_samples, cg.datasets.tr_labels,
+     cg.datasets.feature_num, cg.datasets.label_num) = saved
+
+
+def _visits(eng):
+    return [c for c in eng.calls if c[0] == "visit"]
+
+
+@pytest.mark.parametrize("cls_name,loops,flag_name,history,g_fwd,uses_encoder",
+                         [("CVAEGAN", (5, 4, 3), None, ("recon_loss", "kl_loss", "adv_loss", "class_loss"), 2, True),
+                          ("CGAN", (5, 4, 3), "STEP_PRIOR_ONLY", ("adv_loss", "class_loss"), 1, False),
+                          ("CVAE", (0, 4, 3), "STEP_CVAE", ("recon_loss", "kl_loss", "class_loss"), 1, True)])
+def test_label_visit_trainers_fit_loop(host, cls_name, loops, flag_name, history, g_fwd, uses_encoder):
+    cg = host
+    from cvae_gan_b200 import _lib
+    gc = cg.config.gan_config
+    gc.epochs = 3
+    torch.manual_seed(4)
+    gan = getattr(cg, cls_name)()
+    eng = gan.engine
+    gan.use_cuda_graphs = False
+    gan.fit(cg.datasets.TrDataset())
+    # partition: key order = first occurrence, rows keep their order (cvae_gan.py:238-245)
+    assert list(gan.samples.keys()) == [2, 0, 1]
+    for lab in (0, 1, 2):
+        assert torch.equal(gan.samples[lab], cg.datasets.tr_samples[cg.datasets.tr_labels == lab])
+    # fresh optimisers per fit (cvae_gan.py:75-97)
+    assert eng.adam_steps == [0, 0, 0, 0] and all(float(m.abs().sum()) == 0.0 for m in eng.adam_m + eng.adam_v + eng.grads)
+    # one visit per (epoch, label) in partition order; loops per trainer; e < 200 -> lambda_class = 0 (cvae_gan.py:198-204)
+    flag = getattr(_lib, flag_name) if flag_name else 0
+    vs = _visits(eng)
+    assert [v[1] for v in vs] == [2, 0, 1] * 3
+    assert all(v[2] == 16 and v[4] == loops and v[5] == (_lib.VISIT_LAMBDA_ZERO | flag) for v in vs)
+    assert [v[3] for v in vs[:3]] == [tuple(gan.samples[lab].shape) for lab in (2, 0, 1)]
+    lam_calls = [c[3] for c in eng.calls if c[0] == "ctl_set" and c[3] is not None]
+    assert lam_calls == [0.0, 0.0, 0.0]
+    # the epoch's record is the LAST label's last generator step (cvae_gan.py:219-222): visits 2, 5, 8
+    assert tuple(gan.loss_history) == history
+    col = {"recon_loss": 0.1, "kl_loss": 0.2, "adv_loss": 0.3, "class_loss": 0.4}
+    for key in history:
+        assert gan.loss_history[key] == pytest.approx([k + col[key] for k in (2, 5, 8)])
+    # Philox counter: two values per optimiser step; BatchNorm forward counts
+    n_steps = sum(loops)
+    assert gan._counter == 2 * n_steps * 9
+    nbt = int(gan.generator.state_dict()["main_model.1.num_batches_tracked"])
+    assert nbt == 9 * (loops[0] + loops[1] + g_fwd * loops[2])
+    enc = gan.encoder if uses_encoder else gan._encoder_module
+    assert int(enc.state_dict()["encoder.1.num_batches_tracked"]) == (9 * loops[2] if uses_encoder else 0)
+    assert all(not m.training for m in gan._networks())
+    assert hasattr(gan, "encoder") == uses_encoder and hasattr(gan, "discriminator") == (cls_name != "CVAE")
+
+
+def test_lambda_class_ramp_reaches_the_engine(host):
+    """Epochs >= 200 switch the visits to the lambda_class != 0 graph and hand the scheduled weight to the control block."""
+    cg = host
+    from cvae_gan_b200 import _lib
+    from cvae_gan_b200 import cvae_gan as mod
+    gc = cg.config.gan_config
+    gc.epochs = 2
+    gan = cg.CVAE()
+    gan.use_cuda_graphs = False
+    real = mod.lambda_class_at
+    try:
+        mod.lambda_class_at = lambda e, lam: real(e + 349, lam)       # epochs 349, 350 of the schedule
+        gan.fit(cg.datasets.TrDataset())
+    finally:
+        mod.lambda_class_at = real
+    lam = [c[3] for c in gan.engine.calls if c[0] == "ctl_set" and c[3] is not None]
+    assert lam == pytest.approx([0.1 * 149 / 300, 0.1 * 150 / 300])      # cvae_config lambda_class = 0.1
+    assert all(v[5] == _lib.STEP_CVAE for v in _visits(gan.engine))
+
+
+def test_stale_hyper_parameters_are_refused(host):
+    cg = host
+    gc = cg.config.gan_config
+    gc.epochs = 1
+    gan = cg.CVAEGAN()
+    gan.use_cuda_graphs = False
+    gc.g_lr = 5e-4                                        # the reference would build its optimisers with this value in fit()
+    with pytest.raises(ValueError, match="changed after"):
+        gan.fit(cg.datasets.TrDataset())
+    gan2 = cg.CVAEGAN()
+    gan2.lambda_kl = 0.7                                  # the reference reads self.lambda_kl at every step
+    with pytest.raises(ValueError, match="changed after"):
+        gan2.fit(cg.datasets.TrDataset())
+
+
+def test_vaegan_fit_loop(host):
+    """vae_gan.py:42-157: no partition, one (d_loop, 0, g_loop) visit per EPOCH over all rows with the class weight at 0."""
+    cg = host
+    from cvae_gan_b200 import _lib
+    gc = cg.config.gan_config
+    gc.epochs = 4
+    gan = cg.VAEGAN()
+    eng = gan.engine
+    assert eng.unconditional and eng.tables[0]["encoder.0.weight"][1] == (256, 6) and eng.tables[1]["main_model.0.weight"][1] == (256, 128)
+    assert eng.cfg.lambda_kl == 0.01 and eng.cfg.lambda_adv == 0.1            # vae_gan_config
+    gan.use_cuda_graphs = False
+    gan.fit(cg.datasets.TrDataset())
+    assert torch.equal(gan.samples, cg.datasets.tr_samples)
+    vs = _visits(eng)
+    assert len(vs) == 4 and all(v[1] == 0 and v[2] == 16 and v[3] == (40, 6) and v[4] == (5, 0, 3) and v[5] == _lib.VISIT_LAMBDA_ZERO
+                                for v in vs)
+    assert tuple(gan.loss_history) == ("recon_loss", "kl_loss", "adv_loss")
+    assert gan.loss_history["adv_loss"] == pytest.approx([k + 0.3 for k in range(4)])
+    assert gan._counter == 2 * 8 * 4
+    assert int(gan.generator.state_dict()["main_model.1.num_batches_tracked"]) == 4 * (5 + 2 * 3)
+    assert int(gan.encoder.state_dict()["encoder.1.num_batches_tracked"]) == 4 * 3
+    assert eng.adam_steps == [0, 0, 0, 0] and all(not m.training for m in gan._networks())
+    assert not hasattr(gan, "classifier")
