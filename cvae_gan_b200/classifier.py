@@ -6,8 +6,9 @@ scripts/train_cvae_gan.py:143-165.
 labels, backward, Adam(lr = classifier_config.lr, torch default betas) with a FRESH optimiser state, exactly what
 `Adam(params=self.model.parameters(), lr=...)` gives the reference) whenever `self.model` is a classifier attached to
 an engine - i.e. after `clf.model = gan.classifier` (train_cvae_gan.py:145).  Batches follow the reference's
-`DataLoader(dataset, batch_size, shuffle=True)`: a new permutation per epoch from a generator seeded out of torch's
-default CPU generator (the mechanism of `RandomSampler`), last partial batch included.  Dropout masks come from the
+`DataLoader(dataset, batch_size, shuffle=True)`: per epoch the iterator's base-seed draw, then a permutation from a generator
+seeded out of torch's default CPU generator (the mechanism of `RandomSampler`), last partial batch included - given the same
+generator state the batches ARE the loader's (tests/test_host_fit_logic.py).  Dropout masks come from the
 engine's Philox stream, whereas the reference's dropout draws interleave with the sampler's on the same generator -
 so the trajectory matches the reference statistically, not bit for bit (tests compare F1; the bit-level replay of the
 reference's own sequence lives in oracle/classifier_oracle.py).
@@ -67,7 +68,9 @@ class Classifier:
         step = 0
         seed = int(torch.empty((), dtype=torch.int64).random_().item())   # dropout stream of this fit
         for e in range(int(cc.epochs)):
-            # RandomSampler.__iter__ (shuffle=True, no generator given): seed a fresh generator from the default RNG
+            # iter(DataLoader(..., shuffle=True)) draws twice from the default CPU generator: the iterator's base seed
+            # (_BaseDataLoaderIter), then RandomSampler.__iter__ seeds a private generator for the permutation
+            torch.empty((), dtype=torch.int64).random_()
             g = torch.Generator()
             g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
             perm = torch.randperm(n, generator=g).to(eng.device)

@@ -205,3 +205,92 @@ def test_vaegan_fit_loop(host):
     assert int(gan.encoder.state_dict()["encoder.1.num_batches_tracked"]) == 4 * 3
     assert eng.adam_steps == [0, 0, 0, 0] and all(not m.training for m in gan._networks())
     assert not hasattr(gan, "classifier")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generate_qualified_samples (cvae_gan.py:347-378): the chunk-of-10 / patience-20 loop replayed on fused batches
+# ---------------------------------------------------------------------------------------------------------------------
+def _stream_keep(rows: torch.Tensor, period: int, hits: int) -> torch.Tensor:
+    return ((rows * 2654435761) % 4294967296 // 65536) % period < hits
+
+
+class FilterEngine(FakeEngine):
+    """generate_filter over a deterministic row stream: row r is the vector [r, r, ...] and is accepted iff _stream_keep(r);
+    accepted rows come back compacted in REVERSE order (the kernel's order is whatever the atomics give)."""
+    period, hits = 7, 2
+
+    def generate_filter(self, label, n, thr, z=None, seed=0, row_offset=0, capacity=None, want_logits=False, want_keep=False):
+        rows = torch.arange(row_offset, row_offset + n)
+        keep = _stream_keep(rows, self.period, self.hits)
+        acc = rows[keep].flip(0)
+        x_out = torch.full((n, self.F), -1.0)
+        idx_out = torch.full((n,), -1, dtype=torch.int64)
+        x_out[:len(acc)] = acc[:, None].float().expand(-1, self.F)
+        idx_out[:len(acc)] = acc
+        self.calls.append(("generate_filter", label, n, thr, row_offset))
+        return x_out, idx_out, torch.tensor([len(acc)]), None, keep.to(torch.uint8)
+
+
+@pytest.mark.parametrize("period,hits,num", [(7, 2, 25), (3, 2, 200), (1000, 1, 30), (50, 0, 5), (2, 1, 1), (400, 1, 3000)])
+def test_generate_qualified_samples_replays_the_reference_loop(host, monkeypatch, period, hits, num):
+    cg = host
+    from cvae_gan_b200 import cvae_gan
+    monkeypatch.setattr(cvae_gan, "Engine", FilterEngine)
+    monkeypatch.setattr(FilterEngine, "period", period)
+    monkeypatch.setattr(FilterEngine, "hits", hits)
+    gan = cg.CVAEGAN()
+    gan.generator.eval()
+    gan._gen_rows = 12345                                  # the generation stream continues where earlier calls stopped
+    out = gan.generate_qualified_samples(1, num, 0.5)
+    # the reference's loop, literally, on the same stream
+    result, pos, patience = [], 12345, 20
+    while len(result) < num and patience > 0:
+        n = min(10, num - len(result))
+        rows = torch.arange(pos, pos + n)
+        valid = rows[_stream_keep(rows, period, hits)]
+        pos += n
+        result.extend(valid.tolist())
+        if len(valid) == 0:
+            patience -= 1
+    if result:
+        assert out.shape == (len(result), 6) and out[:, 0].tolist() == [float(r) for r in result]      # same rows, same order
+    else:
+        assert out.numel() == 0 and out.shape == torch.tensor([]).shape
+    assert gan._gen_rows == pos                                # the stream position the loop would have reached
+    assert gan.classifier.training                             # reference quirk: C is left in train mode (cvae_gan.py:363)
+    assert all(c[3] == 0.5 and c[1] == 1 for c in gan.engine.calls if c[0] == "generate_filter")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Classifier.fit (classifier.py:24-45): the batches are the ones DataLoader(dataset, batch_size, shuffle=True) would yield
+# ---------------------------------------------------------------------------------------------------------------------
+def test_classifier_fit_batches_follow_dataloader_shuffle(host):
+    from torch.utils.data import DataLoader, TensorDataset
+    cg = host
+    cc = cg.config.classifier_config
+    saved = (cc.epochs, cc.batch_size)
+    try:
+        cc.epochs, cc.batch_size = 3, 16
+        eng = FakeEngine(6, 3)
+        seen = []
+        eng.max_batch = 64
+        eng.reset_adam = lambda net: eng.calls.append(("reset_adam", net))
+        eng.step_classifier = lambda x, y, lr, seed, counter, loss_out: seen.append((x.clone(), y.clone(), lr, counter))
+        clf = cg.Classifier("T")
+        clf.model.attach(eng, 3)
+        torch.manual_seed(11)
+        clf.fit(cg.datasets.TrDataset())
+        assert ("reset_adam", 3) in eng.calls and len(clf.loss_history) == 3 and not clf.model.training
+        # the reference's loader under the same generator state (one draw precedes the epochs here: the dropout stream's seed)
+        torch.manual_seed(11)
+        torch.empty((), dtype=torch.int64).random_()
+        loader = DataLoader(TensorDataset(cg.datasets.tr_samples, cg.datasets.tr_labels), batch_size=16, shuffle=True)
+        want = [(xb, yb) for _ in range(3) for xb, yb in loader]
+        assert len(seen) == len(want) == 9 and [int(c) for *_, c in seen] == list(range(9))
+        for (x, y, lr, _), (xb, yb) in zip(seen, want):
+            assert torch.equal(x, xb) and torch.equal(y, yb) and lr == cc.lr         # incl. the last partial batch of 8 rows
+        with pytest.raises(ValueError, match="labels must lie"):
+            cg.datasets.tr_labels = cg.datasets.tr_labels + 5
+            clf.fit(cg.datasets.TrDataset())
+    finally:
+        cc.epochs, cc.batch_size = saved
