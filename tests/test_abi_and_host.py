@@ -307,3 +307,29 @@ def test_dataset_tensors_honours_the_dataset_that_is_passed_in():
         assert torch.equal(a, x[10:15]) and b.tolist() == y[10:15].tolist()
     finally:
         cg.datasets.tr_samples, cg.datasets.tr_labels = saved
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(lib, tmp_path):
+    """The drop-in boundary is a C ABI: include/cvaegan_b200.h must compile as C99 (no C++ in the signatures) and a C program
+    that includes it must link against libcvaegan_b200.so and agree with it on the ABI version and the size of CvgConfig.
+    No compute call is made (no GPU here)."""
+    import shutil
+    import subprocess
+    from cvae_gan_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include <stdio.h>\n#include "cvaegan_b200.h"\n'
+                   'int main(void) {\n'
+                   '  CvgConfig c; (void)c;\n'
+                   '  printf("%d %d %d %d\\n", cvg_abi_version(), CVG_ABI_VERSION, cvg_config_bytes(), (int)sizeof(CvgConfig));\n'
+                   '  return cvg_abi_version() == CVG_ABI_VERSION && cvg_config_bytes() == (int)sizeof(CvgConfig) ? 0 : 1;\n}\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libcvaegan_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    a, b, c, d = [int(v) for v in out.stdout.split()]
+    assert a == b == _lib.ABI_VERSION and c == d == C.sizeof(_lib.CvgConfig)
