@@ -144,14 +144,14 @@ def synth_class_tables(device, rows_per_class, seed=0):
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path, timed on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def time_cpu_port(visits: int, warm: int, batch: int, threads: int, rows_per_class=20000):
+def time_cpu_port(visits: int, warm: int, batch: int, threads: int, rows_per_class=20000, hidden=None):
     """Label visits of the reference algorithm (oracle port, torch CPU ops, torch RNG like the reference)."""
     import torch
     from oracle import cvae_gan_oracle as O
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(0)
-    cfg = O.OracleConfig(batch_size=batch)
+    cfg = O.OracleConfig(batch_size=batch, hidden=hidden)
     orc = O.OracleCVAEGAN(F_, K_, cfg).init_like_reference(g)
     orc.make_optimizers()
     xs = [(torch.rand(F_, generator=g) + 0.08 * torch.randn(rows_per_class, F_, generator=g)).clamp(0, 1) for _ in range(K_)]
@@ -521,6 +521,13 @@ def run_ours(args):
         if e2e_fit:
             line["e2e_fit"] = e2e_fit
         if train_wide:
+            if cpu and "value" in train_wide:
+                try:      # the same widened label visit on the host cores (oracle port with OracleConfig.hidden): 1 visit, no warm-up
+                    vw, sw = time_cpu_port(1, 0, BATCH_PER_GPU, cores, hidden=WIDE_HIDDEN)
+                    train_wide["cpu_baseline"] = {"value": vw, "unit": "samples/s", "cores": cores, "kind": "port",
+                                                  "sample": f"1 label visit at batch {BATCH_PER_GPU}, {sw:.1f} s", "ratio": train_wide["value"] / vw}
+                except Exception as ex:
+                    train_wide["cpu_baseline"] = {"error": str(ex)[:200]}
             line["train_wide"] = train_wide
         if dp_par:
             line["dp_parity"] = dp_par
