@@ -294,3 +294,44 @@ def test_classifier_fit_batches_follow_dataloader_shuffle(host):
             clf.fit(cg.datasets.TrDataset())
     finally:
         cc.epochs, cc.batch_size = saved
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# plotting surface (cvae_gan.py:263-337, cgan.py:216-262, cvae.py:203-261, vae_gan.py:180-236, classifier.py:202-303):
+# matplotlib is not in this image; a stand-in module checks that the methods run and save under the reference's file names
+# ---------------------------------------------------------------------------------------------------------------------
+def test_plot_methods_run_and_use_the_reference_file_names(host, monkeypatch, tmp_path):
+    import sys
+    from unittest import mock
+    cg = host
+    plt = mock.MagicMock()
+    mpl = mock.MagicMock()
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    monkeypatch.setattr(cg.config, "path_config", SimpleNamespace(gan_outs=tmp_path), raising=False)
+    want = {"CVAEGAN": ["cvae_gan_loss_history.jpg", "cvae_gan_combined_loss.jpg"], "CGAN": ["cgan_loss_history.jpg", "cgan_combined_loss.jpg"],
+            "CVAE": ["cvae_loss_history.jpg", "cvae_combined_loss.jpg"], "VAEGAN": ["vae_gan_loss_history.jpg", "vae_gan_combined_loss.jpg"]}
+    for name, files in want.items():
+        plt.reset_mock()
+        gan = getattr(cg, name)()
+        for k in gan.loss_history:
+            gan.loss_history[k] = [0.3, -0.2, 0.1]
+        gan.plot_loss_history()
+        saved = [str(c.args[0]) for c in plt.savefig.call_args_list]
+        assert [s.split("/")[-1] for s in saved] == files, (name, saved)
+    # ROC curves: scores come from the engine's classifier forward (the reference scores with the raw network outputs)
+    eng = FakeEngine(6, 3)
+    g = torch.Generator().manual_seed(3)
+    scores = torch.randn(40, 3, generator=g)
+    scores[torch.arange(40), cg.datasets.tr_labels] += 2.0
+    eng.classifier_forward = lambda x: scores
+    clf = cg.Classifier("CVAE_GAN")
+    clf.model.attach(eng, 3)
+    cg.datasets.te_samples, cg.datasets.te_labels = cg.datasets.tr_samples, cg.datasets.tr_labels
+    plt.reset_mock()
+    curves = clf.plot_roc_curve(cg.datasets.TeDataset())
+    assert sorted(curves) == [0, 1, 2] and all(0.8 < c[2] <= 1.0 for c in curves.values())
+    assert str(plt.savefig.call_args_list[-1].args[0]).endswith("CVAE_GAN_roc_curve_multiclass.jpg")
+    binary = clf.plot_roc_curve(cg.datasets.TeDataset(), is_binary=True)
+    assert list(binary) == ["binary"] and str(plt.savefig.call_args_list[-1].args[0]).endswith("CVAE_GAN_roc_curve_binary.jpg")
