@@ -295,8 +295,7 @@ class CVAEGAN:
         eng = self.engine
         num = int(num)
         if self.generator.training:
-            raise RuntimeError("generate_qualified_samples before fit(): the generator is in train mode "
-                               "(batch statistics over chunks of 10 rows); call fit() or generator.eval() first")
+            return self._generate_qualified_train_mode(int(target_label), num, float(confidence_threshold))
         keeps, xs, idxs = [], [], []
         produced, accepted = 0, 0
         base = self._gen_rows
@@ -329,6 +328,31 @@ class CVAEGAN:
         x, idx = x[sel], idx[sel]
         order = torch.argsort(idx)
         return x[order][:got].cpu()
+
+    def _generate_qualified_train_mode(self, target_label: int, num: int, confidence_threshold: float):
+        """The same loop while the generator is still in TRAIN mode (called before `fit()`, or after `generator.train()`): the
+        reference then normalises every chunk of <= 10 rows with that chunk's own batch statistics (and updates the running
+        statistics per chunk), so rows are not independent and the loop is run literally, chunk by chunk, like
+        cvae_gan.py:355-376: train-mode generator forward, eval-mode classifier, filter, one host read-back per chunk.
+        A final chunk of one row fails like torch's BatchNorm does ("Expected more than 1 value per channel when training")."""
+        eng = self.engine
+        result, patience = [], 20
+        while len(result) < num and patience > 0:
+            n = min(10, num - len(result))
+            if n < 2:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size torch.Size([{n}, "
+                                 f"{self.generator.main_model[0].out_features}])")
+            x = eng.generate(target_label, n, seed=self._seed, row_offset=self._gen_rows, train_mode=True)
+            self._gen_rows += n
+            self._bn_calls[NET_GENERATOR] += 1
+            keep = eng.filter_logits(eng.classifier_forward(x), target_label, confidence_threshold)
+            valid = x[keep].cpu()
+            result.extend(valid)
+            if len(valid) == 0:
+                patience -= 1
+        self._sync_bn_counters()
+        self.classifier.train()              # the reference leaves C in train mode (cvae_gan.py:363)
+        return torch.stack(result) if result else torch.tensor([])
 
     def reconstruct_samples(self, samples: torch.Tensor, labels: torch.Tensor):
         """cvae_gan.py:380-397.  The reference ALWAYS raises here: it hands 1-D labels to the generator,

@@ -231,6 +231,18 @@ class FilterEngine(FakeEngine):
         return x_out, idx_out, torch.tensor([len(acc)]), None, keep.to(torch.uint8)
 
 
+    # train-mode path (generator not yet fitted): chunk-by-chunk primitives
+    def generate(self, label, n, z=None, seed=0, row_offset=0, train_mode=False):
+        self.calls.append(("generate", label, n, row_offset, train_mode))
+        return torch.arange(row_offset, row_offset + n)[:, None].float().expand(-1, self.F).contiguous()
+
+    def classifier_forward(self, x):
+        return x
+
+    def filter_logits(self, logits, label, thr):
+        return _stream_keep(logits[:, 0].long(), self.period, self.hits)
+
+
 @pytest.mark.parametrize("period,hits,num", [(7, 2, 25), (3, 2, 200), (1000, 1, 30), (50, 0, 5), (2, 1, 1), (400, 1, 3000)])
 def test_generate_qualified_samples_replays_the_reference_loop(host, monkeypatch, period, hits, num):
     cg = host
@@ -335,3 +347,45 @@ def test_plot_methods_run_and_use_the_reference_file_names(host, monkeypatch, tm
     assert str(plt.savefig.call_args_list[-1].args[0]).endswith("CVAE_GAN_roc_curve_multiclass.jpg")
     binary = clf.plot_roc_curve(cg.datasets.TeDataset(), is_binary=True)
     assert list(binary) == ["binary"] and str(plt.savefig.call_args_list[-1].args[0]).endswith("CVAE_GAN_roc_curve_binary.jpg")
+
+
+@pytest.mark.parametrize("period,hits,num", [(7, 2, 25), (3, 2, 120), (50, 0, 5), (1000, 1, 40), (2, 1, 31)])
+def test_generate_qualified_samples_in_train_mode_runs_the_literal_chunk_loop(host, monkeypatch, period, hits, num):
+    """Before fit() the generator is in train mode: every chunk of <= 10 rows is normalised with its own batch statistics, so
+    the loop of cvae_gan.py:355-376 is run chunk by chunk (train-mode generator forward, classifier, filter); a trailing chunk
+    of ONE row fails like torch's BatchNorm."""
+    cg = host
+    from cvae_gan_b200 import cvae_gan
+    monkeypatch.setattr(cvae_gan, "Engine", FilterEngine)
+    monkeypatch.setattr(FilterEngine, "period", period)
+    monkeypatch.setattr(FilterEngine, "hits", hits)
+    gan = cg.CVAEGAN()
+    assert gan.generator.training
+    gan._gen_rows = 777
+    result, pos, patience, chunks, fails = [], 777, 20, [], False
+    while len(result) < num and patience > 0:
+        n = min(10, num - len(result))
+        if n < 2:
+            fails = True
+            break
+        rows = torch.arange(pos, pos + n)
+        valid = rows[_stream_keep(rows, period, hits)]
+        chunks.append((n, pos))
+        pos += n
+        result.extend(valid.tolist())
+        if len(valid) == 0:
+            patience -= 1
+    if fails:
+        with pytest.raises(ValueError, match="more than 1 value per channel"):
+            gan.generate_qualified_samples(2, num, 0.5)
+        return
+    out = gan.generate_qualified_samples(2, num, 0.5)
+    gen_calls = [c for c in gan.engine.calls if c[0] == "generate"]
+    assert [(c[2], c[3]) for c in gen_calls] == chunks and all(c[1] == 2 and c[4] is True for c in gen_calls)
+    if result:
+        assert out.shape == (len(result), 6) and out[:, 0].tolist() == [float(r) for r in result]
+    else:
+        assert out.numel() == 0
+    assert gan._gen_rows == pos and gan.classifier.training
+    # one train-mode generator forward per chunk reaches num_batches_tracked (BatchNorm counts forwards, also under no_grad)
+    assert int(gan.generator.state_dict()["main_model.1.num_batches_tracked"]) == len(chunks)
